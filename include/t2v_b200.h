@@ -1,0 +1,239 @@
+/*
+ * t2v_b200.h — C ABI of libt2v_b200.so: the sm_100a kernels behind the T2V-Turbo (VideoCrafter2)
+ * latent-video UNet denoising hot path, the LCM scheduler step and the AutoencoderKL decode.
+ *
+ * The reference (Ji4chenLi/t2v-turbo) has NO FFI of its own: its "operator API" is the torch.nn
+ * call surface.  Each entry point below names the reference call sites whose
+ * arithmetic it replaces.  Conventions (all entry points):
+ *   - extern "C", POD structs, raw device pointers, sizes/strides in ELEMENTS;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is retained past the call;
+ *   - work is enqueued on the caller's stream only; no synchronisation, no allocation
+ *     => every call is CUDA-graph capturable;
+ *   - return 0 on success; <0 = argument / shape / alignment error (nothing launched);
+ *     >0 = cudaError_t / CUresult from the launch.  t2v_last_error() describes the last failure
+ *     on the calling thread.  There is no CPU or library fallback.
+ *   - activations are channels-last bf16: a frame batch is [B*T, H, W, C] (C contiguous).
+ */
+#ifndef T2V_B200_H_
+#define T2V_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* t2v_stream_t; /* cudaStream_t */
+
+#define T2V_MAX_DIMS 4
+#define T2V_MAX_TAPS 9
+
+/* epilogue flags for T2VGemmDesc.flags */
+#define T2V_EPI_GEGLU 1u   /* out[m,j] = (acc[m,v_j]+b) * gelu_erf(acc[m,g_j]+b); weights packed by t2v_pack_geglu_rows */
+#define T2V_EPI_OUT_F32 2u /* write fp32 instead of bf16 */
+#define T2V_EPI_GELU 4u    /* out = gelu_erf(acc) (unused by VC2; kept for FeedForward(glu=False)) */
+
+int t2v_version(void);
+const char* t2v_last_error(void);
+
+/*
+ * Implicit GEMM on tcgen05 tensor cores:  out[m, n] = epi( alpha * sum_k A[m, k] * W[n, k] ).
+ *
+ * A is never materialised: row m is a point (x1..x4) of up to two channels-last activation tensors
+ * (concatenated along channels), and the K axis is (tap, channel): k = tap * c_in + c, where each
+ * tap shifts the point by tap_off[tap][*] (out-of-range points read as zero = conv padding) and
+ * may add a channel offset tap_ch_off[tap] (used by the stride-2 parity view).  One CTA tile is the
+ * box[0] x box[1] x box[2] x box[3] block of points (<= 128 rows) times block_n output columns.
+ *
+ * Replaces, with the matching geometry: nn.Linear (attention.py:70-75,348,370,520,537;
+ * openaimodel3d.py:172-178), Conv2d 3x3 / 1x1 (openaimodel3d.py:155-159,179-193,65-72,104-111,666-670),
+ * Conv3d (3,1,1) (openaimodel3d.py:274-296), Conv1d k=1 (attention.py:422-424), and the VAE
+ * decoder convs (ae_modules.py:146-203,108-122,560-600).  Epilogue fusions: bias (per row group,
+ * which carries the ResBlock timestep-embedding add openaimodel3d.py:237-246), residual add
+ * (attention.py:300-311,389,513; openaimodel3d.py:247,309), GEGLU (attention.py:516-523).
+ */
+typedef struct T2VGemmDesc {
+  /* A operand */
+  const void* a[2];                     /* bf16 activation sources; a[1] may be NULL */
+  int32_t a_ch[2];                      /* channels consumed per tap from each source (multiples of 64) */
+  int32_t a_ch_total[2];                /* extent of the channel axis of each source tensor (>= a_ch + max tap_ch_off) */
+  int64_t a_size[T2V_MAX_DIMS];         /* extents of x1..x4 in the INPUT tensors (x1 fastest); unused = 1 */
+  int64_t a_stride[2][T2V_MAX_DIMS];    /* element strides of x1..x4 per source (channel stride = 1) */
+  int32_t box[T2V_MAX_DIMS];            /* tile extents; product in [8,128] and a multiple of 8 */
+  /* K loop */
+  int32_t n_taps;                       /* 1..T2V_MAX_TAPS */
+  int32_t tap_off[T2V_MAX_TAPS][T2V_MAX_DIMS];
+  int32_t tap_ch_off[T2V_MAX_TAPS];
+  /* B operand: weights [b_batches][b_rows][K] bf16, K = n_taps * (a_ch[0] + a_ch[1]) contiguous */
+  const void* b;
+  int64_t b_rows;                       /* N of the GEMM (rows of W); any N >= 1 */
+  int64_t b_batches;                    /* 1 if shared */
+  int64_t b_batch_stride;               /* elements between batches */
+  int32_t b_batch_dim;                  /* index (0..3) of the A dim whose coordinate selects the batch; -1 = none */
+  /* output: row (x1..x4) at sum_j x_j * o_stride[j], columns contiguous */
+  void* out;
+  int64_t o_size[T2V_MAX_DIMS];         /* extents of the OUTPUT point grid (rows outside are dropped) */
+  int64_t o_stride[T2V_MAX_DIMS];
+  int32_t n_out;                        /* columns written: b_rows, or b_rows/2 with T2V_EPI_GEGLU */
+  /* epilogue */
+  const float* bias;                    /* fp32 [bias_rows][b_rows] or NULL */
+  int64_t bias_row_stride;
+  int32_t bias_dim;                     /* A dim whose coordinate / bias_div selects the bias row; -1 = row 0 */
+  int32_t bias_div;
+  const void* residual;                 /* bf16, indexed like out with r_stride; NULL = none */
+  int64_t r_stride[T2V_MAX_DIMS];
+  float alpha;
+  uint32_t flags;
+  int32_t block_n;                      /* 0 = choose; else one of 64,128,160,256 */
+} T2VGemmDesc;
+
+int t2v_gemm(const T2VGemmDesc* desc, t2v_stream_t stream);
+
+/*
+ * Fused scaled-dot-product attention, head_dim 64, no mask, on tcgen05:
+ *   O[b, i, h, :] = softmax_j( scale * Q[b,i,h,:] . K[b,j,h,:] ) V[b,j,h,:]
+ * Q/K/V/O are bf16 with arbitrary batch/token/head strides (head_dim contiguous), so the kernel
+ * reads the projection outputs in place (no "b n (h d) -> (b h) n d" copy).  kv_batch_div lets
+ * several query batches share one K/V batch (cross-attention: one text context per video, 16 frames).
+ * Replaces CrossAttention.forward / efficient_forward core (attention.py:121-149,198-224) for the
+ * spatial self- and cross-attention layers.
+ */
+typedef struct T2VAttnDesc {
+  const void* q; const void* k; const void* v; void* o;
+  int32_t batch, heads, len_q, len_k;
+  int64_t q_stride_b, q_stride_t, q_stride_h;
+  int64_t k_stride_b, k_stride_t, k_stride_h;
+  int64_t v_stride_b, v_stride_t, v_stride_h;
+  int64_t o_stride_b, o_stride_t, o_stride_h;
+  int32_t kv_batch_div;                 /* kv batch index = q batch index / kv_batch_div (>= 1) */
+  float scale;
+} T2VAttnDesc;
+
+int t2v_attn_fwd(const T2VAttnDesc* desc, t2v_stream_t stream);
+
+/*
+ * Short-sequence attention (len <= 32, head_dim 64): one warp per (sequence, head); token stride
+ * is arbitrary so the temporal sequences of a [B*T, H*W, C] activation are read in place
+ * (token stride = H*W*C).  Replaces the temporal CrossAttention core (attention.py:121-149 under
+ * TemporalTransformer, attention.py:471-513).
+ */
+typedef struct T2VShortAttnDesc {
+  const void* q; const void* k; const void* v; void* o;
+  int32_t n_seq_outer, n_seq_inner, heads, len;  /* sequence id = (outer, inner) */
+  int64_t q_stride_outer, q_stride_inner, q_stride_t, q_stride_h;
+  int64_t k_stride_outer, k_stride_inner, k_stride_t, k_stride_h;
+  int64_t v_stride_outer, v_stride_inner, v_stride_t, v_stride_h;
+  int64_t o_stride_outer, o_stride_inner, o_stride_t, o_stride_h;
+  float scale;
+} T2VShortAttnDesc;
+
+int t2v_attn_short_fwd(const T2VShortAttnDesc* desc, t2v_stream_t stream);
+
+/*
+ * GroupNorm (+ optional SiLU) over channels-last activations.
+ * A sample = rows_per_sample consecutive rows of [rows, C]; statistics over (rows_per_sample x C/groups).
+ * The input may be the channel-concatenation of two tensors (UNet skip connections:
+ * openaimodel3d.py:732-734) — the output is the normalised concatenation.
+ * Replaces GroupNorm32/normalization (basics.py:78-89), nn.GroupNorm (attention.py:340-342,
+ * openaimodel3d.py:275-295, ae_modules.py:16-19) and the following SiLU / swish.
+ * workspace: fp32 [n_samples * groups * 2], zero-filled by the call itself.
+ */
+typedef struct T2VGroupNormDesc {
+  const void* x[2]; int32_t ch[2];      /* bf16 sources, channels per source (ch[1] = 0 if single) */
+  int64_t x_row_stride[2];
+  void* out; int64_t out_row_stride;    /* bf16 [rows, ch0+ch1] */
+  const float* gamma; const float* beta;/* fp32 [C] */
+  int64_t rows; int64_t rows_per_sample;
+  int32_t groups; float eps; int32_t silu;
+  float* workspace;
+} T2VGroupNormDesc;
+
+int t2v_groupnorm(const T2VGroupNormDesc* desc, t2v_stream_t stream);
+
+/* LayerNorm over the last dim of bf16 [rows, C]; fp32 affine. Replaces nn.LayerNorm (attention.py:279-281). */
+typedef struct T2VLayerNormDesc {
+  const void* x; int64_t x_row_stride;
+  void* out; int64_t out_row_stride;
+  const float* gamma; const float* beta;
+  int64_t rows; int32_t channels; float eps;
+} T2VLayerNormDesc;
+
+int t2v_layernorm(const T2VLayerNormDesc* desc, t2v_stream_t stream);
+
+/*
+ * Small-M linear on CUDA cores: out[m, n] = act_out( sum_k act_in(x[m,k]) W[n,k] + bias[n] + add[m,n] ).
+ * fp32 in/out, bf16 weights; for the timestep / fps / guidance embedding MLPs and the 22 ResBlock
+ * emb projections (openaimodel3d.py:403-430,683-711,172-178) where M = batch size.
+ */
+typedef struct T2VSmallLinearDesc {
+  const float* x; int64_t x_row_stride;
+  const void* w;                        /* bf16 [N][K] */
+  const float* bias;                    /* fp32 [N] or NULL */
+  const float* add; int64_t add_row_stride; /* fp32 [M][N] or NULL */
+  float* out; int64_t out_row_stride;
+  int32_t m, n, k;
+  int32_t silu_in;                      /* apply SiLU to x on load */
+  int32_t silu_out;
+  int32_t round_bf16;                   /* round the result through bf16 (mimics a bf16 module) */
+} T2VSmallLinearDesc;
+
+int t2v_small_linear(const T2VSmallLinearDesc* desc, t2v_stream_t stream);
+
+/* Sinusoidal embedding: out[m, :] = concat(cos(t*f), sin(t*f)) (timestep_embedding,
+ * utils_diffusion.py:8-32) or concat(sin, cos) when sin_first != 0 (get_w_embedding,
+ * t2v_turbo_vc2_pipeline.py:99-120).  freqs: fp32 [half] (built on the host with the reference's
+ * own formula); out: fp32 [m, 2*half]; round_bf16 mimics the `.to(self.dtype)` cast. */
+int t2v_sinusoidal_embedding(const float* t, const float* freqs, float* out, int32_t m,
+                             int32_t half, int32_t sin_first, int32_t round_bf16,
+                             t2v_stream_t stream);
+
+/* Direct 3x3 convolution for tiny channel counts on the input side (C_in <= 8): latent -> features.
+ * in: channels-last bf16 [N,H,W,Cin]; w: bf16 [Cout][3][3][Cin]; out bf16 [N,H,W,Cout].
+ * Replaces input_blocks.0.0 (openaimodel3d.py:433-437) and the VAE conv_in (ae_modules.py:545-547). */
+int t2v_conv3x3_small_cin(const void* in, const void* w, const float* bias, void* out, int32_t n,
+                          int32_t h, int32_t wdt, int32_t cin, int32_t cout, t2v_stream_t stream);
+
+/* Layout / resampling helpers (all bf16 unless stated). */
+/* [B,C,T,H,W] (any float dtype given by in_dtype: 0 bf16, 1 fp16, 2 fp32) -> [B*T,H,W,C] bf16, times scale */
+int t2v_bcthw_to_frames(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
+                        int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t stream);
+/* [B*T,H,W,C_pad] bf16 (first c channels) -> [B,C,T,H,W] in out_dtype */
+int t2v_frames_to_bcthw(const void* in, int32_t c_pad, void* out, int32_t out_dtype, int32_t b,
+                        int32_t c, int32_t t, int32_t h, int32_t w, t2v_stream_t stream);
+/* nearest 2x upsample of [N,H,W,C] -> [N,2H,2W,C] (F.interpolate nearest: openaimodel3d.py:104-109, ae_modules.py:118-120) */
+int t2v_upsample_nearest2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                           t2v_stream_t stream);
+/* out[r, :] = concat(a[r, :ca], b[r, :cb]) (torch.cat dim=1: openaimodel3d.py:733) */
+int t2v_concat_channels(const void* a, int32_t ca, const void* b, int32_t cb, void* out,
+                        int64_t rows, t2v_stream_t stream);
+/* row softmax over bf16 [rows, cols] in place, with pre-scale (VAE AttnBlock ae_modules.py:60-62) */
+int t2v_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t row_stride, float scale,
+                     t2v_stream_t stream);
+
+/*
+ * Fused LCM scheduler step (T2VTurboScheduler.step, scheduler/t2v_turbo_scheduler.py:367-467):
+ *   x0 = (x - sqrt(1-a_t) * eps) / sqrt(a_t);  den = c_out * x0 + c_skip * x;
+ *   prev = sqrt(a_prev) * den + sqrt(1 - a_prev) * noise
+ * Elementwise over n values; x/eps/noise/prev/den share dtype (0 bf16, 1 fp16, 2 fp32); the
+ * intermediate roundings of the reference's tensor-dtype arithmetic are reproduced (torch divides
+ * by a CPU scalar as a multiply by its fp32 reciprocal, hence inv_sqrt_alpha_t).  noise may be
+ * NULL (single-step sampling: prev = denoised).
+ */
+int t2v_lcm_step(const void* x, const void* eps, const void* noise, void* prev, void* denoised,
+                 int64_t n, int32_t dtype, float inv_sqrt_alpha_t, float sqrt_beta_t, float c_skip,
+                 float c_out, float sqrt_alpha_prev, float sqrt_beta_prev, t2v_stream_t stream);
+
+/* Weight packing helpers (device-side, run once at load). */
+/* conv weight [Cout][Cin][kh*kw] (torch OIHW / OIDHW flattened taps) -> [Cout][taps][Cin] bf16 */
+int t2v_pack_conv_weight(const void* w, int32_t w_dtype, void* out, int32_t cout, int32_t cin,
+                         int32_t taps, t2v_stream_t stream);
+/* GEGLU projection rows [2*inner][K]: interleave value/gate rows in blocks of 16 */
+int t2v_pack_geglu_rows(const void* w, int32_t w_dtype, void* out, const void* bias,
+                        int32_t bias_dtype, float* bias_out, int32_t inner, int32_t k,
+                        t2v_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2V_B200_H_ */

@@ -1,0 +1,326 @@
+// Fused attention forward, head_dim 64, no mask, on tcgen05 (sm_100a).
+//
+//   O[b,i,h,:] = softmax_j(scale * Q[b,i,h,:] . K[b',j,h,:]) V[b',j,h,:],   b' = b / kv_batch_div
+//
+// One CTA = one (batch, head, 128-query tile); two CTAs are co-resident per SM (256 TMEM columns
+// and ~112 KB shared memory each) so one CTA's softmax overlaps the other's MMAs.
+//   warp 0 / lane 0 : TMA producer — Q tile once, K / V tiles (128 keys) through 2-stage rings.
+//                     Q/K/V are read in place from the projection outputs via 4-D tensor maps
+//                     {64, head, token, batch}: no head-split copy.
+//   warp 1 / lane 0 : MMA issuer — S = Q K^T (M128 N128 K64) into TMEM, then O += P V
+//                     (M128 N64 K128) with P from shared memory and V as an MN-major operand.
+//   warp 2          : TMEM allocator.
+//   warps 4..7      : online softmax, thread = query row: tcgen05.ld S, running max / sum in
+//                     fp32 (exp2 with the scale folded in), P -> bf16 -> 128B-swizzled smem,
+//                     lazy rescale of the O accumulator in TMEM, final 1/l scaling and store.
+#include <cuda.h>
+#include <string.h>
+
+#include "../../include/t2v_b200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace t2v {
+
+constexpr int kAtThreads = 256;
+constexpr int kKvStages = 2;
+constexpr int kTile = 128;
+constexpr int kQBytes = kTile * 64 * 2;   // 16 KB
+constexpr int kKBytes = kTile * 64 * 2;   // 16 KB
+constexpr int kPBytes = kTile * kTile * 2;  // 32 KB (two K-major 64-key sub-tiles)
+constexpr int kAtSmem = kQBytes + 2 * kKvStages * kKBytes + kPBytes + 256;
+constexpr int kTmemColsAttn = 256;
+constexpr int kOCol = 128;
+
+struct AttnParams {
+  int32_t heads, len_q, len_k, n_q_tiles, n_kv_tiles, kv_batch_div;
+  float scale_log2;
+  __nv_bfloat16* o;
+  int64_t o_stride_b, o_stride_t, o_stride_h;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAtThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kQBytes;
+  uint8_t* sV = sK + kKvStages * kKBytes;
+  uint8_t* sP = sV + kKvStages * kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // kKvStages
+  uint64_t* k_empty = k_full + kKvStages;  // kKvStages
+  uint64_t* v_full = k_empty + kKvStages;
+  uint64_t* v_empty = v_full + kKvStages;
+  uint64_t* s_full = v_empty + kKvStages;  // 1
+  uint64_t* p_full = s_full + 1;           // 1 (128 arrivals)
+  uint64_t* pv_done = p_full + 1;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int q_tile = blockIdx.x % p.n_q_tiles;
+  const int bh = blockIdx.x / p.n_q_tiles;
+  const int h = bh % p.heads;
+  const int b = bh / p.heads;
+  const int kvb = b / p.kv_batch_div;
+  const int q0 = q_tile * kTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemColsAttn);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_kv = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    mbar_expect_tx(q_full, kQBytes);
+    tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % kKvStages;
+      const uint32_t ph = (j / kKvStages) & 1;
+      mbar_wait(&k_empty[s], ph ^ 1u);
+      mbar_expect_tx(&k_full[s], kKBytes);
+      tma_load_4d(sK + s * kKBytes, &tmK, &k_full[s], 0, h, j * kTile, kvb);
+      mbar_wait(&v_empty[s], ph ^ 1u);
+      mbar_expect_tx(&v_full[s], kKBytes);
+      tma_load_4d(sV + s * kKBytes, &tmV, &v_full[s], 0, h, j * kTile, kvb);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (K-major) x V (MN-major)
+    const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % kKvStages;
+      const uint32_t ph = (j / kKvStages) & 1;
+      // S = Q K_j^T   (S is free: the softmax of tile j-1 finished reading it before p_full(j-1))
+      mbar_wait(&k_full[s], ph);
+      tc_fence_after();
+      const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + s * kKBytes));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss(tmem_base, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+      umma_commit(&k_empty[s]);
+      umma_commit(s_full);
+      // O += P_j V_j
+      mbar_wait(p_full, j & 1);
+      mbar_wait(&v_full[s], ph);
+      tc_fence_after();
+      const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + s * kKBytes));
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        // A: 16 keys = 32 bytes inside the (kk/4)-th 64-key sub-tile; B: 16 key rows = 2048 bytes
+        const uint64_t ad = pdesc + uint64_t((kk >> 2) * (kTile * 128 >> 4)) + 2 * (kk & 3);
+        const uint64_t bd = vdesc + uint64_t(kk * (2048 >> 4));
+        umma_ss(tmem_base + kOCol, ad, bd, idesc_o, (j | kk) != 0);
+      }
+      umma_commit(&v_empty[s]);
+      umma_commit(pv_done);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax / correction / epilogue
+    const int ew = warp - 4;
+    const int r = ew * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr;
+    const uint32_t o_addr = tmem_base + lane_addr + kOCol;
+    uint8_t* p_row = sP + r * 128;
+    const int sw = r & 7;
+    float m_run = -INFINITY;  // running max of scaled (log2-domain) scores
+    float l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv_left = p.len_k - j * kTile;  // valid keys in this tile (>= 1)
+      // pass 1: row max
+      float mx = m_run;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(s_addr + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sv = __uint_as_float(v[i]) * p.scale_log2;
+          if (c0 + i < kv_left) mx = fmaxf(mx, sv);
+        }
+      }
+      const float m_new = mx;
+      // pass 2: p = 2^(s - m_new), row sum, bf16 P -> swizzled smem
+      // (the P buffer is free: PV(j-1) completion was observed below before this point)
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(s_addr + c0, v);
+        tmem_wait_ld();
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sv = __uint_as_float(v[i]) * p.scale_log2;
+          const float e = (c0 + i < kv_left) ? ex2(sv - m_new) : 0.f;
+          pf[i] = e;
+          rs += e;
+        }
+        // 32 keys = 4 chunks of 16 bytes; chunk index within the 128-key row: c0/8 + q
+        uint8_t* sub = p_row + (c0 >> 6) * (kTile * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cc = ((c0 & 63) >> 3) + q;
+          uint4 pk;
+          pk.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
+          pk.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
+          pk.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
+          pk.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
+          *reinterpret_cast<uint4*>(sub + ((cc ^ sw) << 4)) = pk;
+        }
+      }
+      const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+      l_run = l_run * alpha + rs;
+      // lazy correction of the O accumulator (skipped while the running max is stable)
+      if (j > 0) {
+        const bool need = m_new > m_run;
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t ov[16];
+            tmem_ld_32x16(o_addr + c0, ov);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x16(o_addr + c0, ov);
+          }
+          tmem_wait_st();
+        }
+      }
+      m_run = m_new;
+      fence_proxy_async();  // P stores (generic proxy) -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // wait for PV(j): O is updated and the P buffer may be overwritten
+      mbar_wait(pv_done, j & 1);
+      tc_fence_after();
+    }
+    // epilogue: O / l -> bf16 -> global
+    const int qi = q0 + r;
+    const float inv_l = 1.0f / l_run;
+    __nv_bfloat16* orow = p.o + int64_t(b) * p.o_stride_b + int64_t(qi) * p.o_stride_t + int64_t(h) * p.o_stride_h;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t ov[32];
+      tmem_ld_32x32(o_addr + c0, ov);
+      tmem_wait_ld();
+      if (qi < p.len_q) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
+          pk.y = pack_bf16(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
+          pk.z = pack_bf16(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
+          pk.w = pack_bf16(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c0 + q * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemColsAttn);
+  }
+}
+
+}  // namespace t2v
+
+extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
+  using namespace t2v;
+  if (!d || !d->q || !d->k || !d->v || !d->o) return fail(-1, "t2v_attn_fwd: null pointer");
+  if (d->batch < 1 || d->heads < 1 || d->len_q < 1 || d->len_k < 1) return fail(-2, "t2v_attn_fwd: bad sizes");
+  if (d->kv_batch_div < 1 || d->batch % d->kv_batch_div) return fail(-3, "t2v_attn_fwd: batch %% kv_batch_div != 0");
+  if (d->o_stride_b % 8 || d->o_stride_t % 8 || d->o_stride_h % 8 || (reinterpret_cast<uintptr_t>(d->o) & 15))
+    return fail(-4, "t2v_attn_fwd: output must be 16-byte aligned with strides multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int kvb = d->batch / d->kv_batch_div;
+  CUtensorMap tq, tk, tv;
+  {
+    uint64_t dims[4] = {64, uint64_t(d->heads), uint64_t(d->len_q), uint64_t(d->batch)};
+    uint64_t str[4] = {2, uint64_t(d->q_stride_h) * 2, uint64_t(d->q_stride_t) * 2, uint64_t(d->q_stride_b) * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    if (d->heads == 1 && str[1] == 0) str[1] = 128;
+    if (d->batch == 1 && str[3] == 0) str[3] = str[2] * d->len_q;
+    int rc = make_tmap_bf16(&tq, d->q, 4, dims, str, box, "t2v_attn_fwd Q");
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {64, uint64_t(d->heads), uint64_t(d->len_k), uint64_t(kvb)};
+    uint64_t str[4] = {2, uint64_t(d->k_stride_h) * 2, uint64_t(d->k_stride_t) * 2, uint64_t(d->k_stride_b) * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    if (d->heads == 1 && str[1] == 0) str[1] = 128;
+    if (kvb == 1 && str[3] == 0) str[3] = str[2] * d->len_k;
+    int rc = make_tmap_bf16(&tk, d->k, 4, dims, str, box, "t2v_attn_fwd K");
+    if (rc) return rc;
+    uint64_t strv[4] = {2, uint64_t(d->v_stride_h) * 2, uint64_t(d->v_stride_t) * 2, uint64_t(d->v_stride_b) * 2};
+    if (d->heads == 1 && strv[1] == 0) strv[1] = 128;
+    if (kvb == 1 && strv[3] == 0) strv[3] = strv[2] * d->len_k;
+    rc = make_tmap_bf16(&tv, d->v, 4, dims, strv, box, "t2v_attn_fwd V");
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.heads = d->heads;
+  p.len_q = d->len_q;
+  p.len_k = d->len_k;
+  p.n_q_tiles = (d->len_q + kTile - 1) / kTile;
+  p.n_kv_tiles = (d->len_k + kTile - 1) / kTile;
+  p.kv_batch_div = d->kv_batch_div;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.o = static_cast<__nv_bfloat16*>(d->o);
+  p.o_stride_b = d->o_stride_b;
+  p.o_stride_t = d->o_stride_t;
+  p.o_stride_h = d->o_stride_h;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_fwd)");
+    configured = true;
+  }
+  const int64_t grid = int64_t(d->batch) * d->heads * p.n_q_tiles;
+  if (grid > 0x7fffffff) return fail(-5, "t2v_attn_fwd: grid too large");
+  attn_fwd_kernel<<<unsigned(grid), kAtThreads, kAtSmem, stream>>>(tq, tk, tv, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_attn_fwd launch");
+}

@@ -1,0 +1,416 @@
+// Small / HBM-bound kernels around the tensor-core path: embedding MLP rows (M = batch), sinusoidal
+// embeddings, the 4-channel latent convolution, layout conversion at the UNet boundary, nearest
+// upsampling, channel concat, row softmax, the fused LCM scheduler step and weight packing.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../../include/t2v_b200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace t2v {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float load_as_float(const void* p, int64_t i, int dtype) {
+  if (dtype == 0) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+  if (dtype == 1) return __half2float(static_cast<const __half*>(p)[i]);
+  return static_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void store_from_float(void* p, int64_t i, int dtype, float v) {
+  if (dtype == 0) static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else if (dtype == 1) static_cast<__half*>(p)[i] = __float2half_rn(v);
+  else static_cast<float*>(p)[i] = v;
+}
+__device__ __forceinline__ float round_to(float v, int dtype) {
+  if (dtype == 0) return __bfloat162float(__float2bfloat16_rn(v));
+  if (dtype == 1) return __half2float(__float2half_rn(v));
+  return v;
+}
+
+// ------------------------------------------------------------------ small-M linear: warp per output column
+constexpr int kSlMaxM = 8;
+__global__ void __launch_bounds__(256) small_linear_kernel(const T2VSmallLinearDesc d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= d.n) return;
+  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(d.w) + int64_t(warp) * d.k;
+  for (int m0 = 0; m0 < d.m; m0 += kSlMaxM) {
+    float acc[kSlMaxM];
+#pragma unroll
+    for (int i = 0; i < kSlMaxM; ++i) acc[i] = 0.f;
+    for (int k = lane * 8; k < d.k; k += 256) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + k));
+      float wf[8] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y),
+                     bf16_lo(wv.z), bf16_hi(wv.z), bf16_lo(wv.w), bf16_hi(wv.w)};
+#pragma unroll
+      for (int i = 0; i < kSlMaxM; ++i) {
+        if (m0 + i < d.m) {
+          const float* xr = d.x + int64_t(m0 + i) * d.x_row_stride + k;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float xv = __ldg(xr + j);
+            if (d.silu_in) xv = silu_f(xv);
+            acc[i] = fmaf(xv, wf[j], acc[i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kSlMaxM; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kSlMaxM; ++i) {
+        if (m0 + i < d.m) {
+          float v = acc[i];
+          if (d.bias) v += d.bias[warp];
+          if (d.round_bf16) v = round_to(v, 0);
+          if (d.add) v += d.add[int64_t(m0 + i) * d.add_row_stride + warp];
+          if (d.silu_out) v = silu_f(v);
+          if (d.round_bf16) v = round_to(v, 0);
+          d.out[int64_t(m0 + i) * d.out_row_stride + warp] = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ sinusoidal embeddings
+__global__ void sinusoidal_kernel(const float* t, const float* freqs, float* out, int m, int half,
+                                  int sin_first, int round_bf16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * half) return;
+  const int r = i / half, c = i % half;
+  const float arg = t[r] * freqs[c];
+  float s = sinf(arg), co = cosf(arg);
+  if (round_bf16) {
+    s = round_to(s, 0);
+    co = round_to(co, 0);
+  }
+  float* o = out + int64_t(r) * 2 * half;
+  if (sin_first) {
+    o[c] = s;
+    o[half + c] = co;
+  } else {
+    o[c] = co;
+    o[half + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------ 3x3 conv, tiny C_in (latent -> features)
+// one thread = one output pixel x 8 output channels; weights [Cout][9][Cin] bf16 staged in smem.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv3x3_small_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
+                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n, int h,
+                     int wd, int cout) {
+  extern __shared__ float s_w[];  // [cout][9*CIN]
+  for (int i = threadIdx.x; i < cout * 9 * CIN; i += blockDim.x) s_w[i] = __bfloat162float(w[i]);
+  __syncthreads();
+  const int ocv = cout / 8;
+  const int64_t total = int64_t(n) * h * wd * ocv;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int cv = int(idx % ocv);
+    const int64_t pix = idx / ocv;
+    const int x = int(pix % wd);
+    const int y = int((pix / wd) % h);
+    const int64_t img = pix / (int64_t(wd) * h);
+    float patch[9 * CIN];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < wd;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+          patch[(ky * 3 + kx) * CIN + c] =
+              ok ? __bfloat162float(in[((img * h + yy) * wd + xx) * CIN + c]) : 0.f;
+      }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int oc = cv * 8 + j;
+      float a = bias ? bias[oc] : 0.f;
+      const float* wr = s_w + oc * 9 * CIN;
+#pragma unroll
+      for (int q = 0; q < 9 * CIN; ++q) a = fmaf(patch[q], wr[q], a);
+      acc[j] = a;
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]);
+    o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]);
+    o.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + pix * cout + cv * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------ layout conversion
+__global__ void bcthw_to_frames_kernel(const void* in, int in_dtype, __nv_bfloat16* out, int b, int c,
+                                       int t, int h, int w, float scale) {
+  const int64_t total = int64_t(b) * t * h * w * c;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int ci = int(i % c);
+    int64_t r = i / c;
+    const int x = int(r % w); r /= w;
+    const int y = int(r % h); r /= h;
+    const int ti = int(r % t);
+    const int bi = int(r / t);
+    const int64_t src = (((int64_t(bi) * c + ci) * t + ti) * h + y) * w + x;
+    out[i] = __float2bfloat16_rn(load_as_float(in, src, in_dtype) * scale);
+  }
+}
+__global__ void frames_to_bcthw_kernel(const __nv_bfloat16* in, int c_pad, void* out, int out_dtype,
+                                       int b, int c, int t, int h, int w) {
+  const int64_t total = int64_t(b) * c * t * h * w;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    int64_t r = i;
+    const int x = int(r % w); r /= w;
+    const int y = int(r % h); r /= h;
+    const int ti = int(r % t); r /= t;
+    const int ci = int(r % c);
+    const int bi = int(r / c);
+    const int64_t src = (((int64_t(bi) * t + ti) * h + y) * w + x) * c_pad + ci;
+    store_from_float(out, i, out_dtype, __bfloat162float(in[src]));
+  }
+}
+__global__ void upsample2x_kernel(const uint4* in, uint4* out, int n, int h, int w, int cv) {
+  const int64_t total = int64_t(n) * 2 * h * 2 * w * cv;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % cv);
+    int64_t r = i / cv;
+    const int x = int(r % (2 * w)); r /= (2 * w);
+    const int y = int(r % (2 * h));
+    const int64_t img = r / (2 * h);
+    out[i] = __ldg(in + ((img * h + (y >> 1)) * w + (x >> 1)) * cv + c);
+  }
+}
+__global__ void concat_kernel(const uint4* a, int cva, const uint4* b, int cvb, uint4* out, int64_t rows) {
+  const int cv = cva + cvb;
+  const int64_t total = rows * cv;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % cv);
+    const int64_t r = i / cv;
+    out[i] = c < cva ? __ldg(a + r * cva + c) : __ldg(b + r * cvb + (c - cva));
+  }
+}
+
+// ------------------------------------------------------------------ row softmax (bf16 in place), block per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int cols, int64_t row_stride, float scale) {
+  __shared__ float red[32];
+  __nv_bfloat16* row = x + int64_t(blockIdx.x) * row_stride;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, __bfloat162float(row[c]) * scale);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf(__bfloat162float(row[c]) * scale - mx);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    row[c] = __float2bfloat16_rn(__expf(__bfloat162float(row[c]) * scale - mx) * inv);
+}
+
+// ------------------------------------------------------------------ fused LCM step
+__global__ void lcm_step_kernel(const void* x, const void* eps, const void* noise, void* prev, void* den,
+                                int64_t n, int dt, float sa_inv, float sb, float c_skip, float c_out,
+                                float sap, float sbp) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float xv = load_as_float(x, i, dt);
+    const float ev = load_as_float(eps, i, dt);
+    // every tensor op of the reference rounds to the tensor dtype
+    const float t1 = round_to(sb * ev, dt);
+    const float t2 = round_to(xv - t1, dt);
+    const float x0 = round_to(t2 * sa_inv, dt);
+    const float t3 = round_to(c_out * x0, dt);
+    const float t4 = round_to(c_skip * xv, dt);
+    const float dv = round_to(t3 + t4, dt);
+    store_from_float(den, i, dt, dv);
+    if (noise != nullptr) {
+      const float nv = load_as_float(noise, i, dt);
+      const float t5 = round_to(sap * dv, dt);
+      const float t6 = round_to(sbp * nv, dt);
+      store_from_float(prev, i, dt, t5 + t6);
+    } else {
+      store_from_float(prev, i, dt, dv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weight packing
+__global__ void pack_conv_weight_kernel(const void* w, int wdt, __nv_bfloat16* out, int cout, int cin, int taps) {
+  const int64_t total = int64_t(cout) * cin * taps;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % cin);
+    const int tp = int((i / cin) % taps);
+    const int64_t o = i / (int64_t(cin) * taps);
+    out[i] = __float2bfloat16_rn(load_as_float(w, (o * cin + c) * taps + tp, wdt));
+  }
+}
+// packed row index for original row r (r < inner: value row, else gate row), blocks of 16
+__device__ __forceinline__ int64_t geglu_packed_row(int64_t r, int inner) {
+  const bool gate = r >= inner;
+  const int64_t j = gate ? r - inner : r;
+  return (j / 16) * 32 + (gate ? 16 : 0) + (j % 16);
+}
+__global__ void pack_geglu_kernel(const void* w, int wdt, __nv_bfloat16* out, const void* bias, int bdt,
+                                  float* bias_out, int inner, int k) {
+  const int64_t total = int64_t(2) * inner * k;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / k;
+    const int c = int(i % k);
+    const int64_t pr = geglu_packed_row(r, inner);
+    out[pr * k + c] = __float2bfloat16_rn(load_as_float(w, i, wdt));
+    if (c == 0 && bias != nullptr) bias_out[pr] = load_as_float(bias, r, bdt);
+  }
+}
+
+static inline unsigned grid_for(int64_t total, int threads = 256) {
+  int64_t g = (total + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return unsigned(g);
+}
+
+}  // namespace t2v
+
+using namespace t2v;
+
+extern "C" int t2v_small_linear(const T2VSmallLinearDesc* d, t2v_stream_t s) {
+  if (!d || !d->x || !d->w || !d->out) return fail(-1, "t2v_small_linear: null pointer");
+  if (d->k % 8 || d->k <= 0 || d->n <= 0 || d->m <= 0) return fail(-2, "t2v_small_linear: k must be a positive multiple of 8");
+  const int warps_per_block = 8;
+  const unsigned grid = unsigned((d->n + warps_per_block - 1) / warps_per_block);
+  small_linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(*d);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_small_linear launch");
+}
+
+extern "C" int t2v_sinusoidal_embedding(const float* t, const float* freqs, float* out, int32_t m,
+                                        int32_t half, int32_t sin_first, int32_t round_bf16,
+                                        t2v_stream_t s) {
+  if (!t || !freqs || !out || m <= 0 || half <= 0) return fail(-1, "t2v_sinusoidal_embedding: bad argument");
+  sinusoidal_kernel<<<grid_for(int64_t(m) * half), 256, 0, static_cast<cudaStream_t>(s)>>>(t, freqs, out, m, half, sin_first, round_bf16);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_sinusoidal_embedding launch");
+}
+
+extern "C" int t2v_conv3x3_small_cin(const void* in, const void* w, const float* bias, void* out,
+                                     int32_t n, int32_t h, int32_t wd, int32_t cin, int32_t cout,
+                                     t2v_stream_t s) {
+  if (!in || !w || !out) return fail(-1, "t2v_conv3x3_small_cin: null pointer");
+  if (cout % 8 || cout <= 0) return fail(-2, "t2v_conv3x3_small_cin: cout must be a multiple of 8");
+  const size_t smem = size_t(cout) * 9 * cin * sizeof(float);
+  if (smem > 96 * 1024) return fail(-3, "t2v_conv3x3_small_cin: weights do not fit shared memory");
+  const int64_t total = int64_t(n) * h * wd * (cout / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  const __nv_bfloat16* ip = static_cast<const __nv_bfloat16*>(in);
+  const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
+  cudaError_t e = cudaSuccess;
+  if (cin == 4) {
+    static bool cfg = false;
+    if (!cfg) { e = cudaFuncSetAttribute(conv3x3_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
+    if (e == cudaSuccess) conv3x3_small_kernel<4><<<grid_for(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
+  } else if (cin == 8) {
+    static bool cfg = false;
+    if (!cfg) { e = cudaFuncSetAttribute(conv3x3_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
+    if (e == cudaSuccess) conv3x3_small_kernel<8><<<grid_for(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
+  } else {
+    return fail(-4, "t2v_conv3x3_small_cin: cin must be 4 or 8 (got %d)", cin);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_conv3x3_small_cin launch");
+}
+
+extern "C" int t2v_bcthw_to_frames(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
+                                   int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t s) {
+  if (!in || !out) return fail(-1, "t2v_bcthw_to_frames: null pointer");
+  const int64_t total = int64_t(b) * c * t * h * w;
+  bcthw_to_frames_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, t, h, w, scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_bcthw_to_frames launch");
+}
+
+extern "C" int t2v_frames_to_bcthw(const void* in, int32_t c_pad, void* out, int32_t out_dtype, int32_t b,
+                                   int32_t c, int32_t t, int32_t h, int32_t w, t2v_stream_t s) {
+  if (!in || !out) return fail(-1, "t2v_frames_to_bcthw: null pointer");
+  const int64_t total = int64_t(b) * c * t * h * w;
+  frames_to_bcthw_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<const __nv_bfloat16*>(in), c_pad, out, out_dtype, b, c, t, h, w);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_frames_to_bcthw launch");
+}
+
+extern "C" int t2v_upsample_nearest2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                                      t2v_stream_t s) {
+  if (!in || !out || c % 8) return fail(-1, "t2v_upsample_nearest2x: bad argument");
+  const int64_t total = int64_t(n) * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), n, h, w, c / 8);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_upsample_nearest2x launch");
+}
+
+extern "C" int t2v_concat_channels(const void* a, int32_t ca, const void* b, int32_t cb, void* out,
+                                   int64_t rows, t2v_stream_t s) {
+  if (!a || !b || !out || ca % 8 || cb % 8) return fail(-1, "t2v_concat_channels: bad argument");
+  concat_kernel<<<grid_for(rows * ((ca + cb) / 8)), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<const uint4*>(a), ca / 8, static_cast<const uint4*>(b), cb / 8, static_cast<uint4*>(out), rows);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_concat_channels launch");
+}
+
+extern "C" int t2v_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t row_stride, float scale,
+                                t2v_stream_t s) {
+  if (!x || rows <= 0 || cols <= 0) return fail(-1, "t2v_softmax_rows: bad argument");
+  if (rows > 0x7fffffff) return fail(-2, "t2v_softmax_rows: too many rows");
+  softmax_rows_kernel<<<unsigned(rows), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<__nv_bfloat16*>(x), cols, row_stride, scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_softmax_rows launch");
+}
+
+extern "C" int t2v_lcm_step(const void* x, const void* eps, const void* noise, void* prev, void* denoised,
+                            int64_t n, int32_t dtype, float inv_sqrt_alpha_t, float sqrt_beta_t, float c_skip,
+                            float c_out, float sqrt_alpha_prev, float sqrt_beta_prev, t2v_stream_t s) {
+  if (!x || !eps || !prev || !denoised || n <= 0) return fail(-1, "t2v_lcm_step: bad argument");
+  if (dtype < 0 || dtype > 2) return fail(-2, "t2v_lcm_step: dtype must be 0 (bf16), 1 (fp16) or 2 (fp32)");
+  lcm_step_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(s)>>>(x, eps, noise, prev, denoised, n, dtype, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqrt_alpha_prev, sqrt_beta_prev);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_lcm_step launch");
+}
+
+extern "C" int t2v_pack_conv_weight(const void* w, int32_t w_dtype, void* out, int32_t cout, int32_t cin,
+                                    int32_t taps, t2v_stream_t s) {
+  if (!w || !out) return fail(-1, "t2v_pack_conv_weight: null pointer");
+  pack_conv_weight_kernel<<<grid_for(int64_t(cout) * cin * taps), 256, 0, static_cast<cudaStream_t>(s)>>>(w, w_dtype, static_cast<__nv_bfloat16*>(out), cout, cin, taps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_pack_conv_weight launch");
+}
+
+extern "C" int t2v_pack_geglu_rows(const void* w, int32_t w_dtype, void* out, const void* bias,
+                                   int32_t bias_dtype, float* bias_out, int32_t inner, int32_t k,
+                                   t2v_stream_t s) {
+  if (!w || !out || inner % 16) return fail(-1, "t2v_pack_geglu_rows: inner must be a multiple of 16");
+  pack_geglu_kernel<<<grid_for(int64_t(2) * inner * k), 256, 0, static_cast<cudaStream_t>(s)>>>(w, w_dtype, static_cast<__nv_bfloat16*>(out), bias, bias_dtype, bias_out, inner, k);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_pack_geglu_rows launch");
+}

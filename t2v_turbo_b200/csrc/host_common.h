@@ -1,0 +1,39 @@
+// Host-side helpers shared by the C-ABI entry points: error slots, the driver entry point for
+// cuTensorMapEncodeTiled (resolved at run time so the library does not link libcuda), device info.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace t2v {
+
+char* last_error_buf();  // thread-local, 512 bytes
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  return fail(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn();  // nullptr if the driver entry point cannot be resolved
+int num_sms();
+
+// bf16 tiled tensor map with 128-byte swizzle; dims/strides innermost first; strides in BYTES for
+// dims 1..rank-1 (dim 0 is contiguous).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, const char* what);
+
+}  // namespace t2v

@@ -1,0 +1,309 @@
+// GroupNorm(+SiLU) and LayerNorm over channels-last bf16 activations (HBM-bound passes).
+//
+// GroupNorm is two kernels: a statistics pass (per-(sample, group) sum / sum-of-squares, fp32
+// accumulation in registers -> shared -> one global atomic per group per block) and an apply pass
+// that folds mean / rstd / gamma / beta into one fma per element followed by SiLU.  Both passes
+// give each thread a FIXED 8-channel column (16-byte vector loads, fully coalesced across a row)
+// and walk rows, so the per-channel scale / shift live in registers.
+// The input may be the channel concatenation of two tensors (UNet skip connections).
+#include <cuda_bf16.h>
+
+#include "../../include/t2v_b200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace t2v {
+
+struct GnParams {
+  const __nv_bfloat16* x0;
+  const __nv_bfloat16* x1;
+  int32_t ncv0;  // 8-channel vectors in source 0
+  int32_t ncv;   // total 8-channel vectors
+  int64_t rs0, rs1;
+  __nv_bfloat16* out;
+  int64_t out_rs;
+  const float* gamma;
+  const float* beta;
+  int64_t rows_per_sample;
+  int32_t rows_per_block;
+  int32_t cpg;     // channels per group
+  int32_t groups;
+  float eps;
+  int32_t silu;
+  float* ws;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+constexpr int kGnThreads = 256;
+
+// grid: (blocks_per_sample, n_samples)
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) {
+  __shared__ float s_acc[2 * 64];
+  for (int i = threadIdx.x; i < 2 * p.groups; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int sample = blockIdx.y;
+  const int64_t row_begin = int64_t(blockIdx.x) * p.rows_per_block;
+  int64_t row_end = row_begin + p.rows_per_block;
+  if (row_end > p.rows_per_sample) row_end = p.rows_per_sample;
+  const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;  // threads per row
+  const int rpp = kGnThreads / tpr;                         // rows per pass
+  const int rr = threadIdx.x / tpr;
+  const int64_t base_row = int64_t(sample) * p.rows_per_sample;
+  if (rr < rpp) {
+    for (int cv = threadIdx.x % tpr; cv < p.ncv; cv += tpr) {
+      const bool src1 = cv >= p.ncv0;
+      const __nv_bfloat16* xp = src1 ? p.x1 + (cv - p.ncv0) * 8 : p.x0 + cv * 8;
+      const int64_t rs = src1 ? p.rs1 : p.rs0;
+      float s[8], ss[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+      for (int64_t r = row_begin + rr; r < row_end; r += rpp) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(xp + (base_row + r) * rs));
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[j];
+          ss[j] += f[j] * f[j];
+        }
+      }
+      // merge runs of channels that fall into the same group
+      int g_prev = (cv * 8) / p.cpg;
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (cv * 8 + j) / p.cpg;
+        if (g != g_prev) {
+          atomicAdd(&s_acc[2 * g_prev], a);
+          atomicAdd(&s_acc[2 * g_prev + 1], b);
+          a = b = 0.f;
+          g_prev = g;
+        }
+        a += s[j];
+        b += ss[j];
+      }
+      atomicAdd(&s_acc[2 * g_prev], a);
+      atomicAdd(&s_acc[2 * g_prev + 1], b);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * p.groups; i += blockDim.x)
+    atomicAdd(&p.ws[int64_t(sample) * 2 * p.groups + i], s_acc[i]);
+}
+
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) {
+  const int sample = blockIdx.y;
+  const int64_t row_begin = int64_t(blockIdx.x) * p.rows_per_block;
+  int64_t row_end = row_begin + p.rows_per_block;
+  if (row_end > p.rows_per_sample) row_end = p.rows_per_sample;
+  const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;
+  const int rpp = kGnThreads / tpr;
+  const int rr = threadIdx.x / tpr;
+  if (rr >= rpp) return;
+  const int64_t base_row = int64_t(sample) * p.rows_per_sample;
+  const float inv_n = 1.0f / (float(p.rows_per_sample) * float(p.cpg));
+  const float* ws = p.ws + int64_t(sample) * 2 * p.groups;
+  for (int cv = threadIdx.x % tpr; cv < p.ncv; cv += tpr) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cv * 8 + j;
+      const int g = c / p.cpg;
+      const float mean = ws[2 * g] * inv_n;
+      float var = ws[2 * g + 1] * inv_n - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      const float rstd = rsqrtf(var + p.eps);
+      const float ga = __ldg(p.gamma + c);
+      sc[j] = rstd * ga;
+      sh[j] = __ldg(p.beta + c) - mean * rstd * ga;
+    }
+    const bool src1 = cv >= p.ncv0;
+    const __nv_bfloat16* xp = src1 ? p.x1 + (cv - p.ncv0) * 8 : p.x0 + cv * 8;
+    const int64_t rs = src1 ? p.rs1 : p.rs0;
+    __nv_bfloat16* op = p.out + cv * 8;
+    for (int64_t r = row_begin + rr; r < row_end; r += rpp) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xp + (base_row + r) * rs));
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(f[j], sc[j], sh[j]);
+        if (p.silu) y = y / (1.0f + __expf(-y));
+        f[j] = y;
+      }
+      uint4 o;
+      o.x = pack_bf16(f[0], f[1]);
+      o.y = pack_bf16(f[2], f[3]);
+      o.z = pack_bf16(f[4], f[5]);
+      o.w = pack_bf16(f[6], f[7]);
+      *reinterpret_cast<uint4*>(op + (base_row + r) * p.out_rs) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm: one warp per row
+struct LnParams {
+  const __nv_bfloat16* x;
+  int64_t xs;
+  __nv_bfloat16* out;
+  int64_t os;
+  const float* gamma;
+  const float* beta;
+  int64_t rows;
+  int32_t nvec;  // C / 8
+  float eps;
+  float inv_c;
+};
+
+template <int MAXV>  // vectors per lane
+__global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 8 + warp;
+  if (row >= p.rows) return;
+  const __nv_bfloat16* xr = p.x + row * p.xs;
+  float f[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < p.nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      unpack8(u, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * p.inv_c;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < p.nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * p.inv_c + p.eps);
+  __nv_bfloat16* orow = p.out + row * p.os;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < p.nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (f[i][j] - mean) * rstd * g[j] + b[j];
+      uint4 o;
+      o.x = pack_bf16(y[0], y[1]);
+      o.y = pack_bf16(y[2], y[3]);
+      o.z = pack_bf16(y[4], y[5]);
+      o.w = pack_bf16(y[6], y[7]);
+      *reinterpret_cast<uint4*>(orow + v * 8) = o;
+    }
+  }
+}
+
+}  // namespace t2v
+
+extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
+  using namespace t2v;
+  if (!d) return fail(-1, "t2v_groupnorm: null descriptor");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int C = d->ch[0] + d->ch[1];
+  if (!d->x[0] || !d->out || !d->gamma || !d->beta || !d->workspace)
+    return fail(-2, "t2v_groupnorm: null pointer");
+  if (d->ch[0] <= 0 || d->ch[0] % 8 || d->ch[1] < 0 || d->ch[1] % 8)
+    return fail(-3, "t2v_groupnorm: channel counts must be multiples of 8");
+  if (d->ch[1] > 0 && !d->x[1]) return fail(-4, "t2v_groupnorm: x[1] null");
+  if (d->groups < 1 || d->groups > 64 || C % d->groups) return fail(-5, "t2v_groupnorm: bad groups");
+  if (d->rows_per_sample < 1 || d->rows % d->rows_per_sample) return fail(-6, "t2v_groupnorm: rows %% rows_per_sample != 0");
+  if (d->x_row_stride[0] % 8 || d->out_row_stride % 8 || (d->ch[1] && d->x_row_stride[1] % 8))
+    return fail(-7, "t2v_groupnorm: row strides must be multiples of 8 elements");
+  const int64_t n_samples = d->rows / d->rows_per_sample;
+  if (n_samples > 65535) return fail(-8, "t2v_groupnorm: too many samples");
+  GnParams p;
+  p.x0 = static_cast<const __nv_bfloat16*>(d->x[0]);
+  p.x1 = static_cast<const __nv_bfloat16*>(d->x[1]);
+  p.ncv0 = d->ch[0] / 8;
+  p.ncv = C / 8;
+  p.rs0 = d->x_row_stride[0];
+  p.rs1 = d->x_row_stride[1];
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_rs = d->out_row_stride;
+  p.gamma = d->gamma;
+  p.beta = d->beta;
+  p.rows_per_sample = d->rows_per_sample;
+  p.cpg = C / d->groups;
+  p.groups = d->groups;
+  p.eps = d->eps;
+  p.silu = d->silu;
+  p.ws = d->workspace;
+  const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;
+  const int rpp = kGnThreads / tpr;
+  int sms = num_sms();
+  if (sms <= 0) return fail(-110, "t2v_groupnorm: no CUDA device");
+  int64_t want_blocks = (int64_t(sms) * 4 + n_samples - 1) / n_samples;
+  if (want_blocks < 1) want_blocks = 1;
+  int64_t rpb = (d->rows_per_sample + want_blocks - 1) / want_blocks;
+  const int64_t min_rpb = int64_t(rpp) * 4;
+  if (rpb < min_rpb) rpb = min_rpb;
+  rpb = (rpb + rpp - 1) / rpp * rpp;
+  p.rows_per_block = int(rpb);
+  const int64_t bps = (d->rows_per_sample + rpb - 1) / rpb;
+  cudaError_t e = cudaMemsetAsync(d->workspace, 0, sizeof(float) * 2 * d->groups * n_samples, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "t2v_groupnorm memset");
+  dim3 grid((unsigned)bps, (unsigned)n_samples);
+  gn_stats_kernel<<<grid, kGnThreads, 0, stream>>>(p);
+  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "t2v_groupnorm launch");
+  return 0;
+}
+
+extern "C" int t2v_layernorm(const T2VLayerNormDesc* d, t2v_stream_t stream_) {
+  using namespace t2v;
+  if (!d) return fail(-1, "t2v_layernorm: null descriptor");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d->x || !d->out || !d->gamma || !d->beta) return fail(-2, "t2v_layernorm: null pointer");
+  if (d->channels <= 0 || d->channels % 8 || d->channels > 2048)
+    return fail(-3, "t2v_layernorm: channels must be a multiple of 8, <= 2048");
+  if (d->x_row_stride % 8 || d->out_row_stride % 8) return fail(-4, "t2v_layernorm: strides must be multiples of 8");
+  if (d->rows <= 0) return 0;
+  LnParams p;
+  p.x = static_cast<const __nv_bfloat16*>(d->x);
+  p.xs = d->x_row_stride;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.os = d->out_row_stride;
+  p.gamma = d->gamma;
+  p.beta = d->beta;
+  p.rows = d->rows;
+  p.nvec = d->channels / 8;
+  p.eps = d->eps;
+  p.inv_c = 1.0f / float(d->channels);
+  const unsigned grid = unsigned((d->rows + 7) / 8);
+  const int vpl = (p.nvec + 31) / 32;
+  if (vpl <= 2) ln_kernel<2><<<grid, 256, 0, stream>>>(p);
+  else if (vpl <= 5) ln_kernel<5><<<grid, 256, 0, stream>>>(p);
+  else ln_kernel<8><<<grid, 256, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "t2v_layernorm launch");
+  return 0;
+}

@@ -1,0 +1,444 @@
+"""Operator layer: torch tensors in / out, every arithmetic op is a libt2v_b200.so call.
+
+Activations are channels-last bf16.  A frame batch is ``[N, H, W, C]`` (N = B*T); the same memory
+is the token matrix ``[N*H*W, C]`` for every per-token op (Linear / LayerNorm / GEGLU), the
+spatial sequences ``[N, H*W, C]`` and — through strides only — the temporal sequences
+``[B*H*W, T, C]``.  None of the reference's ``rearrange(...).contiguous()`` copies
+(attention.py:379,386,475-511; openaimodel3d.py:38-40,251-253) exist here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (AttnDesc, GemmDesc, GroupNormDesc, LayerNormDesc, ShortAttnDesc, SmallLinearDesc,
+                   check, lib, ptr, stream_ptr)
+
+BF16 = torch.bfloat16
+
+
+# ----------------------------------------------------------------------------- tile planning
+@functools.lru_cache(maxsize=None)
+def plan_box(sizes: tuple, fixed: tuple = (None, None, None, None)) -> tuple:
+    """Pick the <=128-point tile box over a (x1..x4) point grid that wastes the fewest MMA rows."""
+    cands = []
+    for s, f in zip(sizes, fixed):
+        if f is not None:
+            cands.append([f])
+            continue
+        c = {d for d in range(1, min(s, 128) + 1) if s % d == 0}
+        c |= {1 << k for k in range(8) if (1 << k) <= max(1, min(128, 2 * s))}
+        cands.append(sorted(c))
+    best, best_key = None, None
+    total = math.prod(sizes)
+    for b1 in cands[0]:
+        for b2 in cands[1]:
+            if b1 * b2 > 128:
+                break
+            for b3 in cands[2]:
+                if b1 * b2 * b3 > 128:
+                    break
+                for b4 in cands[3]:
+                    rows = b1 * b2 * b3 * b4
+                    if rows > 128:
+                        break
+                    if rows % 8:
+                        continue
+                    tiles = 1
+                    for s, b in zip(sizes, (b1, b2, b3, b4)):
+                        tiles *= -(-s // b)
+                    eff = total / (tiles * 128)
+                    key = (round(eff, 6), b1, b2, b3)
+                    if best_key is None or key > best_key:
+                        best_key, best = key, (b1, b2, b3, b4)
+    if best is None:
+        raise ValueError(f"no tile box for point grid {sizes}")
+    return best
+
+
+def _fill(arr, vals):
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+
+
+def _as_pair(x):
+    if isinstance(x, (tuple, list)):
+        assert len(x) == 2
+        return x[0], x[1]
+    return x, None
+
+
+def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w, n_rows, out,
+              o_size, o_stride, n_out, bias=None, bias_row_stride=0, bias_dim=-1, bias_div=1,
+              residual=None, r_stride=None, alpha=1.0, flags=0, block_n=0, b_batches=1,
+              b_batch_stride=0, b_batch_dim=-1):
+    d = GemmDesc()
+    a0, a1 = a
+    d.a[0] = a0.data_ptr()
+    d.a[1] = a1.data_ptr() if a1 is not None else None
+    _fill(d.a_ch, a_ch)
+    _fill(d.a_ch_total, a_ch_total)
+    _fill(d.a_size, a_size)
+    _fill(d.a_stride[0], a_stride[0])
+    _fill(d.a_stride[1], a_stride[1] if a_stride[1] is not None else (0, 0, 0, 0))
+    _fill(d.box, box)
+    d.n_taps = len(taps)
+    for t, off in enumerate(taps):
+        _fill(d.tap_off[t], off)
+        d.tap_ch_off[t] = int(tap_ch_off[t]) if tap_ch_off is not None else 0
+    d.b = w.data_ptr()
+    d.b_rows = n_rows
+    d.b_batches = b_batches
+    d.b_batch_stride = b_batch_stride
+    d.b_batch_dim = b_batch_dim
+    d.out = out.data_ptr()
+    _fill(d.o_size, o_size)
+    _fill(d.o_stride, o_stride)
+    d.n_out = n_out
+    d.bias = ptr(bias)
+    d.bias_row_stride = bias_row_stride
+    d.bias_dim = bias_dim
+    d.bias_div = bias_div
+    d.residual = ptr(residual)
+    _fill(d.r_stride, r_stride if r_stride is not None else o_stride)
+    d.alpha = alpha
+    d.flags = flags
+    d.block_n = block_n
+    check(lib().t2v_gemm(C.byref(d), stream_ptr()), "t2v_gemm")
+    return out
+
+
+def _check_act(x, name="x"):
+    assert x.is_cuda and x.dtype == BF16 and x.is_contiguous(), f"{name}: need contiguous CUDA bf16"
+
+
+# ----------------------------------------------------------------------------- Linear
+def linear(x, w, bias=None, *, residual=None, geglu=False, gelu=False, out=None, out_f32=False,
+           alpha=1.0, block_n=0):
+    """out[m, :] = epi(x[m, :] @ w.T).  x: [M, K] bf16 (or a pair concatenated along K);
+    w: [N, K] bf16 (GEGLU: rows packed by pack_geglu); bias: fp32 [N]; residual: bf16 [M, n_out]."""
+    x0, x1 = _as_pair(x)
+    _check_act(x0)
+    m = x0.shape[0]
+    k0 = x0.shape[1]
+    k1 = x1.shape[1] if x1 is not None else 0
+    n = w.shape[0]
+    assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == k0 + k1, (w.shape, k0, k1)
+    n_out = n // 2 if geglu else n
+    if out is None:
+        out = torch.empty((m, n_out), device=x0.device, dtype=torch.float32 if out_f32 else BF16)
+    flags = (_lib.EPI_GEGLU if geglu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0) | (_lib.EPI_GELU if gelu else 0)
+    return _gemm_raw(
+        a=(x0, x1), a_ch=(k0, k1), a_ch_total=(k0, k1), a_size=(m, 1, 1, 1),
+        a_stride=((k0, 0, 0, 0), (k1, 0, 0, 0) if x1 is not None else None),
+        box=(128, 1, 1, 1), taps=[(0, 0, 0, 0)], tap_ch_off=None, w=w, n_rows=n, out=out,
+        o_size=(m, 1, 1, 1), o_stride=(out.stride(0), 0, 0, 0), n_out=n_out, bias=bias,
+        residual=residual, r_stride=(residual.stride(0), 0, 0, 0) if residual is not None else None,
+        alpha=alpha, flags=flags, block_n=block_n)
+
+
+def bmm_nt(a, b, *, out=None, alpha=1.0, block_n=0):
+    """Batched out[i] = a[i] @ b[i].T with a: [Bt, M, K], b: [Bt, N, K] bf16 (VAE AttnBlock)."""
+    _check_act(a, "a")
+    _check_act(b, "b")
+    bt, m, k = a.shape
+    n = b.shape[1]
+    if out is None:
+        out = torch.empty((bt, m, n), device=a.device, dtype=BF16)
+    return _gemm_raw(
+        a=(a, None), a_ch=(k, 0), a_ch_total=(k, 0), a_size=(m, bt, 1, 1),
+        a_stride=((k, m * k, 0, 0), None), box=(128, 1, 1, 1), taps=[(0, 0, 0, 0)], tap_ch_off=None,
+        w=b, n_rows=n, out=out, o_size=(m, bt, 1, 1), o_stride=(out.stride(1), out.stride(0), 0, 0),
+        n_out=n, alpha=alpha, block_n=block_n, b_batches=bt, b_batch_stride=n * k, b_batch_dim=1)
+
+
+# ----------------------------------------------------------------------------- convolutions
+_TAPS_3X3 = [(kx - 1, ky - 1, 0, 0) for ky in range(3) for kx in range(3)]
+_TAPS_T3 = [(0, kt - 1, 0, 0) for kt in range(3)]
+
+
+def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0):
+    """3x3 / pad 1 / stride 1 conv over [N,H,W,C] (or a channel-concatenated pair).
+    w: [Cout, 9*C] packed (tap-major); bias: fp32 [rows, Cout], row = frame // bias_div."""
+    x0, x1 = _as_pair(x)
+    _check_act(x0)
+    n, h, wd, c0 = x0.shape
+    c1 = x1.shape[3] if x1 is not None else 0
+    cout = w.shape[0]
+    assert w.shape[1] == 9 * (c0 + c1), (w.shape, c0, c1)
+    if out is None:
+        out = torch.empty((n, h, wd, cout), device=x0.device, dtype=BF16)
+    box = plan_box((wd, h, n, 1))
+    return _gemm_raw(
+        a=(x0, x1), a_ch=(c0, c1), a_ch_total=(c0, c1), a_size=(wd, h, n, 1),
+        a_stride=((c0, wd * c0, h * wd * c0, 0), (c1, wd * c1, h * wd * c1, 0) if x1 is not None else None),
+        box=box, taps=_TAPS_3X3, tap_ch_off=None, w=w, n_rows=cout, out=out,
+        o_size=(wd, h, n, 1), o_stride=(cout, wd * cout, h * wd * cout, 0), n_out=cout, bias=bias,
+        bias_row_stride=cout if bias is not None else 0, bias_dim=2, bias_div=bias_div,
+        residual=residual, block_n=block_n)
+
+
+def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0):
+    """3x3 / pad 1 / stride 2 conv (Downsample, openaimodel3d.py:65-72).  The input is read through a
+    parity view [N, H/2, 2, W/2, 2*C] so every tap is a plain box load."""
+    _check_act(x)
+    n, h, wd, c = x.shape
+    assert h % 2 == 0 and wd % 2 == 0
+    cout = w.shape[0]
+    assert w.shape[1] == 9 * c
+    h2, w2 = h // 2, wd // 2
+    if out is None:
+        out = torch.empty((n, h2, w2, cout), device=x.device, dtype=BF16)
+    taps, choff = [], []
+    for ky in range(3):
+        hpar, dh = (0, 0) if ky == 1 else (1, -1 if ky == 0 else 0)
+        for kx in range(3):
+            wpar, dw = (0, 0) if kx == 1 else (1, -1 if kx == 0 else 0)
+            taps.append((dw, hpar, dh, 0))
+            choff.append(wpar * c)
+    b = plan_box((w2, 1, h2, n), fixed=(None, 1, None, None))
+    return _gemm_raw(
+        a=(x, None), a_ch=(c, 0), a_ch_total=(2 * c, 0), a_size=(w2, 2, h2, n),
+        a_stride=((2 * c, wd * c, 2 * wd * c, h * wd * c), None), box=b, taps=taps, tap_ch_off=choff,
+        w=w, n_rows=cout, out=out, o_size=(w2, 1, h2, n),
+        o_stride=(cout, 0, w2 * cout, h2 * w2 * cout), n_out=cout, bias=bias,
+        bias_row_stride=0, bias_dim=-1, block_n=block_n)
+
+
+def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0):
+    """Conv3d (3,1,1) / pad (1,0,0) over x: [B, T, HW, C] (TemporalConvBlock, openaimodel3d.py:274-296).
+    w: [Cout, 3*C] packed."""
+    _check_act(x)
+    b, t, hw, c = x.shape
+    cout = w.shape[0]
+    assert w.shape[1] == 3 * c
+    if out is None:
+        out = torch.empty((b, t, hw, cout), device=x.device, dtype=BF16)
+    box = plan_box((hw, t, b, 1))
+    return _gemm_raw(
+        a=(x, None), a_ch=(c, 0), a_ch_total=(c, 0), a_size=(hw, t, b, 1),
+        a_stride=((c, hw * c, t * hw * c, 0), None), box=box, taps=_TAPS_T3, tap_ch_off=None, w=w,
+        n_rows=cout, out=out, o_size=(hw, t, b, 1), o_stride=(cout, hw * cout, t * hw * cout, 0),
+        n_out=cout, bias=bias, residual=residual, block_n=block_n)
+
+
+def conv3x3_small_cin(x, w, bias, cout):
+    """Direct conv for the 4-channel latent (input_blocks.0.0 / VAE conv_in). w: [Cout, 9*Cin] packed."""
+    _check_act(x)
+    n, h, wd, cin = x.shape
+    out = torch.empty((n, h, wd, cout), device=x.device, dtype=BF16)
+    check(lib().t2v_conv3x3_small_cin(x.data_ptr(), w.data_ptr(), ptr(bias), out.data_ptr(), n, h, wd, cin,
+                                      cout, stream_ptr()), "t2v_conv3x3_small_cin")
+    return out
+
+
+# ----------------------------------------------------------------------------- normalisation
+_GN_WS: dict = {}
+
+
+def _gn_workspace(device, n):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 4096), device=device, dtype=torch.float32)
+        _GN_WS[key] = ws
+    return ws
+
+
+def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None):
+    """GroupNorm(+SiLU) over token matrix x: [rows, C] (or a pair concatenated along C)."""
+    x0, x1 = _as_pair(x)
+    x0 = x0.reshape(-1, x0.shape[-1])
+    rows, c0 = x0.shape
+    c1 = 0
+    if x1 is not None:
+        x1 = x1.reshape(-1, x1.shape[-1])
+        c1 = x1.shape[1]
+    if out is None:
+        out = torch.empty((rows, c0 + c1), device=x0.device, dtype=BF16)
+    d = GroupNormDesc()
+    d.x[0] = x0.data_ptr()
+    d.x[1] = ptr(x1)
+    d.ch[0], d.ch[1] = c0, c1
+    d.x_row_stride[0] = x0.stride(0)
+    d.x_row_stride[1] = x1.stride(0) if x1 is not None else 0
+    d.out = out.data_ptr()
+    d.out_row_stride = out.stride(0)
+    d.gamma = gamma.data_ptr()
+    d.beta = beta.data_ptr()
+    d.rows = rows
+    d.rows_per_sample = rows_per_sample
+    d.groups = groups
+    d.eps = eps
+    d.silu = 1 if silu else 0
+    ws = _gn_workspace(x0.device, 2 * groups * (rows // rows_per_sample))
+    d.workspace = ws.data_ptr()
+    check(lib().t2v_groupnorm(C.byref(d), stream_ptr()), "t2v_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    d = LayerNormDesc()
+    d.x, d.x_row_stride = x.data_ptr(), x.stride(0)
+    d.out, d.out_row_stride = out.data_ptr(), out.stride(0)
+    d.gamma, d.beta = gamma.data_ptr(), beta.data_ptr()
+    d.rows, d.channels, d.eps = rows, c, eps
+    check(lib().t2v_layernorm(C.byref(d), stream_ptr()), "t2v_layernorm")
+    return out
+
+
+# ----------------------------------------------------------------------------- attention
+def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None):
+    """q: [Bq, Lq, H*64] view, k/v: [Bk, Lk, H*64] views (last dim contiguous; token/batch strides free).
+    Returns o: [Bq, Lq, H*64]."""
+    bq, lq, inner = q.shape
+    bk, lk, _ = k.shape
+    assert inner == heads * 64 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert bq == bk * kv_batch_div
+    if out is None:
+        out = torch.empty((bq, lq, inner), device=q.device, dtype=BF16)
+    d = AttnDesc()
+    d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    d.batch, d.heads, d.len_q, d.len_k = bq, heads, lq, lk
+    d.q_stride_b, d.q_stride_t, d.q_stride_h = q.stride(0), q.stride(1), 64
+    d.k_stride_b, d.k_stride_t, d.k_stride_h = k.stride(0), k.stride(1), 64
+    d.v_stride_b, d.v_stride_t, d.v_stride_h = v.stride(0), v.stride(1), 64
+    d.o_stride_b, d.o_stride_t, d.o_stride_h = out.stride(0), out.stride(1), 64
+    d.kv_batch_div = kv_batch_div
+    d.scale = scale
+    check(lib().t2v_attn_fwd(C.byref(d), stream_ptr()), "t2v_attn_fwd")
+    return out
+
+
+def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None):
+    """Temporal self-attention over token matrices laid out [(b t hw), H*64]: each of the b*hw pixels
+    attends over its t frames (token stride hw*row_stride).  Replaces the '(b hw) t c' regrouping."""
+    rows, inner = q.shape
+    assert rows == b * t * hw and inner == heads * 64
+    if out is None:
+        out = torch.empty((rows, inner), device=q.device, dtype=BF16)
+    d = ShortAttnDesc()
+    d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    d.n_seq_outer, d.n_seq_inner, d.heads, d.len = b, hw, heads, t
+    for name, ten in (("q", q), ("k", k), ("v", v), ("o", out)):
+        rs = ten.stride(0)
+        setattr(d, f"{name}_stride_outer", t * hw * rs)
+        setattr(d, f"{name}_stride_inner", rs)
+        setattr(d, f"{name}_stride_t", hw * rs)
+        setattr(d, f"{name}_stride_h", 64)
+    d.scale = scale
+    check(lib().t2v_attn_short_fwd(C.byref(d), stream_ptr()), "t2v_attn_short_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------- small ops
+def small_linear(x, w, bias=None, *, add=None, silu_in=False, silu_out=False, round_bf16=True, out=None):
+    """fp32 rows x [M,K] times bf16 w [N,K] (embedding MLPs, M = batch)."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and w.dtype == BF16 and w.is_contiguous()
+    m, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    d = SmallLinearDesc()
+    d.x, d.x_row_stride = x.data_ptr(), x.stride(0)
+    d.w, d.bias = w.data_ptr(), ptr(bias)
+    d.add, d.add_row_stride = ptr(add), (add.stride(0) if add is not None else 0)
+    d.out, d.out_row_stride = out.data_ptr(), out.stride(0)
+    d.m, d.n, d.k = m, n, k
+    d.silu_in, d.silu_out, d.round_bf16 = int(silu_in), int(silu_out), int(round_bf16)
+    check(lib().t2v_small_linear(C.byref(d), stream_ptr()), "t2v_small_linear")
+    return out
+
+
+def sinusoidal_embedding(t, freqs, *, sin_first=False, round_bf16=True):
+    assert t.dtype == torch.float32 and freqs.dtype == torch.float32
+    m, half = t.shape[0], freqs.shape[0]
+    out = torch.empty((m, 2 * half), device=t.device, dtype=torch.float32)
+    check(lib().t2v_sinusoidal_embedding(t.data_ptr(), freqs.data_ptr(), out.data_ptr(), m, half,
+                                         int(sin_first), int(round_bf16), stream_ptr()), "t2v_sinusoidal_embedding")
+    return out
+
+
+def bcthw_to_frames(x, scale=1.0):
+    b, c, t, h, w = x.shape
+    x = x.contiguous()
+    out = torch.empty((b * t, h, w, c), device=x.device, dtype=BF16)
+    check(lib().t2v_bcthw_to_frames(x.data_ptr(), _lib.DTYPE_CODE[x.dtype], out.data_ptr(), b, c, t, h, w,
+                                    scale, stream_ptr()), "t2v_bcthw_to_frames")
+    return out
+
+
+def frames_to_bcthw(x, b, c, dtype):
+    n, h, w, cp = x.shape
+    t = n // b
+    out = torch.empty((b, c, t, h, w), device=x.device, dtype=dtype)
+    check(lib().t2v_frames_to_bcthw(x.data_ptr(), cp, out.data_ptr(), _lib.DTYPE_CODE[dtype], b, c, t, h, w,
+                                    stream_ptr()), "t2v_frames_to_bcthw")
+    return out
+
+
+def upsample_nearest2x(x):
+    _check_act(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=BF16)
+    check(lib().t2v_upsample_nearest2x(x.data_ptr(), out.data_ptr(), n, h, w, c, stream_ptr()), "t2v_upsample_nearest2x")
+    return out
+
+
+def concat_channels(a, b):
+    ca, cb = a.shape[-1], b.shape[-1]
+    rows = a.numel() // ca
+    out = torch.empty((*a.shape[:-1], ca + cb), device=a.device, dtype=BF16)
+    check(lib().t2v_concat_channels(a.data_ptr(), ca, b.data_ptr(), cb, out.data_ptr(), rows, stream_ptr()),
+          "t2v_concat_channels")
+    return out
+
+
+def softmax_rows_(x, scale=1.0):
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    check(lib().t2v_softmax_rows(x.data_ptr(), rows, cols, cols, scale, stream_ptr()), "t2v_softmax_rows")
+    return x
+
+
+def lcm_step(x, eps, noise, *, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqrt_alpha_prev, sqrt_beta_prev):
+    assert x.is_contiguous() and eps.is_contiguous() and x.dtype == eps.dtype
+    prev = torch.empty_like(x)
+    den = torch.empty_like(x)
+    check(lib().t2v_lcm_step(x.data_ptr(), eps.data_ptr(), ptr(noise), prev.data_ptr(), den.data_ptr(),
+                             x.numel(), _lib.DTYPE_CODE[x.dtype], inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out,
+                             sqrt_alpha_prev, sqrt_beta_prev, stream_ptr()), "t2v_lcm_step")
+    return prev, den
+
+
+# ----------------------------------------------------------------------------- weight packing
+def pack_conv_weight(w):
+    """torch conv weight [Cout, Cin, *k] -> bf16 [Cout, taps*Cin] (tap-major K)."""
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    w = w.contiguous()
+    out = torch.empty((cout, taps * cin), device=w.device, dtype=BF16)
+    check(lib().t2v_pack_conv_weight(w.data_ptr(), _lib.DTYPE_CODE[w.dtype], out.data_ptr(), cout, cin, taps,
+                                     stream_ptr()), "t2v_pack_conv_weight")
+    return out
+
+
+def pack_geglu(w, bias):
+    """GEGLU proj weight [2*inner, K] (+bias) -> value/gate rows interleaved in blocks of 16."""
+    two_inner, k = w.shape
+    inner = two_inner // 2
+    w = w.contiguous()
+    out = torch.empty((two_inner, k), device=w.device, dtype=BF16)
+    bout = torch.empty((two_inner,), device=w.device, dtype=torch.float32)
+    bias = bias.contiguous()
+    check(lib().t2v_pack_geglu_rows(w.data_ptr(), _lib.DTYPE_CODE[w.dtype], out.data_ptr(), bias.data_ptr(),
+                                    _lib.DTYPE_CODE[bias.dtype], bout.data_ptr(), inner, k, stream_ptr()),
+          "t2v_pack_geglu_rows")
+    return out, bout

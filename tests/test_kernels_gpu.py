@@ -1,0 +1,313 @@
+"""GPU parity tests of every kernel behind the C ABI against plain fp32 torch on the same
+bf16-rounded inputs (per-kernel tolerance: <= ~1 bf16 ulp of the output scale)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _ops():
+    from t2v_turbo_b200 import ops
+    return ops
+
+
+def rnd(*shape, scale=1.0, seed=0, device="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(device)
+
+
+def assert_close(got, ref, rtol=1.6e-2, atol_scale=8e-3, what=""):
+    got = got.float()
+    ref = ref.float()
+    scale = ref.abs().max().item() + 1e-6
+    err = (got - ref).abs()
+    tol = atol_scale * scale + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} mismatches, max err {err.max().item():.4g} "
+                           f"(scale {scale:.4g}), first bad idx {bad.nonzero()[0].tolist()}")
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+
+
+# ----------------------------------------------------------------------------- GEMM geometries
+@pytest.mark.parametrize("m,k,n,bn", [
+    (256, 64, 64, 64), (1000, 320, 320, 0), (640, 1280, 1280, 128), (130, 128, 160, 160),
+    (2560, 320, 2560, 256), (77, 1024, 640, 0), (4096, 512, 512, 0),
+])
+def test_linear(cuda_device, m, k, n, bn):
+    ops = _ops()
+    x = rnd(m, k, seed=1).to(BF16)
+    w = rnd(n, k, scale=k ** -0.5, seed=2).to(BF16)
+    b = rnd(n, seed=3)
+    res = rnd(m, n, seed=4).to(BF16)
+    out = ops.linear(x, w, b, residual=res, block_n=bn)
+    ref = x.float() @ w.float().t() + b + res.float()
+    assert_close(out, ref, what=f"linear {m}x{k}x{n}")
+    out2 = ops.linear(x, w, None, block_n=bn)
+    assert_close(out2, x.float() @ w.float().t(), what="linear nobias")
+
+
+def test_linear_f32_out_and_tail(cuda_device):
+    ops = _ops()
+    x = rnd(300, 192, seed=5).to(BF16)
+    w = rnd(4, 192, scale=0.1, seed=6).to(BF16)   # N = 4 (UNet out conv width)
+    b = rnd(4, seed=7)
+    out = ops.linear(x, w, b)
+    assert out.shape == (300, 4)
+    assert_close(out, x.float() @ w.float().t() + b, what="linear N=4")
+    out = ops.linear(x, w, b, out_f32=True)
+    assert out.dtype == torch.float32
+    assert_close(out, x.float() @ w.float().t() + b, rtol=2e-3, atol_scale=1e-3, what="linear f32")
+
+
+def test_linear_dual_source(cuda_device):
+    ops = _ops()
+    xa = rnd(500, 128, seed=8).to(BF16)
+    xb = rnd(500, 64, seed=9).to(BF16)
+    w = rnd(320, 192, scale=0.08, seed=10).to(BF16)
+    out = ops.linear((xa, xb), w, None)
+    ref = torch.cat([xa, xb], 1).float() @ w.float().t()
+    assert_close(out, ref, what="linear dual")
+
+
+@pytest.mark.parametrize("m,c", [(512, 320), (1000, 64)])
+def test_geglu(cuda_device, m, c):
+    ops = _ops()
+    inner = 4 * c
+    x = rnd(m, c, seed=11).to(BF16)
+    w = rnd(2 * inner, c, scale=c ** -0.5, seed=12).to(BF16)
+    b = rnd(2 * inner, seed=13, scale=0.5).to(BF16)
+    wp, bp = ops.pack_geglu(w, b)
+    out = ops.linear(x, wp, bp, geglu=True)
+    h = x.float() @ w.float().t() + b.float()
+    a, g = h.chunk(2, dim=-1)
+    ref = a * F.gelu(g)
+    assert out.shape == (m, inner)
+    assert_close(out, ref, what="geglu")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (2, 8, 16, 64, 64), (3, 10, 16, 128, 192), (2, 5, 8, 128, 64), (2, 40, 64, 64, 320), (1, 20, 32, 320, 128),
+])
+def test_conv3x3(cuda_device, n, h, w, cin, cout):
+    ops = _ops()
+    x = rnd(n, h, w, cin, seed=14).to(BF16)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=15).to(BF16)
+    b = rnd(cout, seed=16)
+    res = rnd(n, h, w, cout, seed=17).to(BF16)
+    wp = ops.pack_conv_weight(wt)
+    out = ops.conv3x3(x, wp, b.view(1, -1), bias_div=n, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1).permute(0, 2, 3, 1) + res.float()
+    assert_close(out, ref, what=f"conv3x3 {n}x{h}x{w} {cin}->{cout}")
+
+
+def test_conv3x3_rowbias_and_concat(cuda_device):
+    ops = _ops()
+    bsz, t, h, w = 2, 3, 10, 16
+    xa = rnd(bsz * t, h, w, 128, seed=18).to(BF16)
+    xb = rnd(bsz * t, h, w, 64, seed=19).to(BF16)
+    wt = rnd(128, 192, 3, 3, scale=(9 * 192) ** -0.5, seed=20).to(BF16)
+    bias_rows = rnd(bsz, 128, seed=21)   # per-video bias row (timestep embedding add)
+    wp = ops.pack_conv_weight(wt)
+    out = ops.conv3x3((xa, xb), wp, bias_rows, bias_div=t)
+    xin = torch.cat([xa, xb], -1).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, wt.float(), None, padding=1).permute(0, 2, 3, 1)
+    ref = ref + bias_rows.repeat_interleave(t, 0)[:, None, None, :]
+    assert_close(out, ref, what="conv3x3 concat+rowbias")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 16, 64, 64), (3, 20, 32, 128, 128), (2, 10, 16, 64, 192)])
+def test_conv3x3_s2(cuda_device, n, h, w, cin, cout):
+    ops = _ops()
+    x = rnd(n, h, w, cin, seed=22).to(BF16)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=23).to(BF16)
+    b = rnd(cout, seed=24)
+    out = ops.conv3x3_s2(x, ops.pack_conv_weight(wt), b)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert_close(out, ref, what="conv3x3 s2")
+
+
+@pytest.mark.parametrize("b,t,hw,c", [(1, 16, 40, 128), (2, 4, 160, 64), (1, 16, 640, 64)])
+def test_tconv3(cuda_device, b, t, hw, c):
+    ops = _ops()
+    x = rnd(b, t, hw, c, seed=25).to(BF16)
+    wt = rnd(c, c, 3, 1, 1, scale=(3 * c) ** -0.5, seed=26).to(BF16)
+    bias = rnd(c, seed=27)
+    res = rnd(b, t, hw, c, seed=28).to(BF16)
+    out = ops.tconv3(x, ops.pack_conv_weight(wt), bias, residual=res)
+    xin = x.float().permute(0, 3, 1, 2).unsqueeze(-1)  # b c t hw 1
+    ref = F.conv3d(xin, wt.float(), bias, padding=(1, 0, 0)).squeeze(-1).permute(0, 2, 3, 1) + res.float()
+    assert_close(out, ref, what="tconv3")
+
+
+def test_bmm_nt(cuda_device):
+    ops = _ops()
+    a = rnd(3, 200, 128, seed=29).to(BF16)
+    b = rnd(3, 136, 128, seed=30).to(BF16)
+    out = ops.bmm_nt(a, b, alpha=0.5)
+    ref = 0.5 * torch.einsum("bmk,bnk->bmn", a.float(), b.float())
+    assert_close(out, ref, what="bmm_nt")
+
+
+def test_conv_small_cin(cuda_device):
+    ops = _ops()
+    x = rnd(3, 10, 16, 4, seed=31).to(BF16)
+    wt = rnd(64, 4, 3, 3, scale=1 / 6, seed=32).to(BF16)
+    b = rnd(64, seed=33)
+    out = ops.conv3x3_small_cin(x, ops.pack_conv_weight(wt), b, 64)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1).permute(0, 2, 3, 1)
+    assert_close(out, ref, what="conv small cin")
+
+
+# ----------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("n,hw,c,rps_mult,silu", [(4, 160, 320, 1, True), (2, 40, 1280, 2, True), (6, 64, 128, 3, False)])
+def test_groupnorm(cuda_device, n, hw, c, rps_mult, silu):
+    ops = _ops()
+    x = (rnd(n * hw, c, seed=34) * 2 + 0.5).to(BF16)
+    g = rnd(c, seed=35) * 0.2 + 1
+    b = rnd(c, seed=36) * 0.2
+    out = ops.groupnorm(x, g, b, rows_per_sample=hw * rps_mult, eps=1e-5, silu=silu)
+    xs = x.float().view(n // rps_mult, hw * rps_mult, c).permute(0, 2, 1)
+    ref = F.group_norm(xs, 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(n * hw, c)
+    assert_close(out, ref, what="groupnorm")
+
+
+def test_groupnorm_concat(cuda_device):
+    ops = _ops()
+    n, hw = 3, 160
+    xa = rnd(n * hw, 1280, seed=37).to(BF16)
+    xb = (rnd(n * hw, 640, seed=38) * 3).to(BF16)
+    c = 1920
+    g = rnd(c, seed=39) * 0.2 + 1
+    b = rnd(c, seed=40) * 0.2
+    out = ops.groupnorm((xa, xb), g, b, rows_per_sample=hw, eps=1e-5, silu=True)
+    xs = torch.cat([xa, xb], 1).float().view(n, hw, c).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xs, 32, g, b, 1e-5)).permute(0, 2, 1).reshape(n * hw, c)
+    assert_close(out, ref, what="groupnorm concat")
+
+
+@pytest.mark.parametrize("rows,c", [(1000, 320), (77, 1280), (513, 512), (64, 640)])
+def test_layernorm(cuda_device, rows, c):
+    ops = _ops()
+    x = (rnd(rows, c, seed=41) * 1.5 + 0.3).to(BF16)
+    g = rnd(c, seed=42) * 0.2 + 1
+    b = rnd(c, seed=43) * 0.2
+    out = ops.layernorm(x, g, b, 1e-5)
+    ref = F.layer_norm(x.float(), (c,), g, b, 1e-5)
+    assert_close(out, ref, what="layernorm")
+
+
+# ----------------------------------------------------------------------------- attention
+def _sdpa_ref(q, k, v, heads, scale):
+    bq, lq, inner = q.shape
+    bk, lk, _ = k.shape
+    rep = bq // bk
+    qh = q.float().view(bq, lq, heads, 64).transpose(1, 2)
+    kh = k.float().view(bk, lk, heads, 64).transpose(1, 2).repeat_interleave(rep, 0)
+    vh = v.float().view(bk, lk, heads, 64).transpose(1, 2).repeat_interleave(rep, 0)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(bq, lq, inner)
+
+
+@pytest.mark.parametrize("b,lq,lk,heads,rep", [
+    (2, 256, 256, 2, 1), (1, 128, 128, 1, 1), (2, 160, 160, 3, 1), (4, 40, 40, 2, 1), (4, 640, 77, 2, 4), (1, 2560, 2560, 5, 1),
+])
+def test_attention(cuda_device, b, lq, lk, heads, rep):
+    ops = _ops()
+    inner = heads * 64
+    q = rnd(b, lq, inner, seed=44).to(BF16)
+    k = rnd(b // rep, lk, inner, seed=45).to(BF16)
+    v = rnd(b // rep, lk, inner, seed=46).to(BF16)
+    out = ops.attention(q, k, v, heads=heads, scale=0.125, kv_batch_div=rep)
+    ref = _sdpa_ref(q, k, v, heads, 0.125)
+    assert_close(out, ref, what=f"attention b{b} lq{lq} lk{lk} h{heads}")
+
+
+def test_attention_strided_qkv(cuda_device):
+    """q/k/v are column slices of one fused projection output (row stride 3*inner)."""
+    ops = _ops()
+    b, l, heads = 2, 256, 2
+    inner = heads * 64
+    qkv = rnd(b, l, 3 * inner, seed=47).to(BF16)
+    q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
+    out = ops.attention(q, k, v, heads=heads, scale=0.125)
+    ref = _sdpa_ref(q.contiguous(), k.contiguous(), v.contiguous(), heads, 0.125)
+    assert_close(out, ref, what="attention strided")
+
+
+@pytest.mark.parametrize("b,t,hw,heads", [(1, 16, 40, 2), (2, 16, 33, 1), (1, 8, 20, 3), (1, 24, 10, 2)])
+def test_attention_temporal(cuda_device, b, t, hw, heads):
+    ops = _ops()
+    inner = heads * 64
+    q = rnd(b * t * hw, inner, seed=48).to(BF16)
+    k = rnd(b * t * hw, inner, seed=49).to(BF16)
+    v = rnd(b * t * hw, inner, seed=50).to(BF16)
+    out = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=heads, scale=0.125)
+
+    def seqs(x):  # (b t hw) c -> (b hw) t c
+        return x.view(b, t, hw, inner).permute(0, 2, 1, 3).reshape(b * hw, t, inner)
+    ref = _sdpa_ref(seqs(q), seqs(k), seqs(v), heads, 0.125)
+    ref = ref.view(b, hw, t, inner).permute(0, 2, 1, 3).reshape(b * t * hw, inner)
+    assert_close(out, ref, what="attention temporal")
+
+
+# ----------------------------------------------------------------------------- small ops
+def test_small_linear_and_sinusoid(cuda_device):
+    ops = _ops()
+    x = rnd(3, 320, seed=51)
+    w = rnd(1280, 320, scale=320 ** -0.5, seed=52).to(BF16)
+    b = rnd(1280, seed=53)
+    out = ops.small_linear(x, w, b, silu_in=True, silu_out=True, round_bf16=False)
+    ref = F.silu(F.silu(x) @ w.float().t() + b)
+    assert_close(out, ref, rtol=2e-3, atol_scale=1e-4, what="small_linear")
+    t = torch.tensor([999.0, 519.0, 16.0], device="cuda")
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).cuda()
+    emb = ops.sinusoidal_embedding(t, freqs, round_bf16=False)
+    args = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert_close(emb, ref, rtol=1e-4, atol_scale=1e-4, what="sinusoid")
+
+
+def test_layout_and_resample(cuda_device):
+    ops = _ops()
+    x = rnd(2, 4, 3, 6, 8, seed=54).to(BF16)
+    fr = ops.bcthw_to_frames(x, 1.0)
+    assert torch.equal(fr, x.permute(0, 2, 3, 4, 1).reshape(6, 6, 8, 4))
+    back = ops.frames_to_bcthw(fr, 2, 4, torch.float32)
+    assert torch.equal(back, x.float())
+    y = rnd(2, 5, 8, 64, seed=55).to(BF16)
+    up = ops.upsample_nearest2x(y)
+    ref = F.interpolate(y.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    a, bb = rnd(10, 7, 64, seed=56).to(BF16), rnd(10, 7, 128, seed=57).to(BF16)
+    assert torch.equal(ops.concat_channels(a, bb), torch.cat([a, bb], -1))
+    s = rnd(50, 300, seed=58).to(BF16)
+    ref = torch.softmax(s.float() * 0.3, -1)
+    assert_close(ops.softmax_rows_(s.clone(), 0.3), ref, what="softmax rows")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_lcm_step(cuda_device, dtype):
+    ops = _ops()
+    x = rnd(1, 4, 16, 40, 64, seed=59).to(dtype)
+    e = rnd(1, 4, 16, 40, 64, seed=60).to(dtype)
+    nz = rnd(1, 4, 16, 40, 64, seed=61).to(dtype)
+    a_t, a_p = torch.tensor(0.0047), torch.tensor(0.35)
+    c_skip, c_out = torch.tensor(2.5e-9), torch.tensor(1.0)
+    sb, sa = (1 - a_t).sqrt(), a_t.sqrt()
+    x0 = (x - sb.cuda() * e) / sa.cuda()
+    den = c_out.cuda() * x0 + c_skip.cuda() * x
+    prev = a_p.sqrt().cuda() * den + (1 - a_p).sqrt().cuda() * nz
+    p2, d2 = ops.lcm_step(x, e, nz, inv_sqrt_alpha_t=float(1.0 / sa), sqrt_beta_t=float(sb), c_skip=float(c_skip),
+                          c_out=float(c_out), sqrt_alpha_prev=float(a_p.sqrt()), sqrt_beta_prev=float((1 - a_p).sqrt()))
+    tol = dict(rtol=2e-2, atol_scale=1e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol_scale=1e-5)
+    assert_close(d2, den, what="lcm den", **tol)
+    assert_close(p2, prev, what="lcm prev", **tol)
