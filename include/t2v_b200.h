@@ -70,6 +70,7 @@ typedef struct T2VGemmDesc {
   int64_t b_rows;                       /* N of the GEMM (rows of W); any N >= 1 */
   int64_t b_batches;                    /* 1 if shared */
   int64_t b_batch_stride;               /* elements between batches */
+  int64_t b_row_stride;                 /* elements between rows of W; 0 = K (dense) */
   int32_t b_batch_dim;                  /* index (0..3) of the A dim whose coordinate selects the batch; -1 = none */
   /* output: row (x1..x4) at sum_j x_j * o_stride[j], columns contiguous */
   void* out;
@@ -198,6 +199,11 @@ int t2v_conv3x3_small_cin(const void* in, const void* w, const float* bias, void
 /* [B,C,T,H,W] (any float dtype given by in_dtype: 0 bf16, 1 fp16, 2 fp32) -> [B*T,H,W,C] bf16, times scale */
 int t2v_bcthw_to_frames(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
                         int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t stream);
+/* same, followed by a per-pixel channel mix out[o] = sum_c mix[o][c] * scale * in[c] + bias[o]  (c <= 8):
+ * `1/scale_factor * z` + post_quant_conv 1x1 (ddpm3d.py:669, autoencoder.py:111). mix/bias: fp32 device arrays */
+int t2v_bcthw_to_frames_mix(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
+                            int32_t t, int32_t h, int32_t w, float scale, const float* mix,
+                            const float* bias, t2v_stream_t stream);
 /* [B*T,H,W,C_pad] bf16 (first c channels) -> [B,C,T,H,W] in out_dtype */
 int t2v_frames_to_bcthw(const void* in, int32_t c_pad, void* out, int32_t out_dtype, int32_t b,
                         int32_t c, int32_t t, int32_t h, int32_t w, t2v_stream_t stream);

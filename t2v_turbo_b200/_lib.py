@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("b_rows", C.c_int64),
         ("b_batches", C.c_int64),
         ("b_batch_stride", C.c_int64),
+        ("b_row_stride", C.c_int64),
         ("b_batch_dim", C.c_int32),
         ("out", C.c_void_p),
         ("o_size", C.c_int64 * MAX_DIMS),
@@ -123,6 +124,7 @@ SYMBOLS = {
     "t2v_sinusoidal_embedding": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_conv3x3_small_cin": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "t2v_bcthw_to_frames": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "t2v_bcthw_to_frames_mix": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "t2v_frames_to_bcthw": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "t2v_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_concat_channels": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),

@@ -166,6 +166,23 @@ __global__ void bcthw_to_frames_kernel(const void* in, int in_dtype, __nv_bfloat
     out[i] = __float2bfloat16_rn(load_as_float(in, src, in_dtype) * scale);
   }
 }
+__global__ void bcthw_to_frames_mix_kernel(const void* in, int in_dtype, __nv_bfloat16* out, int b, int c,
+                                           int t, int h, int w, float scale, const float* mix,
+                                           const float* bias) {
+  const int64_t total = int64_t(b) * t * h * w;
+  const int64_t plane = int64_t(t) * h * w;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t bi = i / plane, rem = i % plane;  // rem = (t, y, x) flattened, same order in both layouts
+    float v[8];
+    for (int ci = 0; ci < c; ++ci) v[ci] = load_as_float(in, (bi * c + ci) * plane + rem, in_dtype) * scale;
+    for (int o = 0; o < c; ++o) {
+      float a = bias ? bias[o] : 0.f;
+      for (int ci = 0; ci < c; ++ci) a = fmaf(mix[o * c + ci], v[ci], a);
+      out[i * c + o] = __float2bfloat16_rn(a);
+    }
+  }
+}
 __global__ void frames_to_bcthw_kernel(const __nv_bfloat16* in, int c_pad, void* out, int out_dtype,
                                        int b, int c, int t, int h, int w) {
   const int64_t total = int64_t(b) * c * t * h * w;
@@ -351,6 +368,17 @@ extern "C" int t2v_bcthw_to_frames(const void* in, int32_t in_dtype, void* out, 
   bcthw_to_frames_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, t, h, w, scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_bcthw_to_frames launch");
+}
+
+extern "C" int t2v_bcthw_to_frames_mix(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
+                                       int32_t t, int32_t h, int32_t w, float scale, const float* mix,
+                                       const float* bias, t2v_stream_t s) {
+  if (!in || !out || !mix) return fail(-1, "t2v_bcthw_to_frames_mix: null pointer");
+  if (c < 1 || c > 8) return fail(-2, "t2v_bcthw_to_frames_mix: c must be in [1,8]");
+  const int64_t total = int64_t(b) * t * h * w;
+  bcthw_to_frames_mix_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, t, h, w, scale, mix, bias);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_bcthw_to_frames_mix launch");
 }
 
 extern "C" int t2v_frames_to_bcthw(const void* in, int32_t c_pad, void* out, int32_t out_dtype, int32_t b,

@@ -470,8 +470,9 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   }
   {
     uint64_t dims[3] = {uint64_t(K), uint64_t(d->b_rows), uint64_t(d->b_batches < 1 ? 1 : d->b_batches)};
-    uint64_t strides[3] = {2, uint64_t(K) * 2,
-                           uint64_t(d->b_batch_stride > 0 ? d->b_batch_stride : K * d->b_rows) * 2};
+    const uint64_t row_stride = uint64_t(d->b_row_stride > 0 ? d->b_row_stride : K);
+    uint64_t strides[3] = {2, row_stride * 2,
+                           uint64_t(d->b_batch_stride > 0 ? d->b_batch_stride : row_stride * d->b_rows) * 2};
     uint32_t box[3] = {64, uint32_t(bn), 1};
     int rc = make_tmap_bf16(&tmB, d->b, 3, dims, strides, box, "t2v_gemm B");
     if (rc) return rc;

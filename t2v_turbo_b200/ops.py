@@ -75,7 +75,7 @@ def _as_pair(x):
 def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w, n_rows, out,
               o_size, o_stride, n_out, bias=None, bias_row_stride=0, bias_dim=-1, bias_div=1,
               residual=None, r_stride=None, alpha=1.0, flags=0, block_n=0, b_batches=1,
-              b_batch_stride=0, b_batch_dim=-1):
+              b_batch_stride=0, b_batch_dim=-1, b_row_stride=0):
     d = GemmDesc()
     a0, a1 = a
     d.a[0] = a0.data_ptr()
@@ -95,6 +95,7 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     d.b_batches = b_batches
     d.b_batch_stride = b_batch_stride
     d.b_batch_dim = b_batch_dim
+    d.b_row_stride = b_row_stride
     d.out = out.data_ptr()
     _fill(d.o_size, o_size)
     _fill(d.o_stride, o_stride)
