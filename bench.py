@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json headline metric on B200: 4-step T2VTurboVC2Pipeline, one 16-frame 320x512
+video per call (BASELINE config[1]: "T2VTurboVC2Pipeline 4-step inference, 16x320x512, bf16, 1xB200").
+
+A "step" is one full pipeline call (4 UNet forwards + 4 scheduler steps + batched VAE decode) on
+synthetic inputs (random prompt embeddings, random-init weights of the VC2 architecture).
+  value : frames/s, whole job (all ranks), CUDA-event timed, inputs resident in HBM.
+  e2e   : same metric through the public pipeline call with HOST buffers — prompt embeddings in pinned
+          host memory (H2D each step) and the decoded video copied back to pinned host memory (D2H).
+  roofline     : tensor-core roofline of the dominant kernel family (gemm_tc: every Linear / conv),
+                 algorithmic FLOPs / CUDA-event time of those launches, measured live in an eager pass.
+  cpu_baseline : the oracle port of the reference UNet (plain fp32 torch, naive attention) timed on the
+                 host cores on a bounded sample, extrapolated by FLOPs.
+`--impl reference` runs only that CPU arm (the reference is pure Python with no GPU kernels of its
+own; /root/reference does not exist on the GPU box, so the oracle port stands in for it).
+Multi-GPU (torchrun): replicas only — each rank samples its own videos; no data-path collective.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES, HEIGHT, WIDTH, STEPS = 16, 320, 512, 4
+# BASELINE.md §3 (hooked reference forward): algorithmic FLOPs
+UNET_TFLOP, VAE_TFLOP = 12.581, 25.016
+PIPE_TFLOP = STEPS * UNET_TFLOP + VAE_TFLOP   # 75.34
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=float(self.rows[0][1]), reasons=reasons, samples=len(sm))
+
+
+def build_pipeline(device, use_graph=True):
+    import torch
+    from t2v_turbo_b200.configs import VC2_UNET, VC2_VAE_DDCONFIG
+    from t2v_turbo_b200.pipeline import LatentVideoModel, T2VTurboVC2Pipeline
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.unet import UNetModel
+    from t2v_turbo_b200.vae import AutoencoderKL
+    with torch.device(device):
+        unet = UNetModel(**VC2_UNET)
+        vae = AutoencoderKL(VC2_VAE_DDCONFIG, 4)
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for mod in (unet, vae):
+            for name, p in mod.named_parameters():
+                if p.dim() >= 2:
+                    fan_in = p[0].numel()
+                    p.copy_(torch.randn(p.shape, generator=g, device=device) * (0.6 / fan_in ** 0.5))
+                elif name.endswith("weight"):
+                    p.copy_(1.0 + 0.05 * torch.randn(p.shape, generator=g, device=device))
+                else:
+                    p.copy_(0.02 * torch.randn(p.shape, generator=g, device=device))
+    unet.eval()
+    vae.eval()
+    unet.dtype = torch.bfloat16     # what app.py:143 does for bf16 inference
+    t2v = LatentVideoModel(unet, vae, temporal_length=FRAMES)
+    pipe = T2VTurboVC2Pipeline(t2v, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012),
+                               {"params": {"unet_config": {"params": VC2_UNET}}}, use_cuda_graph=use_graph)
+    return pipe
+
+
+def cpu_sample(threads):
+    """One bounded sample of the CPU path: the oracle UNet forward (fp32, naive attention) on 4 of the 16 frames."""
+    import torch
+    from t2v_turbo_b200.configs import VC2_UNET
+    from oracle.unet_oracle import unet_forward, guidance_scale_embedding
+    from t2v_turbo_b200.unet import UNetModel
+    torch.set_num_threads(threads)
+    with torch.device("meta"):
+        shapes = {k: v.shape for k, v in UNetModel(**VC2_UNET).state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for k, shp in shapes.items():
+        if len(shp) >= 2:
+            fan_in = 1
+            for s in shp[1:]:
+                fan_in *= s
+            sd[k] = torch.empty(shp).normal_(0, 0.6 / fan_in ** 0.5, generator=g)
+        elif k.endswith("weight"):
+            sd[k] = torch.ones(shp)
+        else:
+            sd[k] = torch.zeros(shp)
+    t_frames = 4
+    x = torch.randn(1, 4, t_frames, HEIGHT // 8, WIDTH // 8, generator=g)
+    ctx = torch.randn(1, 77, 1024, generator=g)
+    w = guidance_scale_embedding(torch.tensor([7.5]), 256)
+    ts = torch.tensor([999])
+
+    def run():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            unet_forward(sd, VC2_UNET, x, ts, ctx, fps=16, timestep_cond=w)
+        return time.perf_counter() - t0
+    sample_tflop = UNET_TFLOP * t_frames / FRAMES
+    desc = (f"oracle port of UNetModel.forward, fp32, naive attention, {t_frames} of {FRAMES} frames at 40x64 "
+            f"({sample_tflop:.2f} of {PIPE_TFLOP:.2f} TFLOP per video; frames/s extrapolated by FLOPs)")
+    return run, sample_tflop, desc
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    run, sample_tflop, desc = cpu_sample(threads)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    fps = FRAMES / (t * PIPE_TFLOP / sample_tflop)
+    line = dict(impl="reference", metric="4-step 16x320x512 frames/sec", value=fps, unit="frames/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet + KL-VAE decode, bs=1 per GPU"),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=desc),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from t2v_turbo_b200 import ops
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    pipe = build_pipeline(device, use_graph=not args.no_graph)
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    pe_dev = torch.randn(1, 77, 1024, device=device, dtype=torch.bfloat16, generator=gen)
+
+    def call(pe):
+        return pipe(prompt_embeds=pe, height=HEIGHT, width=WIDTH, frames=FRAMES, fps=16, guidance_scale=7.5,
+                    num_inference_steps=STEPS, lcm_origin_steps=50, generator=gen, output_type="pt")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm
+    for _ in range(args.warmup):
+        vid = call(pe_dev)
+    assert tuple(vid.shape) == (1, 3, FRAMES, HEIGHT, WIDTH)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        vid = call(pe_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    finite = bool(torch.isfinite(vid.float()).all())
+
+    # ---------------- end-to-end arm: host buffers in, host buffers out
+    pe_host = pe_dev.cpu().pin_memory()
+    out_host = torch.empty((1, 3, FRAMES, HEIGHT, WIDTH), dtype=torch.bfloat16).pin_memory()
+    for _ in range(2):
+        out_host.copy_(call(pe_host), non_blocking=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        out_host.copy_(call(pe_host), non_blocking=True)   # H2D inside the pipeline call, D2H of the video here
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---------------- UNet forward alone (graph replay), part of the headline metric triple
+    lat = torch.randn(1, 4, FRAMES, HEIGHT // 8, WIDTH // 8, device=device, dtype=torch.bfloat16, generator=gen)
+    ts = torch.full((1,), 999, device=device, dtype=torch.long)
+    wemb = pipe.get_w_embedding(torch.tensor([7.5]), 256).to(device).to(torch.bfloat16)
+    for _ in range(2):
+        pipe._unet_call(lat, ts, pe_dev, wemb, None, 16)
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    u0.record()
+    for _ in range(10):
+        pipe._unet_call(lat, ts, pe_dev, wemb, None, 16)
+    u1.record()
+    torch.cuda.synchronize()
+    unet_ms = u0.elapsed_time(u1) / 10
+
+    # ---------------- launches per step + roofline of the dominant kernel family (eager pass, CUDA events per call)
+    pipe.use_cuda_graph = False
+    call(pe_dev)
+    torch.cuda.synchronize()
+    n0 = ops.LAUNCHES
+    ops.start_profile()
+    call(pe_dev)
+    prof = ops.stop_profile()
+    launches_per_step = ops.LAUNCHES - n0
+    pk = peaks()
+    gemm = prof.get("gemm", dict(ms=0.0, flops=0, calls=0))
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    roofline = dict(bound="tensor", kernel="gemm_tc_kernel (all Linear / Conv2d / Conv3d launches of one pipeline call)",
+                    achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"], peak_source=pk["src"],
+                    traffic=None, launches=gemm["calls"], avg_launch_us=gemm["ms"] * 1e3 / max(1, gemm["calls"]),
+                    share_of_step=gemm["ms"] / tot_ms,
+                    families={k: dict(calls=v["calls"], ms=round(v["ms"], 3), tflops=round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1))
+                              for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})
+
+    if rank == 0:
+        frames_total = FRAMES * args.steps * world
+        value = frames_total / (ms * 1e-3)
+        line = dict(metric="4-step 16x320x512 frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16", data="synthetic",
+                    config=dict(workload="T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet (1.41B) + KL-VAE decode, bs=1 per GPU",
+                                parallelism=f"replicas x{world} (no data-path collective)", cuda_graph=not args.no_graph,
+                                l2="working set per step (2.83 GB weights x4 + activations) >> 126 MB L2; no flush needed",
+                                algorithmic_tflop_per_step=PIPE_TFLOP, output_finite=finite),
+                    unet_fwd_ms=unet_ms, unet_fwd_tflops=UNET_TFLOP / (unet_ms * 1e-3), clocks=clocks,
+                    e2e=dict(value=frames_total / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=pe_host.numel() * 2,
+                             d2h_bytes_per_step=out_host.numel() * 2),
+                    gpu_launches=launches_per_step * args.steps, roofline=roofline,
+                    tensor_frac_of_step=PIPE_TFLOP / (ms / args.steps * 1e-3) / pk["tflops"])
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            run, sample_tflop, desc = cpu_sample(threads)
+            tcpu = run()
+            line["cpu_baseline"] = dict(value=FRAMES / (tcpu * PIPE_TFLOP / sample_tflop), unit="frames/s", cores=threads,
+                                        kind="port", sample=desc + f"; sample took {tcpu:.1f} s")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+"""Generate the parity fixtures under tests/golden/ by executing the UNMODIFIED reference
+(/root/reference, read-only) in the authoring container.  Test infrastructure; run once:
+
+    python oracle/make_goldens.py [--full]
+
+Each fixture stores the config, the seeds, the inputs and the reference's fp32 output.  Weights are
+NOT stored: they are regenerated from (sorted key, shape, seed) by oracle/weights.seeded_state_dict,
+identically here (loaded into the reference modules) and on the GPU box (loaded into the B200 modules).
+`--full` additionally runs BASELINE config 1 (full VC2 UNet, 1x4x16x40x64, fp32; ~2-3 min of CPU)
+and one full-resolution VAE frame.
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(HERE, "shim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from oracle.configs import UNET_CONFIGS, VAE_CONFIGS, unet_inputs  # noqa: E402
+from oracle.weights import seeded_state_dict  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_unet(cfg, seed):
+    from lvdm.modules.networks.openaimodel3d import UNetModel
+    m = UNetModel(**cfg).eval()
+    sd = seeded_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def gen_unet(name, full=False):
+    spec = UNET_CONFIGS[name]
+    cfg = spec["cfg"]
+    t0 = time.time()
+    m = ref_unet(cfg, spec["weight_seed"])
+    outs = []
+    for ts in spec["timesteps"]:
+        inp = unet_inputs(spec, ts)
+        with torch.no_grad():
+            y = m(inp["x"], inp["timesteps"], context=inp["context"], fps=inp["fps"], timestep_cond=inp["timestep_cond"],
+                  motion_cond=inp.get("motion_cond"))
+        outs.append(y.clone())
+        print(f"  {name} t={ts}: out std {y.std():.4f} absmax {y.abs().max():.4f} ({time.time()-t0:.1f}s)")
+    torch.save({"name": name, "timesteps": spec["timesteps"], "outputs": outs,
+                "n_params": sum(p.numel() for p in m.parameters())}, os.path.join(GOLD, f"unet_{name}.pt"))
+
+
+def gen_vae(name):
+    from lvdm.modules.networks.ae_modules import Decoder
+    spec = VAE_CONFIGS[name]
+    dd = spec["ddconfig"]
+    dec = Decoder(**dd).eval()
+    pq = torch.nn.Conv2d(spec["embed_dim"], dd["z_channels"], 1)
+    template = {f"decoder.{k}": v for k, v in dec.state_dict().items()}
+    template.update({f"post_quant_conv.{k}": v for k, v in pq.state_dict().items()})
+    sd = seeded_state_dict(template, spec["weight_seed"])
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+    pq.load_state_dict({k[len("post_quant_conv."):]: v for k, v in sd.items() if k.startswith("post_quant_conv.")})
+    g = torch.Generator().manual_seed(spec["input_seed"])
+    z = torch.randn(spec["z_shape"], generator=g)
+    with torch.no_grad():
+        # ddpm3d.py:666-679 decode_first_stage_2DAE semantics, frame by frame
+        zz = 1.0 / 0.18215 * z
+        frames = [dec(pq(zz[:, :, i])).unsqueeze(2) for i in range(zz.shape[2])]
+        out = torch.cat(frames, dim=2)
+    print(f"  vae {name}: out std {out.std():.4f} absmax {out.abs().max():.4f}")
+    torch.save({"name": name, "z": z, "output": out}, os.path.join(GOLD, f"vae_{name}.pt"))
+
+
+def gen_scheduler():
+    from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
+    s = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
+    table = {}
+    for n, o in [(4, 50), (8, 50), (16, 50), (4, 200), (8, 200), (16, 200), (1, 50)]:
+        s.set_timesteps(n, o)
+        table[(n, o)] = s.timesteps.clone()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 4, 4, 8, 8, generator=g)
+    eps = torch.randn(1, 4, 4, 8, 8, generator=g)
+    s.set_timesteps(4, 50)
+    steps = []
+    for i, t in enumerate(s.timesteps):
+        gen = torch.Generator().manual_seed(100 + i)
+        noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + i))
+        prev, den = s.step(eps, i, t, x, generator=gen, return_dict=False)
+        steps.append({"i": i, "t": int(t), "noise": noise, "prev": prev, "den": den})
+    torch.save({"alphas_cumprod": s.alphas_cumprod.clone(), "timesteps": table, "x": x, "eps": eps, "steps": steps,
+                "scalings": {t: tuple(float(v) for v in s.get_scalings_for_boundary_condition_discrete(t)) for t in (0, 279, 999)}},
+               os.path.join(GOLD, "scheduler.pt"))
+    print("  scheduler: alphas_cumprod[0], [999] =", float(s.alphas_cumprod[0]), float(s.alphas_cumprod[999]))
+
+
+def gen_pipeline():
+    """4-step T2VTurboVC2Pipeline on CPU with the small UNet/VAE through the unmodified reference classes."""
+    from pipeline.t2v_turbo_vc2_pipeline import T2VTurboVC2Pipeline
+    from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
+    from lvdm.modules.networks.ae_modules import Decoder
+    uspec, vspec = UNET_CONFIGS["small"], VAE_CONFIGS["small"]
+    unet = ref_unet(uspec["cfg"], uspec["weight_seed"])
+    dd = vspec["ddconfig"]
+    dec = Decoder(**dd).eval()
+    pq = torch.nn.Conv2d(vspec["embed_dim"], dd["z_channels"], 1)
+    template = {f"decoder.{k}": v for k, v in dec.state_dict().items()}
+    template.update({f"post_quant_conv.{k}": v for k, v in pq.state_dict().items()})
+    sd = seeded_state_dict(template, vspec["weight_seed"])
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+    pq.load_state_dict({k[len("post_quant_conv."):]: v for k, v in sd.items() if k.startswith("post_quant_conv.")})
+
+    class FakeVAE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.decoder, self.post_quant_conv = dec, pq
+
+        def decode(self, z, **kw):
+            return self.decoder(self.post_quant_conv(z))
+
+    class FakeT2V(torch.nn.Module):   # the attributes the pipeline touches (pipeline:27-29,144,216)
+        def __init__(self):
+            super().__init__()
+            self.first_stage_model = FakeVAE()
+            self.model = torch.nn.Module()
+            self.model.diffusion_model = unet
+            self.cond_stage_model = torch.nn.Identity()
+            self.temporal_length = 4
+            self.scale_factor = 0.18215
+
+        def decode_first_stage_2DAE(self, z, **kw):   # ddpm3d.py:666-679
+            z = 1.0 / self.scale_factor * z
+            return torch.cat([self.first_stage_model.decode(z[:, :, i]).unsqueeze(2) for i in range(z.shape[2])], dim=2)
+
+    pipe = T2VTurboVC2Pipeline(FakeT2V(), T2VTurboScheduler(linear_start=0.00085, linear_end=0.012),
+                               {"params": {"unet_config": {"params": uspec["cfg"]}}})
+    g = torch.Generator().manual_seed(5)
+    prompt_embeds = torch.randn(1, 77, uspec["cfg"]["context_dim"], generator=g)
+    res = {}
+    for steps in (4, 8):
+        gen = torch.Generator().manual_seed(1234)
+        lat = pipe(prompt_embeds=prompt_embeds, height=64, width=64, frames=4, fps=16, guidance_scale=7.5,
+                   num_inference_steps=steps, lcm_origin_steps=50, generator=gen, output_type="latent")
+        gen = torch.Generator().manual_seed(1234)
+        vid = pipe(prompt_embeds=prompt_embeds, height=64, width=64, frames=4, fps=16, guidance_scale=7.5,
+                   num_inference_steps=steps, lcm_origin_steps=50, generator=gen, output_type="pt")
+        res[steps] = {"latent": lat, "video": vid}
+        print(f"  pipeline {steps} steps: latent std {lat.std():.4f} video std {vid.std():.4f}")
+    torch.save({"prompt_embeds": prompt_embeds, "results": res}, os.path.join(GOLD, "pipeline_small.pt"))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "pipeline"] + (["unet_full", "vae_full"] if a.full else [])
+    for item in todo:
+        print("generating", item)
+        if item == "scheduler":
+            gen_scheduler()
+        elif item.startswith("unet_"):
+            gen_unet(item[5:])
+        elif item.startswith("vae_"):
+            gen_vae(item[4:])
+        elif item == "pipeline":
+            gen_pipeline()

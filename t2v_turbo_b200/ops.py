@@ -20,6 +20,45 @@ from ._lib import (AttnDesc, GemmDesc, GroupNormDesc, LayerNormDesc, ShortAttnDe
 
 BF16 = torch.bfloat16
 
+# ----------------------------------------------------------------------------- launch accounting
+KERNELS_PER_CALL = {"groupnorm": 2}     # stats + apply (plus one memset node)
+LAUNCHES = 0                            # kernels of libt2v_b200.so enqueued so far (incl. during graph capture)
+_PROF = None                            # list of (family, flops, ev_start, ev_end) while profiling
+_FLOPS: dict = {}
+
+
+def start_profile():
+    """Per-call CUDA-event timing by kernel family (eager mode only; used by bench.py for the roofline)."""
+    global _PROF
+    _PROF = []
+
+
+def stop_profile():
+    """-> {family: dict(calls, ms, flops)} after synchronising."""
+    global _PROF
+    recs, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    out = {}
+    for fam, flops, e0, e1 in recs:
+        d = out.setdefault(fam, dict(calls=0, ms=0.0, flops=0))
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+    return out
+
+
+def _launch(family, flops, fn, *args):
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(family, 1)
+    if _PROF is None:
+        check(fn(*args), "t2v_" + family)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args), "t2v_" + family)
+    e1.record()
+    _PROF.append((family, flops, e0, e1))
+
 
 # ----------------------------------------------------------------------------- tile planning
 @functools.lru_cache(maxsize=None)
@@ -109,7 +148,8 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     d.alpha = alpha
     d.flags = flags
     d.block_n = block_n
-    check(lib().t2v_gemm(C.byref(d), stream_ptr()), "t2v_gemm")
+    _FLOPS["gemm"] = 2 * math.prod(int(v) for v in o_size) * int(n_rows) * len(taps) * (int(a_ch[0]) + int(a_ch[1]))
+    _launch("gemm", _FLOPS.pop("gemm", 0), lib().t2v_gemm, C.byref(d), stream_ptr())
     return out
 
 
@@ -143,18 +183,20 @@ def linear(x, w, bias=None, *, residual=None, geglu=False, gelu=False, out=None,
 
 
 def bmm_nt(a, b, *, out=None, alpha=1.0, block_n=0):
-    """Batched out[i] = a[i] @ b[i].T with a: [Bt, M, K], b: [Bt, N, K] bf16 (VAE AttnBlock)."""
-    _check_act(a, "a")
-    _check_act(b, "b")
+    """Batched out[i] = a[i] @ b[i].T.  a: [Bt, M, K], b: [Bt, N, K] bf16 views with arbitrary batch / row
+    strides (K contiguous) — used by the VAE AttnBlock (ae_modules.py:55-68) on slices of fused projections."""
+    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(2) == 1 and b.stride(2) == 1
     bt, m, k = a.shape
     n = b.shape[1]
+    assert b.shape[0] == bt and b.shape[2] == k and k % 64 == 0, (a.shape, b.shape)
     if out is None:
         out = torch.empty((bt, m, n), device=a.device, dtype=BF16)
     return _gemm_raw(
         a=(a, None), a_ch=(k, 0), a_ch_total=(k, 0), a_size=(m, bt, 1, 1),
-        a_stride=((k, m * k, 0, 0), None), box=(128, 1, 1, 1), taps=[(0, 0, 0, 0)], tap_ch_off=None,
+        a_stride=((a.stride(1), a.stride(0), 0, 0), None), box=(128, 1, 1, 1), taps=[(0, 0, 0, 0)], tap_ch_off=None,
         w=b, n_rows=n, out=out, o_size=(m, bt, 1, 1), o_stride=(out.stride(1), out.stride(0), 0, 0),
-        n_out=n, alpha=alpha, block_n=block_n, b_batches=bt, b_batch_stride=n * k, b_batch_dim=1)
+        n_out=n, alpha=alpha, block_n=block_n, b_batches=bt, b_batch_stride=b.stride(0), b_batch_dim=1,
+        b_row_stride=b.stride(1))
 
 
 # ----------------------------------------------------------------------------- convolutions
@@ -232,8 +274,8 @@ def conv3x3_small_cin(x, w, bias, cout):
     _check_act(x)
     n, h, wd, cin = x.shape
     out = torch.empty((n, h, wd, cout), device=x.device, dtype=BF16)
-    check(lib().t2v_conv3x3_small_cin(x.data_ptr(), w.data_ptr(), ptr(bias), out.data_ptr(), n, h, wd, cin,
-                                      cout, stream_ptr()), "t2v_conv3x3_small_cin")
+    _launch("conv3x3_small_cin", _FLOPS.pop("conv3x3_small_cin", 0), lib().t2v_conv3x3_small_cin, x.data_ptr(), w.data_ptr(), ptr(bias), out.data_ptr(), n, h, wd, cin,
+                                      cout, stream_ptr())
     return out
 
 
@@ -278,7 +320,7 @@ def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None
     d.silu = 1 if silu else 0
     ws = _gn_workspace(x0.device, 2 * groups * (rows // rows_per_sample))
     d.workspace = ws.data_ptr()
-    check(lib().t2v_groupnorm(C.byref(d), stream_ptr()), "t2v_groupnorm")
+    _launch("groupnorm", _FLOPS.pop("groupnorm", 0), lib().t2v_groupnorm, C.byref(d), stream_ptr())
     return out
 
 
@@ -291,7 +333,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     d.out, d.out_row_stride = out.data_ptr(), out.stride(0)
     d.gamma, d.beta = gamma.data_ptr(), beta.data_ptr()
     d.rows, d.channels, d.eps = rows, c, eps
-    check(lib().t2v_layernorm(C.byref(d), stream_ptr()), "t2v_layernorm")
+    _launch("layernorm", _FLOPS.pop("layernorm", 0), lib().t2v_layernorm, C.byref(d), stream_ptr())
     return out
 
 
@@ -314,7 +356,8 @@ def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None):
     d.o_stride_b, d.o_stride_t, d.o_stride_h = out.stride(0), out.stride(1), 64
     d.kv_batch_div = kv_batch_div
     d.scale = scale
-    check(lib().t2v_attn_fwd(C.byref(d), stream_ptr()), "t2v_attn_fwd")
+    _FLOPS["attn_fwd"] = 4 * bq * heads * lq * lk * 64
+    _launch("attn_fwd", _FLOPS.pop("attn_fwd", 0), lib().t2v_attn_fwd, C.byref(d), stream_ptr())
     return out
 
 
@@ -335,7 +378,8 @@ def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None):
         setattr(d, f"{name}_stride_t", hw * rs)
         setattr(d, f"{name}_stride_h", 64)
     d.scale = scale
-    check(lib().t2v_attn_short_fwd(C.byref(d), stream_ptr()), "t2v_attn_short_fwd")
+    _FLOPS["attn_short_fwd"] = 4 * b * hw * heads * t * t * 64
+    _launch("attn_short_fwd", _FLOPS.pop("attn_short_fwd", 0), lib().t2v_attn_short_fwd, C.byref(d), stream_ptr())
     return out
 
 
@@ -354,7 +398,7 @@ def small_linear(x, w, bias=None, *, add=None, silu_in=False, silu_out=False, ro
     d.out, d.out_row_stride = out.data_ptr(), out.stride(0)
     d.m, d.n, d.k = m, n, k
     d.silu_in, d.silu_out, d.round_bf16 = int(silu_in), int(silu_out), int(round_bf16)
-    check(lib().t2v_small_linear(C.byref(d), stream_ptr()), "t2v_small_linear")
+    _launch("small_linear", _FLOPS.pop("small_linear", 0), lib().t2v_small_linear, C.byref(d), stream_ptr())
     return out
 
 
@@ -362,8 +406,8 @@ def sinusoidal_embedding(t, freqs, *, sin_first=False, round_bf16=True):
     assert t.dtype == torch.float32 and freqs.dtype == torch.float32
     m, half = t.shape[0], freqs.shape[0]
     out = torch.empty((m, 2 * half), device=t.device, dtype=torch.float32)
-    check(lib().t2v_sinusoidal_embedding(t.data_ptr(), freqs.data_ptr(), out.data_ptr(), m, half,
-                                         int(sin_first), int(round_bf16), stream_ptr()), "t2v_sinusoidal_embedding")
+    _launch("sinusoidal_embedding", _FLOPS.pop("sinusoidal_embedding", 0), lib().t2v_sinusoidal_embedding, t.data_ptr(), freqs.data_ptr(), out.data_ptr(), m, half,
+                                         int(sin_first), int(round_bf16), stream_ptr())
     return out
 
 
@@ -371,8 +415,8 @@ def bcthw_to_frames(x, scale=1.0):
     b, c, t, h, w = x.shape
     x = x.contiguous()
     out = torch.empty((b * t, h, w, c), device=x.device, dtype=BF16)
-    check(lib().t2v_bcthw_to_frames(x.data_ptr(), _lib.DTYPE_CODE[x.dtype], out.data_ptr(), b, c, t, h, w,
-                                    scale, stream_ptr()), "t2v_bcthw_to_frames")
+    _launch("bcthw_to_frames", _FLOPS.pop("bcthw_to_frames", 0), lib().t2v_bcthw_to_frames, x.data_ptr(), _lib.DTYPE_CODE[x.dtype], out.data_ptr(), b, c, t, h, w,
+                                    scale, stream_ptr())
     return out
 
 
@@ -380,8 +424,8 @@ def frames_to_bcthw(x, b, c, dtype):
     n, h, w, cp = x.shape
     t = n // b
     out = torch.empty((b, c, t, h, w), device=x.device, dtype=dtype)
-    check(lib().t2v_frames_to_bcthw(x.data_ptr(), cp, out.data_ptr(), _lib.DTYPE_CODE[dtype], b, c, t, h, w,
-                                    stream_ptr()), "t2v_frames_to_bcthw")
+    _launch("frames_to_bcthw", _FLOPS.pop("frames_to_bcthw", 0), lib().t2v_frames_to_bcthw, x.data_ptr(), cp, out.data_ptr(), _lib.DTYPE_CODE[dtype], b, c, t, h, w,
+                                    stream_ptr())
     return out
 
 
@@ -389,7 +433,7 @@ def upsample_nearest2x(x):
     _check_act(x)
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=BF16)
-    check(lib().t2v_upsample_nearest2x(x.data_ptr(), out.data_ptr(), n, h, w, c, stream_ptr()), "t2v_upsample_nearest2x")
+    _launch("upsample_nearest2x", _FLOPS.pop("upsample_nearest2x", 0), lib().t2v_upsample_nearest2x, x.data_ptr(), out.data_ptr(), n, h, w, c, stream_ptr())
     return out
 
 
@@ -397,15 +441,14 @@ def concat_channels(a, b):
     ca, cb = a.shape[-1], b.shape[-1]
     rows = a.numel() // ca
     out = torch.empty((*a.shape[:-1], ca + cb), device=a.device, dtype=BF16)
-    check(lib().t2v_concat_channels(a.data_ptr(), ca, b.data_ptr(), cb, out.data_ptr(), rows, stream_ptr()),
-          "t2v_concat_channels")
+    _launch("concat_channels", _FLOPS.pop("concat_channels", 0), lib().t2v_concat_channels, a.data_ptr(), ca, b.data_ptr(), cb, out.data_ptr(), rows, stream_ptr())
     return out
 
 
 def softmax_rows_(x, scale=1.0):
     cols = x.shape[-1]
     rows = x.numel() // cols
-    check(lib().t2v_softmax_rows(x.data_ptr(), rows, cols, cols, scale, stream_ptr()), "t2v_softmax_rows")
+    _launch("softmax_rows", _FLOPS.pop("softmax_rows", 0), lib().t2v_softmax_rows, x.data_ptr(), rows, cols, cols, scale, stream_ptr())
     return x
 
 
@@ -413,9 +456,9 @@ def lcm_step(x, eps, noise, *, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqr
     assert x.is_contiguous() and eps.is_contiguous() and x.dtype == eps.dtype
     prev = torch.empty_like(x)
     den = torch.empty_like(x)
-    check(lib().t2v_lcm_step(x.data_ptr(), eps.data_ptr(), ptr(noise), prev.data_ptr(), den.data_ptr(),
+    _launch("lcm_step", _FLOPS.pop("lcm_step", 0), lib().t2v_lcm_step, x.data_ptr(), eps.data_ptr(), ptr(noise), prev.data_ptr(), den.data_ptr(),
                              x.numel(), _lib.DTYPE_CODE[x.dtype], inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out,
-                             sqrt_alpha_prev, sqrt_beta_prev, stream_ptr()), "t2v_lcm_step")
+                             sqrt_alpha_prev, sqrt_beta_prev, stream_ptr())
     return prev, den
 
 
@@ -426,8 +469,8 @@ def pack_conv_weight(w):
     taps = w[0, 0].numel()
     w = w.contiguous()
     out = torch.empty((cout, taps * cin), device=w.device, dtype=BF16)
-    check(lib().t2v_pack_conv_weight(w.data_ptr(), _lib.DTYPE_CODE[w.dtype], out.data_ptr(), cout, cin, taps,
-                                     stream_ptr()), "t2v_pack_conv_weight")
+    _launch("pack_conv_weight", _FLOPS.pop("pack_conv_weight", 0), lib().t2v_pack_conv_weight, w.data_ptr(), _lib.DTYPE_CODE[w.dtype], out.data_ptr(), cout, cin, taps,
+                                     stream_ptr())
     return out
 
 
@@ -439,7 +482,6 @@ def pack_geglu(w, bias):
     out = torch.empty((two_inner, k), device=w.device, dtype=BF16)
     bout = torch.empty((two_inner,), device=w.device, dtype=torch.float32)
     bias = bias.contiguous()
-    check(lib().t2v_pack_geglu_rows(w.data_ptr(), _lib.DTYPE_CODE[w.dtype], out.data_ptr(), bias.data_ptr(),
-                                    _lib.DTYPE_CODE[bias.dtype], bout.data_ptr(), inner, k, stream_ptr()),
-          "t2v_pack_geglu_rows")
+    _launch("pack_geglu_rows", _FLOPS.pop("pack_geglu_rows", 0), lib().t2v_pack_geglu_rows, w.data_ptr(), _lib.DTYPE_CODE[w.dtype], out.data_ptr(), bias.data_ptr(),
+                                    _lib.DTYPE_CODE[bias.dtype], bout.data_ptr(), inner, k, stream_ptr())
     return out, bout

@@ -1,0 +1,196 @@
+"""`T2VTurboVC2Pipeline` with the reference's call surface (pipeline/t2v_turbo_vc2_pipeline.py:14-220)
+driving the B200 UNet, scheduler-step kernel and batched VAE decode.
+
+`LatentVideoModel` stands in for the slice of `LatentDiffusion` the pipeline touches
+(pipeline:27-29,144,216; ddpm3d.py:666-679): `.model.diffusion_model`, `.first_stage_model`,
+`.cond_stage_model`, `.temporal_length`, `.scale_factor`, `.decode_first_stage_2DAE`.
+
+B200-first additions (all optional, none change results): the UNet forward of a sampling loop is
+captured once into a CUDA graph (static shapes; ~1.3k kernel launches replayed per step) and the
+decode is a second graph; text-context K/V projections are computed once per call, not per step.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Any, Dict, List, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from .scheduler import T2VTurboScheduler
+
+
+class LatentVideoModel(nn.Module):
+    def __init__(self, unet, first_stage_model, cond_stage_model=None, temporal_length=16, scale_factor=0.18215):
+        super().__init__()
+        self.model = nn.Module()
+        self.model.diffusion_model = unet
+        self.first_stage_model = first_stage_model
+        self.cond_stage_model = cond_stage_model if cond_stage_model is not None else nn.Identity()
+        self.temporal_length = temporal_length
+        self.scale_factor = scale_factor
+
+    @torch.no_grad()
+    def decode_first_stage_2DAE(self, z, **kwargs):
+        """ddpm3d.py:666-679: z [b, c, t, h, w] -> [b, 3, t, 8h, 8w]; all frames in one batched decode."""
+        return self.first_stage_model.decode_frames(z, 1.0 / self.scale_factor)
+
+
+class _GraphedCall:
+    """Capture fn(*static_inputs) once per input signature; replay with inputs copied into static buffers."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.cache = {}
+
+    def __call__(self, *tensors):
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        ent = self.cache.get(key)
+        if ent is None:
+            static_in = [t.clone() for t in tensors]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):      # warm-up: lazy packing, workspace allocation, kernel attributes
+                    self.fn(*static_in)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self.fn(*static_in)
+            ent = (g, static_in, static_out)
+            self.cache[key] = ent
+        g, static_in, static_out = ent
+        for dst, src in zip(static_in, tensors):
+            dst.copy_(src)
+        g.replay()
+        return static_out
+
+
+class T2VTurboVC2Pipeline:
+    def __init__(self, pretrained_t2v, scheduler: T2VTurboScheduler, model_config: Dict[str, Any] = None,
+                 use_cuda_graph: bool = True):
+        self.pretrained_t2v = pretrained_t2v
+        self.scheduler = scheduler
+        self.vae = pretrained_t2v.first_stage_model
+        self.unet = pretrained_t2v.model.diffusion_model
+        self.text_encoder = pretrained_t2v.cond_stage_model
+        self.model_config = model_config
+        self.vae_scale_factor = 8
+        self.use_cuda_graph = use_cuda_graph
+        self._unet_graph = None
+        self._vae_graph = None
+        self.launch_counter = None
+
+    # reference: DiffusionPipeline properties
+    @property
+    def _execution_device(self):
+        for p in self.unet.parameters():
+            return p.device
+        return torch.device("cuda")
+
+    @property
+    def device(self):
+        return self._execution_device
+
+    @property
+    def dtype(self):
+        return getattr(self.unet, "dtype", torch.float32)
+
+    def to(self, *a, **k):
+        self.pretrained_t2v.to(*a, **k)
+        self._unet_graph = self._vae_graph = None
+        return self
+
+    def _encode_prompt(self, prompt, device, num_videos_per_prompt, prompt_embeds=None):
+        if prompt_embeds is None:
+            prompt_embeds = self.text_encoder(prompt)
+        prompt_embeds = prompt_embeds.to(device=device)
+        bs_embed, seq_len, _ = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_videos_per_prompt, 1)
+        return prompt_embeds.view(bs_embed * num_videos_per_prompt, seq_len, -1)
+
+    def prepare_latents(self, batch_size, num_channels_latents, frames, height, width, dtype, device, generator, latents=None):
+        shape = (batch_size, num_channels_latents, frames, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if latents is None:
+            gen_dev = generator.device if generator is not None else device
+            latents = torch.randn(shape, generator=generator, device=gen_dev, dtype=dtype).to(device)
+        else:
+            latents = latents.to(device)
+        return latents * self.scheduler.init_noise_sigma
+
+    def get_w_embedding(self, w, embedding_dim=512, dtype=torch.float32):
+        """pipeline:99-120 — host-side, once per call (plain torch on a [bs] vector)."""
+        assert len(w.shape) == 1
+        w = w * 1000.0
+        half_dim = embedding_dim // 2
+        emb = torch.log(torch.tensor(10000.0)) / (half_dim - 1)
+        emb = torch.exp(torch.arange(half_dim, dtype=dtype) * -emb)
+        emb = w.to(dtype)[:, None] * emb[None, :]
+        emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=1)
+        if embedding_dim % 2 == 1:
+            emb = torch.nn.functional.pad(emb, (0, 1))
+        return emb
+
+    def _unet_call(self, latents, ts, ctx, w_emb, motion, fps):
+        if not self.use_cuda_graph:
+            return self.unet(latents, ts, context=ctx, fps=fps, timestep_cond=w_emb, motion_cond=motion)
+        if self._unet_graph is None or self._unet_graph[0] != (fps, motion is None):
+            if motion is None:
+                fn = lambda x, t, c, w: self.unet(x, t, context=c, fps=fps, timestep_cond=w)  # noqa: E731
+            else:
+                fn = lambda x, t, c, w, m: self.unet(x, t, context=c, fps=fps, timestep_cond=w, motion_cond=m)  # noqa: E731
+            self._unet_graph = ((fps, motion is None), _GraphedCall(fn))
+        args = (latents, ts, ctx, w_emb) if motion is None else (latents, ts, ctx, w_emb, motion)
+        return self._unet_graph[1](*args)
+
+    def _decode(self, denoised):
+        if not self.use_cuda_graph:
+            return self.pretrained_t2v.decode_first_stage_2DAE(denoised)
+        if self._vae_graph is None:
+            self._vae_graph = _GraphedCall(lambda z: self.pretrained_t2v.decode_first_stage_2DAE(z))
+        return self._vae_graph(denoised)
+
+    @torch.no_grad()
+    def __call__(self, prompt: Union[str, List[str]] = None, height: Optional[int] = 320, width: Optional[int] = 512,
+                 frames: int = 16, fps: int = 16, guidance_scale: float = 7.5, motion_gs: float = 0.1,
+                 use_motion_cond: bool = False, percentage: float = 0.3, num_videos_per_prompt: Optional[int] = 1,
+                 generator=None, latents: Optional[torch.Tensor] = None, num_inference_steps: int = 4,
+                 lcm_origin_steps: int = 50, prompt_embeds: Optional[torch.Tensor] = None,
+                 output_type: Optional[str] = "pil"):
+        unet_config = self.model_config["params"]["unet_config"]
+        frames = self.pretrained_t2v.temporal_length if frames < 0 else frames
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        device = self._execution_device
+        prompt_embeds = self._encode_prompt(prompt, device, num_videos_per_prompt, prompt_embeds=prompt_embeds)
+        self.scheduler.set_timesteps(num_inference_steps, lcm_origin_steps)
+        timesteps = self.scheduler.timesteps
+        num_channels_latents = unet_config["params"]["in_channels"]
+        latents = self.prepare_latents(batch_size * num_videos_per_prompt, num_channels_latents, frames, height, width,
+                                       prompt_embeds.dtype, device, generator, latents)
+        bs = batch_size * num_videos_per_prompt
+        ctx = prompt_embeds.to(self.dtype)
+        w = torch.tensor(guidance_scale).repeat(bs)
+        w_embedding = self.get_w_embedding(w, embedding_dim=256).to(device).to(self.dtype)
+        ms_t_threshold = self.scheduler.config.num_train_timesteps * (1 - percentage)
+        denoised = None
+        for i, t in enumerate(timesteps):
+            ts = torch.full((bs,), int(t), device=device, dtype=torch.long)
+            motion = None
+            if use_motion_cond:
+                motion_gs_pt = torch.tensor(motion_gs).repeat(bs)
+                if t < ms_t_threshold:
+                    motion_gs_pt = torch.zeros_like(motion_gs_pt)
+                motion = self.get_w_embedding(motion_gs_pt, embedding_dim=256, dtype=self.dtype).to(device)
+            model_pred = self._unet_call(latents, ts, ctx, w_embedding, motion, fps)
+            latents, denoised = self.scheduler.step(model_pred, i, t, latents, generator=generator, return_dict=False)
+        if not output_type == "latent":
+            videos = self._decode(denoised)
+        else:
+            videos = denoised
+        return videos

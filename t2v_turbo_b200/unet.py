@@ -405,11 +405,13 @@ class UNetModel(nn.Module):
 
     def _context_kv(self, P, context, dev):
         key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
-        if self._ctx_cache is not None and self._ctx_cache[0] == key:
+        capturing = torch.cuda.is_current_stream_capturing()   # a graph must contain the projection itself
+        if not capturing and self._ctx_cache is not None and self._ctx_cache[0] == key:
             return self._ctx_cache[1]
         ctx = context.to(device=dev, dtype=BF16).reshape(-1, context.shape[-1]).contiguous()
         kv = ops.linear(ctx, P["ctx_w"], None).view(context.shape[0], context.shape[1], -1)
-        self._ctx_cache = (key, kv, context)
+        if not capturing:
+            self._ctx_cache = (key, kv, context)
         return kv
 
     def _block(self, blk: _PackedBlock, x, geom, temporal, ctx_kv, kv_slice):
