@@ -106,8 +106,8 @@ def build_pipeline(device, use_graph=True):
     return pipe
 
 
-def cpu_sample(threads):
-    """One bounded sample of the CPU path: the oracle UNet forward (fp32, naive attention) on 4 of the 16 frames."""
+def cpu_sample(threads, t_frames=2):
+    """One bounded sample of the CPU path: the oracle UNet forward (fp32, naive attention) on t_frames of the 16 frames."""
     import torch
     from t2v_turbo_b200.configs import VC2_UNET
     from oracle.unet_oracle import unet_forward, guidance_scale_embedding
@@ -127,7 +127,6 @@ def cpu_sample(threads):
             sd[k] = torch.ones(shp)
         else:
             sd[k] = torch.zeros(shp)
-    t_frames = 4
     x = torch.randn(1, 4, t_frames, HEIGHT // 8, WIDTH // 8, generator=g)
     ctx = torch.randn(1, 77, 1024, generator=g)
     w = guidance_scale_embedding(torch.tensor([7.5]), 256)

@@ -87,6 +87,13 @@ typedef struct T2VGemmDesc {
   float alpha;
   uint32_t flags;
   int32_t block_n;                      /* 0 = choose; else one of 64,128,160,256 */
+  /* split-K for small-M layers: K is cut into split_k slices accumulated in fp32 into `workspace`
+   * ([points][b_rows] floats, zeroed by the call) and a finalize kernel applies the epilogue.
+   * 0 = automatic (only when a large-enough workspace is given and the tile grid cannot fill the SMs),
+   * 1 = off.  Not available with GEGLU or batched B. */
+  int32_t split_k;
+  void* workspace;
+  int64_t workspace_bytes;
 } T2VGemmDesc;
 
 int t2v_gemm(const T2VGemmDesc* desc, t2v_stream_t stream);

@@ -310,6 +310,14 @@ static inline unsigned grid_for(int64_t total, int threads = 256) {
   return unsigned(g);
 }
 
+// one resident wave: every block stages the whole weight tensor in shared memory exactly once
+static inline unsigned small_conv_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  const int64_t cap = 2 * (num_sms() > 0 ? num_sms() : 148);
+  if (g > cap) g = cap;
+  return unsigned(g < 1 ? 1 : g);
+}
+
 }  // namespace t2v
 
 using namespace t2v;
@@ -349,11 +357,11 @@ extern "C" int t2v_conv3x3_small_cin(const void* in, const void* w, const float*
   if (cin == 4) {
     static bool cfg = false;
     if (!cfg) { e = cudaFuncSetAttribute(conv3x3_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
-    if (e == cudaSuccess) conv3x3_small_kernel<4><<<grid_for(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
+    if (e == cudaSuccess) conv3x3_small_kernel<4><<<small_conv_grid(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
   } else if (cin == 8) {
     static bool cfg = false;
     if (!cfg) { e = cudaFuncSetAttribute(conv3x3_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
-    if (e == cudaSuccess) conv3x3_small_kernel<8><<<grid_for(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
+    if (e == cudaSuccess) conv3x3_small_kernel<8><<<small_conv_grid(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
   } else {
     return fail(-4, "t2v_conv3x3_small_cin: cin must be 4 or 8 (got %d)", cin);
   }

@@ -3,7 +3,7 @@
 //
 //   out[m, n] = epi( alpha * sum_{tap, c} A[point(m) + off(tap), c] * W[n, tap * c_in + c] )
 //
-// Design (one CTA per SM, persistent over output tiles):
+// Design (one CTA per SM, persistent over output tiles, 384 threads):
 //   warp 0 / lane 0 : TMA producer.  A tile = 5-D box {64 ch, b1, b2, b3, b4} of the channels-last
 //                     activation (im2col-free: the tap shift is a coordinate offset; out-of-range
 //                     coordinates are zero-filled by TMA = conv padding); B tile = {64, BLOCK_N}
@@ -11,9 +11,12 @@
 //   warp 1 / lane 0 : MMA issuer. 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per 64-wide k-block,
 //                     fp32 accumulators in TMEM, double buffered (2 x BLOCK_N columns).
 //   warp 2          : TMEM allocator.
-//   warps 4..7      : epilogue.  tcgen05.ld (thread = output row), bias / residual / GEGLU,
-//                     bf16 (or fp32) vector stores.  Overlaps the next tile's main loop.
+//   warps 4..11     : epilogue, two warpgroups splitting the accumulator columns in 32-column chunks.
+//                     tcgen05.ld (thread = output row), bias / residual / GEGLU, 16-byte stores.
+//                     Overlaps the next tile's main loop.
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+// Split-K (small-M layers): the K range is cut into split_k slices handled by different CTAs which
+// accumulate fp32 partials with vector reductions into a workspace; a finalize kernel applies the epilogue.
 #include <cuda.h>
 #include <string.h>
 
@@ -27,13 +30,17 @@ struct GemmParams {
   int32_t box[4];
   int32_t ntile[4];
   int32_t n_tiles_n;
-  int32_t num_tiles;
+  int32_t n_tiles_mn;  // m tiles * n tiles
+  int32_t num_tiles;   // n_tiles_mn * split_k
   int32_t rows_in_box;
   int32_t n_taps;
   int32_t tap_off[T2V_MAX_TAPS][4];
   int32_t tap_ch_off[T2V_MAX_TAPS];
   int32_t kb_per_tap;
   int32_t kb_src0;
+  int32_t total_kb;
+  int32_t split_k;
+  int32_t kb_per_split;
   int32_t b_batch_dim;
   int32_t n_rows_b;  // N
   int32_t n_out;
@@ -49,14 +56,21 @@ struct GemmParams {
   float alpha;
   uint32_t flags;
   int32_t vec_ok;
+  int32_t bias_vec_ok;
   uint32_t a_tile_bytes;
+  float* ws;  // split-K workspace [points][N] fp32
+  int32_t epi_mode;  // 0 = direct row stores, 1 = smem-staged TMA store (+ TMA residual load)
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiBufBytes = 128 * 64;               // 128 rows x 32 bf16 columns, 64-byte swizzle
+constexpr int kEpiBufs = 3;                          // per epilogue warpgroup
+constexpr int kEpiBytes = 2 * kEpiBufs * kEpiBufBytes;  // 48 KB
+constexpr int kSmemBudget = 227 * 1024 - kEpiBytes - 2048;
 
 template <int BN>
 struct GemmCfg {
@@ -66,28 +80,48 @@ struct GemmCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kBarBytes = (2 * kStages + 4 + 2 * kEpiBufs) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
 };
 
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one ex2 + one rcp + 6 fma
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = 1.0f - poly * __expf(-ax * ax);
+  return copysignf(e, x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 }
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;  // [2 warpgroups][kEpiBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,6 +130,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    if (p.epi_mode == 1) {
+      tma_prefetch_desc(&tmOut);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmRes);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -104,8 +142,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps);
     }
+    for (int i = 0; i < 2 * kEpiBufs; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -117,44 +156,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_kb = p.n_taps * p.kb_per_tap;
-
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_n;
-      int m_tile = tile / p.n_tiles_n;
+      const int ks = tile / p.n_tiles_mn;
+      const int mn = tile - ks * p.n_tiles_mn;
+      const int n_tile = mn % p.n_tiles_n;
+      int m_tile = mn / p.n_tiles_n;
       int o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         o[j] = (m_tile % p.ntile[j]) * p.box[j];
         m_tile /= p.ntile[j];
       }
-      const int bbatch = p.b_batch_dim >= 0 ? o[p.b_batch_dim] : 0;
-      for (int tap = 0; tap < p.n_taps; ++tap) {
+      int bbatch = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j == p.b_batch_dim) bbatch = o[j];
+      const int kb_begin = ks * p.kb_per_split;
+      const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+      int tap = kb_begin / p.kb_per_tap;
+      int kb = kb_begin - tap * p.kb_per_tap;
+      for (int idx = kb_begin; idx < kb_end; ++idx) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * Cfg::kStageBytes;
+        uint8_t* sB = sA + kATileBytes;
+        mbar_expect_tx(&full_bar[stage], p.a_tile_bytes + Cfg::kBTileBytes);
         const int c1 = o[0] + p.tap_off[tap][0];
         const int c2 = o[1] + p.tap_off[tap][1];
         const int c3 = o[2] + p.tap_off[tap][2];
         const int c4 = o[3] + p.tap_off[tap][3];
         const int ch0 = p.tap_ch_off[tap];
-        for (int kb = 0; kb < p.kb_per_tap; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sA = smem + stage * Cfg::kStageBytes;
-          uint8_t* sB = sA + kATileBytes;
-          mbar_expect_tx(&full_bar[stage], p.a_tile_bytes + Cfg::kBTileBytes);
-          if (kb < p.kb_src0)
-            tma_load_5d(sA, &tmA0, &full_bar[stage], ch0 + kb * kBlockK, c1, c2, c3, c4);
-          else
-            tma_load_5d(sA, &tmA1, &full_bar[stage], ch0 + (kb - p.kb_src0) * kBlockK, c1, c2, c3,
-                        c4);
-          tma_load_3d(sB, &tmB, &full_bar[stage], (tap * p.kb_per_tap + kb) * kBlockK, n_tile * BN,
-                      bbatch);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        if (kb < p.kb_src0)
+          tma_load_5d(sA, &tmA0, &full_bar[stage], ch0 + kb * kBlockK, c1, c2, c3, c4);
+        else
+          tma_load_5d(sA, &tmA1, &full_bar[stage], ch0 + (kb - p.kb_src0) * kBlockK, c1, c2, c3, c4);
+        tma_load_3d(sB, &tmB, &full_bar[stage], idx * kBlockK, n_tile * BN, bbatch);
+        if (++kb == p.kb_per_tap) {
+          kb = 0;
+          ++tap;
+        }
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
@@ -165,12 +211,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int ks = tile / p.n_tiles_mn;
+      const int kb_begin = ks * p.kb_per_split;
+      const int n_kb = min(kb_begin + p.kb_per_split, p.total_kb) - kb_begin;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
-      for (int kb = 0; kb < total_kb; ++kb) {
+      for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -189,22 +238,192 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       umma_commit(&tfull_bar[acc]);
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int r = ew * 32 + lane;
+  } else if (warp >= 4 && p.epi_mode == 1) {
+    // ------------------------------------------------------------ epilogue, smem-staged (8 warps = 2 warpgroups)
+    // Each warpgroup owns 3 staging buffers of 128 rows x 32 bf16 (64-byte swizzle).  Per 32-column
+    // output chunk: [residual chunk arrives by TMA] -> tcgen05.ld -> bias / GEGLU / +residual -> bf16 row
+    // into smem -> warpgroup barrier -> one thread issues the TMA store (clips rows / columns outside the
+    // output, fully coalesced, no LSU traffic).  Residual loads run two chunks ahead.
+    const int ew = warp - 4;
+    const int lg = ew & 3;
+    const int g = ew >> 2;
+    const int r = lg * 32 + lane;
+    const bool leader = (lg == 0 && lane == 0);
     const bool geglu = (p.flags & T2V_EPI_GEGLU) != 0;
-    const bool out_f32 = (p.flags & T2V_EPI_OUT_F32) != 0;
     const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
+    const bool has_res = p.residual != nullptr;
+    const int acc_cw = geglu ? 64 : 32;  // accumulator columns per 32-column output chunk
+    const int chunks_per_tile = BN / acc_cw;
+    uint8_t* ebuf = smem_epi + g * kEpiBufs * kEpiBufBytes;
+    uint64_t* rbar = res_bar + g * kEpiBufs;
+    const uint32_t res_bytes = uint32_t(p.rows_in_box) * 64u;
+    const int sw = (r >> 1) & 3;
+    uint32_t q = 0;  // chunks processed so far by this warpgroup (buffer = q % 3)
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles_n;
       int m_tile = tile / p.n_tiles_n;
+      int o[4];
+      int64_t bias_row = 0;
+      {
+        int rr = r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = (m_tile % p.ntile[j]) * p.box[j];
+          m_tile /= p.ntile[j];
+          const int ij = rr % p.box[j];
+          rr /= p.box[j];
+          if (j == p.bias_dim) bias_row = (o[j] + ij) / p.bias_div;
+        }
+      }
+      const float* bias = p.bias ? p.bias + bias_row * p.bias_row_stride : nullptr;
+      const int n_base = n_tile * BN;
+      if (has_res && leader) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = g + 2 * i;
+          if (c < chunks_per_tile && n_base + c * acc_cw < p.n_rows_b) {
+            const uint32_t buf = (q + i) % kEpiBufs;
+            mbar_expect_tx(&rbar[buf], res_bytes);
+            tma_load_5d(ebuf + buf * kEpiBufBytes, &tmRes, &rbar[buf], (n_base + c * acc_cw) / (acc_cw / 32), o[0], o[1],
+                        o[2], o[3]);
+          }
+        }
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(lg * 32) << 16);
+      bool arrived = false;
+#pragma unroll 1
+      for (int c = g; c < chunks_per_tile && n_base + c * acc_cw < p.n_rows_b; c += 2) {
+        const uint32_t buf = q % kEpiBufs;
+        const uint32_t rphase = (q / kEpiBufs) & 1u;
+        const int n0 = n_base + c * acc_cw;  // first W row (accumulator column) of this chunk
+        const int oc0 = geglu ? (n0 >> 1) : n0;
+        uint32_t v[32];
+        float f[32];
+        tmem_ld_32x32(taddr + c * acc_cw, v);
+        tmem_wait_ld();
+        const bool fast_bias = (bias != nullptr) && p.bias_vec_ok && (n0 + acc_cw <= p.n_rows_b);
+        if (geglu) {
+          uint32_t v2[32];
+          tmem_ld_32x32(taddr + c * acc_cw + 32, v2);
+          tmem_wait_ld();
+          // packed W rows: [16 value | 16 gate] per 32 accumulator columns
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = p.alpha * __uint_as_float(hh == 0 ? v[j] : v2[j]);
+              float gt = p.alpha * __uint_as_float(hh == 0 ? v[j + 16] : v2[j + 16]);
+              if (bias != nullptr) {
+                a += __ldg(bias + n0 + hh * 32 + j);
+                gt += __ldg(bias + n0 + hh * 32 + 16 + j);
+              }
+              f[hh * 16 + j] = a * gelu_erf(gt);
+            }
+          }
+        } else if (fast_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 bv = __ldg(b4 + k4);
+            f[4 * k4 + 0] = fmaf(p.alpha, __uint_as_float(v[4 * k4 + 0]), bv.x);
+            f[4 * k4 + 1] = fmaf(p.alpha, __uint_as_float(v[4 * k4 + 1]), bv.y);
+            f[4 * k4 + 2] = fmaf(p.alpha, __uint_as_float(v[4 * k4 + 2]), bv.z);
+            f[4 * k4 + 3] = fmaf(p.alpha, __uint_as_float(v[4 * k4 + 3]), bv.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = p.alpha * __uint_as_float(v[j]);
+            if (bias != nullptr && n0 + j < p.n_rows_b) f[j] += __ldg(bias + n0 + j);
+          }
+        }
+        // last TMEM read of this tile by this warp: release the accumulator early
+        if (!(c + 2 < chunks_per_tile && n_base + (c + 2) * acc_cw < p.n_rows_b)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          arrived = true;
+        }
+        if (gelu && !geglu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        uint8_t* row = ebuf + buf * kEpiBufBytes + r * 64;
+        if (has_res) {
+          mbar_wait(&rbar[buf], rphase);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(row + ((k4 ^ sw) << 4));
+            f[k4 * 8 + 0] += bf16_lo(rv.x);
+            f[k4 * 8 + 1] += bf16_hi(rv.x);
+            f[k4 * 8 + 2] += bf16_lo(rv.y);
+            f[k4 * 8 + 3] += bf16_hi(rv.y);
+            f[k4 * 8 + 4] += bf16_lo(rv.z);
+            f[k4 * 8 + 5] += bf16_hi(rv.z);
+            f[k4 * 8 + 6] += bf16_lo(rv.w);
+            f[k4 * 8 + 7] += bf16_hi(rv.w);
+          }
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          uint4 ov;
+          ov.x = pack_bf16(f[k4 * 8 + 0], f[k4 * 8 + 1]);
+          ov.y = pack_bf16(f[k4 * 8 + 2], f[k4 * 8 + 3]);
+          ov.z = pack_bf16(f[k4 * 8 + 4], f[k4 * 8 + 5]);
+          ov.w = pack_bf16(f[k4 * 8 + 6], f[k4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(row + ((k4 ^ sw) << 4)) = ov;
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + g, 128);
+        if (leader) {
+          tma_store_5d(&tmOut, ebuf + buf * kEpiBufBytes, oc0, o[0], o[1], o[2], o[3]);
+          bulk_commit_group();
+          bulk_wait_group_read<1>();  // every store but the one just issued has finished reading smem
+          if (has_res) {
+            const int c2 = c + 4;
+            if (c2 < chunks_per_tile && n_base + c2 * acc_cw < p.n_rows_b) {
+              const uint32_t buf2 = (q + 2) % kEpiBufs;
+              mbar_expect_tx(&rbar[buf2], res_bytes);
+              tma_load_5d(ebuf + buf2 * kEpiBufBytes, &tmRes, &rbar[buf2], (n_base + c2 * acc_cw) / (acc_cw / 32), o[0],
+                          o[1], o[2], o[3]);
+            }
+          }
+        }
+        ++q;
+      }
+      if (!arrived) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+    }
+    if (leader) bulk_wait_group_read<0>();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (8 warps)
+    const int ew = warp - 4;
+    const int lg = ew & 3;     // TMEM lane group == warp % 4
+    const int half = ew >> 2;  // which interleaved set of 32-column chunks
+    const int r = lg * 32 + lane;
+    const bool geglu = (p.flags & T2V_EPI_GEGLU) != 0;
+    const bool out_f32 = (p.flags & T2V_EPI_OUT_F32) != 0;
+    const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
+    const bool split = p.split_k > 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int ks = tile / p.n_tiles_mn;
+      const int mn = tile - ks * p.n_tiles_mn;
+      const int n_tile = mn % p.n_tiles_n;
+      int m_tile = mn / p.n_tiles_n;
       // row -> point
       bool valid = r < p.rows_in_box;
-      int64_t out_off = 0, res_off = 0;
+      int64_t out_off = 0, res_off = 0, point = 0, pmul = 1;
       int64_t bias_row = 0;
       {
         int rr = r;
@@ -218,6 +437,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           valid = valid && (x < p.o_size[j]);
           out_off += x * p.o_stride[j];
           res_off += x * p.r_stride[j];
+          point += x * pmul;
+          pmul *= p.o_size[j];
           if (j == p.bias_dim) bias_row = x / p.bias_div;
         }
       }
@@ -225,89 +446,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(ew * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(lg * 32) << 16);
 
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_wait_ld();
         const int n0 = n_tile * BN + c0;  // column in W-row space
-        if (n0 >= p.n_rows_b) continue;   // warp-uniform
-        float f[32];
+        if (n0 < p.n_rows_b) {            // warp-uniform
+          const bool full_in = (n0 + 32 <= p.n_rows_b);
+          float f[32];
+          if (split) {
+            // fp32 partial sums -> workspace (the epilogue is applied by the finalize kernel)
+            if (valid) {
+              float* wp = p.ws + point * p.n_rows_b + n0;
+              if (full_in && (p.n_rows_b & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = p.alpha * __uint_as_float(v[j]);
-          if (bias != nullptr && n0 + j < p.n_rows_b) f[j] += __ldg(bias + n0 + j);
-        }
-        int ncols, oc0;
-        if (geglu) {
-          // packed rows: 16 value columns followed by their 16 gate columns
+                for (int q = 0; q < 8; ++q)
+                  red_add_v4(wp + 4 * q, p.alpha * __uint_as_float(v[4 * q]), p.alpha * __uint_as_float(v[4 * q + 1]),
+                             p.alpha * __uint_as_float(v[4 * q + 2]), p.alpha * __uint_as_float(v[4 * q + 3]));
+              } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[j] * gelu_erf(f[j + 16]);
-          ncols = 16;
-          oc0 = n0 >> 1;
-        } else {
-          if (gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          }
-          ncols = 32;
-          oc0 = n0;
-        }
-        const bool full_chunk = (oc0 + ncols <= p.n_out);
-        if (!valid) {
-          // row outside the output grid: nothing to store
-        } else if (p.vec_ok && full_chunk) {
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(p.residual) + res_off + oc0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < ncols) {
-                const uint4 rv = __ldg(rp + q);
-                f[q * 8 + 0] += bf16_lo(rv.x);
-                f[q * 8 + 1] += bf16_hi(rv.x);
-                f[q * 8 + 2] += bf16_lo(rv.y);
-                f[q * 8 + 3] += bf16_hi(rv.y);
-                f[q * 8 + 4] += bf16_lo(rv.z);
-                f[q * 8 + 5] += bf16_hi(rv.z);
-                f[q * 8 + 6] += bf16_lo(rv.w);
-                f[q * 8 + 7] += bf16_hi(rv.w);
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < p.n_rows_b) atomicAdd(wp + j, p.alpha * __uint_as_float(v[j]));
               }
             }
-          }
-          if (out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + oc0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q * 4 < ncols) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + oc0);
+            if (bias != nullptr && full_in && p.bias_vec_ok) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < ncols) {
-                uint4 ov;
-                ov.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
-                ov.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
-                ov.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
-                ov.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
-                op[q] = ov;
+              for (int q = 0; q < 8; ++q) {
+                const float4 bv = __ldg(b4 + q);
+                f[4 * q + 0] = fmaf(p.alpha, __uint_as_float(v[4 * q + 0]), bv.x);
+                f[4 * q + 1] = fmaf(p.alpha, __uint_as_float(v[4 * q + 1]), bv.y);
+                f[4 * q + 2] = fmaf(p.alpha, __uint_as_float(v[4 * q + 2]), bv.z);
+                f[4 * q + 3] = fmaf(p.alpha, __uint_as_float(v[4 * q + 3]), bv.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                f[j] = p.alpha * __uint_as_float(v[j]);
+                if (bias != nullptr && n0 + j < p.n_rows_b) f[j] += __ldg(bias + n0 + j);
               }
             }
-          }
-        } else {
+            int ncols, oc0;
+            if (geglu) {
+              // packed rows: 16 value columns followed by their 16 gate columns
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncols && oc0 + j < p.n_out) {
-              float val = f[j];
-              if (p.residual != nullptr)
-                val += __bfloat162float(
-                    reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + oc0 + j]);
-              if (out_f32)
-                reinterpret_cast<float*>(p.out)[out_off + oc0 + j] = val;
-              else
-                reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + oc0 + j] = __float2bfloat16_rn(val);
+              for (int j = 0; j < 16; ++j) f[j] = f[j] * gelu_erf(f[j + 16]);
+              ncols = 16;
+              oc0 = n0 >> 1;
+            } else {
+              if (gelu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              }
+              ncols = 32;
+              oc0 = n0;
+            }
+            const bool full_chunk = (oc0 + ncols <= p.n_out);
+            if (!valid) {
+              // row outside the output grid: nothing to store
+            } else if (p.vec_ok && full_chunk) {
+              if (p.residual != nullptr) {
+                const uint4* rp = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + res_off + oc0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (q * 8 < ncols) {
+                    const uint4 rv = __ldg(rp + q);
+                    f[q * 8 + 0] += bf16_lo(rv.x);
+                    f[q * 8 + 1] += bf16_hi(rv.x);
+                    f[q * 8 + 2] += bf16_lo(rv.y);
+                    f[q * 8 + 3] += bf16_hi(rv.y);
+                    f[q * 8 + 4] += bf16_lo(rv.z);
+                    f[q * 8 + 5] += bf16_hi(rv.z);
+                    f[q * 8 + 6] += bf16_lo(rv.w);
+                    f[q * 8 + 7] += bf16_hi(rv.w);
+                  }
+                }
+              }
+              if (out_f32) {
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + oc0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (q * 4 < ncols) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+              } else {
+                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + oc0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (q * 8 < ncols) {
+                    uint4 ov;
+                    ov.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
+                    ov.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
+                    ov.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
+                    ov.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
+                    op[q] = ov;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncols && oc0 + j < p.n_out) {
+                  float val = f[j];
+                  if (p.residual != nullptr)
+                    val += __bfloat162float(
+                        reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + oc0 + j]);
+                  if (out_f32)
+                    reinterpret_cast<float*>(p.out)[out_off + oc0 + j] = val;
+                  else
+                    reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + oc0 + j] = __float2bfloat16_rn(val);
+                }
+              }
             }
           }
         }
@@ -327,9 +579,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 }
 
+// split-K finalize: out[point, n] = epi(ws[point, n]) ; one thread = 4 consecutive columns
+__global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, int64_t n_points) {
+  const int nq = (p.n_rows_b + 3) >> 2;
+  const int64_t total = n_points * nq;
+  const bool out_f32 = (p.flags & T2V_EPI_OUT_F32) != 0;
+  const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t point = i / nq;
+    const int n0 = int(i - point * nq) * 4;
+    int64_t rem = point, out_off = 0, res_off = 0, bias_row = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t x = rem % p.o_size[j];
+      rem /= p.o_size[j];
+      out_off += x * p.o_stride[j];
+      res_off += x * p.r_stride[j];
+      if (j == p.bias_dim) bias_row = x / p.bias_div;
+    }
+    const float* wp = p.ws + point * p.n_rows_b + n0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n0 + j < p.n_rows_b) {
+        float v = wp[j];
+        if (p.bias) v += p.bias[bias_row * p.bias_row_stride + n0 + j];
+        if (gelu) v = gelu_erf(v);
+        if (p.residual) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + n0 + j]);
+        if (out_f32)
+          reinterpret_cast<float*>(p.out)[out_off + n0 + j] = v;
+        else
+          reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + n0 + j] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
 template <int BN>
-static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                       const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& to,
+                       const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -341,13 +628,13 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "no CUDA device");
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, p);
+  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, to, tr, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "gemm_tc launch");
   return 0;
 }
 
-static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu) {
+static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms) {
   const int cands[4] = {256, 160, 128, 64};
   double best = -1.0;
   int best_bn = 128;
@@ -357,16 +644,15 @@ static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu) 
     const double eff_n = double(n_rows) / double(nt * bn);
     const int64_t tiles = nt * m_tiles;
     const int64_t waves = (tiles + sms - 1) / sms;
-    const double eff_w = double(tiles) / double(waves * sms);
-    // wide tiles halve the shared-memory operand traffic per flop
-    const double eff_t = bn >= 256 ? 1.0 : bn >= 160 ? 0.97 : bn >= 128 ? 0.93 : 0.80;
+    const double eff_w = tiles >= sms ? double(tiles) / double(waves * sms) : 1.0;  // small grids use split-K
+    // wide tiles halve the shared-memory / L2 operand traffic per flop
+    const double eff_t = bn >= 256 ? 1.0 : bn >= 160 ? 0.95 : bn >= 128 ? 0.90 : 0.70;
     const double score = eff_n * eff_w * eff_t;
     if (score > best) {
       best = score;
       best_bn = bn;
     }
   }
-  (void)geglu;
   return best_bn;
 }
 
@@ -381,11 +667,12 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   if (d->a_ch[0] <= 0 || d->a_ch[0] % 64 != 0 || d->a_ch[1] < 0 || d->a_ch[1] % 64 != 0)
     return fail(-4, "t2v_gemm: a_ch must be positive multiples of 64 (got %d, %d)", d->a_ch[0], d->a_ch[1]);
   if (d->a_ch[1] > 0 && !d->a[1]) return fail(-5, "t2v_gemm: a[1] is null but a_ch[1]=%d", d->a_ch[1]);
-  int64_t rows_in_box = 1;
+  int64_t rows_in_box = 1, n_points = 1;
   for (int j = 0; j < 4; ++j) {
     if (d->box[j] < 1 || d->a_size[j] < 1 || d->o_size[j] < 1)
       return fail(-6, "t2v_gemm: box/a_size/o_size[%d] must be >= 1", j);
     rows_in_box *= d->box[j];
+    n_points *= d->o_size[j];
   }
   if (rows_in_box > 128 || rows_in_box % 8 != 0)
     return fail(-7, "t2v_gemm: box product %lld must be a multiple of 8 and <= 128", (long long)rows_in_box);
@@ -414,11 +701,39 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "t2v_gemm: no CUDA device");
   int bn = d->block_n;
-  if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms, geglu);
+  if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms);
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
   p.n_tiles_n = int((d->b_rows + bn - 1) / bn);
-  const int64_t num_tiles = m_tiles * p.n_tiles_n;
+  const int64_t tiles_mn = m_tiles * p.n_tiles_n;
+  p.total_kb = int(K / 64);
+  // split-K: explicit, or automatic when the tile grid cannot fill the SMs
+  int split = d->split_k;
+  if (split < 0) return fail(-15, "t2v_gemm: split_k must be >= 0");
+  if (split == 0) {
+    split = 1;
+    if (!geglu && d->b_batch_dim < 0 && d->workspace && tiles_mn * 2 <= sms && p.total_kb >= 16 &&
+        d->workspace_bytes >= n_points * d->b_rows * 4) {
+      split = int(sms / tiles_mn);
+      if (split > p.total_kb / 8) split = p.total_kb / 8;
+      if (split > 32) split = 32;
+      if (split < 1) split = 1;
+    }
+  }
+  if (split > 1) {
+    if (geglu) return fail(-16, "t2v_gemm: split_k is not supported with GEGLU");
+    if (d->b_batch_dim >= 0) return fail(-17, "t2v_gemm: split_k is not supported for batched B");
+    const int64_t need = n_points * d->b_rows * 4;
+    if (!d->workspace || d->workspace_bytes < need)
+      return fail(-18, "t2v_gemm: split_k needs a %lld-byte fp32 workspace", (long long)need);
+    p.kb_per_split = (p.total_kb + split - 1) / split;
+    split = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty slices
+  } else {
+    p.kb_per_split = p.total_kb;
+  }
+  p.split_k = split;
+  const int64_t num_tiles = tiles_mn * split;
   if (num_tiles > 0x7fffffff) return fail(-14, "t2v_gemm: too many tiles");
+  p.n_tiles_mn = int(tiles_mn);
   p.num_tiles = int(num_tiles);
   p.rows_in_box = int(rows_in_box);
   p.n_taps = d->n_taps;
@@ -440,6 +755,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   p.alpha = d->alpha;
   p.flags = d->flags;
   p.a_tile_bytes = uint32_t(rows_in_box * 128);
+  p.ws = static_cast<float*>(d->workspace);
   // vector epilogue: 16-byte aligned rows
   const int out_el = (d->flags & T2V_EPI_OUT_F32) ? 4 : 2;
   bool vec_ok = (d->n_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0);
@@ -449,9 +765,34 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     for (int j = 0; j < 4; ++j) vec_ok = vec_ok && (d->r_stride[j] % 8 == 0);
   }
   p.vec_ok = vec_ok ? 1 : 0;
+  p.bias_vec_ok = (d->bias && (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 && d->bias_row_stride % 4 == 0) ? 1 : 0;
+
+  // staged (TMA-store) epilogue whenever the output rows are 16-byte addressable bf16
+  bool staged = vec_ok && split == 1 && !(d->flags & T2V_EPI_OUT_F32) && (!geglu || bn % 64 == 0);
+  p.epi_mode = staged ? 1 : 0;
 
   // tensor maps
-  CUtensorMap tmA[2], tmB;
+  CUtensorMap tmA[2], tmB, tmOut, tmRes;
+  memset(&tmOut, 0, sizeof(tmOut));
+  memset(&tmRes, 0, sizeof(tmRes));
+  if (staged) {
+    for (int which = 0; which < (d->residual ? 2 : 1); ++which) {
+      uint64_t dims[5], strides[5];
+      uint32_t box[5];
+      dims[0] = uint64_t(d->n_out);
+      strides[0] = 2;
+      box[0] = 32;
+      for (int j = 0; j < 4; ++j) {
+        dims[j + 1] = uint64_t(d->o_size[j]);
+        strides[j + 1] = uint64_t(which == 0 ? d->o_stride[j] : d->r_stride[j]) * 2;
+        box[j + 1] = uint32_t(d->box[j]);
+        if (d->o_size[j] == 1 && strides[j + 1] == 0) strides[j + 1] = 16;
+      }
+      int rc = make_tmap_bf16(which == 0 ? &tmOut : &tmRes, which == 0 ? d->out : d->residual, 5, dims, strides, box,
+                              which == 0 ? "t2v_gemm out" : "t2v_gemm residual", 64);
+      if (rc) return rc;
+    }
+  }
   for (int s = 0; s < 2; ++s) {
     const int src = (s == 1 && d->a_ch[1] == 0) ? 0 : s;
     uint64_t dims[5], strides[5];
@@ -469,18 +810,33 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {uint64_t(K), uint64_t(d->b_rows), uint64_t(d->b_batches < 1 ? 1 : d->b_batches)};
     const uint64_t row_stride = uint64_t(d->b_row_stride > 0 ? d->b_row_stride : K);
+    uint64_t dims[3] = {uint64_t(K), uint64_t(d->b_rows), uint64_t(d->b_batches < 1 ? 1 : d->b_batches)};
     uint64_t strides[3] = {2, row_stride * 2,
                            uint64_t(d->b_batch_stride > 0 ? d->b_batch_stride : row_stride * d->b_rows) * 2};
     uint32_t box[3] = {64, uint32_t(bn), 1};
     int rc = make_tmap_bf16(&tmB, d->b, 3, dims, strides, box, "t2v_gemm B");
     if (rc) return rc;
   }
-  switch (bn) {
-    case 64: return launch_gemm<64>(tmA[0], tmA[1], tmB, p, stream);
-    case 128: return launch_gemm<128>(tmA[0], tmA[1], tmB, p, stream);
-    case 160: return launch_gemm<160>(tmA[0], tmA[1], tmB, p, stream);
-    default: return launch_gemm<256>(tmA[0], tmA[1], tmB, p, stream);
+  if (split > 1) {
+    cudaError_t e = cudaMemsetAsync(d->workspace, 0, size_t(n_points) * d->b_rows * 4, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "t2v_gemm workspace memset");
   }
+  int rc;
+  switch (bn) {
+    case 64: rc = launch_gemm<64>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+    case 128: rc = launch_gemm<128>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+    case 160: rc = launch_gemm<160>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+    default: rc = launch_gemm<256>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+  }
+  if (rc) return rc;
+  if (split > 1) {
+    const int64_t total = n_points * ((d->b_rows + 3) / 4);
+    int64_t grid = (total + 255) / 256;
+    if (grid > sms * 8) grid = sms * 8;
+    gemm_finalize_kernel<<<unsigned(grid), 256, 0, stream>>>(p, n_points);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "gemm_finalize launch");
+  }
+  return 0;
 }

@@ -35,7 +35,8 @@ int num_sms() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+                   const uint64_t* strides_bytes, const uint32_t* box, const char* what,
+                   int swizzle_bytes) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(-100, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
@@ -57,7 +58,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                   (unsigned long long)strides_bytes[i]);
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                  gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail((int)r, "%s: cuTensorMapEncodeTiled failed (CUresult %d)", what, (int)r);
   return 0;

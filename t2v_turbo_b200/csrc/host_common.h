@@ -33,7 +33,9 @@ int num_sms();
 
 // bf16 tiled tensor map with 128-byte swizzle; dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1 (dim 0 is contiguous).
+// swizzle_bytes: 128 (operand tiles, 128-byte rows) or 64 (epilogue staging tiles, 64-byte rows)
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, const char* what);
+                   const uint64_t* strides_bytes, const uint32_t* box, const char* what,
+                   int swizzle_bytes = 128);
 
 }  // namespace t2v

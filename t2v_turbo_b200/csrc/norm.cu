@@ -63,14 +63,23 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
       float s[8], ss[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-      for (int64_t r = row_begin + rr; r < row_end; r += rpp) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(xp + (base_row + r) * rs));
-        float f[8];
-        unpack8(v, f);
+      // 4 independent 16-byte loads in flight per thread (memory-level parallelism)
+      for (int64_t r = row_begin + rr; r < row_end; r += 4 * rpp) {
+        uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s[j] += f[j];
-          ss[j] += f[j] * f[j];
+        for (int u = 0; u < 4; ++u) {
+          const int64_t ru = r + int64_t(u) * rpp;
+          v[u] = ru < row_end ? __ldg(reinterpret_cast<const uint4*>(xp + (base_row + ru) * rs)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s[j] += f[j];
+            ss[j] += f[j] * f[j];
+          }
         }
       }
       // merge runs of channels that fall into the same group
@@ -127,22 +136,33 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) 
     const __nv_bfloat16* xp = src1 ? p.x1 + (cv - p.ncv0) * 8 : p.x0 + cv * 8;
     const int64_t rs = src1 ? p.rs1 : p.rs0;
     __nv_bfloat16* op = p.out + cv * 8;
-    for (int64_t r = row_begin + rr; r < row_end; r += rpp) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xp + (base_row + r) * rs));
-      float f[8];
-      unpack8(v, f);
+    for (int64_t r = row_begin + rr; r < row_end; r += 4 * rpp) {
+      uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float y = fmaf(f[j], sc[j], sh[j]);
-        if (p.silu) y = y / (1.0f + __expf(-y));
-        f[j] = y;
+      for (int u = 0; u < 4; ++u) {
+        const int64_t ru = r + int64_t(u) * rpp;
+        if (ru < row_end) v[u] = __ldg(reinterpret_cast<const uint4*>(xp + (base_row + ru) * rs));
       }
-      uint4 o;
-      o.x = pack_bf16(f[0], f[1]);
-      o.y = pack_bf16(f[2], f[3]);
-      o.z = pack_bf16(f[4], f[5]);
-      o.w = pack_bf16(f[6], f[7]);
-      *reinterpret_cast<uint4*>(op + (base_row + r) * p.out_rs) = o;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t ru = r + int64_t(u) * rpp;
+        if (ru < row_end) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y = fmaf(f[j], sc[j], sh[j]);
+            if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+            f[j] = y;
+          }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]);
+          o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]);
+          o.w = pack_bf16(f[6], f[7]);
+          *reinterpret_cast<uint4*>(op + (base_row + ru) * p.out_rs) = o;
+        }
+      }
     }
   }
 }

@@ -25,6 +25,7 @@ KERNELS_PER_CALL = {"groupnorm": 2}     # stats + apply (plus one memset node)
 LAUNCHES = 0                            # kernels of libt2v_b200.so enqueued so far (incl. during graph capture)
 _PROF = None                            # list of (family, flops, ev_start, ev_end) while profiling
 _FLOPS: dict = {}
+_TAG: dict = {}
 
 
 def start_profile():
@@ -33,14 +34,14 @@ def start_profile():
     _PROF = []
 
 
-def stop_profile():
-    """-> {family: dict(calls, ms, flops)} after synchronising."""
+def stop_profile(by_tag=False):
+    """-> {family (or family+shape tag): dict(calls, ms, flops)} after synchronising."""
     global _PROF
     recs, _PROF = _PROF, None
     torch.cuda.synchronize()
     out = {}
-    for fam, flops, e0, e1 in recs:
-        d = out.setdefault(fam, dict(calls=0, ms=0.0, flops=0))
+    for fam, flops, e0, e1, tag in recs:
+        d = out.setdefault((fam + " " + tag) if by_tag else fam, dict(calls=0, ms=0.0, flops=0))
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += flops
@@ -57,7 +58,7 @@ def _launch(family, flops, fn, *args):
     e0.record()
     check(fn(*args), "t2v_" + family)
     e1.record()
-    _PROF.append((family, flops, e0, e1))
+    _PROF.append((family, flops, e0, e1, _TAG.pop(family, "")))
 
 
 # ----------------------------------------------------------------------------- tile planning
@@ -114,7 +115,7 @@ def _as_pair(x):
 def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w, n_rows, out,
               o_size, o_stride, n_out, bias=None, bias_row_stride=0, bias_dim=-1, bias_div=1,
               residual=None, r_stride=None, alpha=1.0, flags=0, block_n=0, b_batches=1,
-              b_batch_stride=0, b_batch_dim=-1, b_row_stride=0):
+              b_batch_stride=0, b_batch_dim=-1, b_row_stride=0, split_k=0):
     d = GemmDesc()
     a0, a1 = a
     d.a[0] = a0.data_ptr()
@@ -148,9 +149,30 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     d.alpha = alpha
     d.flags = flags
     d.block_n = block_n
+    d.split_k = split_k
+    ws = _splitk_workspace(out.device)
+    d.workspace = ws.data_ptr()
+    d.workspace_bytes = ws.numel() * 4
     _FLOPS["gemm"] = 2 * math.prod(int(v) for v in o_size) * int(n_rows) * len(taps) * (int(a_ch[0]) + int(a_ch[1]))
+    if _PROF is not None:
+        _TAG["gemm"] = (f"M={math.prod(int(v) for v in o_size)} N={int(n_rows)} K={len(taps)}x{int(a_ch[0]) + int(a_ch[1])} "
+                        f"box={tuple(int(b) for b in box)} bn={block_n} flags={flags} res={int(residual is not None)}")
     _launch("gemm", _FLOPS.pop("gemm", 0), lib().t2v_gemm, C.byref(d), stream_ptr())
     return out
+
+
+_SPLITK_WS: dict = {}
+SPLITK_WS_BYTES = 32 << 20
+
+
+def _splitk_workspace(device):
+    """Persistent fp32 scratch for split-K partial sums (per device and stream; zeroed by each call that uses it)."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = torch.empty(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
+        _SPLITK_WS[key] = ws
+    return ws
 
 
 def _check_act(x, name="x"):
@@ -159,7 +181,7 @@ def _check_act(x, name="x"):
 
 # ----------------------------------------------------------------------------- Linear
 def linear(x, w, bias=None, *, residual=None, geglu=False, gelu=False, out=None, out_f32=False,
-           alpha=1.0, block_n=0):
+           alpha=1.0, block_n=0, split_k=0):
     """out[m, :] = epi(x[m, :] @ w.T).  x: [M, K] bf16 (or a pair concatenated along K);
     w: [N, K] bf16 (GEGLU: rows packed by pack_geglu); bias: fp32 [N]; residual: bf16 [M, n_out]."""
     x0, x1 = _as_pair(x)
@@ -179,7 +201,7 @@ def linear(x, w, bias=None, *, residual=None, geglu=False, gelu=False, out=None,
         box=(128, 1, 1, 1), taps=[(0, 0, 0, 0)], tap_ch_off=None, w=w, n_rows=n, out=out,
         o_size=(m, 1, 1, 1), o_stride=(out.stride(0), 0, 0, 0), n_out=n_out, bias=bias,
         residual=residual, r_stride=(residual.stride(0), 0, 0, 0) if residual is not None else None,
-        alpha=alpha, flags=flags, block_n=block_n)
+        alpha=alpha, flags=flags, block_n=block_n, split_k=split_k)
 
 
 def bmm_nt(a, b, *, out=None, alpha=1.0, block_n=0):
@@ -204,7 +226,7 @@ _TAPS_3X3 = [(kx - 1, ky - 1, 0, 0) for ky in range(3) for kx in range(3)]
 _TAPS_T3 = [(0, kt - 1, 0, 0) for kt in range(3)]
 
 
-def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0):
+def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, split_k=0):
     """3x3 / pad 1 / stride 1 conv over [N,H,W,C] (or a channel-concatenated pair).
     w: [Cout, 9*C] packed (tap-major); bias: fp32 [rows, Cout], row = frame // bias_div."""
     x0, x1 = _as_pair(x)
@@ -222,7 +244,7 @@ def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0):
         box=box, taps=_TAPS_3X3, tap_ch_off=None, w=w, n_rows=cout, out=out,
         o_size=(wd, h, n, 1), o_stride=(cout, wd * cout, h * wd * cout, 0), n_out=cout, bias=bias,
         bias_row_stride=cout if bias is not None else 0, bias_dim=2, bias_div=bias_div,
-        residual=residual, block_n=block_n)
+        residual=residual, block_n=block_n, split_k=split_k)
 
 
 def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0):
@@ -252,7 +274,7 @@ def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0):
         bias_row_stride=0, bias_dim=-1, block_n=block_n)
 
 
-def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0):
+def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0, split_k=0):
     """Conv3d (3,1,1) / pad (1,0,0) over x: [B, T, HW, C] (TemporalConvBlock, openaimodel3d.py:274-296).
     w: [Cout, 3*C] packed."""
     _check_act(x)
@@ -266,7 +288,7 @@ def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0):
         a=(x, None), a_ch=(c, 0), a_ch_total=(c, 0), a_size=(hw, t, b, 1),
         a_stride=((c, hw * c, t * hw * c, 0), None), box=box, taps=_TAPS_T3, tap_ch_off=None, w=w,
         n_rows=cout, out=out, o_size=(hw, t, b, 1), o_stride=(cout, hw * cout, t * hw * cout, 0),
-        n_out=cout, bias=bias, residual=residual, block_n=block_n)
+        n_out=cout, bias=bias, residual=residual, block_n=block_n, split_k=split_k)
 
 
 def conv3x3_small_cin(x, w, bias, cout):
@@ -357,6 +379,8 @@ def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None):
     d.kv_batch_div = kv_batch_div
     d.scale = scale
     _FLOPS["attn_fwd"] = 4 * bq * heads * lq * lk * 64
+    if _PROF is not None:
+        _TAG["attn_fwd"] = f"B={bq} H={heads} Lq={lq} Lk={lk}"
     _launch("attn_fwd", _FLOPS.pop("attn_fwd", 0), lib().t2v_attn_fwd, C.byref(d), stream_ptr())
     return out
 

@@ -51,6 +51,29 @@ def test_linear(cuda_device, m, k, n, bn):
     assert_close(out2, x.float() @ w.float().t(), what="linear nobias")
 
 
+@pytest.mark.parametrize("m,k,n,split", [(640, 1280, 1280, 4), (640, 5120, 1280, 0), (2560, 2560, 320, 3), (77, 1024, 2560, 0)])
+def test_linear_split_k(cuda_device, m, k, n, split):
+    ops = _ops()
+    x = rnd(m, k, seed=70).to(BF16)
+    w = rnd(n, k, scale=k ** -0.5, seed=71).to(BF16)
+    b = rnd(n, seed=72)
+    res = rnd(m, n, seed=73).to(BF16)
+    out = ops.linear(x, w, b, residual=res, split_k=split)
+    assert_close(out, x.float() @ w.float().t() + b + res.float(), what=f"linear split_k={split}")
+
+
+def test_conv3x3_level3_split_k(cuda_device):
+    """the 5x8 level: M = 640 points, K = 9*1280 -> automatic split-K"""
+    ops = _ops()
+    x = rnd(16, 5, 8, 1280, seed=74).to(BF16)
+    wt = rnd(1280, 1280, 3, 3, scale=(9 * 1280) ** -0.5, seed=75).to(BF16)
+    b = rnd(1, 1280, seed=76)
+    res = rnd(16, 5, 8, 1280, seed=77).to(BF16)
+    out = ops.conv3x3(x, ops.pack_conv_weight(wt), b, bias_div=16, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b[0], padding=1).permute(0, 2, 3, 1) + res.float()
+    assert_close(out, ref, what="conv3x3 5x8 split-K")
+
+
 def test_linear_f32_out_and_tail(cuda_device):
     ops = _ops()
     x = rnd(300, 192, seed=5).to(BF16)
