@@ -86,7 +86,7 @@ typedef struct T2VGemmDesc {
   int64_t r_stride[T2V_MAX_DIMS];
   float alpha;
   uint32_t flags;
-  int32_t block_n;                      /* 0 = choose; else one of 64,128,160,256 */
+  int32_t block_n;                      /* 0 = choose; else one of 32,64,128,160,256 */
   /* split-K for small-M layers: K is cut into split_k slices accumulated in fp32 into `workspace`
    * ([points][b_rows] floats, zeroed by the call) and a finalize kernel applies the epilogue.
    * 0 = automatic (only when a large-enough workspace is given and the tile grid cannot fill the SMs),

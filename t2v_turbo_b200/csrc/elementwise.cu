@@ -101,14 +101,18 @@ __global__ void sinusoidal_kernel(const float* t, const float* freqs, float* out
 }
 
 // ------------------------------------------------------------------ 3x3 conv, tiny C_in (latent -> features)
-// one thread = one output pixel x 8 output channels; weights [Cout][9][Cin] bf16 staged in smem.
+// one thread = one output pixel x 8 output channels; weights staged in smem as fp32 [tap*CIN][Cout]
+// (lanes of a warp read consecutive output channels -> conflict-free 16-byte shared loads).
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv3x3_small_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n, int h,
                      int wd, int cout) {
-  extern __shared__ float s_w[];  // [cout][9*CIN]
-  for (int i = threadIdx.x; i < cout * 9 * CIN; i += blockDim.x) s_w[i] = __bfloat162float(w[i]);
+  extern __shared__ float s_w[];  // [9*CIN][cout]
+  for (int i = threadIdx.x; i < cout * 9 * CIN; i += blockDim.x) {
+    const int oc = i / (9 * CIN), q = i % (9 * CIN);  // global layout [cout][9*CIN]
+    s_w[q * cout + oc] = __bfloat162float(w[i]);
+  }
   __syncthreads();
   const int ocv = cout / 8;
   const int64_t total = int64_t(n) * h * wd * ocv;
@@ -119,28 +123,34 @@ conv3x3_small_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* 
     const int x = int(pix % wd);
     const int y = int((pix / wd) % h);
     const int64_t img = pix / (int64_t(wd) * h);
-    float patch[9 * CIN];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[cv * 8 + j] : 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int yy = y + ky - 1, xx = x + kx - 1;
-        const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < wd;
+        if (yy < 0 || yy >= h || xx < 0 || xx >= wd) continue;
+        const __nv_bfloat16* ip = in + ((img * h + yy) * wd + xx) * CIN;
+        float pv[CIN];
+        if (CIN == 4) {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(ip));
+          pv[0] = bf16_lo(u.x); pv[1] = bf16_hi(u.x); pv[2] = bf16_lo(u.y); pv[3] = bf16_hi(u.y);
+        } else {
 #pragma unroll
-        for (int c = 0; c < CIN; ++c)
-          patch[(ky * 3 + kx) * CIN + c] =
-              ok ? __bfloat162float(in[((img * h + yy) * wd + xx) * CIN + c]) : 0.f;
+          for (int c = 0; c < CIN; ++c) pv[c] = __bfloat162float(ip[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + c) * cout + cv * 8);
+          const float4 w0 = wr[0], w1 = wr[1];
+          acc[0] = fmaf(pv[c], w0.x, acc[0]); acc[1] = fmaf(pv[c], w0.y, acc[1]);
+          acc[2] = fmaf(pv[c], w0.z, acc[2]); acc[3] = fmaf(pv[c], w0.w, acc[3]);
+          acc[4] = fmaf(pv[c], w1.x, acc[4]); acc[5] = fmaf(pv[c], w1.y, acc[5]);
+          acc[6] = fmaf(pv[c], w1.z, acc[6]); acc[7] = fmaf(pv[c], w1.w, acc[7]);
+        }
       }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int oc = cv * 8 + j;
-      float a = bias ? bias[oc] : 0.f;
-      const float* wr = s_w + oc * 9 * CIN;
-#pragma unroll
-      for (int q = 0; q < 9 * CIN; ++q) a = fmaf(patch[q], wr[q], a);
-      acc[j] = a;
-    }
     uint4 o;
     o.x = pack_bf16(acc[0], acc[1]);
     o.y = pack_bf16(acc[2], acc[3]);

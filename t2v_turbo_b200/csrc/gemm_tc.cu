@@ -80,7 +80,7 @@ struct GemmCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kBarBytes = (2 * kStages + 4 + 2 * kEpiBufs) * 8 + 16;
+  static constexpr int kBarBytes = (2 * kStages + 4 + 2 * kEpiBufs) * 8 + 16 + 2 * 256 * 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
 };
 
@@ -122,6 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;  // [2 warpgroups][kEpiBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiBufs);
+  float* bias_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [2 accumulators][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,11 +244,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // Each warpgroup owns 3 staging buffers of 128 rows x 32 bf16 (64-byte swizzle).  Per 32-column
     // output chunk: [residual chunk arrives by TMA] -> tcgen05.ld -> bias / GEGLU / +residual -> bf16 row
     // into smem -> warpgroup barrier -> one thread issues the TMA store (clips rows / columns outside the
-    // output, fully coalesced, no LSU traffic).  Residual loads run two chunks ahead.
+    // output, fully coalesced, no LSU traffic).  Residual loads run two chunks ahead, the TMEM load of the
+    // next chunk is issued before the current chunk is written out, and the tile's bias row is staged in
+    // shared memory once per tile (broadcast reads) while the accumulator is still being computed.
     const int ew = warp - 4;
     const int lg = ew & 3;
     const int g = ew >> 2;
     const int r = lg * 32 + lane;
+    const int et = ew * 32 + lane;  // 0..255 within the epilogue
     const bool leader = (lg == 0 && lane == 0);
     const bool geglu = (p.flags & T2V_EPI_GEGLU) != 0;
     const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
@@ -266,20 +270,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int n_tile = tile % p.n_tiles_n;
       int m_tile = tile / p.n_tiles_n;
       int o[4];
-      int64_t bias_row = 0;
+      int64_t bias_row = 0, bias_row_first = 0, bias_row_last = 0;
       {
-        int rr = r;
+        int rr = r, rl = p.rows_in_box - 1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           o[j] = (m_tile % p.ntile[j]) * p.box[j];
           m_tile /= p.ntile[j];
           const int ij = rr % p.box[j];
           rr /= p.box[j];
-          if (j == p.bias_dim) bias_row = (o[j] + ij) / p.bias_div;
+          const int il = rl % p.box[j];
+          rl /= p.box[j];
+          if (j == p.bias_dim) {
+            bias_row = (o[j] + ij) / p.bias_div;
+            bias_row_first = o[j] / p.bias_div;
+            int64_t xl = o[j] + il;
+            if (xl > p.o_size[j] - 1) xl = p.o_size[j] - 1;
+            bias_row_last = xl / p.bias_div;
+          }
         }
       }
-      const float* bias = p.bias ? p.bias + bias_row * p.bias_row_stride : nullptr;
       const int n_base = n_tile * BN;
+      const bool bias_uniform = (p.bias != nullptr) && (bias_row_first == bias_row_last);  // CTA-uniform
+      const float* bias = p.bias ? p.bias + bias_row * p.bias_row_stride : nullptr;
+      float* sbias = bias_smem + acc * 256;
+      if (bias_uniform) {
+        if (et < BN) {
+          const int n = n_base + et;
+          sbias[et] = n < p.n_rows_b ? __ldg(p.bias + bias_row_first * p.bias_row_stride + n) : 0.f;
+        }
+      }
       if (has_res && leader) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -292,21 +312,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
+      if (bias_uniform) named_bar_sync(3, 256);  // bias row visible to both warpgroups
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(lg * 32) << 16);
       bool arrived = false;
+      uint32_t v[32];
+      if (g < chunks_per_tile && n_base + g * acc_cw < p.n_rows_b) tmem_ld_32x32(taddr + g * acc_cw, v);
 #pragma unroll 1
       for (int c = g; c < chunks_per_tile && n_base + c * acc_cw < p.n_rows_b; c += 2) {
         const uint32_t buf = q % kEpiBufs;
         const uint32_t rphase = (q / kEpiBufs) & 1u;
         const int n0 = n_base + c * acc_cw;  // first W row (accumulator column) of this chunk
         const int oc0 = geglu ? (n0 >> 1) : n0;
-        uint32_t v[32];
+        const bool has_next = (c + 2 < chunks_per_tile) && (n_base + (c + 2) * acc_cw < p.n_rows_b);
         float f[32];
-        tmem_ld_32x32(taddr + c * acc_cw, v);
         tmem_wait_ld();
-        const bool fast_bias = (bias != nullptr) && p.bias_vec_ok && (n0 + acc_cw <= p.n_rows_b);
         if (geglu) {
           uint32_t v2[32];
           tmem_ld_32x32(taddr + c * acc_cw + 32, v2);
@@ -318,18 +339,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int j = 0; j < 16; ++j) {
               float a = p.alpha * __uint_as_float(hh == 0 ? v[j] : v2[j]);
               float gt = p.alpha * __uint_as_float(hh == 0 ? v[j + 16] : v2[j + 16]);
-              if (bias != nullptr) {
+              if (bias_uniform) {
+                a += sbias[c * acc_cw + hh * 32 + j];
+                gt += sbias[c * acc_cw + hh * 32 + 16 + j];
+              } else if (bias != nullptr) {
                 a += __ldg(bias + n0 + hh * 32 + j);
                 gt += __ldg(bias + n0 + hh * 32 + 16 + j);
               }
               f[hh * 16 + j] = a * gelu_erf(gt);
             }
           }
-        } else if (fast_bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+        } else if (bias_uniform) {
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + c * acc_cw);
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
-            const float4 bv = __ldg(b4 + k4);
+            const float4 bv = b4[k4];
             f[4 * k4 + 0] = fmaf(p.alpha, __uint_as_float(v[4 * k4 + 0]), bv.x);
             f[4 * k4 + 1] = fmaf(p.alpha, __uint_as_float(v[4 * k4 + 1]), bv.y);
             f[4 * k4 + 2] = fmaf(p.alpha, __uint_as_float(v[4 * k4 + 2]), bv.z);
@@ -342,8 +366,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (bias != nullptr && n0 + j < p.n_rows_b) f[j] += __ldg(bias + n0 + j);
           }
         }
-        // last TMEM read of this tile by this warp: release the accumulator early
-        if (!(c + 2 < chunks_per_tile && n_base + (c + 2) * acc_cw < p.n_rows_b)) {
+        if (has_next) {
+          tmem_ld_32x32(taddr + (c + 2) * acc_cw, v);  // in flight while this chunk is written out
+        } else {
+          // last TMEM read of this tile by this warp: release the accumulator early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -635,10 +661,10 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 }
 
 static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms) {
-  const int cands[4] = {256, 160, 128, 64};
+  const int cands[5] = {256, 160, 128, 64, 32};
   double best = -1.0;
   int best_bn = 128;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
     const int64_t nt = (n_rows + bn - 1) / bn;
     const double eff_n = double(n_rows) / double(nt * bn);
@@ -646,7 +672,7 @@ static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms) {
     const int64_t waves = (tiles + sms - 1) / sms;
     const double eff_w = tiles >= sms ? double(tiles) / double(waves * sms) : 1.0;  // small grids use split-K
     // wide tiles halve the shared-memory / L2 operand traffic per flop
-    const double eff_t = bn >= 256 ? 1.0 : bn >= 160 ? 0.95 : bn >= 128 ? 0.90 : 0.70;
+    const double eff_t = bn >= 256 ? 1.0 : bn >= 160 ? 0.95 : bn >= 128 ? 0.90 : bn >= 64 ? 0.70 : 0.45;
     const double score = eff_n * eff_w * eff_t;
     if (score > best) {
       best = score;
@@ -702,7 +728,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   if (sms <= 0) return fail(-110, "t2v_gemm: no CUDA device");
   int bn = d->block_n;
   if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms);
-  if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
   p.n_tiles_n = int((d->b_rows + bn - 1) / bn);
   const int64_t tiles_mn = m_tiles * p.n_tiles_n;
   p.total_kb = int(K / 64);
@@ -824,6 +850,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   }
   int rc;
   switch (bn) {
+    case 32: rc = launch_gemm<32>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
     case 64: rc = launch_gemm<64>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
     case 128: rc = launch_gemm<128>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
     case 160: rc = launch_gemm<160>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
