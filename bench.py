@@ -106,7 +106,7 @@ def build_pipeline(device, use_graph=True):
     return pipe
 
 
-def cpu_sample(threads, t_frames=2):
+def cpu_sample(threads, t_frames=4):
     """One bounded sample of the CPU path: the oracle UNet forward (fp32, naive attention) on t_frames of the 16 frames."""
     import torch
     from t2v_turbo_b200.configs import VC2_UNET
@@ -146,7 +146,7 @@ def cpu_sample(threads, t_frames=2):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 16)   # measured on the 128-core box: 16 threads 1.8 s/frame, 32: 3.4 s, 64: 3.0 s
     run, sample_tflop, desc = cpu_sample(threads)
     for _ in range(args.warmup):
         run()
@@ -286,7 +286,7 @@ def main():
                     gpu_launches=launches_per_step * args.steps, roofline=roofline,
                     tensor_frac_of_step=PIPE_TFLOP / (ms / args.steps * 1e-3) / pk["tflops"])
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = min(os.cpu_count() or 1, 16)
             run, sample_tflop, desc = cpu_sample(threads)
             tcpu = run()
             line["cpu_baseline"] = dict(value=FRAMES / (tcpu * PIPE_TFLOP / sample_tflop), unit="frames/s", cores=threads,

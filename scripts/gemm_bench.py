@@ -24,6 +24,8 @@ CASES = {
     "conv1280": ("conv", (16, 10, 16, 1280), 0, 1280, dict(res=True)),
     "conv1280_l3": ("conv", (16, 5, 8, 1280), 0, 1280, dict(res=True)),
     "tconv320": ("tconv", (1, 16, 2560, 320), 0, 320, dict()),
+    "vae512": ("conv", (16, 80, 128, 512), 0, 512, dict(res=True)),
+    "big1280": ("linear", 40960, 1280, 1280, dict(res=True)),
     "tconv1280_l3": ("tconv", (1, 16, 40, 1280), 0, 1280, dict()),
 }
 names = sys.argv[1:] or list(CASES)
@@ -59,11 +61,17 @@ for name in names:
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # GPU-only time: 20 back-to-back launches captured in a CUDA graph (no host launch overhead)
     reps = 20
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            fn()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3

@@ -52,6 +52,7 @@ class GemmDesc(C.Structure):
         ("flags", C.c_uint32),
         ("block_n", C.c_int32),
         ("split_k", C.c_int32),
+        ("tune", C.c_int32),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
     ]

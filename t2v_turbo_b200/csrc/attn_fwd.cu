@@ -97,10 +97,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_alloc(tmem_slot, kTmemColsAttn);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const int n_kv = p.n_kv_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -320,7 +322,7 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
   }
   const int64_t grid = int64_t(d->batch) * d->heads * p.n_q_tiles;
   if (grid > 0x7fffffff) return fail(-5, "t2v_attn_fwd: grid too large");
-  attn_fwd_kernel<<<unsigned(grid), kAtThreads, kAtSmem, stream>>>(tq, tk, tv, p);
+  launch_kernel(attn_fwd_kernel, dim3(unsigned(grid)), dim3(kAtThreads), kAtSmem, stream, tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_attn_fwd launch");
 }

@@ -46,6 +46,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return uint32_t(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 __global__ void __launch_bounds__(kSaWarps * 32) attn_short_mma_kernel(const T2VShortAttnDesc d, int64_t n_tasks) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(128) uint8_t smem[kSaWarps][3][16 * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t task = int64_t(blockIdx.x) * kSaWarps + warp;
@@ -178,6 +180,8 @@ constexpr int kSaThreads = 128;
 
 template <int LEN_PAD>
 __global__ void __launch_bounds__(kSaThreads) attn_short_kernel(const T2VShortAttnDesc d, int64_t n_tasks) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int TASKS = kSaThreads / LEN_PAD;
   __shared__ __align__(16) __nv_bfloat16 s_k[TASKS][LEN_PAD][64];
   __shared__ __align__(16) __nv_bfloat16 s_v[TASKS][LEN_PAD][64];
@@ -293,10 +297,10 @@ extern "C" int t2v_attn_short_fwd(const T2VShortAttnDesc* d, t2v_stream_t stream
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (d->len <= 16) {
     const int64_t blocks = (n_tasks + kSaWarps - 1) / kSaWarps;
-    attn_short_mma_kernel<<<unsigned(blocks), kSaWarps * 32, 0, stream>>>(*d, n_tasks);
+    launch_kernel(attn_short_mma_kernel, dim3(unsigned(blocks)), dim3(kSaWarps * 32), 0, stream, *d, n_tasks);
   } else {
     const int64_t blocks = (n_tasks + (kSaThreads / 32) - 1) / (kSaThreads / 32);
-    attn_short_kernel<32><<<unsigned(blocks), kSaThreads, 0, stream>>>(*d, n_tasks);
+    launch_kernel(attn_short_kernel<32>, dim3(unsigned(blocks)), dim3(kSaThreads), 0, stream, *d, n_tasks);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_attn_short_fwd launch");

@@ -31,6 +31,8 @@ __device__ __forceinline__ float round_to(float v, int dtype) {
 // ------------------------------------------------------------------ small-M linear: warp per output column
 constexpr int kSlMaxM = 8;
 __global__ void __launch_bounds__(256) small_linear_kernel(const T2VSmallLinearDesc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= d.n) return;
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const T2VSmallLinearD
 // ------------------------------------------------------------------ sinusoidal embeddings
 __global__ void sinusoidal_kernel(const float* t, const float* freqs, float* out, int m, int half,
                                   int sin_first, int round_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m * half) return;
   const int r = i / half, c = i % half;
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(256)
 conv3x3_small_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n, int h,
                      int wd, int cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];  // [9*CIN][cout]
   for (int i = threadIdx.x; i < cout * 9 * CIN; i += blockDim.x) {
     const int oc = i / (9 * CIN), q = i % (9 * CIN);  // global layout [cout][9*CIN]
@@ -163,6 +169,8 @@ conv3x3_small_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* 
 // ------------------------------------------------------------------ layout conversion
 __global__ void bcthw_to_frames_kernel(const void* in, int in_dtype, __nv_bfloat16* out, int b, int c,
                                        int t, int h, int w, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(b) * t * h * w * c;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -179,6 +187,8 @@ __global__ void bcthw_to_frames_kernel(const void* in, int in_dtype, __nv_bfloat
 __global__ void bcthw_to_frames_mix_kernel(const void* in, int in_dtype, __nv_bfloat16* out, int b, int c,
                                            int t, int h, int w, float scale, const float* mix,
                                            const float* bias) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(b) * t * h * w;
   const int64_t plane = int64_t(t) * h * w;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -195,6 +205,8 @@ __global__ void bcthw_to_frames_mix_kernel(const void* in, int in_dtype, __nv_bf
 }
 __global__ void frames_to_bcthw_kernel(const __nv_bfloat16* in, int c_pad, void* out, int out_dtype,
                                        int b, int c, int t, int h, int w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(b) * c * t * h * w;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -209,6 +221,8 @@ __global__ void frames_to_bcthw_kernel(const __nv_bfloat16* in, int c_pad, void*
   }
 }
 __global__ void upsample2x_kernel(const uint4* in, uint4* out, int n, int h, int w, int cv) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(n) * 2 * h * 2 * w * cv;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -221,6 +235,8 @@ __global__ void upsample2x_kernel(const uint4* in, uint4* out, int n, int h, int
   }
 }
 __global__ void concat_kernel(const uint4* a, int cva, const uint4* b, int cvb, uint4* out, int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = cva + cvb;
   const int64_t total = rows * cv;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -233,6 +249,8 @@ __global__ void concat_kernel(const uint4* a, int cva, const uint4* b, int cvb, 
 
 // ------------------------------------------------------------------ row softmax (bf16 in place), block per row
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int cols, int64_t row_stride, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   __nv_bfloat16* row = x + int64_t(blockIdx.x) * row_stride;
   float mx = -INFINITY;
@@ -259,6 +277,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int
 __global__ void lcm_step_kernel(const void* x, const void* eps, const void* noise, void* prev, void* den,
                                 int64_t n, int dt, float sa_inv, float sb, float c_skip, float c_out,
                                 float sap, float sbp) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += int64_t(gridDim.x) * blockDim.x) {
     const float xv = load_as_float(x, i, dt);
@@ -284,6 +304,8 @@ __global__ void lcm_step_kernel(const void* x, const void* eps, const void* nois
 
 // ------------------------------------------------------------------ weight packing
 __global__ void pack_conv_weight_kernel(const void* w, int wdt, __nv_bfloat16* out, int cout, int cin, int taps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(cout) * cin * taps;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -301,6 +323,8 @@ __device__ __forceinline__ int64_t geglu_packed_row(int64_t r, int inner) {
 }
 __global__ void pack_geglu_kernel(const void* w, int wdt, __nv_bfloat16* out, const void* bias, int bdt,
                                   float* bias_out, int inner, int k) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(2) * inner * k;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -337,7 +361,7 @@ extern "C" int t2v_small_linear(const T2VSmallLinearDesc* d, t2v_stream_t s) {
   if (d->k % 8 || d->k <= 0 || d->n <= 0 || d->m <= 0) return fail(-2, "t2v_small_linear: k must be a positive multiple of 8");
   const int warps_per_block = 8;
   const unsigned grid = unsigned((d->n + warps_per_block - 1) / warps_per_block);
-  small_linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(*d);
+  launch_kernel(small_linear_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(s), *d);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_small_linear launch");
 }
@@ -346,7 +370,7 @@ extern "C" int t2v_sinusoidal_embedding(const float* t, const float* freqs, floa
                                         int32_t half, int32_t sin_first, int32_t round_bf16,
                                         t2v_stream_t s) {
   if (!t || !freqs || !out || m <= 0 || half <= 0) return fail(-1, "t2v_sinusoidal_embedding: bad argument");
-  sinusoidal_kernel<<<grid_for(int64_t(m) * half), 256, 0, static_cast<cudaStream_t>(s)>>>(t, freqs, out, m, half, sin_first, round_bf16);
+  launch_kernel(sinusoidal_kernel, dim3(grid_for(int64_t(m) * half)), dim3(256), 0, static_cast<cudaStream_t>(s), t, freqs, out, m, half, sin_first, round_bf16);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_sinusoidal_embedding launch");
 }
@@ -367,11 +391,11 @@ extern "C" int t2v_conv3x3_small_cin(const void* in, const void* w, const float*
   if (cin == 4) {
     static bool cfg = false;
     if (!cfg) { e = cudaFuncSetAttribute(conv3x3_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
-    if (e == cudaSuccess) conv3x3_small_kernel<4><<<small_conv_grid(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
+    if (e == cudaSuccess) launch_kernel(conv3x3_small_kernel<4>, dim3(small_conv_grid(total)), dim3(256), smem, st, ip, wp, bias, op, n, h, wd, cout);
   } else if (cin == 8) {
     static bool cfg = false;
     if (!cfg) { e = cudaFuncSetAttribute(conv3x3_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
-    if (e == cudaSuccess) conv3x3_small_kernel<8><<<small_conv_grid(total), 256, smem, st>>>(ip, wp, bias, op, n, h, wd, cout);
+    if (e == cudaSuccess) launch_kernel(conv3x3_small_kernel<8>, dim3(small_conv_grid(total)), dim3(256), smem, st, ip, wp, bias, op, n, h, wd, cout);
   } else {
     return fail(-4, "t2v_conv3x3_small_cin: cin must be 4 or 8 (got %d)", cin);
   }
@@ -383,7 +407,7 @@ extern "C" int t2v_bcthw_to_frames(const void* in, int32_t in_dtype, void* out, 
                                    int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t s) {
   if (!in || !out) return fail(-1, "t2v_bcthw_to_frames: null pointer");
   const int64_t total = int64_t(b) * c * t * h * w;
-  bcthw_to_frames_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, t, h, w, scale);
+  launch_kernel(bcthw_to_frames_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(s), in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, t, h, w, scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_bcthw_to_frames launch");
 }
@@ -394,7 +418,7 @@ extern "C" int t2v_bcthw_to_frames_mix(const void* in, int32_t in_dtype, void* o
   if (!in || !out || !mix) return fail(-1, "t2v_bcthw_to_frames_mix: null pointer");
   if (c < 1 || c > 8) return fail(-2, "t2v_bcthw_to_frames_mix: c must be in [1,8]");
   const int64_t total = int64_t(b) * t * h * w;
-  bcthw_to_frames_mix_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, t, h, w, scale, mix, bias);
+  launch_kernel(bcthw_to_frames_mix_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(s), in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, t, h, w, scale, mix, bias);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_bcthw_to_frames_mix launch");
 }
@@ -403,7 +427,7 @@ extern "C" int t2v_frames_to_bcthw(const void* in, int32_t c_pad, void* out, int
                                    int32_t c, int32_t t, int32_t h, int32_t w, t2v_stream_t s) {
   if (!in || !out) return fail(-1, "t2v_frames_to_bcthw: null pointer");
   const int64_t total = int64_t(b) * c * t * h * w;
-  frames_to_bcthw_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<const __nv_bfloat16*>(in), c_pad, out, out_dtype, b, c, t, h, w);
+  launch_kernel(frames_to_bcthw_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(s), static_cast<const __nv_bfloat16*>(in), c_pad, out, out_dtype, b, c, t, h, w);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_frames_to_bcthw launch");
 }
@@ -412,7 +436,7 @@ extern "C" int t2v_upsample_nearest2x(const void* in, void* out, int32_t n, int3
                                       t2v_stream_t s) {
   if (!in || !out || c % 8) return fail(-1, "t2v_upsample_nearest2x: bad argument");
   const int64_t total = int64_t(n) * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), n, h, w, c / 8);
+  launch_kernel(upsample2x_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(s), static_cast<const uint4*>(in), static_cast<uint4*>(out), n, h, w, c / 8);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_upsample_nearest2x launch");
 }
@@ -420,7 +444,7 @@ extern "C" int t2v_upsample_nearest2x(const void* in, void* out, int32_t n, int3
 extern "C" int t2v_concat_channels(const void* a, int32_t ca, const void* b, int32_t cb, void* out,
                                    int64_t rows, t2v_stream_t s) {
   if (!a || !b || !out || ca % 8 || cb % 8) return fail(-1, "t2v_concat_channels: bad argument");
-  concat_kernel<<<grid_for(rows * ((ca + cb) / 8)), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<const uint4*>(a), ca / 8, static_cast<const uint4*>(b), cb / 8, static_cast<uint4*>(out), rows);
+  launch_kernel(concat_kernel, dim3(grid_for(rows * ((ca + cb) / 8))), dim3(256), 0, static_cast<cudaStream_t>(s), static_cast<const uint4*>(a), ca / 8, static_cast<const uint4*>(b), cb / 8, static_cast<uint4*>(out), rows);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_concat_channels launch");
 }
@@ -429,7 +453,7 @@ extern "C" int t2v_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t row
                                 t2v_stream_t s) {
   if (!x || rows <= 0 || cols <= 0) return fail(-1, "t2v_softmax_rows: bad argument");
   if (rows > 0x7fffffff) return fail(-2, "t2v_softmax_rows: too many rows");
-  softmax_rows_kernel<<<unsigned(rows), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<__nv_bfloat16*>(x), cols, row_stride, scale);
+  launch_kernel(softmax_rows_kernel, dim3(unsigned(rows)), dim3(256), 0, static_cast<cudaStream_t>(s), static_cast<__nv_bfloat16*>(x), cols, row_stride, scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_softmax_rows launch");
 }
@@ -439,7 +463,7 @@ extern "C" int t2v_lcm_step(const void* x, const void* eps, const void* noise, v
                             float c_out, float sqrt_alpha_prev, float sqrt_beta_prev, t2v_stream_t s) {
   if (!x || !eps || !prev || !denoised || n <= 0) return fail(-1, "t2v_lcm_step: bad argument");
   if (dtype < 0 || dtype > 2) return fail(-2, "t2v_lcm_step: dtype must be 0 (bf16), 1 (fp16) or 2 (fp32)");
-  lcm_step_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(s)>>>(x, eps, noise, prev, denoised, n, dtype, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqrt_alpha_prev, sqrt_beta_prev);
+  launch_kernel(lcm_step_kernel, dim3(grid_for(n)), dim3(256), 0, static_cast<cudaStream_t>(s), x, eps, noise, prev, denoised, n, dtype, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqrt_alpha_prev, sqrt_beta_prev);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_lcm_step launch");
 }
@@ -447,7 +471,7 @@ extern "C" int t2v_lcm_step(const void* x, const void* eps, const void* noise, v
 extern "C" int t2v_pack_conv_weight(const void* w, int32_t w_dtype, void* out, int32_t cout, int32_t cin,
                                     int32_t taps, t2v_stream_t s) {
   if (!w || !out) return fail(-1, "t2v_pack_conv_weight: null pointer");
-  pack_conv_weight_kernel<<<grid_for(int64_t(cout) * cin * taps), 256, 0, static_cast<cudaStream_t>(s)>>>(w, w_dtype, static_cast<__nv_bfloat16*>(out), cout, cin, taps);
+  launch_kernel(pack_conv_weight_kernel, dim3(grid_for(int64_t(cout) * cin * taps)), dim3(256), 0, static_cast<cudaStream_t>(s), w, w_dtype, static_cast<__nv_bfloat16*>(out), cout, cin, taps);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_pack_conv_weight launch");
 }
@@ -456,7 +480,7 @@ extern "C" int t2v_pack_geglu_rows(const void* w, int32_t w_dtype, void* out, co
                                    int32_t bias_dtype, float* bias_out, int32_t inner, int32_t k,
                                    t2v_stream_t s) {
   if (!w || !out || inner % 16) return fail(-1, "t2v_pack_geglu_rows: inner must be a multiple of 16");
-  pack_geglu_kernel<<<grid_for(int64_t(2) * inner * k), 256, 0, static_cast<cudaStream_t>(s)>>>(w, w_dtype, static_cast<__nv_bfloat16*>(out), bias, bias_dtype, bias_out, inner, k);
+  launch_kernel(pack_geglu_kernel, dim3(grid_for(int64_t(2) * inner * k)), dim3(256), 0, static_cast<cudaStream_t>(s), w, w_dtype, static_cast<__nv_bfloat16*>(out), bias, bias_dtype, bias_out, inner, k);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_pack_geglu_rows launch");
 }

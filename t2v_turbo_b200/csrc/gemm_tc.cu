@@ -60,44 +60,57 @@ struct GemmParams {
   uint32_t a_tile_bytes;
   float* ws;  // split-K workspace [points][N] fp32
   int32_t epi_mode;  // 0 = direct row stores, 1 = smem-staged TMA store (+ TMA residual load)
+  int32_t n_stages;  // pipeline stages in use
+  int32_t b_resident;     // 1: the CTA keeps its whole [BN x K] weight slab in smem and streams A only
+  uint32_t stage_bytes;   // bytes per pipeline stage (A tile, + B tile unless resident)
+  uint32_t smem_ring_off; // offset of the stage ring (after the resident B slab, if any)
+  uint32_t smem_epi_off;  // offset of the epilogue staging buffers
+  int32_t split_producers;  // 1: warp 0 loads A, warp 3 loads B
+  int32_t dbg;              // timing experiments only (results are wrong when non-zero)
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWGs = 3;                            // epilogue warpgroups (128 threads = 128 accumulator rows each)
+constexpr int kThreads = 128 + 128 * kEpiWGs;
+constexpr int kEpiWarps = 4 * kEpiWGs;
 constexpr int kEpiBufBytes = 128 * 64;               // 128 rows x 32 bf16 columns, 64-byte swizzle
 constexpr int kEpiBufs = 3;                          // per epilogue warpgroup
-constexpr int kEpiBytes = 2 * kEpiBufs * kEpiBufBytes;  // 48 KB
-constexpr int kSmemBudget = 227 * 1024 - kEpiBytes - 2048;
+constexpr int kEpiBytes = kEpiWGs * kEpiBufs * kEpiBufBytes;
+constexpr int kMaxStages = 12;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kSmemBudget = kSmemLimit - kEpiBytes - 4096;
 
-template <int BN>
+// PAIR: two CTAs of a cluster work on one 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA stages its own
+// 128 rows of A and HALF of the weight tile, so the L2->SM operand traffic per FLOP drops by a third to a half.
+template <int BN, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int kBTileBytes = BN * kBlockK * 2;
+  static constexpr int kBTileBytes = (PAIR ? BN / 2 : BN) * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;   // streaming mode
   static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kBarBytes = (2 * kStages + 4 + 2 * kEpiBufs) * 8 + 16 + 2 * 256 * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+  static constexpr int kBarBytes = (2 * kMaxStages + 5 + kEpiWGs * kEpiBufs) * 8 + 16 + 16 + 2 * 256 * 4;
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one ex2 + one rcp + 6 fma
-__device__ __forceinline__ float fast_erf(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = 1.0f - poly * __expf(-ax * ax);
-  return copysignf(e, x);
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
+// gelu_erf(g) = g * Phi(g),  Phi(g) = 1 - 0.5 erfc(|g|/sqrt2) for g >= 0, 0.5 erfc(|g|/sqrt2) otherwise;
+// erfc(u) ~ t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-u^2), t = 1/(1 + p u)  (Abramowitz-Stegun 7.1.26,
+// |error| <= 1.5e-7).  The 0.5 and the exp->exp2 scale are folded into the constants:
+// 2 MUFU (rcp, ex2) + ~13 FMA-pipe instructions per element.
+__device__ __forceinline__ float gelu_erf(float g) {
+  constexpr float kS = 1.2011224087864498f;                 // sqrt(log2 e)
+  const float up = fabsf(g) * (0.70710678118654752f * kS);  // u * sqrt(log2 e)
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f / kS, up, 1.0f)));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-up * up));
+  const float h = p * t * e;  // 0.5 erfc(|g| / sqrt2)
+  return g * (g >= 0.f ? 1.0f - h : h);
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -105,27 +118,33 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint8_t* smem_epi = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* smem_ring = smem + p.smem_ring_off;  // resident B slab (if any) lives in [smem, smem_ring)
+  uint8_t* smem_epi = smem + p.smem_epi_off;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;  // [2 warpgroups][kEpiBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiBufs);
-  float* bias_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [2 accumulators][256]
+  uint64_t* bres_bar = tempty_bar + 2;  // resident weight slab landed
+  uint64_t* res_bar = bres_bar + 1;     // [2 warpgroups][kEpiBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWGs * kEpiBufs);
+  // [2 accumulators][256] floats, 16-byte aligned for float4 reads
+  float* bias_smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -137,39 +156,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(&full_bar[s], (!PAIR && p.split_producers) ? 2 : 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(bres_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kEpiWarps);
+      mbar_init(&tempty_bar[a], PAIR ? 2 * kEpiWarps : kEpiWarps);  // PAIR: both CTAs' epilogues release the leader
     }
-    for (int i = 0; i < 2 * kEpiBufs; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kEpiWGs * kEpiBufs; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if ((warp == 0 || (warp == 3 && p.split_producers)) && lane == 0) {
+    // ------------------------------------------------------------ TMA producer(s)
+    const bool do_a = (warp == 0);
+    const bool do_b = !p.b_resident && (p.split_producers ? (warp == 3) : true);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    if (p.b_resident && warp == 0) {
+      // weight-stationary: this CTA only ever works on n-tile (blockIdx.x % n_tiles_n) — the grid is a
+      // multiple of n_tiles_n — so its [BN x K] slab is loaded once and every tile streams A only
+      const int n_tile = blockIdx.x % p.n_tiles_n;
+      mbar_expect_tx(bres_bar, uint32_t(p.total_kb) * uint32_t(Cfg::kBTileBytes));
+      for (int kb = 0; kb < p.total_kb; ++kb)
+        tma_load_3d(smem + kb * Cfg::kBTileBytes, &tmB, bres_bar, kb * kBlockK, n_tile * BN, 0);
+    }
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
       const int ks = tile / p.n_tiles_mn;
       const int mn = tile - ks * p.n_tiles_mn;
       const int n_tile = mn % p.n_tiles_n;
-      int m_tile = mn / p.n_tiles_n;
+      int m_tile = (mn / p.n_tiles_n) * (PAIR ? 2 : 1) + int(cta_rank);
       int o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        o[j] = (m_tile % p.ntile[j]) * p.box[j];
+        o[j] = (j < 3 ? m_tile % p.ntile[j] : m_tile) * p.box[j];  // last dim unbounded: a tile past the end is all out-of-range
         m_tile /= p.ntile[j];
       }
       int bbatch = 0;
@@ -181,63 +219,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int tap = kb_begin / p.kb_per_tap;
       int kb = kb_begin - tap * p.kb_per_tap;
       for (int idx = kb_begin; idx < kb_end; ++idx) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sA = smem + stage * Cfg::kStageBytes;
+        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem_ring + stage * p.stage_bytes;
         uint8_t* sB = sA + kATileBytes;
-        mbar_expect_tx(&full_bar[stage], p.a_tile_bytes + Cfg::kBTileBytes);
-        const int c1 = o[0] + p.tap_off[tap][0];
-        const int c2 = o[1] + p.tap_off[tap][1];
-        const int c3 = o[2] + p.tap_off[tap][2];
-        const int c4 = o[3] + p.tap_off[tap][3];
-        const int ch0 = p.tap_ch_off[tap];
-        if (kb < p.kb_src0)
-          tma_load_5d(sA, &tmA0, &full_bar[stage], ch0 + kb * kBlockK, c1, c2, c3, c4);
-        else
-          tma_load_5d(sA, &tmA1, &full_bar[stage], ch0 + (kb - p.kb_src0) * kBlockK, c1, c2, c3, c4);
-        tma_load_3d(sB, &tmB, &full_bar[stage], idx * kBlockK, n_tile * BN, bbatch);
+        if (PAIR) {
+          // The leader's barrier expects the bytes of BOTH CTAs; the peer only issues its loads (their
+          // complete_tx lands on the leader's barrier).  The peer can never run a phase ahead: its stage is
+          // released by the same multicast commit that follows the leader's barrier completing.  (A remote
+          // arrive per k-block would cost a cluster-scope release fence on the critical path.)
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (p.a_tile_bytes + uint32_t(Cfg::kBTileBytes)));
+          const int c1 = o[0] + p.tap_off[tap][0];
+          const int c2 = o[1] + p.tap_off[tap][1];
+          const int c3 = o[2] + p.tap_off[tap][2];
+          const int c4 = o[3] + p.tap_off[tap][3];
+          const int ch0 = p.tap_ch_off[tap];
+          if (kb < p.kb_src0)
+            tma_load_5d_2sm(sA, &tmA0, &full_bar[stage], ch0 + kb * kBlockK, c1, c2, c3, c4);
+          else
+            tma_load_5d_2sm(sA, &tmA1, &full_bar[stage], ch0 + (kb - p.kb_src0) * kBlockK, c1, c2, c3, c4);
+          tma_load_3d_2sm(sB, &tmB, &full_bar[stage], idx * kBlockK, n_tile * BN + int(cta_rank) * (BN / 2), 0);
+        } else {
+        mbar_expect_tx(&full_bar[stage], (do_a ? p.a_tile_bytes : 0u) + (do_b ? uint32_t(Cfg::kBTileBytes) : 0u));
+        if (do_a) {
+          const int c1 = o[0] + p.tap_off[tap][0];
+          const int c2 = o[1] + p.tap_off[tap][1];
+          const int c3 = o[2] + p.tap_off[tap][2];
+          const int c4 = o[3] + p.tap_off[tap][3];
+          const int ch0 = p.tap_ch_off[tap];
+          if (kb < p.kb_src0)
+            tma_load_5d(sA, &tmA0, &full_bar[stage], ch0 + kb * kBlockK, c1, c2, c3, c4);
+          else
+            tma_load_5d(sA, &tmA1, &full_bar[stage], ch0 + (kb - p.kb_src0) * kBlockK, c1, c2, c3, c4);
+        }
+        if (do_b) tma_load_3d(sB, &tmB, &full_bar[stage], idx * kBlockK, n_tile * BN, bbatch);
+        }
         if (++kb == p.kb_per_tap) {
           kb = 0;
           ++tap;
         }
-        if (++stage == Cfg::kStages) {
+        if (++stage == p.n_stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, 0);
+  } else if (warp == 1 && lane == 0 && (!PAIR || cta_rank == 0)) {
+    // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA issues for both)
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    if (p.b_resident) mbar_wait(bres_bar, 0);
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const int ks = tile / p.n_tiles_mn;
       const int kb_begin = ks * p.kb_per_split;
       const int n_kb = min(kb_begin + p.kb_per_split, p.total_kb) - kb_begin;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      mbar_wait_relaxed(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
       for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t a_addr = smem_u32(smem_ring + stage * p.stage_bytes);
         const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(a_addr + kATileBytes);
+        const uint64_t bdesc = umma_desc_sw128(p.b_resident ? smem_u32(smem + (kb_begin + kb) * Cfg::kBTileBytes)
+                                                            : a_addr + kATileBytes);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // advance 16 elements (32 bytes) along K inside the 128B swizzle atom: +2 in addr>>4 units
-          umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (PAIR)
+            umma_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          else
+            umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == Cfg::kStages) {
+        if (PAIR)
+          umma_commit_2sm(&empty_bar[stage]);
+        else
+          umma_commit(&empty_bar[stage]);
+        if (++stage == p.n_stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(&tfull_bar[acc]);
+      if (PAIR)
+        umma_commit_2sm(&tfull_bar[acc]);
+      else
+        umma_commit(&tfull_bar[acc]);
     }
   } else if (warp >= 4 && p.epi_mode == 1) {
     // ------------------------------------------------------------ epilogue, smem-staged (8 warps = 2 warpgroups)
@@ -256,6 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool geglu = (p.flags & T2V_EPI_GEGLU) != 0;
     const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
     const bool has_res = p.residual != nullptr;
+    const bool alpha_one = (p.alpha == 1.0f);
     const int acc_cw = geglu ? 64 : 32;  // accumulator columns per 32-column output chunk
     const int chunks_per_tile = BN / acc_cw;
     uint8_t* ebuf = smem_epi + g * kEpiBufs * kEpiBufBytes;
@@ -264,18 +334,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int sw = (r >> 1) & 3;
     uint32_t q = 0;  // chunks processed so far by this warpgroup (buffer = q % 3)
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles_n;
-      int m_tile = tile / p.n_tiles_n;
+      int m_tile = (tile / p.n_tiles_n) * (PAIR ? 2 : 1) + int(cta_rank);
       int o[4];
       int64_t bias_row = 0, bias_row_first = 0, bias_row_last = 0;
       {
         int rr = r, rl = p.rows_in_box - 1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          o[j] = (m_tile % p.ntile[j]) * p.box[j];
+          o[j] = (j < 3 ? m_tile % p.ntile[j] : m_tile) * p.box[j];
           m_tile /= p.ntile[j];
           const int ij = rr % p.box[j];
           rr /= p.box[j];
@@ -303,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (has_res && leader) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int c = g + 2 * i;
+          const int c = g + kEpiWGs * i;
           if (c < chunks_per_tile && n_base + c * acc_cw < p.n_rows_b) {
             const uint32_t buf = (q + i) % kEpiBufs;
             mbar_expect_tx(&rbar[buf], res_bytes);
@@ -312,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
-      if (bias_uniform) named_bar_sync(3, 256);  // bias row visible to both warpgroups
+      if (bias_uniform) named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);  // bias row visible to all warpgroups
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(lg * 32) << 16);
@@ -320,25 +390,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t v[32];
       if (g < chunks_per_tile && n_base + g * acc_cw < p.n_rows_b) tmem_ld_32x32(taddr + g * acc_cw, v);
 #pragma unroll 1
-      for (int c = g; c < chunks_per_tile && n_base + c * acc_cw < p.n_rows_b; c += 2) {
+      for (int c = g; c < chunks_per_tile && n_base + c * acc_cw < p.n_rows_b; c += kEpiWGs) {
         const uint32_t buf = q % kEpiBufs;
         const uint32_t rphase = (q / kEpiBufs) & 1u;
         const int n0 = n_base + c * acc_cw;  // first W row (accumulator column) of this chunk
         const int oc0 = geglu ? (n0 >> 1) : n0;
-        const bool has_next = (c + 2 < chunks_per_tile) && (n_base + (c + 2) * acc_cw < p.n_rows_b);
+        const bool has_next = (c + kEpiWGs < chunks_per_tile) && (n_base + (c + kEpiWGs) * acc_cw < p.n_rows_b);
         float f[32];
         tmem_wait_ld();
-        if (geglu) {
-          uint32_t v2[32];
-          tmem_ld_32x32(taddr + c * acc_cw + 32, v2);
-          tmem_wait_ld();
-          // packed W rows: [16 value | 16 gate] per 32 accumulator columns
+        if (p.dbg & 4) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        } else if (geglu) {
+          // packed W rows: [16 value | 16 gate] per 32 accumulator columns; two such groups per output chunk
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
+            if (hh == 1) {
+              tmem_ld_32x32(taddr + c * acc_cw + 32, v);
+              tmem_wait_ld();
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float a = p.alpha * __uint_as_float(hh == 0 ? v[j] : v2[j]);
-              float gt = p.alpha * __uint_as_float(hh == 0 ? v[j + 16] : v2[j + 16]);
+              float a = __uint_as_float(v[j]);
+              float gt = __uint_as_float(v[j + 16]);
+              if (!alpha_one) {
+                a *= p.alpha;
+                gt *= p.alpha;
+              }
               if (bias_uniform) {
                 a += sbias[c * acc_cw + hh * 32 + j];
                 gt += sbias[c * acc_cw + hh * 32 + 16 + j];
@@ -367,12 +445,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         if (has_next) {
-          tmem_ld_32x32(taddr + (c + 2) * acc_cw, v);  // in flight while this chunk is written out
+          tmem_ld_32x32(taddr + (c + kEpiWGs) * acc_cw, v);  // in flight while this chunk is written out
         } else {
           // last TMEM read of this tile by this warp: release the accumulator early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if (PAIR)
+              mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & kPeerBitMask);
+            else
+              mbar_arrive(&tempty_bar[acc]);
+          }
           arrived = true;
         }
         if (gelu && !geglu) {
@@ -404,14 +487,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           ov.w = pack_bf16(f[k4 * 8 + 6], f[k4 * 8 + 7]);
           *reinterpret_cast<uint4*>(row + ((k4 ^ sw) << 4)) = ov;
         }
-        fence_proxy_async();
-        named_bar_sync(1 + g, 128);
+        if (!(p.dbg & 2)) {
+          fence_proxy_async();
+          named_bar_sync(1 + g, 128);
+        }
         if (leader) {
-          tma_store_5d(&tmOut, ebuf + buf * kEpiBufBytes, oc0, o[0], o[1], o[2], o[3]);
+          if (!(p.dbg & 1)) tma_store_5d(&tmOut, ebuf + buf * kEpiBufBytes, oc0, o[0], o[1], o[2], o[3]);
           bulk_commit_group();
           bulk_wait_group_read<1>();  // every store but the one just issued has finished reading smem
           if (has_res) {
-            const int c2 = c + 4;
+            const int c2 = c + 2 * kEpiWGs;
             if (c2 < chunks_per_tile && n_base + c2 * acc_cw < p.n_rows_b) {
               const uint32_t buf2 = (q + 2) % kEpiBufs;
               mbar_expect_tx(&rbar[buf2], res_bytes);
@@ -425,7 +510,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (!arrived) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+            if (PAIR)
+              mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & kPeerBitMask);
+            else
+              mbar_arrive(&tempty_bar[acc]);
+          }
       }
     }
     if (leader) bulk_wait_group_read<0>();
@@ -433,20 +523,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp - 4;
     const int lg = ew & 3;     // TMEM lane group == warp % 4
-    const int half = ew >> 2;  // which interleaved set of 32-column chunks
+    const int half = ew >> 2;  // which interleaved set of 32-column chunks (one per warpgroup)
     const int r = lg * 32 + lane;
     const bool geglu = (p.flags & T2V_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & T2V_EPI_OUT_F32) != 0;
     const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
     const bool split = p.split_k > 1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int ks = tile / p.n_tiles_mn;
       const int mn = tile - ks * p.n_tiles_mn;
       const int n_tile = mn % p.n_tiles_n;
-      int m_tile = mn / p.n_tiles_n;
+      int m_tile = (mn / p.n_tiles_n) * (PAIR ? 2 : 1) + int(cta_rank);
       // row -> point
       bool valid = r < p.rows_in_box;
       int64_t out_off = 0, res_off = 0, point = 0, pmul = 1;
@@ -455,7 +545,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int rr = r;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int oj = (m_tile % p.ntile[j]) * p.box[j];
+          const int oj = (j < 3 ? m_tile % p.ntile[j] : m_tile) * p.box[j];
           m_tile /= p.ntile[j];
           const int ij = rr % p.box[j];
           rr /= p.box[j];
@@ -475,7 +565,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t taddr = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(lg * 32) << 16);
 
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      for (int c0 = half * 32; c0 < BN; c0 += 32 * kEpiWGs) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_wait_ld();
@@ -593,20 +683,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+            if (PAIR)
+              mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & kPeerBitMask);
+            else
+              mbar_arrive(&tempty_bar[acc]);
+          }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still be reading operands / signalling barriers in this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR)
+      tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else
+      tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+__global__ void __launch_bounds__(256) zero_f32_kernel(float4* p, int64_t n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // split-K finalize: out[point, n] = epi(ws[point, n]) ; one thread = 4 consecutive columns
 __global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, int64_t n_points) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nq = (p.n_rows_b + 3) >> 2;
   const int64_t total = n_points * nq;
   const bool out_f32 = (p.flags & T2V_EPI_OUT_F32) != 0;
@@ -640,21 +748,48 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, 
   }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& to,
                        const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc)");
     configured = true;
   }
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "no CUDA device");
-  int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, to, tr, p);
+  int grid;
+  if (PAIR) {
+    const int pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
+    grid = 2 * pairs;
+  } else {
+    grid = p.num_tiles < sms ? p.num_tiles : sms;
+  }
+  GemmParams pp = p;
+  int stages;
+  if (p.b_resident) {
+    const int slab = p.total_kb * Cfg::kBTileBytes;
+    pp.smem_ring_off = uint32_t(slab);
+    pp.stage_bytes = kATileBytes;
+    stages = (kSmemLimit - (Cfg::kBarBytes + 1024) - kEpiBytes - slab) / kATileBytes;
+    grid = (sms / p.n_tiles_n) * p.n_tiles_n;  // keeps n_tile fixed per CTA
+    if (grid > p.num_tiles) grid = p.num_tiles;
+  } else {
+    pp.smem_ring_off = 0;
+    pp.stage_bytes = Cfg::kStageBytes;
+    stages = Cfg::kStages;
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (p.n_stages > 0 && p.n_stages < stages) stages = p.n_stages;
+  if (stages < 2) return fail(-111, "gemm_tc: shared memory layout leaves %d pipeline stages", stages);
+  pp.n_stages = stages;
+  pp.smem_epi_off = pp.smem_ring_off + uint32_t(stages) * pp.stage_bytes;
+  const size_t smem_bytes = size_t(pp.smem_epi_off) + kEpiBytes + Cfg::kBarBytes + 1024;
+  if (smem_bytes > size_t(kSmemLimit)) return fail(-112, "gemm_tc: %zu bytes of shared memory needed", smem_bytes);
+  launch_kernel_cluster(gemm_tc_kernel<BN, PAIR>, dim3(grid), dim3(kThreads), smem_bytes, stream, PAIR ? 2u : 1u, a0, a1, b,
+                        to, tr, pp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "gemm_tc launch");
   return 0;
@@ -727,6 +862,52 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "t2v_gemm: no CUDA device");
   int bn = d->block_n;
+  // weight-stationary mode for small K: the CTA's [BN x K] slab stays in shared memory
+  bool resident = false;
+  if ((d->tune & 0x400) && d->b_batch_dim < 0 && d->split_k <= 1) {  // opt-in: measured slower than streaming
+    const int cands[4] = {256, 160, 128, 64};
+    double best = 0.0;
+    for (int i = 0; i < 4; ++i) {
+      const int c = cands[i];
+      if (bn != 0 && c != bn) continue;
+      if (geglu && c % 64 != 0) continue;
+      const int64_t slab = int64_t(c) * K * 2;
+      if (slab > 100 * 1024) continue;
+      const int64_t nt = (d->b_rows + c - 1) / c;
+      if (nt > sms) continue;
+      const int64_t ctas = (sms / nt) * nt;
+      if (m_tiles * nt < 3 * ctas) continue;  // needs several tiles per CTA to pay for the slab load
+      const double eff = double(ctas) / sms * double(d->b_rows) / double(nt * c) * (c >= 128 ? 1.0 : 0.85);
+      if (eff > best) {
+        best = eff;
+        if (eff >= 0.80) {
+          resident = true;
+          bn = c;
+        }
+      }
+    }
+    if (resident) {
+      // re-pick the best candidate (the loop keeps the last one above threshold; choose the max)
+      double top = 0.0;
+      int top_bn = bn;
+      for (int i = 0; i < 4; ++i) {
+        const int c = cands[i];
+        if (d->block_n != 0 && c != d->block_n) continue;
+        if (geglu && c % 64 != 0) continue;
+        if (int64_t(c) * K * 2 > 100 * 1024) continue;
+        const int64_t nt = (d->b_rows + c - 1) / c;
+        if (nt > sms) continue;
+        const int64_t ctas = (sms / nt) * nt;
+        if (m_tiles * nt < 3 * ctas) continue;
+        const double eff = double(ctas) / sms * double(d->b_rows) / double(nt * c) * (c >= 128 ? 1.0 : 0.85);
+        if (eff > top) {
+          top = eff;
+          top_bn = c;
+        }
+      }
+      bn = top_bn;
+    }
+  }
   if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
   p.n_tiles_n = int((d->b_rows + bn - 1) / bn);
@@ -796,6 +977,19 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   // staged (TMA-store) epilogue whenever the output rows are 16-byte addressable bf16
   bool staged = vec_ok && split == 1 && !(d->flags & T2V_EPI_OUT_F32) && (!geglu || bn % 64 == 0);
   p.epi_mode = staged ? 1 : 0;
+  // CTA pairs (cta_group::2): 256-row tiles, each CTA stages half of the weight tile
+  const int64_t pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+  // measured: +10 % at K >= 1024 (1441 TFLOP/s on 512->512 3x3 convs = the cuBLAS sustained level), a loss at small K
+  const bool pair = staged && !resident && !(d->tune & 0x800) && d->b_batch_dim < 0 && bn >= 128 && m_tiles >= 2 &&
+                    pair_tiles >= sms / 2 && p.total_kb >= 16;
+  if (pair) {
+    p.n_tiles_mn = int(pair_tiles);
+    p.num_tiles = int(pair_tiles);
+  }
+  p.n_stages = d->tune & 0xff;  // 0 = all stages of the instantiation
+  p.split_producers = (d->tune & 0x100) ? 1 : 0;
+  p.dbg = (d->tune >> 12) & 0xf;  // bit0: no TMA store, bit1: no smem write/fence/barrier, bit2: no TMEM loads
+  p.b_resident = (resident && split == 1) ? 1 : 0;
 
   // tensor maps
   CUtensorMap tmA[2], tmB, tmOut, tmRes;
@@ -840,28 +1034,38 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     uint64_t dims[3] = {uint64_t(K), uint64_t(d->b_rows), uint64_t(d->b_batches < 1 ? 1 : d->b_batches)};
     uint64_t strides[3] = {2, row_stride * 2,
                            uint64_t(d->b_batch_stride > 0 ? d->b_batch_stride : row_stride * d->b_rows) * 2};
-    uint32_t box[3] = {64, uint32_t(bn), 1};
+    uint32_t box[3] = {64, uint32_t(pair ? bn / 2 : bn), 1};
     int rc = make_tmap_bf16(&tmB, d->b, 3, dims, strides, box, "t2v_gemm B");
     if (rc) return rc;
   }
   if (split > 1) {
-    cudaError_t e = cudaMemsetAsync(d->workspace, 0, size_t(n_points) * d->b_rows * 4, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "t2v_gemm workspace memset");
+    const int64_t n4 = (n_points * d->b_rows + 3) / 4;  // workspace is a multiple of 16 bytes
+    int64_t zg = (n4 + 255) / 256;
+    if (zg > sms * 4) zg = sms * 4;
+    launch_kernel(zero_f32_kernel, dim3(unsigned(zg)), dim3(256), 0, stream, static_cast<float4*>(d->workspace), n4);
   }
   int rc;
-  switch (bn) {
-    case 32: rc = launch_gemm<32>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-    case 64: rc = launch_gemm<64>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-    case 128: rc = launch_gemm<128>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-    case 160: rc = launch_gemm<160>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-    default: rc = launch_gemm<256>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+  if (pair) {
+    switch (bn) {
+      case 128: rc = launch_gemm<128, true>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+      case 160: rc = launch_gemm<160, true>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+      default: rc = launch_gemm<256, true>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+    }
+  } else {
+    switch (bn) {
+      case 32: rc = launch_gemm<32, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+      case 64: rc = launch_gemm<64, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+      case 128: rc = launch_gemm<128, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+      case 160: rc = launch_gemm<160, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+      default: rc = launch_gemm<256, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
+    }
   }
   if (rc) return rc;
   if (split > 1) {
     const int64_t total = n_points * ((d->b_rows + 3) / 4);
     int64_t grid = (total + 255) / 256;
     if (grid > sms * 8) grid = sms * 8;
-    gemm_finalize_kernel<<<unsigned(grid), 256, 0, stream>>>(p, n_points);
+    launch_kernel(gemm_finalize_kernel, dim3(unsigned(grid)), dim3(256), 0, stream, p, n_points);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "gemm_finalize launch");
   }

@@ -1,6 +1,7 @@
 #include "host_common.h"
 
 #include <mutex>
+#include <stdlib.h>
 
 #include "../../include/t2v_b200.h"
 
@@ -22,6 +23,15 @@ EncodeTiledFn encode_tiled_fn() {
     (void)cudaGetLastError();
   });
   return fn;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("T2V_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

@@ -42,8 +42,16 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 
 constexpr int kGnThreads = 256;
 
+__global__ void gn_zero_kernel(float* ws, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ws[i] = 0.f;
+}
+
 // grid: (blocks_per_sample, n_samples)
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_acc[2 * 64];
   for (int i = threadIdx.x; i < 2 * p.groups; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
@@ -107,6 +115,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
 }
 
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int sample = blockIdx.y;
   const int64_t row_begin = int64_t(blockIdx.x) * p.rows_per_block;
   int64_t row_end = row_begin + p.rows_per_block;
@@ -183,6 +193,8 @@ struct LnParams {
 
 template <int MAXV>  // vectors per lane
 __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
@@ -288,11 +300,11 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   rpb = (rpb + rpp - 1) / rpp * rpp;
   p.rows_per_block = int(rpb);
   const int64_t bps = (d->rows_per_sample + rpb - 1) / rpb;
-  cudaError_t e = cudaMemsetAsync(d->workspace, 0, sizeof(float) * 2 * d->groups * n_samples, stream);
-  if (e != cudaSuccess) return cuda_fail(e, "t2v_groupnorm memset");
+  launch_kernel(gn_zero_kernel, dim3(1), dim3(256), 0, stream, d->workspace, int(2 * d->groups * n_samples));
+  cudaError_t e;
   dim3 grid((unsigned)bps, (unsigned)n_samples);
-  gn_stats_kernel<<<grid, kGnThreads, 0, stream>>>(p);
-  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(p);
+  launch_kernel(gn_stats_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
+  launch_kernel(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "t2v_groupnorm launch");
   return 0;
@@ -320,9 +332,9 @@ extern "C" int t2v_layernorm(const T2VLayerNormDesc* d, t2v_stream_t stream_) {
   p.inv_c = 1.0f / float(d->channels);
   const unsigned grid = unsigned((d->rows + 7) / 8);
   const int vpl = (p.nvec + 31) / 32;
-  if (vpl <= 2) ln_kernel<2><<<grid, 256, 0, stream>>>(p);
-  else if (vpl <= 5) ln_kernel<5><<<grid, 256, 0, stream>>>(p);
-  else ln_kernel<8><<<grid, 256, 0, stream>>>(p);
+  if (vpl <= 2) launch_kernel(ln_kernel<2>, dim3(grid), dim3(256), 0, stream, p);
+  else if (vpl <= 5) launch_kernel(ln_kernel<5>, dim3(grid), dim3(256), 0, stream, p);
+  else launch_kernel(ln_kernel<8>, dim3(grid), dim3(256), 0, stream, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "t2v_layernorm launch");
   return 0;

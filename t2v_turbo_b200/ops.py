@@ -150,6 +150,7 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     d.flags = flags
     d.block_n = block_n
     d.split_k = split_k
+    d.tune = GEMM_TUNE
     ws = _splitk_workspace(out.device)
     d.workspace = ws.data_ptr()
     d.workspace_bytes = ws.numel() * 4
@@ -161,6 +162,8 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     return out
 
 
+import os as _os
+GEMM_TUNE = int(_os.environ.get("T2V_GEMM_TUNE", "0"), 0)   # experiments only: see T2VGemmDesc.tune
 _SPLITK_WS: dict = {}
 SPLITK_WS_BYTES = 32 << 20
 

@@ -74,6 +74,48 @@ def test_conv3x3_level3_split_k(cuda_device):
     assert_close(out, ref, what="conv3x3 5x8 split-K")
 
 
+@pytest.mark.parametrize("m,k,n,bn,geglu", [
+    (9600 + 64, 320, 320, 0, False),      # odd number of 128-row tiles (+ ragged tail): last pair has an empty half
+    (16384, 640, 1280, 256, False), (16384, 320, 640, 128, False), (12800, 1280, 320, 160, False),
+    (16384, 320, 2560, 256, True), (20480, 64, 512, 128, True),
+])
+def test_linear_cta_pairs(cuda_device, m, k, n, bn, geglu):
+    """shapes large enough for the cta_group::2 path (>= 74 pair tiles)"""
+    ops = _ops()
+    x = rnd(m, k, seed=80).to(BF16)
+    w = rnd(n, k, scale=k ** -0.5, seed=81).to(BF16)
+    b = rnd(n, seed=82)
+    if geglu:
+        wp, bp = ops.pack_geglu(w, b.to(BF16))
+        out = ops.linear(x, wp, bp, geglu=True, block_n=bn)
+        h = x.float() @ w.float().t() + b.to(BF16).float()
+        a, g = h.chunk(2, dim=-1)
+        ref = a * F.gelu(g)
+    else:
+        res = rnd(m, n, seed=83).to(BF16)
+        out = ops.linear(x, w, b, residual=res, block_n=bn)
+        ref = x.float() @ w.float().t() + b + res.float()
+    assert_close(out, ref, what=f"linear pair {m}x{k}x{n}")
+
+
+def test_conv_cta_pairs(cuda_device):
+    ops = _ops()
+    x = rnd(16, 40, 64, 64, seed=84).to(BF16)
+    wt = rnd(320, 64, 3, 3, scale=(9 * 64) ** -0.5, seed=85).to(BF16)
+    b = rnd(2, 320, seed=86)
+    res = rnd(16, 40, 64, 320, seed=87).to(BF16)
+    out = ops.conv3x3(x, ops.pack_conv_weight(wt), b, bias_div=8, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), None, padding=1).permute(0, 2, 3, 1) + res.float()
+    ref = ref + b.repeat_interleave(8, 0)[:, None, None, :]
+    assert_close(out, ref, what="conv3x3 pair")
+    xt = rnd(1, 16, 2560, 64, seed=88).to(BF16)
+    wtt = rnd(128, 64, 3, 1, 1, scale=(3 * 64) ** -0.5, seed=89).to(BF16)
+    bt = rnd(128, seed=90)
+    out = ops.tconv3(xt, ops.pack_conv_weight(wtt), bt)
+    ref = F.conv3d(xt.float().permute(0, 3, 1, 2).unsqueeze(-1), wtt.float(), bt, padding=(1, 0, 0)).squeeze(-1).permute(0, 2, 3, 1)
+    assert_close(out, ref, what="tconv3 pair")
+
+
 def test_linear_f32_out_and_tail(cuda_device):
     ops = _ops()
     x = rnd(300, 192, seed=5).to(BF16)
