@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="videos per pipeline call per GPU (headline = 1)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -180,29 +181,27 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch
-    import torch.distributed as dist
+    from t2v_turbo_b200 import dist as t2v_dist
     from t2v_turbo_b200 import ops
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    t2v_dist.init_replicas("nccl", device)
     pipe = build_pipeline(device, use_graph=not args.no_graph)
     gen = torch.Generator(device=device).manual_seed(1234 + rank)
-    pe_dev = torch.randn(1, 77, 1024, device=device, dtype=torch.bfloat16, generator=gen)
+    bs = args.batch
+    pe_dev = torch.randn(bs, 77, 1024, device=device, dtype=torch.bfloat16, generator=gen)
 
     def call(pe):
         return pipe(prompt_embeds=pe, height=HEIGHT, width=WIDTH, frames=FRAMES, fps=16, guidance_scale=7.5,
                     num_inference_steps=STEPS, lcm_origin_steps=50, generator=gen, output_type="pt")
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        t2v_dist.barrier(device)
 
     # ---------------- device-resident arm
     for _ in range(args.warmup):
         vid = call(pe_dev)
-    assert tuple(vid.shape) == (1, 3, FRAMES, HEIGHT, WIDTH)
+    assert tuple(vid.shape) == (bs, 3, FRAMES, HEIGHT, WIDTH)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -218,7 +217,7 @@ def main():
 
     # ---------------- end-to-end arm: host buffers in, host buffers out
     pe_host = pe_dev.cpu().pin_memory()
-    out_host = torch.empty((1, 3, FRAMES, HEIGHT, WIDTH), dtype=torch.bfloat16).pin_memory()
+    out_host = torch.empty((bs, 3, FRAMES, HEIGHT, WIDTH), dtype=torch.bfloat16).pin_memory()
     for _ in range(2):
         out_host.copy_(call(pe_host), non_blocking=True)
     barrier()
@@ -230,15 +229,12 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = t2v_dist.max_over_ranks([ms, ms_e2e], device)   # the slowest replica defines the job time
 
     # ---------------- UNet forward alone (graph replay), part of the headline metric triple
-    lat = torch.randn(1, 4, FRAMES, HEIGHT // 8, WIDTH // 8, device=device, dtype=torch.bfloat16, generator=gen)
-    ts = torch.full((1,), 999, device=device, dtype=torch.long)
-    wemb = pipe.get_w_embedding(torch.tensor([7.5]), 256).to(device).to(torch.bfloat16)
+    lat = torch.randn(bs, 4, FRAMES, HEIGHT // 8, WIDTH // 8, device=device, dtype=torch.bfloat16, generator=gen)
+    ts = torch.full((bs,), 999, device=device, dtype=torch.long)
+    wemb = pipe.get_w_embedding(torch.tensor([7.5]).repeat(bs), 256).to(device).to(torch.bfloat16)
     for _ in range(2):
         pipe._unet_call(lat, ts, pe_dev, wemb, None, 16)
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,20 +267,20 @@ def main():
                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})
 
     if rank == 0:
-        frames_total = FRAMES * args.steps * world
+        frames_total = FRAMES * bs * args.steps * world
         value = frames_total / (ms * 1e-3)
         line = dict(metric="4-step 16x320x512 frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic",
-                    config=dict(workload="T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet (1.41B) + KL-VAE decode, bs=1 per GPU",
+                    config=dict(workload="T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet (1.41B) + KL-VAE decode, bs=%d per GPU" % bs,
                                 parallelism=f"replicas x{world} (no data-path collective)", cuda_graph=not args.no_graph,
                                 l2="working set per step (2.83 GB weights x4 + activations) >> 126 MB L2; no flush needed",
-                                algorithmic_tflop_per_step=PIPE_TFLOP, output_finite=finite),
-                    unet_fwd_ms=unet_ms, unet_fwd_tflops=UNET_TFLOP / (unet_ms * 1e-3), clocks=clocks,
+                                algorithmic_tflop_per_step=PIPE_TFLOP * bs, output_finite=finite),
+                    unet_fwd_ms=unet_ms, unet_fwd_tflops=UNET_TFLOP * bs / (unet_ms * 1e-3), clocks=clocks,
                     e2e=dict(value=frames_total / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=pe_host.numel() * 2,
                              d2h_bytes_per_step=out_host.numel() * 2),
                     gpu_launches=launches_per_step * args.steps, roofline=roofline,
-                    tensor_frac_of_step=PIPE_TFLOP / (ms / args.steps * 1e-3) / pk["tflops"])
+                    tensor_frac_of_step=PIPE_TFLOP * bs / (ms / args.steps * 1e-3) / pk["tflops"])
         if world == 1 and not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 16)
             run, sample_tflop, desc = cpu_sample(threads)
@@ -292,8 +288,7 @@ def main():
             line["cpu_baseline"] = dict(value=FRAMES / (tcpu * PIPE_TFLOP / sample_tflop), unit="frames/s", cores=threads,
                                         kind="port", sample=desc + f"; sample took {tcpu:.1f} s")
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    t2v_dist.shutdown()
 
 
 if __name__ == "__main__":

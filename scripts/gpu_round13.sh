@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "attention" 2>&1 | tail -n 4
+timeout 600 python -m pytest tests/test_model_gpu.py -m gpu -q -x 2>&1 | tail -n 3
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench7.json 2> gpurun_out/bench7.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench7.json')); print(d['value'], d['unet_fwd_ms'], {k:v for k,v in d['roofline']['families'].items() if k in ('gemm','attn_fwd','groupnorm')})"; tail -n 2 gpurun_out/bench7.err
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --batch 2 > gpurun_out/bench7_bs2.json 2> gpurun_out/bench7_bs2.err; echo "bench bs2 rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench7_bs2.json')); print(d['value'], d['unet_fwd_ms'], d['ms_per_step'])"; tail -n 2 gpurun_out/bench7_bs2.err

@@ -161,61 +161,85 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t o_addr = tmem_base + lane_addr + kOCol;
     uint8_t* p_row = sP + r * 128;
     const int sw = r & 7;
-    float m_run = -INFINITY;  // running max of scaled (log2-domain) scores
+    // Online softmax with a LAZY reference: exponentials are taken against m_ref, which is only raised when a
+    // row's scores exceed it by more than 2^8 (then P / l / O are rescaled exactly).  Softmax is shift
+    // invariant, so the result is unchanged, but the steady state is ONE pass over S per tile
+    // (fma + ex2 + add + max per element) instead of a max pass followed by an exp pass.
+    constexpr float kLazy = 8.0f;
+    float m_ref = -INFINITY;  // exponent reference (log2 domain, scale folded in)
     float l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv_left = p.len_k - j * kTile;  // valid keys in this tile (>= 1)
-      // pass 1: row max
-      float mx = m_run;
+      if (j == 0) {
+        // first tile: exact row max
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kTile; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c0, v);
-        tmem_wait_ld();
+        for (int c0 = 0; c0 < kTile; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c0, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = __uint_as_float(v[i]) * p.scale_log2;
-          if (c0 + i < kv_left) mx = fmaxf(mx, sv);
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
+        m_ref = mx * p.scale_log2;
       }
-      const float m_new = mx;
-      // pass 2: p = 2^(s - m_new), row sum, bf16 P -> swizzled smem
-      // (the P buffer is free: PV(j-1) completion was observed below before this point)
-      float rs = 0.f;
+      float rs = 0.f, raw_max = -INFINITY;
+      auto exp_pass = [&](float ref) {
+        rs = 0.f;
+        raw_max = -INFINITY;
+        const float nref = -ref;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kTile; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c0, v);
-        tmem_wait_ld();
-        float pf[32];
+        for (int c0 = 0; c0 < kTile; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c0, v);
+          tmem_wait_ld();
+          float pf[32];
+          if (c0 + 32 <= kv_left) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = __uint_as_float(v[i]) * p.scale_log2;
-          const float e = (c0 + i < kv_left) ? ex2(sv - m_new) : 0.f;
-          pf[i] = e;
-          rs += e;
-        }
-        // 32 keys = 4 chunks of 16 bytes; chunk index within the 128-key row: c0/8 + q
-        uint8_t* sub = p_row + (c0 >> 6) * (kTile * 128);
+            for (int i = 0; i < 32; ++i) {
+              const float sv = __uint_as_float(v[i]);
+              raw_max = fmaxf(raw_max, sv);
+              const float e = ex2(fmaf(sv, p.scale_log2, nref));
+              pf[i] = e;
+              rs += e;
+            }
+          } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cc = ((c0 & 63) >> 3) + q;
-          uint4 pk;
-          pk.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
-          pk.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
-          pk.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
-          pk.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(sub + ((cc ^ sw) << 4)) = pk;
+            for (int i = 0; i < 32; ++i) {
+              const float sv = __uint_as_float(v[i]);
+              const bool ok = c0 + i < kv_left;
+              if (ok) raw_max = fmaxf(raw_max, sv);
+              const float e = ok ? ex2(fmaf(sv, p.scale_log2, nref)) : 0.f;
+              pf[i] = e;
+              rs += e;
+            }
+          }
+          // 32 keys = 4 chunks of 16 bytes; chunk index within the 128-key row: c0/8 + q
+          uint8_t* sub = p_row + (c0 >> 6) * (kTile * 128);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int cc = ((c0 & 63) >> 3) + q;
+            uint4 pk;
+            pk.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
+            pk.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
+            pk.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
+            pk.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(sub + ((cc ^ sw) << 4)) = pk;
+          }
         }
-      }
-      const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-      l_run = l_run * alpha + rs;
-      // lazy correction of the O accumulator (skipped while the running max is stable)
-      if (j > 0) {
-        const bool need = m_new > m_run;
-        if (__any_sync(0xffffffffu, need)) {
+      };
+      // (the P buffer is free: PV(j-1) completion was observed at the end of the previous iteration)
+      exp_pass(m_ref);
+      const float tile_max = raw_max * p.scale_log2;
+      if (__any_sync(0xffffffffu, tile_max > m_ref + kLazy)) {
+        // rare: raise the reference for the rows that need it, rescale l and O, redo this tile's P
+        const float new_ref = fmaxf(m_ref, tile_max);
+        const float alpha = ex2(m_ref - new_ref);  // 1 for rows that keep their reference
+        l_run *= alpha;
+        if (j > 0) {
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 16) {
             uint32_t ov[16];
@@ -227,8 +251,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           tmem_wait_st();
         }
+        m_ref = new_ref;
+        exp_pass(m_ref);
       }
-      m_run = m_new;
+      l_run += rs;
       fence_proxy_async();  // P stores (generic proxy) -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
