@@ -146,7 +146,8 @@ int t2v_attn_short_fwd(const T2VShortAttnDesc* desc, t2v_stream_t stream);
  * openaimodel3d.py:732-734) — the output is the normalised concatenation.
  * Replaces GroupNorm32/normalization (basics.py:78-89), nn.GroupNorm (attention.py:340-342,
  * openaimodel3d.py:275-295, ae_modules.py:16-19) and the following SiLU / swish.
- * workspace: fp32 [n_samples * groups * 2], zero-filled by the call itself.
+ * workspace: fp32 [n_samples * groups * 2 + 1]; must be ZERO on entry and is left zeroed on return (the
+ * kernels clean it themselves, so a buffer zeroed once at allocation can be reused by every call on a stream).
  */
 typedef struct T2VGroupNormDesc {
   const void* x[2]; int32_t ch[2];      /* bf16 sources, channels per source (ch[1] = 0 if single) */

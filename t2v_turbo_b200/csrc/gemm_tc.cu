@@ -95,22 +95,19 @@ struct GemmCfg {
   static constexpr int kBarBytes = (2 * kMaxStages + 5 + kEpiWGs * kEpiBufs) * 8 + 16 + 16 + 2 * 256 * 4;
 };
 
-// gelu_erf(g) = g * Phi(g),  Phi(g) = 1 - 0.5 erfc(|g|/sqrt2) for g >= 0, 0.5 erfc(|g|/sqrt2) otherwise;
-// erfc(u) ~ t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-u^2), t = 1/(1 + p u)  (Abramowitz-Stegun 7.1.26,
-// |error| <= 1.5e-7).  The 0.5 and the exp->exp2 scale are folded into the constants:
-// 2 MUFU (rcp, ex2) + ~13 FMA-pipe instructions per element.
+// erf-GELU: g * Phi(g) with Phi(g) = sigmoid(g (c0 + c1 g^2 + c2 g^4)) — a minimax fit of logit(Phi) by an odd
+// polynomial, max |error| 2.6e-5 over the reals (0.3 % of a bf16 ulp at unit scale; scripts in DESIGN.md §3).
+// g^2 is clamped at 81 so the quartic term cannot turn the polynomial over for huge |g|.
+// Cost: 5 FMA-pipe + 1 min + 2 MUFU (ex2, rcp); the GEGLU epilogue is FMA-pipe bound, so this matters.
 __device__ __forceinline__ float gelu_erf(float g) {
-  constexpr float kS = 1.2011224087864498f;                 // sqrt(log2 e)
-  const float up = fabsf(g) * (0.70710678118654752f * kS);  // u * sqrt(log2 e)
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f / kS, up, 1.0f)));
-  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-  p = fmaf(p, t, 0.5f * 1.421413741f);
-  p = fmaf(p, t, 0.5f * -0.284496736f);
-  p = fmaf(p, t, 0.5f * 0.254829592f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-up * up));
-  const float h = p * t * e;  // 0.5 erfc(|g| / sqrt2)
-  return g * (g >= 0.f ? 1.0f - h : h);
+  constexpr float kL = -1.4426950408889634f;  // -log2(e): sigmoid(p) = 1 / (1 + 2^(-p log2 e))
+  const float g2 = fminf(g * g, 81.0f);
+  float p = fmaf(g2, kL * -0.0007030335803817405f, kL * 0.07401129203239541f);
+  p = fmaf(g2, p, kL * 1.5950157686368724f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(g * p));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return g * r;
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -409,20 +406,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               tmem_ld_32x32(taddr + c * acc_cw + 32, v);
               tmem_wait_ld();
             }
+            float bv[32];
+            if (bias_uniform) {
+              const float4* b4 = reinterpret_cast<const float4*>(sbias + c * acc_cw + hh * 32);
+#pragma unroll
+              for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 t4 = b4[k4];
+                bv[4 * k4 + 0] = t4.x;
+                bv[4 * k4 + 1] = t4.y;
+                bv[4 * k4 + 2] = t4.z;
+                bv[4 * k4 + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bv[j] = bias != nullptr ? __ldg(bias + n0 + hh * 32 + j) : 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float a = __uint_as_float(v[j]);
               float gt = __uint_as_float(v[j + 16]);
-              if (!alpha_one) {
-                a *= p.alpha;
-                gt *= p.alpha;
-              }
-              if (bias_uniform) {
-                a += sbias[c * acc_cw + hh * 32 + j];
-                gt += sbias[c * acc_cw + hh * 32 + 16 + j];
-              } else if (bias != nullptr) {
-                a += __ldg(bias + n0 + hh * 32 + j);
-                gt += __ldg(bias + n0 + hh * 32 + 16 + j);
+              if (alpha_one) {
+                a += bv[j];
+                gt += bv[j + 16];
+              } else {
+                a = fmaf(p.alpha, a, bv[j]);
+                gt = fmaf(p.alpha, gt, bv[j + 16]);
               }
               f[hh * 16 + j] = a * gelu_erf(gt);
             }

@@ -31,6 +31,7 @@ struct GnParams {
   float eps;
   int32_t silu;
   float* ws;
+  unsigned* ticket;  // lives right after the sums in the workspace
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -114,9 +115,31 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
     atomicAdd(&p.ws[int64_t(sample) * 2 * p.groups + i], s_acc[i]);
 }
 
+// The statistics workspace is SELF-CLEANING: every apply block copies its sample's sums to shared memory, then
+// takes a ticket; the block that draws the last ticket knows every block has read the sums and zeroes them (and
+// the ticket counter), so the next GroupNorm call finds a zeroed workspace without a memset / zero kernel.
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) {
   pdl_launch_dependents();
   pdl_wait();
+  __shared__ float s_ws[2 * 64];
+  __shared__ int s_last;
+  {
+    const float* wsg = p.ws + int64_t(blockIdx.y) * 2 * p.groups;
+    for (int i = threadIdx.x; i < 2 * p.groups; i += blockDim.x) s_ws[i] = __ldcg(wsg + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned total = gridDim.x * gridDim.y;
+      const unsigned ticket = atomicAdd(p.ticket, 1u);
+      s_last = (ticket == total - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      const int n = 2 * p.groups * int(gridDim.y);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) p.ws[i] = 0.f;
+      if (threadIdx.x == 0) *p.ticket = 0u;
+    }
+  }
   const int sample = blockIdx.y;
   const int64_t row_begin = int64_t(blockIdx.x) * p.rows_per_block;
   int64_t row_end = row_begin + p.rows_per_block;
@@ -124,10 +147,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) 
   const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;
   const int rpp = kGnThreads / tpr;
   const int rr = threadIdx.x / tpr;
-  if (rr >= rpp) return;
+  if (rr >= rpp) return;  // (after the block-wide ticket protocol above)
   const int64_t base_row = int64_t(sample) * p.rows_per_sample;
   const float inv_n = 1.0f / (float(p.rows_per_sample) * float(p.cpg));
-  const float* ws = p.ws + int64_t(sample) * 2 * p.groups;
+  const float* ws = s_ws;
   for (int cv = threadIdx.x % tpr; cv < p.ncv; cv += tpr) {
     float sc[8], sh[8];
 #pragma unroll
@@ -300,7 +323,8 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   rpb = (rpb + rpp - 1) / rpp * rpp;
   p.rows_per_block = int(rpb);
   const int64_t bps = (d->rows_per_sample + rpb - 1) / rpb;
-  launch_kernel(gn_zero_kernel, dim3(1), dim3(256), 0, stream, d->workspace, int(2 * d->groups * n_samples));
+  // workspace layout: [n_samples][groups][2] sums + one ticket word; zero on entry (self-cleaning, see gn_apply_kernel)
+  p.ticket = reinterpret_cast<unsigned*>(d->workspace + 2 * d->groups * n_samples);
   cudaError_t e;
   dim3 grid((unsigned)bps, (unsigned)n_samples);
   launch_kernel(gn_stats_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);

@@ -312,7 +312,7 @@ def _gn_workspace(device, n):
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _GN_WS.get(key)
     if ws is None or ws.numel() < n:
-        ws = torch.empty(max(n, 4096), device=device, dtype=torch.float32)
+        ws = torch.zeros(max(n, 4096), device=device, dtype=torch.float32)   # zero once: t2v_groupnorm leaves it clean
         _GN_WS[key] = ws
     return ws
 
@@ -343,7 +343,7 @@ def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None
     d.groups = groups
     d.eps = eps
     d.silu = 1 if silu else 0
-    ws = _gn_workspace(x0.device, 2 * groups * (rows // rows_per_sample))
+    ws = _gn_workspace(x0.device, 2 * groups * (rows // rows_per_sample) + 1)
     d.workspace = ws.data_ptr()
     _launch("groupnorm", _FLOPS.pop("groupnorm", 0), lib().t2v_groupnorm, C.byref(d), stream_ptr())
     return out
