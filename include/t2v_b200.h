@@ -92,7 +92,7 @@ typedef struct T2VGemmDesc {
    * 0 = automatic (only when a large-enough workspace is given and the tile grid cannot fill the SMs),
    * 1 = off.  Not available with GEGLU or batched B. */
   int32_t split_k;
-  int32_t tune;                         /* 0 = defaults. bits 0-7: pipeline stages to use; bit 8: separate TMA producer threads for A and B; bit 10: enable the weight-stationary mode (keeps the [BN x K] slab in smem; measured slower); bit 11: disable CTA pairs (cta_group::2); bits 12-15: timing experiments (wrong results) */
+  int32_t tune;                         /* 0 = defaults. bits 0-7: pipeline stages to use; bit 11: disable CTA pairs (cta_group::2); bits 12-15: timing experiments (wrong results) */
   void* workspace;
   int64_t workspace_bytes;
 } T2VGemmDesc;

@@ -61,11 +61,7 @@ struct GemmParams {
   float* ws;  // split-K workspace [points][N] fp32
   int32_t epi_mode;  // 0 = direct row stores, 1 = smem-staged TMA store (+ TMA residual load)
   int32_t n_stages;  // pipeline stages in use
-  int32_t b_resident;     // 1: the CTA keeps its whole [BN x K] weight slab in smem and streams A only
-  uint32_t stage_bytes;   // bytes per pipeline stage (A tile, + B tile unless resident)
-  uint32_t smem_ring_off; // offset of the stage ring (after the resident B slab, if any)
   uint32_t smem_epi_off;  // offset of the epilogue staging buffers
-  int32_t split_producers;  // 1: warp 0 loads A, warp 3 loads B
   int32_t dbg;              // timing experiments only (results are wrong when non-zero)
 };
 
@@ -125,19 +121,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint8_t* smem_ring = smem + p.smem_ring_off;  // resident B slab (if any) lives in [smem, smem_ring)
   uint8_t* smem_epi = smem + p.smem_epi_off;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* bres_bar = tempty_bar + 2;  // resident weight slab landed
-  uint64_t* res_bar = bres_bar + 1;     // [2 warpgroups][kEpiBufs]
+  uint64_t* res_bar = tempty_bar + 2;  // [kEpiWGs][kEpiBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWGs * kEpiBufs);
   // [2 accumulators][256] floats, 16-byte aligned for float4 reads
   float* bias_smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);  // provably warp-uniform (see the role branches)
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const int tile0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
@@ -154,10 +148,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(&full_bar[s], (!PAIR && p.split_producers) ? 2 : 1);
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(bres_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], PAIR ? 2 * kEpiWarps : kEpiWarps);  // PAIR: both CTAs' epilogues release the leader
@@ -182,20 +175,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
 
-  if ((warp == 0 || (warp == 3 && p.split_producers)) && lane == 0) {
-    // ------------------------------------------------------------ TMA producer(s)
-    const bool do_a = (warp == 0);
-    const bool do_b = !p.b_resident && (p.split_producers ? (warp == 3) : true);
+  // Role branches: `warp` is broadcast through a shuffle so that the compiler can prove it warp-uniform, and the
+  // single issuing lane is chosen by elect.sync.  With a plain `threadIdx.x == k` test ptxas treats every value in
+  // the branch as divergent and wraps each TMA / MMA instruction in a waterfall loop of R2UR.BROADCASTs (measured:
+  // 12-24 % of the conv GEMMs' time, because the single issuing thread could no longer keep up with the tensor pipe).
+  if (warp == 0 && elect_one()) {
+    // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    if (p.b_resident && warp == 0) {
-      // weight-stationary: this CTA only ever works on n-tile (blockIdx.x % n_tiles_n) — the grid is a
-      // multiple of n_tiles_n — so its [BN x K] slab is loaded once and every tile streams A only
-      const int n_tile = blockIdx.x % p.n_tiles_n;
-      mbar_expect_tx(bres_bar, uint32_t(p.total_kb) * uint32_t(Cfg::kBTileBytes));
-      for (int kb = 0; kb < p.total_kb; ++kb)
-        tma_load_3d(smem + kb * Cfg::kBTileBytes, &tmB, bres_bar, kb * kBlockK, n_tile * BN, 0);
-    }
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
       const int ks = tile / p.n_tiles_mn;
       const int mn = tile - ks * p.n_tiles_mn;
@@ -211,62 +198,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j == p.b_batch_dim) bbatch = o[j];
+      const int b_row = PAIR ? n_tile * BN + int(cta_rank) * (BN / 2) : n_tile * BN;
       const int kb_begin = ks * p.kb_per_split;
       const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
       int tap = kb_begin / p.kb_per_tap;
       int kb = kb_begin - tap * p.kb_per_tap;
-      for (int idx = kb_begin; idx < kb_end; ++idx) {
-        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sA = smem_ring + stage * p.stage_bytes;
-        uint8_t* sB = sA + kATileBytes;
-        if (PAIR) {
-          // The leader's barrier expects the bytes of BOTH CTAs; the peer only issues its loads (their
-          // complete_tx lands on the leader's barrier).  The peer can never run a phase ahead: its stage is
-          // released by the same multicast commit that follows the leader's barrier completing.  (A remote
-          // arrive per k-block would cost a cluster-scope release fence on the critical path.)
-          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (p.a_tile_bytes + uint32_t(Cfg::kBTileBytes)));
-          const int c1 = o[0] + p.tap_off[tap][0];
-          const int c2 = o[1] + p.tap_off[tap][1];
-          const int c3 = o[2] + p.tap_off[tap][2];
-          const int c4 = o[3] + p.tap_off[tap][3];
-          const int ch0 = p.tap_ch_off[tap];
-          if (kb < p.kb_src0)
-            tma_load_5d_2sm(sA, &tmA0, &full_bar[stage], ch0 + kb * kBlockK, c1, c2, c3, c4);
-          else
-            tma_load_5d_2sm(sA, &tmA1, &full_bar[stage], ch0 + (kb - p.kb_src0) * kBlockK, c1, c2, c3, c4);
-          tma_load_3d_2sm(sB, &tmB, &full_bar[stage], idx * kBlockK, n_tile * BN + int(cta_rank) * (BN / 2), 0);
-        } else {
-        mbar_expect_tx(&full_bar[stage], (do_a ? p.a_tile_bytes : 0u) + (do_b ? uint32_t(Cfg::kBTileBytes) : 0u));
-        if (do_a) {
-          const int c1 = o[0] + p.tap_off[tap][0];
-          const int c2 = o[1] + p.tap_off[tap][1];
-          const int c3 = o[2] + p.tap_off[tap][2];
-          const int c4 = o[3] + p.tap_off[tap][3];
-          const int ch0 = p.tap_ch_off[tap];
-          if (kb < p.kb_src0)
-            tma_load_5d(sA, &tmA0, &full_bar[stage], ch0 + kb * kBlockK, c1, c2, c3, c4);
-          else
-            tma_load_5d(sA, &tmA1, &full_bar[stage], ch0 + (kb - p.kb_src0) * kBlockK, c1, c2, c3, c4);
+      int idx = kb_begin;
+      while (idx < kb_end) {
+        // everything that depends on the tap is hoisted out of the per-k-block loop: the issuing thread has
+        // ~320 cycles per k-block at BN = 160 and every dependent instruction costs it 4+ of them
+        const int c1 = o[0] + p.tap_off[tap][0];
+        const int c2 = o[1] + p.tap_off[tap][1];
+        const int c3 = o[2] + p.tap_off[tap][2];
+        const int c4 = o[3] + p.tap_off[tap][3];
+        const int ch0 = p.tap_ch_off[tap];
+        const int kb_hi = min(p.kb_per_tap, kb + (kb_end - idx));
+        for (; kb < kb_hi; ++kb, ++idx) {
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          uint8_t* sB = sA + kATileBytes;
+          const bool src0 = kb < p.kb_src0;
+          const CUtensorMap* tmA = src0 ? &tmA0 : &tmA1;
+          const int ch = ch0 + (src0 ? kb : kb - p.kb_src0) * kBlockK;
+          if (PAIR) {
+            // The leader's barrier expects the bytes of BOTH CTAs; the peer only issues its loads (their
+            // complete_tx lands on the leader's barrier).  The peer can never run a phase ahead: its stage is
+            // released by the same multicast commit that follows the leader's barrier completing.  (A remote
+            // arrive per k-block would cost a cluster-scope release fence on the critical path.)
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (p.a_tile_bytes + uint32_t(Cfg::kBTileBytes)));
+            tma_load_5d_2sm(sA, tmA, &full_bar[stage], ch, c1, c2, c3, c4);
+            tma_load_3d_2sm(sB, &tmB, &full_bar[stage], idx * kBlockK, b_row, 0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], p.a_tile_bytes + uint32_t(Cfg::kBTileBytes));
+            tma_load_5d(sA, tmA, &full_bar[stage], ch, c1, c2, c3, c4);
+            tma_load_3d(sB, &tmB, &full_bar[stage], idx * kBlockK, b_row, bbatch);
+          }
+          if (++stage == p.n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        if (do_b) tma_load_3d(sB, &tmB, &full_bar[stage], idx * kBlockK, n_tile * BN, bbatch);
-        }
-        if (++kb == p.kb_per_tap) {
-          kb = 0;
-          ++tap;
-        }
-        if (++stage == p.n_stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        kb = 0;
+        ++tap;
       }
     }
-  } else if (warp == 1 && lane == 0 && (!PAIR || cta_rank == 0)) {
+  } else if (warp == 1 && (!PAIR || cta_rank == 0) && elect_one()) {
     // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA issues for both)
     constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    if (p.b_resident) mbar_wait(bres_bar, 0);
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const int ks = tile / p.n_tiles_mn;
       const int kb_begin = ks * p.kb_per_split;
@@ -279,10 +260,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_ring + stage * p.stage_bytes);
+        const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(p.b_resident ? smem_u32(smem + (kb_begin + kb) * Cfg::kBTileBytes)
-                                                            : a_addr + kATileBytes);
+        const uint64_t bdesc = umma_desc_sw128(a_addr + kATileBytes);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // advance 16 elements (32 bytes) along K inside the 128B swizzle atom: +2 in addr>>4 units
@@ -318,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int g = ew >> 2;
     const int r = lg * 32 + lane;
     const int et = ew * 32 + lane;  // 0..255 within the epilogue
-    const bool leader = (lg == 0 && lane == 0);
+    const bool lead_warp = (lg == 0);  // its elected lane issues this warpgroup's TMA loads / stores (always the same lane)
     const bool geglu = (p.flags & T2V_EPI_GEGLU) != 0;
     const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
     const bool has_res = p.residual != nullptr;
@@ -367,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           sbias[et] = n < p.n_rows_b ? __ldg(p.bias + bias_row_first * p.bias_row_stride + n) : 0.f;
         }
       }
-      if (has_res && leader) {
+      if (has_res && lead_warp && elect_one()) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int c = g + kEpiWGs * i;
@@ -499,7 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           fence_proxy_async();
           named_bar_sync(1 + g, 128);
         }
-        if (leader) {
+        if (lead_warp && elect_one()) {
           if (!(p.dbg & 1)) tma_store_5d(&tmOut, ebuf + buf * kEpiBufBytes, oc0, o[0], o[1], o[2], o[3]);
           bulk_commit_group();
           bulk_wait_group_read<1>();  // every store but the one just issued has finished reading smem
@@ -526,7 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
       }
     }
-    if (leader) bulk_wait_group_read<0>();
+    if (lead_warp && elect_one()) bulk_wait_group_read<0>();
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp - 4;
@@ -776,24 +756,12 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     grid = p.num_tiles < sms ? p.num_tiles : sms;
   }
   GemmParams pp = p;
-  int stages;
-  if (p.b_resident) {
-    const int slab = p.total_kb * Cfg::kBTileBytes;
-    pp.smem_ring_off = uint32_t(slab);
-    pp.stage_bytes = kATileBytes;
-    stages = (kSmemLimit - (Cfg::kBarBytes + 1024) - kEpiBytes - slab) / kATileBytes;
-    grid = (sms / p.n_tiles_n) * p.n_tiles_n;  // keeps n_tile fixed per CTA
-    if (grid > p.num_tiles) grid = p.num_tiles;
-  } else {
-    pp.smem_ring_off = 0;
-    pp.stage_bytes = Cfg::kStageBytes;
-    stages = Cfg::kStages;
-  }
+  int stages = Cfg::kStages;
   if (stages > kMaxStages) stages = kMaxStages;
   if (p.n_stages > 0 && p.n_stages < stages) stages = p.n_stages;
   if (stages < 2) return fail(-111, "gemm_tc: shared memory layout leaves %d pipeline stages", stages);
   pp.n_stages = stages;
-  pp.smem_epi_off = pp.smem_ring_off + uint32_t(stages) * pp.stage_bytes;
+  pp.smem_epi_off = uint32_t(stages) * uint32_t(Cfg::kStageBytes);
   const size_t smem_bytes = size_t(pp.smem_epi_off) + kEpiBytes + Cfg::kBarBytes + 1024;
   if (smem_bytes > size_t(kSmemLimit)) return fail(-112, "gemm_tc: %zu bytes of shared memory needed", smem_bytes);
   launch_kernel_cluster(gemm_tc_kernel<BN, PAIR>, dim3(grid), dim3(kThreads), smem_bytes, stream, PAIR ? 2u : 1u, a0, a1, b,
@@ -870,52 +838,6 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "t2v_gemm: no CUDA device");
   int bn = d->block_n;
-  // weight-stationary mode for small K: the CTA's [BN x K] slab stays in shared memory
-  bool resident = false;
-  if ((d->tune & 0x400) && d->b_batch_dim < 0 && d->split_k <= 1) {  // opt-in: measured slower than streaming
-    const int cands[4] = {256, 160, 128, 64};
-    double best = 0.0;
-    for (int i = 0; i < 4; ++i) {
-      const int c = cands[i];
-      if (bn != 0 && c != bn) continue;
-      if (geglu && c % 64 != 0) continue;
-      const int64_t slab = int64_t(c) * K * 2;
-      if (slab > 100 * 1024) continue;
-      const int64_t nt = (d->b_rows + c - 1) / c;
-      if (nt > sms) continue;
-      const int64_t ctas = (sms / nt) * nt;
-      if (m_tiles * nt < 3 * ctas) continue;  // needs several tiles per CTA to pay for the slab load
-      const double eff = double(ctas) / sms * double(d->b_rows) / double(nt * c) * (c >= 128 ? 1.0 : 0.85);
-      if (eff > best) {
-        best = eff;
-        if (eff >= 0.80) {
-          resident = true;
-          bn = c;
-        }
-      }
-    }
-    if (resident) {
-      // re-pick the best candidate (the loop keeps the last one above threshold; choose the max)
-      double top = 0.0;
-      int top_bn = bn;
-      for (int i = 0; i < 4; ++i) {
-        const int c = cands[i];
-        if (d->block_n != 0 && c != d->block_n) continue;
-        if (geglu && c % 64 != 0) continue;
-        if (int64_t(c) * K * 2 > 100 * 1024) continue;
-        const int64_t nt = (d->b_rows + c - 1) / c;
-        if (nt > sms) continue;
-        const int64_t ctas = (sms / nt) * nt;
-        if (m_tiles * nt < 3 * ctas) continue;
-        const double eff = double(ctas) / sms * double(d->b_rows) / double(nt * c) * (c >= 128 ? 1.0 : 0.85);
-        if (eff > top) {
-          top = eff;
-          top_bn = c;
-        }
-      }
-      bn = top_bn;
-    }
-  }
   if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
   p.n_tiles_n = int((d->b_rows + bn - 1) / bn);
@@ -988,16 +910,14 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   // CTA pairs (cta_group::2): 256-row tiles, each CTA stages half of the weight tile
   const int64_t pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
   // measured: +10 % at K >= 1024 (1441 TFLOP/s on 512->512 3x3 convs = the cuBLAS sustained level), a loss at small K
-  const bool pair = staged && !resident && !(d->tune & 0x800) && d->b_batch_dim < 0 && bn >= 128 && m_tiles >= 2 &&
+  const bool pair = staged && !(d->tune & 0x800) && d->b_batch_dim < 0 && bn >= 128 && m_tiles >= 2 &&
                     pair_tiles >= sms / 2 && p.total_kb >= 16;
   if (pair) {
     p.n_tiles_mn = int(pair_tiles);
     p.num_tiles = int(pair_tiles);
   }
   p.n_stages = d->tune & 0xff;  // 0 = all stages of the instantiation
-  p.split_producers = (d->tune & 0x100) ? 1 : 0;
   p.dbg = (d->tune >> 12) & 0xf;  // bit0: no TMA store, bit1: no smem write/fence/barrier, bit2: no TMEM loads
-  p.b_resident = (resident && split == 1) ? 1 : 0;
 
   // tensor maps
   CUtensorMap tmA[2], tmB, tmOut, tmRes;
