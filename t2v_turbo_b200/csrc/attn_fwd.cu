@@ -65,7 +65,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* pv_done = p_full + 1;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);  // provably warp-uniform: lean TMA / MMA issue code
   const int lane = threadIdx.x & 31;
 
   const int q_tile = blockIdx.x % p.n_q_tiles;
@@ -105,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_wait();
   const int n_kv = p.n_kv_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ------------------------------------------------------------ TMA producer
     mbar_expect_tx(q_full, kQBytes);
     tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
@@ -119,7 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_expect_tx(&v_full[s], kKBytes);
       tma_load_4d(sV + s * kKBytes, &tmV, &v_full[s], 0, h, j * kTile, kvb);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (K-major) x V (MN-major)
@@ -187,49 +187,58 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         m_ref = mx * p.scale_log2;
       }
       float rs = 0.f, raw_max = -INFINITY;
+      // One pass over the 128 scores of this row: the TMEM load of the next 32-column chunk is in flight while the
+      // current chunk is exponentiated and written to the P tile.
+      auto exp_chunk = [&](const uint32_t (&v)[32], int c0, float nref) {
+        uint32_t pk[16];
+        if (c0 + 32 <= kv_left) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+            raw_max = fmaxf(raw_max, fmaxf(s0, s1));
+            const float e0 = ex2(fmaf(s0, p.scale_log2, nref));
+            const float e1 = ex2(fmaf(s1, p.scale_log2, nref));
+            rs += e0 + e1;
+            pk[i >> 1] = pack_bf16(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+            const bool ok0 = c0 + i < kv_left, ok1 = c0 + i + 1 < kv_left;
+            if (ok0) raw_max = fmaxf(raw_max, s0);
+            if (ok1) raw_max = fmaxf(raw_max, s1);
+            const float e0 = ok0 ? ex2(fmaf(s0, p.scale_log2, nref)) : 0.f;
+            const float e1 = ok1 ? ex2(fmaf(s1, p.scale_log2, nref)) : 0.f;
+            rs += e0 + e1;
+            pk[i >> 1] = pack_bf16(e0, e1);
+          }
+        }
+        // 32 keys = 4 chunks of 16 bytes; chunk index within the 128-key row: c0/8 + q
+        uint8_t* sub = p_row + (c0 >> 6) * (kTile * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cc = ((c0 & 63) >> 3) + q;
+          *reinterpret_cast<uint4*>(sub + ((cc ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      };
       auto exp_pass = [&](float ref) {
         rs = 0.f;
         raw_max = -INFINITY;
         const float nref = -ref;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTile; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c0, v);
-          tmem_wait_ld();
-          float pf[32];
-          if (c0 + 32 <= kv_left) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float sv = __uint_as_float(v[i]);
-              raw_max = fmaxf(raw_max, sv);
-              const float e = ex2(fmaf(sv, p.scale_log2, nref));
-              pf[i] = e;
-              rs += e;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float sv = __uint_as_float(v[i]);
-              const bool ok = c0 + i < kv_left;
-              if (ok) raw_max = fmaxf(raw_max, sv);
-              const float e = ok ? ex2(fmaf(sv, p.scale_log2, nref)) : 0.f;
-              pf[i] = e;
-              rs += e;
-            }
-          }
-          // 32 keys = 4 chunks of 16 bytes; chunk index within the 128-key row: c0/8 + q
-          uint8_t* sub = p_row + (c0 >> 6) * (kTile * 128);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int cc = ((c0 & 63) >> 3) + q;
-            uint4 pk;
-            pk.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
-            pk.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
-            pk.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
-            pk.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(sub + ((cc ^ sw) << 4)) = pk;
-          }
-        }
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(s_addr, va);
+        tmem_wait_ld();
+        tmem_ld_32x32(s_addr + 32, vb);
+        exp_chunk(va, 0, nref);
+        tmem_wait_ld();
+        tmem_ld_32x32(s_addr + 64, va);
+        exp_chunk(vb, 32, nref);
+        tmem_wait_ld();
+        tmem_ld_32x32(s_addr + 96, vb);
+        exp_chunk(va, 64, nref);
+        tmem_wait_ld();
+        exp_chunk(vb, 96, nref);
       };
       // (the P buffer is free: PV(j-1) completion was observed at the end of the previous iteration)
       exp_pass(m_ref);
