@@ -146,6 +146,8 @@ int t2v_attn_short_fwd(const T2VShortAttnDesc* desc, t2v_stream_t stream);
  * openaimodel3d.py:732-734) — the output is the normalised concatenation.
  * Replaces GroupNorm32/normalization (basics.py:78-89), nn.GroupNorm (attention.py:340-342,
  * openaimodel3d.py:275-295, ae_modules.py:16-19) and the following SiLU / swish.
+ * Samples that fit a thread-block cluster's shared memory run as ONE kernel (cluster per sample, statistics
+ * exchanged through distributed shared memory, workspace untouched); larger samples use a statistics + apply pair.
  * workspace: fp32 [n_samples * groups * 2 + 1]; must be ZERO on entry and is left zeroed on return (the
  * kernels clean it themselves, so a buffer zeroed once at allocation can be reused by every call on a stream).
  */
@@ -157,6 +159,7 @@ typedef struct T2VGroupNormDesc {
   int64_t rows; int64_t rows_per_sample;
   int32_t groups; float eps; int32_t silu;
   float* workspace;
+  int32_t mode;                         /* 0 = automatic; 1 = force the two-kernel path; 2 = require the single-kernel cluster path */
 } T2VGroupNormDesc;
 
 int t2v_groupnorm(const T2VGroupNormDesc* desc, t2v_stream_t stream);

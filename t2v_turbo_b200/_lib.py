@@ -91,6 +91,7 @@ class GroupNormDesc(C.Structure):
         ("rows", C.c_int64), ("rows_per_sample", C.c_int64),
         ("groups", C.c_int32), ("eps", C.c_float), ("silu", C.c_int32),
         ("workspace", C.c_void_p),
+        ("mode", C.c_int32),
     ]
 
 

@@ -1,6 +1,11 @@
 // GroupNorm(+SiLU) and LayerNorm over channels-last bf16 activations (HBM-bound passes).
 //
-// GroupNorm is two kernels: a statistics pass (per-(sample, group) sum / sum-of-squares, fp32
+// GroupNorm has two implementations.  When one sample fits the shared memory of a thread-block cluster (every
+// UNet GroupNorm except the widest concatenated ones) ONE kernel does everything: the cluster's CTAs bulk-copy
+// their row slabs into shared memory, exchange per-group partial sums through distributed shared memory, and
+// normalise out of shared memory — the activation is read from HBM/L2 once and no workspace is touched.
+// Otherwise (VAE frames: up to 160k rows x 512 channels per sample) it
+// is two kernels: a statistics pass (per-(sample, group) sum / sum-of-squares, fp32
 // accumulation in registers -> shared -> one global atomic per group per block) and an apply pass
 // that folds mean / rstd / gamma / beta into one fma per element followed by SiLU.  Both passes
 // give each thread a FIXED 8-channel column (16-byte vector loads, fully coalesced across a row)
@@ -200,6 +205,137 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) 
   }
 }
 
+// ------------------------------------------------------------------ single-kernel GroupNorm: one cluster per sample
+constexpr int kGcThreads = 512;
+constexpr int kGcMaxSlab = 200 * 1024;   // per-CTA slab limit (1 CTA / SM); <= 110 KB lets two CTAs share an SM
+
+// grid = n_samples * CL CTAs, cluster = CL CTAs = one sample; CTA `rank` owns rows [rank*rpb, (rank+1)*rpb).
+// dynamic smem: [rpb rows x ncv x 16 B slab][2*groups partial sums][2*groups totals][mbarrier]
+__global__ void __launch_bounds__(kGcThreads) gn_cluster_kernel(const GnParams p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const uint32_t cl = cluster_nctarank();
+  const uint32_t rank = cluster_ctarank();
+  const int sample = blockIdx.x / cl;
+  const int64_t row_begin = int64_t(rank) * p.rows_per_block;
+  int64_t row_end = row_begin + p.rows_per_block;
+  if (row_end > p.rows_per_sample) row_end = p.rows_per_sample;
+  const int nrows = row_end > row_begin ? int(row_end - row_begin) : 0;
+  const uint32_t row_bytes = uint32_t(p.ncv) * 16u;
+  uint4* slab = reinterpret_cast<uint4*>(gsm);
+  float* s_acc = reinterpret_cast<float*>(gsm + size_t(p.rows_per_block) * row_bytes);
+  float* s_tot = s_acc + 128;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_tot + 128);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 2 * p.groups; i += blockDim.x) s_acc[i] = 0.f;
+  pdl_launch_dependents();
+  __syncthreads();
+  pdl_wait();
+  const int64_t base_row = int64_t(sample) * p.rows_per_sample + row_begin;
+  if (threadIdx.x < 32) {
+    // one bulk copy per row and source, issued by the 32 lanes of warp 0; all land on one mbarrier
+    if (threadIdx.x == 0) mbar_expect_tx(bar, uint32_t(nrows) * row_bytes);
+    __syncwarp();
+    const uint32_t b0 = uint32_t(p.ncv0) * 16u, b1 = row_bytes - b0;
+    if (b1 == 0 && p.rs0 == int64_t(p.ncv0) * 8) {
+      // dense rows: the slab is one contiguous range -> a few large copies instead of one per row
+      constexpr uint32_t kChunk = 8192;
+      const uint32_t total = uint32_t(nrows) * row_bytes;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.x0 + base_row * p.rs0);
+      for (uint32_t off = threadIdx.x * kChunk; off < total; off += 32 * kChunk)
+        bulk_load_1d(gsm + off, src + off, total - off < kChunk ? total - off : kChunk, bar);
+    } else {
+      for (int r = threadIdx.x; r < nrows; r += 32) {
+        uint8_t* dst = gsm + size_t(r) * row_bytes;
+        bulk_load_1d(dst, p.x0 + (base_row + r) * p.rs0, b0, bar);
+        if (b1) bulk_load_1d(dst + b0, p.x1 + (base_row + r) * p.rs1, b1, bar);
+      }
+    }
+  }
+  mbar_wait(bar, 0);
+
+  const int tpr = p.ncv < kGcThreads ? p.ncv : kGcThreads;  // threads per row
+  const int rpp = kGcThreads / tpr;                         // rows per pass
+  const int rr = threadIdx.x / tpr;
+  const int cv0 = threadIdx.x % tpr;
+  if (rr < rpp) {
+    for (int cv = cv0; cv < p.ncv; cv += tpr) {
+      float s[8], ss[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+      for (int r = rr; r < nrows; r += rpp) {
+        float f[8];
+        unpack8(slab[size_t(r) * p.ncv + cv], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[j];
+          ss[j] += f[j] * f[j];
+        }
+      }
+      int g_prev = (cv * 8) / p.cpg;
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (cv * 8 + j) / p.cpg;
+        if (g != g_prev) {
+          atomicAdd(&s_acc[2 * g_prev], a);
+          atomicAdd(&s_acc[2 * g_prev + 1], b);
+          a = b = 0.f;
+          g_prev = g;
+        }
+        a += s[j];
+        b += ss[j];
+      }
+      atomicAdd(&s_acc[2 * g_prev], a);
+      atomicAdd(&s_acc[2 * g_prev + 1], b);
+    }
+  }
+  cluster_sync_all();  // every CTA's partial sums are final (release / acquire at cluster scope)
+  if (threadIdx.x < 2 * p.groups) {
+    float t = 0.f;
+    for (uint32_t k = 0; k < cl; ++k) t += ld_dsmem_f32(s_acc + threadIdx.x, k);
+    s_tot[threadIdx.x] = t;
+  }
+  cluster_sync_all();  // totals visible block-wide; no CTA runs ahead (or exits) while a peer still reads its sums
+
+  if (rr >= rpp) return;
+  const float inv_n = 1.0f / (float(p.rows_per_sample) * float(p.cpg));
+  for (int cv = cv0; cv < p.ncv; cv += tpr) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cv * 8 + j;
+      const int g = c / p.cpg;
+      const float mean = s_tot[2 * g] * inv_n;
+      float var = s_tot[2 * g + 1] * inv_n - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      const float rstd = rsqrtf(var + p.eps);
+      const float ga = __ldg(p.gamma + c);
+      sc[j] = rstd * ga;
+      sh[j] = __ldg(p.beta + c) - mean * rstd * ga;
+    }
+    __nv_bfloat16* op = p.out + cv * 8 + base_row * p.out_rs;
+    for (int r = rr; r < nrows; r += rpp) {
+      float f[8];
+      unpack8(slab[size_t(r) * p.ncv + cv], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(f[j], sc[j], sh[j]);
+        if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+        f[j] = y;
+      }
+      uint4 o;
+      o.x = pack_bf16(f[0], f[1]);
+      o.y = pack_bf16(f[2], f[3]);
+      o.z = pack_bf16(f[4], f[5]);
+      o.w = pack_bf16(f[6], f[7]);
+      *reinterpret_cast<uint4*>(op + int64_t(r) * p.out_rs) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm: one warp per row
 struct LnParams {
   const __nv_bfloat16* x;
@@ -311,10 +447,43 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   p.eps = d->eps;
   p.silu = d->silu;
   p.ws = d->workspace;
-  const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;
-  const int rpp = kGnThreads / tpr;
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "t2v_groupnorm: no CUDA device");
+  // ---- single-kernel path: one thread-block cluster per sample, the sample lives in the cluster's shared memory
+  // Measured on B200 (scripts/gn_bench.py): the cluster kernel wins only while the whole tensor is small (its load /
+  // reduce / store phases run in lock-step across the GPU); above ~4 MB the statistics + apply pair streams better.
+  const bool small = d->rows * int64_t(C) * 2 <= (4 << 20);
+  if (d->mode == 2 || (d->mode == 0 && small)) {
+    static int max_cl = -1;  // largest usable cluster size (16 needs the non-portable opt-in)
+    if (max_cl < 0) {
+      cudaError_t e1 = cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGcMaxSlab + 2048);
+      cudaError_t e2 = cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      max_cl = (e1 == cudaSuccess) ? (e2 == cudaSuccess ? 16 : 8) : 0;
+      (void)cudaGetLastError();
+    }
+    const int64_t row_bytes = int64_t(C) * 2;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d->x[0]) % 16 == 0) &&
+                         (d->ch[1] == 0 || reinterpret_cast<uintptr_t>(d->x[1]) % 16 == 0);
+    while (max_cl >= 1 && aligned) {
+      int cl = max_cl;
+      while (cl > 1 && (d->rows_per_sample + cl - 1) / cl < 8) cl >>= 1;  // keep >= 8 rows per CTA
+      const int64_t rpb = (d->rows_per_sample + cl - 1) / cl;
+      const int64_t slab = rpb * row_bytes;
+      if (slab > kGcMaxSlab || n_samples * cl > 0x7fffffff) break;
+      p.rows_per_block = int(rpb);
+      p.ticket = nullptr;
+      const size_t smem = size_t(slab) + 2 * 128 * sizeof(float) + 16;
+      cudaError_t e = launch_kernel_cluster(gn_cluster_kernel, dim3(unsigned(n_samples * cl)), dim3(kGcThreads), smem,
+                                            stream, unsigned(cl), p);
+      if (e == cudaSuccess) return 0;
+      (void)cudaGetLastError();
+      if (cl < max_cl) break;  // the failure is not about the cluster size
+      max_cl = cl / 2;         // this device cannot co-schedule clusters of `cl` CTAs: never ask again
+    }
+    if (d->mode == 2) return fail(-9, "t2v_groupnorm: the single-kernel cluster path is not available for this shape");
+  }
+  const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;
+  const int rpp = kGnThreads / tpr;
   int64_t want_blocks = (int64_t(sms) * 4 + n_samples - 1) / n_samples;
   if (want_blocks < 1) want_blocks = 1;
   int64_t rpb = (d->rows_per_sample + want_blocks - 1) / want_blocks;

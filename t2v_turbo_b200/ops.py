@@ -277,6 +277,49 @@ def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0):
         bias_row_stride=0, bias_dim=-1, block_n=block_n)
 
 
+# nearest-2x upsample + 3x3 conv == four 2x2 convs on the LOW-resolution input, one per output parity (py, px):
+# output row 2y+py reads upsampled rows 2y+py-1 .. 2y+py+1, i.e. source rows {y-1, y, y} (py=0) or {y, y, y+1}
+# (py=1); taps that hit the same source row are pre-summed.  Zero padding of the upsampled image maps onto TMA
+# out-of-bounds zero fill of the source.  4/9 of the FLOPs and no materialised upsampled tensor.
+_UP_ROWS = (((-1, (0,)), (0, (1, 2))), ((0, (0, 1)), (1, (2,))))   # parity -> [(source offset, kernel taps summed)]
+
+
+def pack_upconv_weight(w):
+    """conv weight [Cout, Cin, 3, 3] after a nearest-2x upsample -> bf16 [4 phases][Cout, 4*Cin] (tap-major K)."""
+    w = w.detach().float()
+    phases = []
+    for py in range(2):
+        for px in range(2):
+            taps = []
+            for _, kys in _UP_ROWS[py]:
+                for _, kxs in _UP_ROWS[px]:
+                    taps.append(sum(w[:, :, ky, kx] for ky in kys for kx in kxs))
+            phases.append(torch.cat(taps, dim=1))
+    return torch.stack(phases).to(BF16).contiguous()
+
+
+def upconv3x3(x, w_phases, bias=None, *, out=None, block_n=0):
+    """Upsample(nearest, 2x) + Conv2d(3x3, pad 1) (openaimodel3d.py:75-108, ae_modules.py:50-63) on [N,H,W,C]
+    -> [N,2H,2W,Cout].  w_phases from pack_upconv_weight; bias fp32 [Cout]."""
+    _check_act(x)
+    n, h, wd, c = x.shape
+    cout = w_phases.shape[1]
+    assert w_phases.shape == (4, cout, 4 * c), (w_phases.shape, c)
+    if out is None:
+        out = torch.empty((n, 2 * h, 2 * wd, cout), device=x.device, dtype=BF16)
+    box = plan_box((wd, h, n, 1))
+    for py in range(2):
+        for px in range(2):
+            taps = [(dx, dy, 0, 0) for dy, _ in _UP_ROWS[py] for dx, _ in _UP_ROWS[px]]
+            _gemm_raw(
+                a=(x, None), a_ch=(c, 0), a_ch_total=(c, 0), a_size=(wd, h, n, 1),
+                a_stride=((c, wd * c, h * wd * c, 0), None), box=box, taps=taps, tap_ch_off=None,
+                w=w_phases[2 * py + px], n_rows=cout, out=out[:, py::2, px::2, :],
+                o_size=(wd, h, n, 1), o_stride=(2 * cout, 4 * wd * cout, 4 * h * wd * cout, 0), n_out=cout,
+                bias=bias, bias_row_stride=0, bias_dim=-1, block_n=block_n)
+    return out
+
+
 def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0, split_k=0):
     """Conv3d (3,1,1) / pad (1,0,0) over x: [B, T, HW, C] (TemporalConvBlock, openaimodel3d.py:274-296).
     w: [Cout, 3*C] packed."""
@@ -317,7 +360,7 @@ def _gn_workspace(device, n):
     return ws
 
 
-def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None):
+def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None, mode=0):
     """GroupNorm(+SiLU) over token matrix x: [rows, C] (or a pair concatenated along C)."""
     x0, x1 = _as_pair(x)
     x0 = x0.reshape(-1, x0.shape[-1])
@@ -345,6 +388,7 @@ def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None
     d.silu = 1 if silu else 0
     ws = _gn_workspace(x0.device, 2 * groups * (rows // rows_per_sample) + 1)
     d.workspace = ws.data_ptr()
+    d.mode = mode   # 0 auto, 1 two-kernel path, 2 single-kernel cluster path (tests)
     _launch("groupnorm", _FLOPS.pop("groupnorm", 0), lib().t2v_groupnorm, C.byref(d), stream_ptr())
     return out
 

@@ -337,7 +337,7 @@ class UNetModel(nn.Module):
                 elif isinstance(layer, Downsample):
                     items.append(("down", (ops.pack_conv_weight(layer.op.weight.detach()), _f32(layer.op.bias))))
                 elif isinstance(layer, Upsample):
-                    items.append(("up", (ops.pack_conv_weight(layer.conv.weight.detach()), _f32(layer.conv.bias).view(1, -1))))
+                    items.append(("up", (ops.pack_upconv_weight(layer.conv.weight), _f32(layer.conv.bias))))
                 elif isinstance(layer, nn.Conv2d):
                     items.append(("conv_in", None))
                 else:
@@ -494,7 +494,7 @@ class UNetModel(nn.Module):
                 hh, ww = hh // 2, ww // 2
                 geom = (b, t, hh, ww)
             elif kind == "up":
-                h = ops.conv3x3(ops.upsample_nearest2x(h), pk[0], pk[1], bias_div=b * t)
+                h = ops.upconv3x3(h, pk[0], pk[1])
                 hh, ww = hh * 2, ww * 2
                 geom = (b, t, hh, ww)
             elif kind == "conv_in":

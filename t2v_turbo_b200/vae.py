@@ -143,7 +143,7 @@ class AutoencoderKL(nn.Module):
             blocks = [_PRes(b) for b in up.block]
             ups = None
             if i_level != 0:
-                ups = (ops.pack_conv_weight(up.upsample.conv.weight.detach()), _f32(up.upsample.conv.bias).view(1, -1))
+                ups = (ops.pack_upconv_weight(up.upsample.conv.weight), _f32(up.upsample.conv.bias))
             P["up"].append((blocks, ups))
         P["norm_out"] = (_f32(d.norm_out.weight), _f32(d.norm_out.bias))
         P["conv_out"] = (ops.pack_conv_weight(d.conv_out.weight.detach()), _f32(d.conv_out.bias).view(1, -1), d.conv_out.weight.shape[0])
@@ -202,7 +202,7 @@ class AutoencoderKL(nn.Module):
             for pr in blocks:
                 h = self._res(pr, h)
             if ups is not None:
-                h = ops.conv3x3(ops.upsample_nearest2x(h), ups[0], ups[1], bias_div=h.shape[0])
+                h = ops.upconv3x3(h, ups[0], ups[1])
         n, hh2, ww2, ch = h.shape
         hn = ops.groupnorm(h.view(-1, ch), P["norm_out"][0], P["norm_out"][1], rows_per_sample=hh2 * ww2, eps=1e-6, silu=True)
         w, bias, cout = P["conv_out"]

@@ -196,6 +196,21 @@ def test_conv3x3_s2(cuda_device, n, h, w, cin, cout):
     assert_close(out, ref, what="conv3x3 s2")
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 16, 64, 64), (3, 20, 32, 128, 64), (2, 5, 8, 128, 256), (1, 40, 64, 64, 128)])
+def test_upconv3x3(cuda_device, n, h, w, cin, cout):
+    """nearest-2x upsample + 3x3 conv as four pre-summed 2x2 convs on the low-resolution input
+    (reference: Upsample.forward, openaimodel3d.py:96-108 / ae_modules.py:58-63)."""
+    ops = _ops()
+    x = rnd(n, h, w, cin, seed=29).to(BF16)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=30).to(BF16)
+    b = rnd(cout, seed=31)
+    out = ops.upconv3x3(x, ops.pack_upconv_weight(wt), b)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, wt.float(), b, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert_close(out, ref, what="upconv3x3")
+
+
 @pytest.mark.parametrize("b,t,hw,c", [(1, 16, 40, 128), (2, 4, 160, 64), (1, 16, 640, 64)])
 def test_tconv3(cuda_device, b, t, hw, c):
     ops = _ops()
@@ -229,13 +244,16 @@ def test_conv_small_cin(cuda_device):
 
 
 # ----------------------------------------------------------------------------- norms
-@pytest.mark.parametrize("n,hw,c,rps_mult,silu", [(4, 160, 320, 1, True), (2, 40, 1280, 2, True), (6, 64, 128, 3, False)])
-def test_groupnorm(cuda_device, n, hw, c, rps_mult, silu):
+# mode 1 = statistics + apply kernel pair, mode 2 = single-kernel cluster path (must not fall back), 0 = automatic
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n,hw,c,rps_mult,silu", [(4, 160, 320, 1, True), (2, 40, 1280, 2, True), (6, 64, 128, 3, False),
+                                                  (16, 2560, 320, 1, True), (3, 77, 64, 1, False), (2, 7, 2560, 1, True)])
+def test_groupnorm(cuda_device, n, hw, c, rps_mult, silu, mode):
     ops = _ops()
     x = (rnd(n * hw, c, seed=34) * 2 + 0.5).to(BF16)
     g = rnd(c, seed=35) * 0.2 + 1
     b = rnd(c, seed=36) * 0.2
-    out = ops.groupnorm(x, g, b, rows_per_sample=hw * rps_mult, eps=1e-5, silu=silu)
+    out = ops.groupnorm(x, g, b, rows_per_sample=hw * rps_mult, eps=1e-5, silu=silu, mode=mode)
     xs = x.float().view(n // rps_mult, hw * rps_mult, c).permute(0, 2, 1)
     ref = F.group_norm(xs, 32, g, b, 1e-5)
     if silu:
@@ -244,7 +262,22 @@ def test_groupnorm(cuda_device, n, hw, c, rps_mult, silu):
     assert_close(out, ref, what="groupnorm")
 
 
-def test_groupnorm_concat(cuda_device):
+def test_groupnorm_too_large_for_cluster(cuda_device):
+    """A VAE-sized sample (40960 rows x 128 ch = 10 MB) cannot live in a cluster's shared memory: automatic mode
+    uses the two-kernel path, and demanding the cluster path is an error rather than a silent fallback."""
+    ops = _ops()
+    x = rnd(40960, 128, seed=44).to(BF16)
+    g = rnd(128, seed=45) * 0.2 + 1
+    b = rnd(128, seed=46) * 0.2
+    out = ops.groupnorm(x, g, b, rows_per_sample=40960, eps=1e-6, silu=True)
+    ref = F.silu(F.group_norm(x.float().view(1, 40960, 128).permute(0, 2, 1), 32, g, b, 1e-6)).permute(0, 2, 1).reshape(40960, 128)
+    assert_close(out, ref, what="groupnorm big")
+    with pytest.raises(RuntimeError):
+        ops.groupnorm(x, g, b, rows_per_sample=40960, eps=1e-6, silu=True, mode=2)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_groupnorm_concat(cuda_device, mode):
     ops = _ops()
     n, hw = 3, 160
     xa = rnd(n * hw, 1280, seed=37).to(BF16)
@@ -252,7 +285,7 @@ def test_groupnorm_concat(cuda_device):
     c = 1920
     g = rnd(c, seed=39) * 0.2 + 1
     b = rnd(c, seed=40) * 0.2
-    out = ops.groupnorm((xa, xb), g, b, rows_per_sample=hw, eps=1e-5, silu=True)
+    out = ops.groupnorm((xa, xb), g, b, rows_per_sample=hw, eps=1e-5, silu=True, mode=mode)
     xs = torch.cat([xa, xb], 1).float().view(n, hw, c).permute(0, 2, 1)
     ref = F.silu(F.group_norm(xs, 32, g, b, 1e-5)).permute(0, 2, 1).reshape(n * hw, c)
     assert_close(out, ref, what="groupnorm concat")
