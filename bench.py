@@ -41,6 +41,18 @@ def peaks():
     return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+def ncu_gemm_traffic():
+    """DRAM bytes (read + write) per gemm_tc launch, averaged over the launches of one pipeline step, from the committed
+    ncu capture of scripts/profile_step.py (profiles/README.md); None when the summary is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_launches_step_v5_summary.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    rows = [v for k, v in d.items() if "gemm_tc_kernel" in k]
+    n = sum(v["launches"] for v in rows)
+    return sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in rows) / n if n else None
+
+
 class ClockSampler:
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
@@ -261,7 +273,7 @@ def main():
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     roofline = dict(bound="tensor", kernel="gemm_tc_kernel (all Linear / Conv2d / Conv3d launches of one pipeline call)",
                     achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"], peak_source=pk["src"],
-                    traffic=None, launches=gemm["calls"], avg_launch_us=gemm["ms"] * 1e3 / max(1, gemm["calls"]),
+                    traffic=ncu_gemm_traffic(), traffic_unit="DRAM bytes per launch (ncu, avg over one step)", launches=gemm["calls"], avg_launch_us=gemm["ms"] * 1e3 / max(1, gemm["calls"]),
                     share_of_step=gemm["ms"] / tot_ms,
                     families={k: dict(calls=v["calls"], ms=round(v["ms"], 3), tflops=round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1))
                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})
