@@ -95,6 +95,21 @@ typedef struct T2VGemmDesc {
   int32_t tune;                         /* 0 = defaults. bits 0-7: pipeline stages to use; bit 11: disable CTA pairs (cta_group::2); bits 12-15: timing experiments (wrong results) */
   void* workspace;
   int64_t workspace_bytes;
+  /* LayerNorm folded into the GEMM that consumes it (attention.py:279-281 feeding to_q/to_k/to_v and GEGLU.proj):
+   * with W' = W * gamma (per input channel), col_sum[n] = sum_k W'[n,k], bias' = W beta + bias, and per input row
+   * row_stats[m] = (rstd_m, -rstd_m * mean_m) from t2v_layernorm_stats,
+   *   LN(x) W^T + bias  ==  rstd_m * (x W'^T)[m,n] + (-rstd_m mean_m) * col_sum[n] + bias'[n],
+   * so the normalised activation is never written.  Plain [M,K] x [N,K] GEMMs only (one tap, a_size[1..3] = 1),
+   * alpha = 1, bf16 output, bias (if any) a single [N] vector.  NULL = off. */
+  const float* row_stats;               /* fp32 [M][2] */
+  const float* col_sum;                 /* fp32 [N] (GEGLU: packed like the bias) */
+  /* The statistics can also be accumulated by the GEMM that PRODUCES the LayerNorm input (the out-projection +
+   * residual / proj_in GEMMs of a transformer block): with row_accum set, the epilogue adds (sum, sum of squares)
+   * of every output row into row_accum[m] (fp32 [M][2], zeroed by the caller; plain [M,K] x [N,K], N % 32 == 0).
+   * The consumer then passes that buffer as row_stats with ln_raw = 1, ln_channels = N_producer, ln_eps:
+   * no LayerNorm kernel runs at all.  row_stats and row_accum are mutually exclusive in one call. */
+  int32_t ln_raw; int32_t ln_channels; float ln_eps;
+  float* row_accum;
 } T2VGemmDesc;
 
 int t2v_gemm(const T2VGemmDesc* desc, t2v_stream_t stream);
@@ -173,6 +188,10 @@ typedef struct T2VLayerNormDesc {
 } T2VLayerNormDesc;
 
 int t2v_layernorm(const T2VLayerNormDesc* desc, t2v_stream_t stream);
+
+/* Per-row LayerNorm statistics only: stats[row] = (rstd, -rstd * mean), fp32 [rows][2] (desc->out, gamma, beta are
+ * ignored).  Feeds T2VGemmDesc.row_stats. */
+int t2v_layernorm_stats(const T2VLayerNormDesc* desc, float* stats, t2v_stream_t stream);
 
 /*
  * Small-M linear on CUDA cores: out[m, n] = act_out( sum_k act_in(x[m,k]) W[n,k] + bias[n] + add[m,n] ).

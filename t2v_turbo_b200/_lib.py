@@ -55,6 +55,10 @@ class GemmDesc(C.Structure):
         ("tune", C.c_int32),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
+        ("row_stats", C.c_void_p),
+        ("col_sum", C.c_void_p),
+        ("ln_raw", C.c_int32), ("ln_channels", C.c_int32), ("ln_eps", C.c_float),
+        ("row_accum", C.c_void_p),
     ]
 
 
@@ -125,6 +129,7 @@ SYMBOLS = {
     "t2v_attn_short_fwd": (C.c_int, [C.POINTER(ShortAttnDesc), _vp]),
     "t2v_groupnorm": (C.c_int, [C.POINTER(GroupNormDesc), _vp]),
     "t2v_layernorm": (C.c_int, [C.POINTER(LayerNormDesc), _vp]),
+    "t2v_layernorm_stats": (C.c_int, [C.POINTER(LayerNormDesc), _vp, _vp]),
     "t2v_small_linear": (C.c_int, [C.POINTER(SmallLinearDesc), _vp]),
     "t2v_sinusoidal_embedding": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_conv3x3_small_cin": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -61,6 +61,11 @@ struct GemmParams {
   float* ws;  // split-K workspace [points][N] fp32
   int32_t epi_mode;  // 0 = direct row stores, 1 = smem-staged TMA store (+ TMA residual load)
   int32_t n_stages;  // pipeline stages in use
+  const float2* row_stats;  // folded LayerNorm: per input row (rstd, -rstd*mean); nullptr = off
+  const float* col_sum;     // folded LayerNorm: per output column sum_k W'[n,k]
+  int32_t ln_raw;           // row_stats holds raw (sum x, sum x^2) per row (accumulated by a producer GEMM)
+  float ln_inv_c, ln_eps;   // 1 / channels and eps for ln_raw
+  float* row_accum;         // LN == 2: fp32 [M][2], += (sum, sum of squares) of each output row
   uint32_t smem_epi_off;  // offset of the epilogue staging buffers
   int32_t dbg;              // timing experiments only (results are wrong when non-zero)
 };
@@ -76,7 +81,7 @@ constexpr int kEpiBufs = 3;                          // per epilogue warpgroup
 constexpr int kEpiBytes = kEpiWGs * kEpiBufs * kEpiBufBytes;
 constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kSmemBudget = kSmemLimit - kEpiBytes - 4096;
+constexpr int kSmemBudget = kSmemLimit - kEpiBytes - 6144;
 
 // PAIR: two CTAs of a cluster work on one 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA stages its own
 // 128 rows of A and HALF of the weight tile, so the L2->SM operand traffic per FLOP drops by a third to a half.
@@ -88,7 +93,7 @@ struct GemmCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;   // streaming mode
   static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kBarBytes = (2 * kMaxStages + 5 + kEpiWGs * kEpiBufs) * 8 + 16 + 16 + 2 * 256 * 4;
+  static constexpr int kBarBytes = (2 * kMaxStages + 5 + kEpiWGs * kEpiBufs) * 8 + 16 + 16 + 4 * 256 * 4;
 };
 
 // erf-GELU: g * Phi(g) with Phi(g) = sigmoid(g (c0 + c1 g^2 + c2 g^4)) — a minimax fit of logit(Phi) by an odd
@@ -106,12 +111,19 @@ __device__ __forceinline__ float gelu_erf(float g) {
   return g * r;
 }
 
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
 
-template <int BN, bool PAIR>
+// LN: 0 = plain epilogue; 1 = this GEMM CONSUMES a LayerNorm (folded: per-row statistics applied in the epilogue);
+// 2 = this GEMM PRODUCES a LayerNorm input (its epilogue accumulates per-row sum / sum of squares of the output).
+// Separate instantiations keep the extra registers / instructions out of the plain kernels (measured: +10 % on the
+// epilogue-bound GEMMs when the paths shared one kernel).
+template <int BN, bool PAIR, int LN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -303,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
     const bool has_res = p.residual != nullptr;
     const bool alpha_one = (p.alpha == 1.0f);
+    constexpr bool has_ln = (LN == 1);  // LayerNorm folded into this GEMM (host guarantees alpha == 1, plain [M, K] A)
     const int acc_cw = geglu ? 64 : 32;  // accumulator columns per 32-column output chunk
     const int chunks_per_tile = BN / acc_cw;
     uint8_t* ebuf = smem_epi + g * kEpiBufs * kEpiBufBytes;
@@ -338,15 +351,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       const int n_base = n_tile * BN;
-      const bool bias_uniform = (p.bias != nullptr) && (bias_row_first == bias_row_last);  // CTA-uniform
+      // (with a folded LayerNorm the column vectors are always staged; its bias, if any, is a plain [N] vector)
+      const bool bias_uniform = has_ln || ((p.bias != nullptr) && (bias_row_first == bias_row_last));  // CTA-uniform
       const float* bias = p.bias ? p.bias + bias_row * p.bias_row_stride : nullptr;
       float* sbias = bias_smem + acc * 256;
+      float* scs = bias_smem + 512 + acc * 256;
       if (bias_uniform) {
         if (et < BN) {
           const int n = n_base + et;
-          sbias[et] = n < p.n_rows_b ? __ldg(p.bias + bias_row_first * p.bias_row_stride + n) : 0.f;
+          sbias[et] = (p.bias != nullptr && n < p.n_rows_b) ? __ldg(p.bias + bias_row_first * p.bias_row_stride + n) : 0.f;
+          if (has_ln) scs[et] = n < p.n_rows_b ? __ldg(p.col_sum + n) : 0.f;
         }
       }
+      float ln_rs = 1.f, ln_rm = 0.f;
+      if (has_ln) {
+        const int64_t m = int64_t(o[0]) + r;
+        if (m < p.o_size[0]) {
+          const float2 st = __ldcg(p.row_stats + m);
+          if (p.ln_raw) {
+            const float mean = st.x * p.ln_inv_c;
+            const float var = fmaxf(fmaf(st.y, p.ln_inv_c, -mean * mean), 0.f);
+            ln_rs = rsqrtf(var + p.ln_eps);
+            ln_rm = -ln_rs * mean;
+          } else {
+            ln_rs = st.x;
+            ln_rm = st.y;
+          }
+        }
+      }
+      float acc_sum = 0.f, acc_sq = 0.f;  // LN == 2: this thread's row, this tile
       if (has_res && lead_warp && elect_one()) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -386,6 +419,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               tmem_ld_32x32(taddr + c * acc_cw + 32, v);
               tmem_wait_ld();
             }
+            if (has_ln) {
+              // out = rstd * acc + (-rstd * mean) * colsum[n] + bias'[n]   (LayerNorm folded into W', see t2v_b200.h)
+              const float4* b4 = reinterpret_cast<const float4*>(sbias + c * acc_cw + hh * 32);
+              const float4* s4 = reinterpret_cast<const float4*>(scs + c * acc_cw + hh * 32);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 ba = b4[k4], sa = s4[k4], bg = b4[k4 + 4], sg = s4[k4 + 4];
+                const float av[4] = {fmaf(ln_rm, sa.x, ba.x), fmaf(ln_rm, sa.y, ba.y), fmaf(ln_rm, sa.z, ba.z), fmaf(ln_rm, sa.w, ba.w)};
+                const float gv[4] = {fmaf(ln_rm, sg.x, bg.x), fmaf(ln_rm, sg.y, bg.y), fmaf(ln_rm, sg.z, bg.z), fmaf(ln_rm, sg.w, bg.w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float a = fmaf(ln_rs, __uint_as_float(v[4 * k4 + i]), av[i]);
+                  const float gt = fmaf(ln_rs, __uint_as_float(v[16 + 4 * k4 + i]), gv[i]);
+                  f[hh * 16 + 4 * k4 + i] = a * gelu_erf(gt);
+                }
+              }
+              continue;
+            }
             float bv[32];
             if (bias_uniform) {
               const float4* b4 = reinterpret_cast<const float4*>(sbias + c * acc_cw + hh * 32);
@@ -414,6 +465,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
               f[hh * 16 + j] = a * gelu_erf(gt);
             }
+          }
+        } else if (has_ln) {
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + c * acc_cw);
+          const float4* s4 = reinterpret_cast<const float4*>(scs + c * acc_cw);
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 bv = b4[k4], sv = s4[k4];
+            f[4 * k4 + 0] = fmaf(ln_rs, __uint_as_float(v[4 * k4 + 0]), fmaf(ln_rm, sv.x, bv.x));
+            f[4 * k4 + 1] = fmaf(ln_rs, __uint_as_float(v[4 * k4 + 1]), fmaf(ln_rm, sv.y, bv.y));
+            f[4 * k4 + 2] = fmaf(ln_rs, __uint_as_float(v[4 * k4 + 2]), fmaf(ln_rm, sv.z, bv.z));
+            f[4 * k4 + 3] = fmaf(ln_rs, __uint_as_float(v[4 * k4 + 3]), fmaf(ln_rm, sv.w, bv.w));
           }
         } else if (bias_uniform) {
           const float4* b4 = reinterpret_cast<const float4*>(sbias + c * acc_cw);
@@ -466,6 +528,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             f[k4 * 8 + 7] += bf16_hi(rv.w);
           }
         }
+        if (LN == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            acc_sum += f[j];
+            acc_sq = fmaf(f[j], f[j], acc_sq);
+          }
+        }
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           uint4 ov;
@@ -504,6 +573,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             else
               mbar_arrive(&tempty_bar[acc]);
           }
+      }
+      if (LN == 2) {
+        const int64_t m = int64_t(o[0]) + r;
+        if (m < p.o_size[0] && g < chunks_per_tile && n_base + g * acc_cw < p.n_rows_b) red_add_v2(p.row_accum + 2 * m, acc_sum, acc_sq);
       }
     }
     if (lead_warp && elect_one()) bulk_wait_group_read<0>();
@@ -720,10 +793,21 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, 
       if (j == p.bias_dim) bias_row = x / p.bias_div;
     }
     const float* wp = p.ws + point * p.n_rows_b + n0;
+    float fsum = 0.f, fsq = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (n0 + j < p.n_rows_b) {
         float v = wp[j];
+        if (p.row_stats) {  // folded LayerNorm (A is a plain [M, K] matrix: point == row)
+          const float2 st = __ldcg(p.row_stats + point);
+          float rs = st.x, rm = st.y;
+          if (p.ln_raw) {
+            const float mean = st.x * p.ln_inv_c;
+            rs = rsqrtf(fmaxf(fmaf(st.y, p.ln_inv_c, -mean * mean), 0.f) + p.ln_eps);
+            rm = -rs * mean;
+          }
+          v = fmaf(rs, v, rm * __ldg(p.col_sum + n0 + j));
+        }
         if (p.bias) v += p.bias[bias_row * p.bias_row_stride + n0 + j];
         if (gelu) v = gelu_erf(v);
         if (p.residual) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + n0 + j]);
@@ -731,18 +815,21 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, 
           reinterpret_cast<float*>(p.out)[out_off + n0 + j] = v;
         else
           reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + n0 + j] = __float2bfloat16_rn(v);
+        fsum += v;
+        fsq = fmaf(v, v, fsq);
       }
     }
+    if (p.row_accum) red_add_v2(p.row_accum + 2 * point, fsum, fsq);
   }
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int LN = 0>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& to,
                        const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, PAIR>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc)");
     configured = true;
   }
@@ -764,19 +851,21 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   pp.smem_epi_off = uint32_t(stages) * uint32_t(Cfg::kStageBytes);
   const size_t smem_bytes = size_t(pp.smem_epi_off) + kEpiBytes + Cfg::kBarBytes + 1024;
   if (smem_bytes > size_t(kSmemLimit)) return fail(-112, "gemm_tc: %zu bytes of shared memory needed", smem_bytes);
-  launch_kernel_cluster(gemm_tc_kernel<BN, PAIR>, dim3(grid), dim3(kThreads), smem_bytes, stream, PAIR ? 2u : 1u, a0, a1, b,
+  launch_kernel_cluster(gemm_tc_kernel<BN, PAIR, LN>, dim3(grid), dim3(kThreads), smem_bytes, stream, PAIR ? 2u : 1u, a0, a1, b,
                         to, tr, pp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "gemm_tc launch");
   return 0;
 }
 
-static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms) {
+static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu, bool wide_only) {
   const int cands[5] = {256, 160, 128, 64, 32};
   double best = -1.0;
   int best_bn = 128;
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
+    if (geglu && bn % 64 != 0) continue;
+    if (wide_only && bn < 128) continue;  // the LayerNorm-aware kernels are only instantiated for wide tiles  // value/gate pairs live in 64-column accumulator groups (staged epilogue)
     const int64_t nt = (n_rows + bn - 1) / bn;
     const double eff_n = double(n_rows) / double(nt * bn);
     const int64_t tiles = nt * m_tiles;
@@ -838,7 +927,9 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "t2v_gemm: no CUDA device");
   int bn = d->block_n;
-  if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms);
+  const int ln_mode = d->row_stats ? 1 : (d->row_accum ? 2 : 0);
+  if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms, geglu, ln_mode != 0);
+  if (ln_mode != 0 && bn < 128) return fail(-19, "t2v_gemm: LayerNorm-aware GEMMs need block_n >= 128");
   if (bn != 32 && bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
   p.n_tiles_n = int((d->b_rows + bn - 1) / bn);
   const int64_t tiles_mn = m_tiles * p.n_tiles_n;
@@ -893,6 +984,25 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   p.flags = d->flags;
   p.a_tile_bytes = uint32_t(rows_in_box * 128);
   p.ws = static_cast<float*>(d->workspace);
+  p.row_stats = reinterpret_cast<const float2*>(d->row_stats);
+  p.col_sum = d->col_sum;
+  p.ln_raw = d->ln_raw;
+  p.ln_inv_c = d->ln_channels > 0 ? 1.0f / float(d->ln_channels) : 0.f;
+  p.ln_eps = d->ln_eps;
+  p.row_accum = d->row_accum;
+  if (d->row_stats && d->row_accum) return fail(-19, "t2v_gemm: row_stats and row_accum are mutually exclusive");
+  if (d->row_stats && d->ln_raw && d->ln_channels <= 0) return fail(-19, "t2v_gemm: ln_raw needs ln_channels");
+  if (d->row_accum) {
+    if (d->a_size[1] != 1 || d->a_size[2] != 1 || d->a_size[3] != 1 || d->n_taps != 1 || geglu || (d->flags & T2V_EPI_OUT_F32) ||
+        d->b_rows % 32 || (reinterpret_cast<uintptr_t>(d->row_accum) & 7))
+      return fail(-19, "t2v_gemm: row_accum needs a plain [M, K] x [N, K] GEMM with N %% 32 == 0 and bf16 output");
+  }
+  if (d->row_stats) {
+    if (!d->col_sum) return fail(-19, "t2v_gemm: row_stats needs col_sum");
+    if (d->a_size[1] != 1 || d->a_size[2] != 1 || d->a_size[3] != 1 || d->n_taps != 1 || d->alpha != 1.0f ||
+        d->bias_dim >= 0 || (d->flags & T2V_EPI_OUT_F32) || (reinterpret_cast<uintptr_t>(d->row_stats) & 7))
+      return fail(-19, "t2v_gemm: a folded LayerNorm needs a plain [M, K] x [N, K] GEMM, alpha = 1, [N] bias, bf16 output");
+  }
   // vector epilogue: 16-byte aligned rows
   const int out_el = (d->flags & T2V_EPI_OUT_F32) ? 4 : 2;
   bool vec_ok = (d->n_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0);
@@ -906,6 +1016,8 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
 
   // staged (TMA-store) epilogue whenever the output rows are 16-byte addressable bf16
   bool staged = vec_ok && split == 1 && !(d->flags & T2V_EPI_OUT_F32) && (!geglu || bn % 64 == 0);
+  if (ln_mode != 0 && split == 1 && !staged)
+    return fail(-19, "t2v_gemm: LayerNorm-aware GEMMs need 16-byte aligned bf16 output rows");
   p.epi_mode = staged ? 1 : 0;
   // CTA pairs (cta_group::2): 256-row tiles, each CTA stages half of the weight tile
   const int64_t pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
@@ -973,21 +1085,32 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     launch_kernel(zero_f32_kernel, dim3(unsigned(zg)), dim3(256), 0, stream, static_cast<float4*>(d->workspace), n4);
   }
   int rc;
-  if (pair) {
-    switch (bn) {
-      case 128: rc = launch_gemm<128, true>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-      case 160: rc = launch_gemm<160, true>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-      default: rc = launch_gemm<256, true>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-    }
+#define T2V_GEMM_CASE(BN_, PAIR_, LN_) rc = launch_gemm<BN_, PAIR_, LN_>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream)
+#define T2V_GEMM_WIDE(LN_)                                                       \
+  do {                                                                           \
+    if (pair) {                                                                  \
+      if (bn == 128) T2V_GEMM_CASE(128, true, LN_);                              \
+      else if (bn == 160) T2V_GEMM_CASE(160, true, LN_);                         \
+      else T2V_GEMM_CASE(256, true, LN_);                                        \
+    } else {                                                                     \
+      if (bn == 128) T2V_GEMM_CASE(128, false, LN_);                             \
+      else if (bn == 160) T2V_GEMM_CASE(160, false, LN_);                        \
+      else T2V_GEMM_CASE(256, false, LN_);                                       \
+    }                                                                            \
+  } while (0)
+  if (ln_mode == 1) {
+    T2V_GEMM_WIDE(1);
+  } else if (ln_mode == 2) {
+    T2V_GEMM_WIDE(2);
+  } else if (bn == 32) {
+    T2V_GEMM_CASE(32, false, 0);
+  } else if (bn == 64) {
+    T2V_GEMM_CASE(64, false, 0);
   } else {
-    switch (bn) {
-      case 32: rc = launch_gemm<32, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-      case 64: rc = launch_gemm<64, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-      case 128: rc = launch_gemm<128, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-      case 160: rc = launch_gemm<160, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-      default: rc = launch_gemm<256, false>(tmA[0], tmA[1], tmB, tmOut, tmRes, p, stream); break;
-    }
+    T2V_GEMM_WIDE(0);
   }
+#undef T2V_GEMM_WIDE
+#undef T2V_GEMM_CASE
   if (rc) return rc;
   if (split > 1) {
     const int64_t total = n_points * ((d->b_rows + 3) / 4);

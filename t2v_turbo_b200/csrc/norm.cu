@@ -412,6 +412,50 @@ __global__ void __launch_bounds__(256) ln_kernel(const LnParams p) {
   }
 }
 
+// statistics only: one warp per row -> (rstd, -rstd * mean); two-pass in registers like ln_kernel
+template <int MAXV>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const LnParams p, float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 8 + warp;
+  if (row >= p.rows) return;
+  const __nv_bfloat16* xr = p.x + row * p.xs;
+  float f[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < p.nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      unpack8(u, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * p.inv_c;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < p.nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (lane == 0) {
+    const float rstd = rsqrtf(sq * p.inv_c + p.eps);
+    stats[row] = make_float2(rstd, -rstd * mean);
+  }
+}
+
 }  // namespace t2v
 
 extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
@@ -530,5 +574,34 @@ extern "C" int t2v_layernorm(const T2VLayerNormDesc* d, t2v_stream_t stream_) {
   else launch_kernel(ln_kernel<8>, dim3(grid), dim3(256), 0, stream, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "t2v_layernorm launch");
+  return 0;
+}
+
+extern "C" int t2v_layernorm_stats(const T2VLayerNormDesc* d, float* stats, t2v_stream_t stream_) {
+  using namespace t2v;
+  if (!d || !d->x || !stats) return fail(-1, "t2v_layernorm_stats: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (d->channels <= 0 || d->channels % 8 || d->channels > 2048)
+    return fail(-3, "t2v_layernorm_stats: channels must be a multiple of 8, <= 2048");
+  if (d->x_row_stride % 8 || (reinterpret_cast<uintptr_t>(stats) & 7)) return fail(-4, "t2v_layernorm_stats: bad stride / alignment");
+  if (d->rows <= 0) return 0;
+  LnParams p;
+  p.x = static_cast<const __nv_bfloat16*>(d->x);
+  p.xs = d->x_row_stride;
+  p.out = nullptr;
+  p.os = 0;
+  p.gamma = p.beta = nullptr;
+  p.rows = d->rows;
+  p.nvec = d->channels / 8;
+  p.eps = d->eps;
+  p.inv_c = 1.0f / float(d->channels);
+  const unsigned grid = unsigned((d->rows + 7) / 8);
+  const int vpl = (p.nvec + 31) / 32;
+  float2* st = reinterpret_cast<float2*>(stats);
+  if (vpl <= 2) launch_kernel(ln_stats_kernel<2>, dim3(grid), dim3(256), 0, stream, p, st);
+  else if (vpl <= 5) launch_kernel(ln_stats_kernel<5>, dim3(grid), dim3(256), 0, stream, p, st);
+  else launch_kernel(ln_stats_kernel<8>, dim3(grid), dim3(256), 0, stream, p, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "t2v_layernorm_stats launch");
   return 0;
 }

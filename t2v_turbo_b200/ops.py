@@ -115,7 +115,7 @@ def _as_pair(x):
 def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w, n_rows, out,
               o_size, o_stride, n_out, bias=None, bias_row_stride=0, bias_dim=-1, bias_div=1,
               residual=None, r_stride=None, alpha=1.0, flags=0, block_n=0, b_batches=1,
-              b_batch_stride=0, b_batch_dim=-1, b_row_stride=0, split_k=0):
+              b_batch_stride=0, b_batch_dim=-1, b_row_stride=0, split_k=0, ln=None, row_accum=None):
     d = GemmDesc()
     a0, a1 = a
     d.a[0] = a0.data_ptr()
@@ -151,6 +151,12 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     d.block_n = block_n
     d.split_k = split_k
     d.tune = GEMM_TUNE
+    if ln is not None:   # folded LayerNorm: (row_stats [M,2] fp32, col_sum [N] fp32[, (channels, eps) if the stats are raw sums])
+        d.row_stats, d.col_sum = ln[0].data_ptr(), ln[1].data_ptr()
+        if len(ln) > 2:
+            d.ln_raw, d.ln_channels, d.ln_eps = 1, int(ln[2][0]), float(ln[2][1])
+    if row_accum is not None:   # fp32 [M,2], zeroed by the caller: += (sum, sum of squares) of each output row
+        d.row_accum = row_accum.data_ptr()
     ws = _splitk_workspace(out.device)
     d.workspace = ws.data_ptr()
     d.workspace_bytes = ws.numel() * 4
@@ -184,9 +190,12 @@ def _check_act(x, name="x"):
 
 # ----------------------------------------------------------------------------- Linear
 def linear(x, w, bias=None, *, residual=None, geglu=False, gelu=False, out=None, out_f32=False,
-           alpha=1.0, block_n=0, split_k=0):
+           alpha=1.0, block_n=0, split_k=0, ln=None, row_accum=None):
     """out[m, :] = epi(x[m, :] @ w.T).  x: [M, K] bf16 (or a pair concatenated along K);
-    w: [N, K] bf16 (GEGLU: rows packed by pack_geglu); bias: fp32 [N]; residual: bf16 [M, n_out]."""
+    w: [N, K] bf16 (GEGLU: rows packed by pack_geglu); bias: fp32 [N]; residual: bf16 [M, n_out].
+    ln = (row_stats, col_sum[, (channels, eps)]): x is the UN-normalised LayerNorm input and w / bias / col_sum come
+    from fold_layernorm; with the third element row_stats holds the raw sums a producer GEMM accumulated.
+    row_accum: fp32 [M, 2] (zeroed): this GEMM adds (sum, sum of squares) of each output row (it produces a LayerNorm input)."""
     x0, x1 = _as_pair(x)
     _check_act(x0)
     m = x0.shape[0]
@@ -204,7 +213,7 @@ def linear(x, w, bias=None, *, residual=None, geglu=False, gelu=False, out=None,
         box=(128, 1, 1, 1), taps=[(0, 0, 0, 0)], tap_ch_off=None, w=w, n_rows=n, out=out,
         o_size=(m, 1, 1, 1), o_stride=(out.stride(0), 0, 0, 0), n_out=n_out, bias=bias,
         residual=residual, r_stride=(residual.stride(0), 0, 0, 0) if residual is not None else None,
-        alpha=alpha, flags=flags, block_n=block_n, split_k=split_k)
+        alpha=alpha, flags=flags, block_n=block_n, split_k=split_k, ln=ln, row_accum=row_accum)
 
 
 def bmm_nt(a, b, *, out=None, alpha=1.0, block_n=0):
@@ -407,6 +416,29 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 
 
 # ----------------------------------------------------------------------------- attention
+def layernorm_stats(x, eps=1e-5, out=None):
+    """Per-row (rstd, -rstd*mean) of x [rows, C] -> fp32 [rows, 2]; consumed by linear(..., ln=...)."""
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
+    d = LayerNormDesc()
+    d.x, d.x_row_stride = x.data_ptr(), x.stride(0)
+    d.rows, d.channels, d.eps = rows, c, eps
+    _launch("layernorm", _FLOPS.pop("layernorm", 0), lib().t2v_layernorm_stats, C.byref(d), out.data_ptr(), stream_ptr())
+    return out
+
+
+def fold_layernorm(w, bias, gamma, beta):
+    """Fold LayerNorm's affine into the Linear that consumes it (load-time, fp32 math):
+    returns (w' bf16 [N,K] = w*gamma, bias' fp32 [N] = w @ beta + bias, col_sum fp32 [N] = sum_k float(w'[n,k]))."""
+    w32 = w.detach().float()
+    wp = (w32 * gamma.float()[None, :]).to(BF16).contiguous()
+    bp = w32 @ beta.float()
+    if bias is not None:
+        bp = bp + bias.float()
+    return wp, bp.contiguous(), wp.float().sum(1).contiguous()
+
+
 def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None):
     """q: [Bq, Lq, H*64] view, k/v: [Bk, Lk, H*64] views (last dim contiguous; token/batch strides free).
     Returns o: [Bq, Lq, H*64]."""

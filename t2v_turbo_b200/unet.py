@@ -146,22 +146,28 @@ def _f32(t):
 
 
 class _PackedAttn:
-    def __init__(self, attn: CrossAttention, fuse_qkv: bool):
+    """to_q (| to_k | to_v) with the preceding LayerNorm folded in (ops.fold_layernorm): the projection GEMM reads the
+    un-normalised residual stream and its epilogue applies the per-row statistics."""
+
+    def __init__(self, attn: CrossAttention, fuse_qkv: bool, norm: nn.LayerNorm):
         self.heads, self.scale = attn.heads, attn.scale
         self.inner = attn.heads * attn.dim_head
-        if fuse_qkv:
-            self.w_qkv = torch.cat([_w2d(attn.to_q.weight), _w2d(attn.to_k.weight), _w2d(attn.to_v.weight)], 0).contiguous()
-        else:
-            self.w_q = _w2d(attn.to_q.weight)
+        ws = [attn.to_q.weight] + ([attn.to_k.weight, attn.to_v.weight] if fuse_qkv else [])
+        w = torch.cat([x.detach().float() for x in ws], 0)
+        self.w_qkv, self.b_qkv, self.cs_qkv = ops.fold_layernorm(w, None, norm.weight.detach(), norm.bias.detach())
+        self.fused = fuse_qkv
         self.w_o, self.b_o = _w2d(attn.to_out[0].weight), _f32(attn.to_out[0].bias)
 
 
 class _PackedBlock:
     def __init__(self, blk: BasicTransformerBlock, cross: bool):
-        self.a1 = _PackedAttn(blk.attn1, True)
-        self.a2 = _PackedAttn(blk.attn2, not cross)
-        self.ln = [(_f32(n.weight), _f32(n.bias), n.eps) for n in (blk.norm1, blk.norm2, blk.norm3)]
-        self.w_ff1, self.b_ff1 = ops.pack_geglu(blk.ff.net[0].proj.weight.detach().to(BF16), blk.ff.net[0].proj.bias.detach().float())
+        self.a1 = _PackedAttn(blk.attn1, True, blk.norm1)
+        self.a2 = _PackedAttn(blk.attn2, not cross, blk.norm2)
+        self.ln_eps = [n.eps for n in (blk.norm1, blk.norm2, blk.norm3)]
+        proj = blk.ff.net[0].proj
+        wf, bf, cs = ops.fold_layernorm(proj.weight, proj.bias, blk.norm3.weight.detach(), blk.norm3.bias.detach())
+        self.w_ff1, self.b_ff1 = ops.pack_geglu(wf, bf)
+        _, self.cs_ff1 = ops.pack_geglu(wf, cs)
         self.w_ff2, self.b_ff2 = _w2d(blk.ff.net[2].weight), _f32(blk.ff.net[2].bias)
 
 
@@ -287,6 +293,7 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(_gn(ch), nn.SiLU(), out_conv)
         self._packed = None
         self._ctx_cache = None
+        self._ln_state = None
 
     # ------------------------------------------------------------------ packing
     def invalidate_packed(self):
@@ -414,35 +421,61 @@ class UNetModel(nn.Module):
             self._ctx_cache = (key, kv, context)
         return kv
 
-    def _block(self, blk: _PackedBlock, x, geom, temporal, ctx_kv, kv_slice):
+    # ---- LayerNorm row-statistics workspace: one fp32 [rows, 2] slice per LayerNorm instance, all zeroed by a single
+    # memset at the start of a forward.  The first forward of a geometry sizes it (individually zeroed tensors).
+    def _ln_begin(self, key):
+        st = self._ln_state
+        if st is None or st["key"] != key:
+            st = self._ln_state = dict(key=key, buf=None, need=0, cursor=0)
+        elif st["buf"] is None and st["need"] > 0:
+            st["buf"] = torch.empty((st["need"], 2), device=key[-1], dtype=torch.float32)
+        if st["buf"] is not None:
+            st["buf"].zero_()
+            st["cursor"] = 0
+        else:
+            st["need"] = 0
+
+    def _ln_slice(self, rows, device):
+        st = self._ln_state
+        if st["buf"] is None:
+            st["need"] += rows
+            return torch.zeros((rows, 2), device=device, dtype=torch.float32)
+        off = st["cursor"]
+        st["cursor"] = off + rows
+        return st["buf"][off:off + rows]
+
+    def _block(self, blk: _PackedBlock, x, acc1, geom, temporal, ctx_kv, kv_slice):
         b, t, hh, ww = geom
         hw = hh * ww
         a1 = blk.a1
         inner = a1.inner
-        n1 = ops.layernorm(x, *blk.ln[0])
-        qkv = ops.linear(n1, a1.w_qkv, None)
+        # The three LayerNorms never run as kernels: the GEMM that produces each LayerNorm input accumulates the
+        # per-row sum / sum of squares in its epilogue (row_accum), and the GEMM that consumes the normalised
+        # activation applies them (ln=..., weights pre-multiplied by gamma: ops.fold_layernorm).
+        c = x.shape[1]
+        acc2, acc3 = self._ln_slice(x.shape[0], x.device), self._ln_slice(x.shape[0], x.device)
+        qkv = ops.linear(x, a1.w_qkv, a1.b_qkv, ln=(acc1, a1.cs_qkv, (c, blk.ln_eps[0])))
         q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
         if temporal:
             att = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=a1.heads, scale=a1.scale)
         else:
             att = ops.attention(q.view(b * t, hw, inner), k.view(b * t, hw, inner), v.view(b * t, hw, inner),
                                 heads=a1.heads, scale=a1.scale).view(-1, inner)
-        x = ops.linear(att, a1.w_o, a1.b_o, residual=x)
+        x = ops.linear(att, a1.w_o, a1.b_o, residual=x, row_accum=acc2)
         a2 = blk.a2
-        n2 = ops.layernorm(x, *blk.ln[1])
+        ln2 = (acc2, a2.cs_qkv, (c, blk.ln_eps[1]))
         if temporal:
-            qkv = ops.linear(n2, a2.w_qkv, None)
+            qkv = ops.linear(x, a2.w_qkv, a2.b_qkv, ln=ln2)
             q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
             att = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=a2.heads, scale=a2.scale)
         else:
-            q = ops.linear(n2, a2.w_q, None)
+            q = ops.linear(x, a2.w_qkv, a2.b_qkv, ln=ln2)
             off, kin = kv_slice
             kc, vc = ctx_kv[:, :, off:off + kin], ctx_kv[:, :, off + kin:off + 2 * kin]
             att = ops.attention(q.view(b * t, hw, inner), kc, vc, heads=a2.heads, scale=a2.scale,
                                 kv_batch_div=t).view(-1, inner)
-        x = ops.linear(att, a2.w_o, a2.b_o, residual=x)
-        n3 = ops.layernorm(x, *blk.ln[2])
-        g = ops.linear(n3, blk.w_ff1, blk.b_ff1, geglu=True)
+        x = ops.linear(att, a2.w_o, a2.b_o, residual=x, row_accum=acc3)
+        g = ops.linear(x, blk.w_ff1, blk.b_ff1, geglu=True, ln=(acc3, blk.cs_ff1, (c, blk.ln_eps[2])))
         return ops.linear(g, blk.w_ff2, blk.b_ff2, residual=x)
 
     def _transformer(self, pt: _PackedTransformer, h, geom, ctx_kv):
@@ -451,8 +484,9 @@ class UNetModel(nn.Module):
         x_in = h.view(-1, c)
         rps = hh * ww * (t if pt.temporal else 1)
         xn = ops.groupnorm(x_in, pt.gn[0], pt.gn[1], rows_per_sample=rps, eps=pt.gn[2], silu=False)
-        x = ops.linear(xn, pt.w_in, pt.b_in)
-        x = self._block(pt.blk, x, geom, pt.temporal, ctx_kv, pt.kv_slice)
+        acc1 = self._ln_slice(xn.shape[0], xn.device)
+        x = ops.linear(xn, pt.w_in, pt.b_in, row_accum=acc1)
+        x = self._block(pt.blk, x, acc1, geom, pt.temporal, ctx_kv, pt.kv_slice)
         out = ops.linear(x, pt.w_out, pt.b_out, residual=x_in)
         return out.view(b * t, hh, ww, c)
 
@@ -515,6 +549,7 @@ class UNetModel(nn.Module):
         P = self._packed
         dev = x.device
         b, _, t, hh, ww = x.shape
+        self._ln_begin((b, t, hh, ww, dev))
         emb_rows = self._embedding(P, timesteps, fps, timestep_cond, motion_cond, b, dev)
         ctx_kv = self._context_kv(P, context, dev) if P["ctx_w"] is not None else None
         h = ops.bcthw_to_frames(x, 1.0)

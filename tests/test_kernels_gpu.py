@@ -155,6 +155,70 @@ def test_geglu(cuda_device, m, c):
     assert_close(out, ref, what="geglu")
 
 
+# LayerNorm folded into the consuming Linear (attention.py:279-281 -> to_q/to_k/to_v, GEGLU.proj): the GEMM reads the
+# un-normalised x, the epilogue applies rstd / mean per row.  Reference: LN then Linear in fp32.
+@pytest.mark.parametrize("m,c,n,bias,split_k", [(1000, 320, 960, False, 0), (2560, 1280, 1280, True, 0), (640, 1280, 1280, False, 0),
+                                                 (130, 640, 320, True, 4), (77, 320, 320, True, 0)])
+def test_linear_folded_layernorm(cuda_device, m, c, n, bias, split_k):
+    ops = _ops()
+    x = (rnd(m, c, seed=51) * 1.7 + 0.8).to(BF16)          # non-zero mean: the mean correction matters
+    w = rnd(n, c, scale=c ** -0.5, seed=52)
+    b = rnd(n, seed=53) if bias else None
+    g = rnd(c, seed=54) * 0.3 + 1
+    be = rnd(c, seed=55) * 0.3
+    wp, bp, cs = ops.fold_layernorm(w, b, g, be)
+    st = ops.layernorm_stats(x, 1e-5)
+    xf = x.float()
+    mu, var = xf.mean(1), xf.var(1, unbiased=False)
+    torch.testing.assert_close(st[:, 0], (var + 1e-5).rsqrt(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(st[:, 1], -(var + 1e-5).rsqrt() * mu, rtol=1e-4, atol=1e-5)
+    out = ops.linear(x, wp, bp, ln=(st, cs), split_k=split_k)
+    ref = F.linear(F.layer_norm(xf, (c,), g, be, 1e-5), w, b)
+    assert_close(out, ref, what="linear + folded layernorm")
+
+
+@pytest.mark.parametrize("m,k,c,n,split_k", [(1000, 320, 320, 960, 0), (2560, 1280, 1280, 1280, 0), (640, 1280, 1280, 3840, 0),
+                                              (300, 2048, 640, 640, 4)])
+def test_layernorm_stats_from_producer_gemm(cuda_device, m, k, c, n, split_k):
+    """No LayerNorm kernel at all: GEMM 1 (out-projection + residual) accumulates per-row sum / sum of squares of its
+    output in the epilogue, GEMM 2 consumes them (raw) with the LayerNorm folded into its weights."""
+    ops = _ops()
+    a = rnd(m, k, seed=61).to(BF16)
+    w1 = rnd(c, k, scale=k ** -0.5, seed=62).to(BF16)
+    b1 = rnd(c, seed=63)
+    res = (rnd(m, c, seed=64) + 0.4).to(BF16)
+    acc = torch.zeros(m, 2, device=a.device, dtype=torch.float32)
+    x = ops.linear(a, w1, b1, residual=res, row_accum=acc, split_k=split_k)
+    xf = x.float()
+    torch.testing.assert_close(acc[:, 0], xf.sum(1), rtol=2e-3, atol=0.15)       # sums of the pre-rounding fp32 values
+    torch.testing.assert_close(acc[:, 1], (xf * xf).sum(1), rtol=4e-3, atol=0.15)
+    w2 = rnd(n, c, scale=c ** -0.5, seed=65)
+    g = rnd(c, seed=66) * 0.3 + 1
+    be = rnd(c, seed=67) * 0.3
+    wp, bp, cs = ops.fold_layernorm(w2, None, g, be)
+    out = ops.linear(x, wp, bp, ln=(acc, cs, (c, 1e-5)))
+    ref = F.linear(F.layer_norm(xf, (c,), g, be, 1e-5), w2)
+    assert_close(out, ref, what="producer-accumulated layernorm")
+
+
+@pytest.mark.parametrize("m,c", [(1000, 320), (256, 640)])
+def test_geglu_folded_layernorm(cuda_device, m, c):
+    ops = _ops()
+    inner = 4 * c
+    x = (rnd(m, c, seed=56) * 1.5 - 0.6).to(BF16)
+    w = rnd(2 * inner, c, scale=c ** -0.5, seed=57)
+    b = rnd(2 * inner, seed=58, scale=0.5)
+    g = rnd(c, seed=59) * 0.3 + 1
+    be = rnd(c, seed=60) * 0.3
+    wf, bf, cs = ops.fold_layernorm(w, b, g, be)
+    wp, bp = ops.pack_geglu(wf, bf)
+    _, csp = ops.pack_geglu(wf, cs)
+    out = ops.linear(x, wp, bp, geglu=True, ln=(ops.layernorm_stats(x, 1e-5), csp))
+    h = F.linear(F.layer_norm(x.float(), (c,), g, be, 1e-5), w, b)
+    a, gate = h.chunk(2, dim=-1)
+    assert_close(out, a * F.gelu(gate), what="geglu + folded layernorm")
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout", [
     (2, 8, 16, 64, 64), (3, 10, 16, 128, 192), (2, 5, 8, 128, 64), (2, 40, 64, 64, 320), (1, 20, 32, 320, 128),
 ])
