@@ -110,6 +110,13 @@ typedef struct T2VGemmDesc {
    * no LayerNorm kernel runs at all.  row_stats and row_accum are mutually exclusive in one call. */
   int32_t ln_raw; int32_t ln_channels; float ln_eps;
   float* row_accum;
+  /* GroupNorm statistics from the producing GEMM (basics.py:78-89 after every conv / proj_out): with col_accum set
+   * the epilogue adds, for every output point, its bf16-rounded channel values and their squares into
+   * col_accum[sample][channel][2] (fp32, zeroed by the caller), sample = sum_j coord[j] * cs_mult[j] over the output
+   * point grid (o_size); t2v_groupnorm then takes these per-channel sums (T2VGroupNormDesc.chan_sums) instead of
+   * running its statistics pass.  Needs N % 32 == 0, box[0] % 8 == 0, cs_mult[0] == 0, bf16 output. */
+  float* col_accum;
+  int32_t cs_mult[4];
 } T2VGemmDesc;
 
 int t2v_gemm(const T2VGemmDesc* desc, t2v_stream_t stream);
@@ -175,6 +182,12 @@ typedef struct T2VGroupNormDesc {
   int32_t groups; float eps; int32_t silu;
   float* workspace;
   int32_t mode;                         /* 0 = automatic; 1 = force the two-kernel path; 2 = require the single-kernel cluster path */
+  /* Optional: per-channel (sum, sum of squares) accumulated by the GEMMs that produced x[0] / x[1]
+   * (T2VGemmDesc.col_accum): fp32 [n_samples * chan_group][ch[i]][2].  When chan_sums[0] is set only the apply kernel
+   * runs (no statistics pass, workspace unused); chan_group producer samples are summed per GroupNorm sample (a
+   * GroupNorm over (t, h, w) fed with per-frame sums: chan_group = t). */
+  const float* chan_sums[2];
+  int32_t chan_group;
 } T2VGroupNormDesc;
 
 int t2v_groupnorm(const T2VGroupNormDesc* desc, t2v_stream_t stream);

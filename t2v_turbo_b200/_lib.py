@@ -59,6 +59,8 @@ class GemmDesc(C.Structure):
         ("col_sum", C.c_void_p),
         ("ln_raw", C.c_int32), ("ln_channels", C.c_int32), ("ln_eps", C.c_float),
         ("row_accum", C.c_void_p),
+        ("col_accum", C.c_void_p),
+        ("cs_mult", C.c_int32 * 4),
     ]
 
 
@@ -96,6 +98,8 @@ class GroupNormDesc(C.Structure):
         ("groups", C.c_int32), ("eps", C.c_float), ("silu", C.c_int32),
         ("workspace", C.c_void_p),
         ("mode", C.c_int32),
+        ("chan_sums", C.c_void_p * 2),
+        ("chan_group", C.c_int32),
     ]
 
 

@@ -66,6 +66,8 @@ struct GemmParams {
   int32_t ln_raw;           // row_stats holds raw (sum x, sum x^2) per row (accumulated by a producer GEMM)
   float ln_inv_c, ln_eps;   // 1 / channels and eps for ln_raw
   float* row_accum;         // LN == 2: fp32 [M][2], += (sum, sum of squares) of each output row
+  float* col_accum;         // LN == 3: fp32 [samples][N][2], += per-channel (sum, sum of squares) of the output rows
+  int32_t cs_mult[4];       // LN == 3: sample index of an output point = sum_j coord[j] * cs_mult[j]
   uint32_t smem_epi_off;  // offset of the epilogue staging buffers
   int32_t dbg;              // timing experiments only (results are wrong when non-zero)
 };
@@ -121,6 +123,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // LN: 0 = plain epilogue; 1 = this GEMM CONSUMES a LayerNorm (folded: per-row statistics applied in the epilogue);
 // 2 = this GEMM PRODUCES a LayerNorm input (its epilogue accumulates per-row sum / sum of squares of the output).
+// 3 = this GEMM PRODUCES a GroupNorm input: per-(sample, channel) sum / sum of squares of the bf16 output, reduced
+//     over the tile's rows out of the staging buffer (the GroupNorm statistics pass disappears).
 // Separate instantiations keep the extra registers / instructions out of the plain kernels (measured: +10 % on the
 // epilogue-bound GEMMs when the paths shared one kernel).
 template <int BN, bool PAIR, int LN>
@@ -380,6 +384,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       float acc_sum = 0.f, acc_sq = 0.f;  // LN == 2: this thread's row, this tile
+      // LN == 3: this thread reduces channel pair (r & 15) over rows [16 (r >> 4), +16) in two half-blocks of 8 rows;
+      // a half-block never straddles samples (host: box[0] % 8 == 0, cs_mult[0] == 0)
+      int64_t cs_off[2] = {0, 0};
+      int cs_nv[2] = {0, 0};  // valid rows (0..8) of each half-block: rows run along dim 0, the box may overhang the tensor
+      if (LN == 3) {
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          int rr = (r >> 4) * 16 + hb * 8;
+          bool ok = rr < p.rows_in_box;
+          int64_t smp = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ij = rr % p.box[j];
+            rr /= p.box[j];
+            const int64_t xj = int64_t(o[j]) + ij;
+            ok = ok && (xj < p.o_size[j]);
+            smp += xj * p.cs_mult[j];
+          }
+          const int i0 = ((r >> 4) * 16 + hb * 8) % p.box[0];
+          int64_t nv = p.o_size[0] - (int64_t(o[0]) + i0);
+          nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
+          cs_nv[hb] = ok ? int(nv) : 0;
+          cs_off[hb] = smp * int64_t(p.n_rows_b) * 2;
+        }
+      }
       if (has_res && lead_warp && elect_one()) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -547,6 +576,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (!(p.dbg & 2)) {
           fence_proxy_async();
           named_bar_sync(1 + g, 128);
+        }
+        if (LN == 3) {
+          // column sums of this 128 x 32 chunk from the staged bf16 rows (exactly the values GroupNorm will read)
+          const int cp = r & 15;  // channel pair: 4 bytes at word (cp & 3) of 16-byte chunk (cp >> 2)
+          const uint8_t* cbase = ebuf + buf * kEpiBufBytes + (cp & 3) * 4;
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const int r0 = (r >> 4) * 16 + hb * 8;
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ii = i ^ ((lane >> 4) & 1);  // the two half-warps read rows of opposite parity: no bank conflict
+              const int rw = r0 + ii;
+              uint32_t u = *reinterpret_cast<const uint32_t*>(cbase + rw * 64 + ((((cp >> 2) ^ (rw >> 1)) & 3) << 4));
+              if (ii >= cs_nv[hb]) u = 0u;
+              const float lo = bf16_lo(u), hi = bf16_hi(u);
+              s0 += lo;
+              q0 = fmaf(lo, lo, q0);
+              s1 += hi;
+              q1 = fmaf(hi, hi, q1);
+            }
+            if (cs_nv[hb] > 0 && oc0 + 2 * cp < p.n_out) red_add_v4(p.col_accum + cs_off[hb] + (oc0 + 2 * cp) * 2, s0, q0, s1, q1);
+          }
         }
         if (lead_warp && elect_one()) {
           if (!(p.dbg & 1)) tma_store_5d(&tmOut, ebuf + buf * kEpiBufBytes, oc0, o[0], o[1], o[2], o[3]);
@@ -794,6 +846,7 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, 
     }
     const float* wp = p.ws + point * p.n_rows_b + n0;
     float fsum = 0.f, fsq = 0.f;
+    float cv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (n0 + j < p.n_rows_b) {
@@ -817,9 +870,21 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, 
           reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + n0 + j] = __float2bfloat16_rn(v);
         fsum += v;
         fsq = fmaf(v, v, fsq);
+        cv[j] = out_f32 ? v : __bfloat162float(__float2bfloat16_rn(v));
       }
     }
     if (p.row_accum) red_add_v2(p.row_accum + 2 * point, fsum, fsq);
+    if (p.col_accum && n0 + 3 < p.n_rows_b) {
+      int64_t rem2 = point, smp = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        smp += (rem2 % p.o_size[j]) * p.cs_mult[j];
+        rem2 /= p.o_size[j];
+      }
+      float* ca = p.col_accum + (smp * p.n_rows_b + n0) * 2;
+      red_add_v4(ca, cv[0], cv[0] * cv[0], cv[1], cv[1] * cv[1]);
+      red_add_v4(ca + 4, cv[2], cv[2] * cv[2], cv[3], cv[3] * cv[3]);
+    }
   }
 }
 
@@ -927,7 +992,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "t2v_gemm: no CUDA device");
   int bn = d->block_n;
-  const int ln_mode = d->row_stats ? 1 : (d->row_accum ? 2 : 0);
+  const int ln_mode = d->row_stats ? 1 : (d->row_accum ? 2 : (d->col_accum ? 3 : 0));
   if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms, geglu, ln_mode != 0);
   if (ln_mode != 0 && bn < 128) return fail(-19, "t2v_gemm: LayerNorm-aware GEMMs need block_n >= 128");
   if (bn != 32 && bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
@@ -990,6 +1055,14 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   p.ln_inv_c = d->ln_channels > 0 ? 1.0f / float(d->ln_channels) : 0.f;
   p.ln_eps = d->ln_eps;
   p.row_accum = d->row_accum;
+  p.col_accum = d->col_accum;
+  for (int j = 0; j < 4; ++j) p.cs_mult[j] = d->cs_mult[j];
+  if (d->col_accum) {
+    if (d->row_stats || d->row_accum) return fail(-20, "t2v_gemm: col_accum excludes row_stats / row_accum");
+    if (geglu || (d->flags & T2V_EPI_OUT_F32) || d->b_rows % 32 || d->n_out != d->b_rows || d->box[0] % 8 || d->cs_mult[0] != 0 ||
+        d->b_batch_dim >= 0 || (reinterpret_cast<uintptr_t>(d->col_accum) & 15))
+      return fail(-20, "t2v_gemm: col_accum needs bf16 output, N %% 32 == 0, box[0] %% 8 == 0, cs_mult[0] == 0, no batched B");
+  }
   if (d->row_stats && d->row_accum) return fail(-19, "t2v_gemm: row_stats and row_accum are mutually exclusive");
   if (d->row_stats && d->ln_raw && d->ln_channels <= 0) return fail(-19, "t2v_gemm: ln_raw needs ln_channels");
   if (d->row_accum) {
@@ -1102,6 +1175,8 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     T2V_GEMM_WIDE(1);
   } else if (ln_mode == 2) {
     T2V_GEMM_WIDE(2);
+  } else if (ln_mode == 3) {
+    T2V_GEMM_WIDE(3);
   } else if (bn == 32) {
     T2V_GEMM_CASE(32, false, 0);
   } else if (bn == 64) {

@@ -37,6 +37,10 @@ struct GnParams {
   int32_t silu;
   float* ws;
   unsigned* ticket;  // lives right after the sums in the workspace
+  // statistics supplied by the producing GEMMs (T2VGemmDesc.col_accum): per source fp32 [samples*cs_group][ch][2]
+  const float* cs0;
+  const float* cs1;
+  int32_t cs_group;  // producer samples per GroupNorm sample (temporal GroupNorm over per-frame sums: t)
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -128,7 +132,27 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) 
   pdl_wait();
   __shared__ float s_ws[2 * 64];
   __shared__ int s_last;
-  {
+  if (p.cs0 != nullptr) {
+    // group statistics from the per-channel sums the producing GEMMs accumulated: no statistics pass, no workspace
+    for (int i = threadIdx.x; i < 2 * p.groups; i += blockDim.x) s_ws[i] = 0.f;
+    __syncthreads();
+    const int c_total = p.ncv * 8, c0n = p.ncv0 * 8;
+    for (int c = threadIdx.x; c < c_total; c += blockDim.x) {
+      const bool src1 = c >= c0n;
+      const float* cs = src1 ? p.cs1 : p.cs0;
+      const int cl = src1 ? c - c0n : c;
+      const int cn = src1 ? c_total - c0n : c0n;
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < p.cs_group; ++k) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(cs) + (int64_t(blockIdx.y) * p.cs_group + k) * cn + cl);
+        a += v.x;
+        b += v.y;
+      }
+      atomicAdd(&s_ws[2 * (c / p.cpg)], a);
+      atomicAdd(&s_ws[2 * (c / p.cpg) + 1], b);
+    }
+    __syncthreads();
+  } else {
     const float* wsg = p.ws + int64_t(blockIdx.y) * 2 * p.groups;
     for (int i = threadIdx.x; i < 2 * p.groups; i += blockDim.x) s_ws[i] = __ldcg(wsg + i);
     __syncthreads();
@@ -463,7 +487,7 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   if (!d) return fail(-1, "t2v_groupnorm: null descriptor");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int C = d->ch[0] + d->ch[1];
-  if (!d->x[0] || !d->out || !d->gamma || !d->beta || !d->workspace)
+  if (!d->x[0] || !d->out || !d->gamma || !d->beta || (!d->workspace && !d->chan_sums[0]))
     return fail(-2, "t2v_groupnorm: null pointer");
   if (d->ch[0] <= 0 || d->ch[0] % 8 || d->ch[1] < 0 || d->ch[1] % 8)
     return fail(-3, "t2v_groupnorm: channel counts must be multiples of 8");
@@ -491,13 +515,19 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   p.eps = d->eps;
   p.silu = d->silu;
   p.ws = d->workspace;
+  p.cs0 = d->chan_sums[0];
+  p.cs1 = d->chan_sums[1];
+  p.cs_group = d->chan_group < 1 ? 1 : d->chan_group;
+  const bool have_sums = d->chan_sums[0] != nullptr;
+  if (have_sums && d->ch[1] > 0 && !d->chan_sums[1]) return fail(-10, "t2v_groupnorm: chan_sums[1] missing for the second source");
+  if (!have_sums) p.cs0 = p.cs1 = nullptr;
   int sms = num_sms();
   if (sms <= 0) return fail(-110, "t2v_groupnorm: no CUDA device");
   // ---- single-kernel path: one thread-block cluster per sample, the sample lives in the cluster's shared memory
   // Measured on B200 (scripts/gn_bench.py): the cluster kernel wins only while the whole tensor is small (its load /
   // reduce / store phases run in lock-step across the GPU); above ~4 MB the statistics + apply pair streams better.
   const bool small = d->rows * int64_t(C) * 2 <= (4 << 20);
-  if (d->mode == 2 || (d->mode == 0 && small)) {
+  if (!have_sums && (d->mode == 2 || (d->mode == 0 && small))) {
     static int max_cl = -1;  // largest usable cluster size (16 needs the non-portable opt-in)
     if (max_cl < 0) {
       cudaError_t e1 = cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGcMaxSlab + 2048);
@@ -540,7 +570,7 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   p.ticket = reinterpret_cast<unsigned*>(d->workspace + 2 * d->groups * n_samples);
   cudaError_t e;
   dim3 grid((unsigned)bps, (unsigned)n_samples);
-  launch_kernel(gn_stats_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
+  if (!have_sums) launch_kernel(gn_stats_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
   launch_kernel(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "t2v_groupnorm launch");

@@ -115,7 +115,7 @@ def _as_pair(x):
 def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w, n_rows, out,
               o_size, o_stride, n_out, bias=None, bias_row_stride=0, bias_dim=-1, bias_div=1,
               residual=None, r_stride=None, alpha=1.0, flags=0, block_n=0, b_batches=1,
-              b_batch_stride=0, b_batch_dim=-1, b_row_stride=0, split_k=0, ln=None, row_accum=None):
+              b_batch_stride=0, b_batch_dim=-1, b_row_stride=0, split_k=0, ln=None, row_accum=None, col_accum=None):
     d = GemmDesc()
     a0, a1 = a
     d.a[0] = a0.data_ptr()
@@ -157,6 +157,9 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
             d.ln_raw, d.ln_channels, d.ln_eps = 1, int(ln[2][0]), float(ln[2][1])
     if row_accum is not None:   # fp32 [M,2], zeroed by the caller: += (sum, sum of squares) of each output row
         d.row_accum = row_accum.data_ptr()
+    if col_accum is not None:   # (fp32 [samples, N, 2] zeroed by the caller, cs_mult): GroupNorm statistics of the output
+        d.col_accum = col_accum[0].data_ptr()
+        _fill(d.cs_mult, col_accum[1])
     ws = _splitk_workspace(out.device)
     d.workspace = ws.data_ptr()
     d.workspace_bytes = ws.numel() * 4
@@ -169,6 +172,28 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
 
 
 import os as _os
+# GroupNorm statistics in the producing GEMM's epilogue (T2VGemmDesc.col_accum -> T2VGroupNormDesc.chan_sums): built,
+# parity-tested, and measured SLOWER on B200 than the statistics kernel it removes (bench: 151.0 frames/s off, 140.7
+# with every K >= 1152 producer fused, 147.1 with K >= 2304): the per-chunk column reduction adds ~130 instructions
+# and, worse, every tile issues its reductions to the same few (frame, channel) addresses — 21 M vector atomics onto
+# 16 KB for one VAE conv.  It therefore stays OFF by default; the next step is a per-CTA shared-memory table flushed on
+# frame change.  T2V_GN_FUSE = off | conv (producers with K >= T2V_GN_FUSE_MIN_K, per-frame consumers) | all.
+GN_FUSE = _os.environ.get("T2V_GN_FUSE", "off")
+GN_FUSE_MIN_K = int(_os.environ.get("T2V_GN_FUSE_MIN_K", "1152"))
+
+
+def gn_fuse_producer(k_total, grid=None, fixed=(None, None, None, None)):
+    """Should a GEMM with reduction length k_total over the output point grid `grid` accumulate GroupNorm statistics
+    for its consumer?  (The epilogue reduces rows in runs of 8 along dim 0: the tile box must allow that.)"""
+    if GN_FUSE == "off" or (GN_FUSE == "conv" and k_total < GN_FUSE_MIN_K):
+        return False
+    return grid is None or plan_box(tuple(int(v) for v in grid), fixed)[0] % 8 == 0
+
+
+def gn_fuse_temporal():
+    return GN_FUSE == "all"
+
+
 GEMM_TUNE = int(_os.environ.get("T2V_GEMM_TUNE", "0"), 0)   # experiments only: see T2VGemmDesc.tune
 _SPLITK_WS: dict = {}
 SPLITK_WS_BYTES = 32 << 20
@@ -216,6 +241,26 @@ def linear(x, w, bias=None, *, residual=None, geglu=False, gelu=False, out=None,
         alpha=alpha, flags=flags, block_n=block_n, split_k=split_k, ln=ln, row_accum=row_accum)
 
 
+def linear_frames(x, w, bias=None, *, hw, residual=None, out=None, stats=None, block_n=0, split_k=0):
+    """linear() over a token matrix [n_frames*hw, K] tiled per frame, so that the epilogue can accumulate the per-frame
+    per-channel GroupNorm statistics of the output (stats: fp32 [n_frames, N, 2], zeroed)."""
+    _check_act(x)
+    m, k = x.shape
+    assert m % hw == 0
+    nf = m // hw
+    n = w.shape[0]
+    assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == k
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=BF16)
+    assert out.stride(0) == n and x.stride(0) == k and (residual is None or residual.stride(0) == n)
+    box = plan_box((hw, nf, 1, 1))
+    return _gemm_raw(
+        a=(x, None), a_ch=(k, 0), a_ch_total=(k, 0), a_size=(hw, nf, 1, 1), a_stride=((k, hw * k, 0, 0), None),
+        box=box, taps=[(0, 0, 0, 0)], tap_ch_off=None, w=w, n_rows=n, out=out,
+        o_size=(hw, nf, 1, 1), o_stride=(n, hw * n, 0, 0), n_out=n, bias=bias, residual=residual,
+        block_n=block_n, split_k=split_k, col_accum=(stats, (0, 1, 0, 0)) if stats is not None else None)
+
+
 def bmm_nt(a, b, *, out=None, alpha=1.0, block_n=0):
     """Batched out[i] = a[i] @ b[i].T.  a: [Bt, M, K], b: [Bt, N, K] bf16 views with arbitrary batch / row
     strides (K contiguous) — used by the VAE AttnBlock (ae_modules.py:55-68) on slices of fused projections."""
@@ -238,9 +283,10 @@ _TAPS_3X3 = [(kx - 1, ky - 1, 0, 0) for ky in range(3) for kx in range(3)]
 _TAPS_T3 = [(0, kt - 1, 0, 0) for kt in range(3)]
 
 
-def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, split_k=0):
+def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, split_k=0, stats=None):
     """3x3 / pad 1 / stride 1 conv over [N,H,W,C] (or a channel-concatenated pair).
-    w: [Cout, 9*C] packed (tap-major); bias: fp32 [rows, Cout], row = frame // bias_div."""
+    w: [Cout, 9*C] packed (tap-major); bias: fp32 [rows, Cout], row = frame // bias_div.
+    stats: fp32 [N, Cout, 2] (zeroed): per-frame per-channel (sum, sum of squares) of the output for the next GroupNorm."""
     x0, x1 = _as_pair(x)
     _check_act(x0)
     n, h, wd, c0 = x0.shape
@@ -256,10 +302,11 @@ def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, 
         box=box, taps=_TAPS_3X3, tap_ch_off=None, w=w, n_rows=cout, out=out,
         o_size=(wd, h, n, 1), o_stride=(cout, wd * cout, h * wd * cout, 0), n_out=cout, bias=bias,
         bias_row_stride=cout if bias is not None else 0, bias_dim=2, bias_div=bias_div,
-        residual=residual, block_n=block_n, split_k=split_k)
+        residual=residual, block_n=block_n, split_k=split_k,
+        col_accum=(stats, (0, 0, 1, 0)) if stats is not None else None)
 
 
-def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0):
+def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0, stats=None):
     """3x3 / pad 1 / stride 2 conv (Downsample, openaimodel3d.py:65-72).  The input is read through a
     parity view [N, H/2, 2, W/2, 2*C] so every tap is a plain box load."""
     _check_act(x)
@@ -283,7 +330,8 @@ def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0):
         a_stride=((2 * c, wd * c, 2 * wd * c, h * wd * c), None), box=b, taps=taps, tap_ch_off=choff,
         w=w, n_rows=cout, out=out, o_size=(w2, 1, h2, n),
         o_stride=(cout, 0, w2 * cout, h2 * w2 * cout), n_out=cout, bias=bias,
-        bias_row_stride=0, bias_dim=-1, block_n=block_n)
+        bias_row_stride=0, bias_dim=-1, block_n=block_n,
+        col_accum=(stats, (0, 0, 0, 1)) if stats is not None else None)
 
 
 # nearest-2x upsample + 3x3 conv == four 2x2 convs on the LOW-resolution input, one per output parity (py, px):
@@ -307,7 +355,7 @@ def pack_upconv_weight(w):
     return torch.stack(phases).to(BF16).contiguous()
 
 
-def upconv3x3(x, w_phases, bias=None, *, out=None, block_n=0):
+def upconv3x3(x, w_phases, bias=None, *, out=None, block_n=0, stats=None):
     """Upsample(nearest, 2x) + Conv2d(3x3, pad 1) (openaimodel3d.py:75-108, ae_modules.py:50-63) on [N,H,W,C]
     -> [N,2H,2W,Cout].  w_phases from pack_upconv_weight; bias fp32 [Cout]."""
     _check_act(x)
@@ -325,11 +373,12 @@ def upconv3x3(x, w_phases, bias=None, *, out=None, block_n=0):
                 a_stride=((c, wd * c, h * wd * c, 0), None), box=box, taps=taps, tap_ch_off=None,
                 w=w_phases[2 * py + px], n_rows=cout, out=out[:, py::2, px::2, :],
                 o_size=(wd, h, n, 1), o_stride=(2 * cout, 4 * wd * cout, 4 * h * wd * cout, 0), n_out=cout,
-                bias=bias, bias_row_stride=0, bias_dim=-1, block_n=block_n)
+                bias=bias, bias_row_stride=0, bias_dim=-1, block_n=block_n,
+                col_accum=(stats, (0, 0, 1, 0)) if stats is not None else None)
     return out
 
 
-def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0, split_k=0):
+def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0, split_k=0, stats=None):
     """Conv3d (3,1,1) / pad (1,0,0) over x: [B, T, HW, C] (TemporalConvBlock, openaimodel3d.py:274-296).
     w: [Cout, 3*C] packed."""
     _check_act(x)
@@ -343,7 +392,8 @@ def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0, split_k=0):
         a=(x, None), a_ch=(c, 0), a_ch_total=(c, 0), a_size=(hw, t, b, 1),
         a_stride=((c, hw * c, t * hw * c, 0), None), box=box, taps=_TAPS_T3, tap_ch_off=None, w=w,
         n_rows=cout, out=out, o_size=(hw, t, b, 1), o_stride=(cout, hw * cout, t * hw * cout, 0),
-        n_out=cout, bias=bias, residual=residual, block_n=block_n, split_k=split_k)
+        n_out=cout, bias=bias, residual=residual, block_n=block_n, split_k=split_k,
+        col_accum=(stats, (0, 1, t, 0)) if stats is not None else None)   # per-frame sums [B*T, Cout, 2]
 
 
 def conv3x3_small_cin(x, w, bias, cout):
@@ -369,7 +419,7 @@ def _gn_workspace(device, n):
     return ws
 
 
-def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None, mode=0):
+def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None, mode=0, chan_sums=None, chan_group=1):
     """GroupNorm(+SiLU) over token matrix x: [rows, C] (or a pair concatenated along C)."""
     x0, x1 = _as_pair(x)
     x0 = x0.reshape(-1, x0.shape[-1])
@@ -398,6 +448,11 @@ def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None
     ws = _gn_workspace(x0.device, 2 * groups * (rows // rows_per_sample) + 1)
     d.workspace = ws.data_ptr()
     d.mode = mode   # 0 auto, 1 two-kernel path, 2 single-kernel cluster path (tests)
+    if chan_sums is not None:   # per-channel sums from the producing GEMMs (one per source): statistics pass skipped
+        cs0, cs1 = _as_pair(chan_sums)
+        d.chan_sums[0] = cs0.data_ptr()
+        d.chan_sums[1] = ptr(cs1)
+        d.chan_group = chan_group
     _launch("groupnorm", _FLOPS.pop("groupnorm", 0), lib().t2v_groupnorm, C.byref(d), stream_ptr())
     return out
 

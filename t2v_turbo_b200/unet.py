@@ -145,6 +145,10 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
+import os as _os
+_DBG_TAGS = set(_os.environ["T2V_GN_FUSE_TAGS"].split(",")) if "T2V_GN_FUSE_TAGS" in _os.environ else None   # debugging only
+
+
 class _PackedAttn:
     """to_q (| to_k | to_v) with the preceding LayerNorm folded in (ops.fold_layernorm): the projection GEMM reads the
     un-normalised residual stream and its epilogue applies the per-row statistics."""
@@ -421,28 +425,41 @@ class UNetModel(nn.Module):
             self._ctx_cache = (key, kv, context)
         return kv
 
-    # ---- LayerNorm row-statistics workspace: one fp32 [rows, 2] slice per LayerNorm instance, all zeroed by a single
-    # memset at the start of a forward.  The first forward of a geometry sizes it (individually zeroed tensors).
+    # ---- statistics workspace.  LayerNorm row sums (fp32 [rows, 2]) and GroupNorm channel sums (fp32 [frames, C, 2]) are
+    # accumulated by the epilogues of the GEMMs that produce the tensors; every instance gets its own slice of one
+    # buffer that a single memset zeroes at the start of a forward.  The first forward of a geometry sizes the buffer
+    # (individually zeroed tensors).
     def _ln_begin(self, key):
         st = self._ln_state
         if st is None or st["key"] != key:
             st = self._ln_state = dict(key=key, buf=None, need=0, cursor=0)
         elif st["buf"] is None and st["need"] > 0:
-            st["buf"] = torch.empty((st["need"], 2), device=key[-1], dtype=torch.float32)
+            st["buf"] = torch.empty((st["need"],), device=key[-1], dtype=torch.float32)
         if st["buf"] is not None:
             st["buf"].zero_()
             st["cursor"] = 0
         else:
             st["need"] = 0
 
-    def _ln_slice(self, rows, device):
+    def _ws_alloc(self, nfloats, device):
+        nfloats = (nfloats + 3) // 4 * 4   # 16-byte aligned slices (vector reductions)
         st = self._ln_state
         if st["buf"] is None:
-            st["need"] += rows
-            return torch.zeros((rows, 2), device=device, dtype=torch.float32)
+            st["need"] += nfloats
+            return torch.zeros((nfloats,), device=device, dtype=torch.float32)
         off = st["cursor"]
-        st["cursor"] = off + rows
-        return st["buf"][off:off + rows]
+        st["cursor"] = off + nfloats
+        return st["buf"][off:off + nfloats]
+
+    def _ln_slice(self, rows, device):
+        return self._ws_alloc(rows * 2, device)[:rows * 2].view(rows, 2)
+
+    def _gn_slice(self, frames, channels, device, k_total, tag="", grid=None, fixed=(None, None, None, None)):
+        """Channel-sum slice for a producer GEMM with reduction length k_total, or None when the fusion does not pay
+        (ops.gn_fuse_producer): the consuming GroupNorm then runs its own statistics pass."""
+        if not ops.gn_fuse_producer(k_total, grid, fixed) or (_DBG_TAGS is not None and tag not in _DBG_TAGS):
+            return None
+        return self._ws_alloc(frames * channels * 2, device)[:frames * channels * 2].view(frames, channels, 2)
 
     def _block(self, blk: _PackedBlock, x, acc1, geom, temporal, ctx_kv, kv_slice):
         b, t, hh, ww = geom
@@ -478,63 +495,80 @@ class UNetModel(nn.Module):
         g = ops.linear(x, blk.w_ff1, blk.b_ff1, geglu=True, ln=(acc3, blk.cs_ff1, (c, blk.ln_eps[2])))
         return ops.linear(g, blk.w_ff2, blk.b_ff2, residual=x)
 
-    def _transformer(self, pt: _PackedTransformer, h, geom, ctx_kv):
+    def _transformer(self, pt: _PackedTransformer, h, h_stats, geom, ctx_kv):
+        """h_stats: per-frame channel sums of h from its producer (or None: GroupNorm runs its own statistics pass).
+        Returns (out, per-frame channel sums of out)."""
         b, t, hh, ww = geom
         c = h.shape[-1]
         x_in = h.view(-1, c)
         rps = hh * ww * (t if pt.temporal else 1)
-        xn = ops.groupnorm(x_in, pt.gn[0], pt.gn[1], rows_per_sample=rps, eps=pt.gn[2], silu=False)
+        xn = ops.groupnorm(x_in, pt.gn[0], pt.gn[1], rows_per_sample=rps, eps=pt.gn[2], silu=False,
+                           chan_sums=h_stats if (not pt.temporal or ops.gn_fuse_temporal()) else None,
+                           chan_group=t if pt.temporal else 1)
         acc1 = self._ln_slice(xn.shape[0], xn.device)
         x = ops.linear(xn, pt.w_in, pt.b_in, row_accum=acc1)
         x = self._block(pt.blk, x, acc1, geom, pt.temporal, ctx_kv, pt.kv_slice)
-        out = ops.linear(x, pt.w_out, pt.b_out, residual=x_in)
-        return out.view(b * t, hh, ww, c)
+        so = self._gn_slice(b * t, c, h.device, c, "tr", (hh * ww, b * t, 1, 1))
+        out = ops.linear_frames(x, pt.w_out, pt.b_out, hw=hh * ww, residual=x_in, stats=so)
+        return out.view(b * t, hh, ww, c), so
 
-    def _resblock(self, pr: _PackedRes, x, emb_rows, geom):
+    def _resblock(self, pr: _PackedRes, x, x_stats, emb_rows, geom):
+        """x: tensor or (h, skip) pair; x_stats: matching per-frame channel sums (or None).  Every conv of the block
+        accumulates the GroupNorm statistics of its output, so only the apply pass of each GroupNorm runs."""
         b, t, hh, ww = geom
         hw = hh * ww
+        nf = b * t
         x0, x1 = x if isinstance(x, tuple) else (x, None)
+        dev = x0.device
         cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
-        hn = ops.groupnorm(x, pr.gn1[0], pr.gn1[1], rows_per_sample=hw, eps=pr.gn1[2], silu=True)
+        hn = ops.groupnorm(x, pr.gn1[0], pr.gn1[1], rows_per_sample=hw, eps=pr.gn1[2], silu=True, chan_sums=x_stats)
         off, cout = pr.emb_slice
         rowbias = emb_rows[:, off:off + cout].contiguous()
-        h = ops.conv3x3(hn.view(b * t, hh, ww, cin), pr.w1, rowbias, bias_div=t)
-        hn2 = ops.groupnorm(h.view(-1, cout), pr.gn2[0], pr.gn2[1], rows_per_sample=hw, eps=pr.gn2[2], silu=True)
+        s1 = self._gn_slice(nf, cout, dev, 9 * cin, "res1", (ww, hh, nf, 1))
+        h = ops.conv3x3(hn.view(nf, hh, ww, cin), pr.w1, rowbias, bias_div=t, stats=s1)
+        hn2 = ops.groupnorm(h.view(-1, cout), pr.gn2[0], pr.gn2[1], rows_per_sample=hw, eps=pr.gn2[2], silu=True, chan_sums=s1)
         if pr.w_skip is None:
             res = x0
         else:
             xa = x0.view(-1, x0.shape[-1])
             xb = x1.view(-1, x1.shape[-1]) if x1 is not None else None
-            res = ops.linear((xa, xb) if xb is not None else xa, pr.w_skip, pr.b_skip).view(b * t, hh, ww, cout)
-        h = ops.conv3x3(hn2.view(b * t, hh, ww, cout), pr.w2, pr.b2, bias_div=b * t, residual=res)
+            res = ops.linear((xa, xb) if xb is not None else xa, pr.w_skip, pr.b_skip).view(nf, hh, ww, cout)
+        s2 = self._gn_slice(nf, cout, dev, 9 * cout, "res2", (ww, hh, nf, 1))
+        h = ops.conv3x3(hn2.view(nf, hh, ww, cout), pr.w2, pr.b2, bias_div=nf, residual=res, stats=s2)
         if pr.tconv is not None:
             ident = h.view(b, t, hw, cout)
-            y = ident
+            y, ys = ident, s2
             for i, (gn, w, bias) in enumerate(pr.tconv):
-                yn = ops.groupnorm(y.view(-1, cout), gn[0], gn[1], rows_per_sample=t * hw, eps=gn[2], silu=True)
-                y = ops.tconv3(yn.view(b, t, hw, cout), w, bias, residual=ident if i == 3 else None)
-            h = y.view(b * t, hh, ww, cout)
-        return h
+                yn = ops.groupnorm(y.view(-1, cout), gn[0], gn[1], rows_per_sample=t * hw, eps=gn[2], silu=True,
+                                   chan_sums=ys if ops.gn_fuse_temporal() else None, chan_group=t)
+                ys = self._gn_slice(nf, cout, dev, 3 * cout, "tconv", (hw, t, b, 1))
+                y = ops.tconv3(yn.view(b, t, hw, cout), w, bias, residual=ident if i == 3 else None, stats=ys)
+            h, s2 = y.view(nf, hh, ww, cout), ys
+        return h, s2
 
-    def _run_seq(self, items, h, emb_rows, geom, ctx_kv, P):
+    def _run_seq(self, items, h, h_stats, emb_rows, geom, ctx_kv, P):
+        """h / h_stats: activation (or (h, skip) pair) and the per-frame channel sums its producer accumulated."""
         b, t, hh, ww = geom
         for kind, pk in items:
             if kind == "res":
-                h = self._resblock(pk, h, emb_rows, geom)
+                h, h_stats = self._resblock(pk, h, h_stats, emb_rows, geom)
             elif kind in ("st", "tt"):
-                h = self._transformer(pk, h, geom, ctx_kv)
+                h, h_stats = self._transformer(pk, h, h_stats, geom, ctx_kv)
             elif kind == "down":
-                h = ops.conv3x3_s2(h, pk[0], pk[1])
+                h_stats = self._gn_slice(b * t, pk[0].shape[0], h.device, pk[0].shape[1], "down", (ww // 2, 1, hh // 2, b * t), (None, 1, None, None))
+                h = ops.conv3x3_s2(h, pk[0], pk[1], stats=h_stats)
                 hh, ww = hh // 2, ww // 2
                 geom = (b, t, hh, ww)
             elif kind == "up":
-                h = ops.upconv3x3(h, pk[0], pk[1])
+                h_stats = self._gn_slice(b * t, pk[0].shape[1], h.device, pk[0].shape[2], "up", (ww, hh, b * t, 1))
+                h = ops.upconv3x3(h, pk[0], pk[1], stats=h_stats)
                 hh, ww = hh * 2, ww * 2
                 geom = (b, t, hh, ww)
             elif kind == "conv_in":
                 w, bias = P["conv_in"]
                 h = ops.conv3x3_small_cin(h, w, bias, self.model_channels)
-        return h, geom
+                h_stats = None   # 4-channel direct conv: the first GroupNorm computes its own statistics
+        return h, h_stats, geom
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -555,17 +589,20 @@ class UNetModel(nn.Module):
         h = ops.bcthw_to_frames(x, 1.0)
         geom = (b, t, hh, ww)
         hs = []
+        st = None
         for i, items in enumerate(P["input"]):
-            h, geom = self._run_seq(items, h, emb_rows, geom, ctx_kv, P)
+            h, st, geom = self._run_seq(items, h, st, emb_rows, geom, ctx_kv, P)
             if i == 0 and P["init_attn"] is not None:
-                h, geom = self._run_seq(P["init_attn"], h, emb_rows, geom, ctx_kv, P)
-            hs.append(h)
-        h, geom = self._run_seq(P["middle"], h, emb_rows, geom, ctx_kv, P)
+                h, st, geom = self._run_seq(P["init_attn"], h, st, emb_rows, geom, ctx_kv, P)
+            hs.append((h, st))
+        h, st, geom = self._run_seq(P["middle"], h, st, emb_rows, geom, ctx_kv, P)
         for items in P["output"]:
-            h, geom = self._run_seq([items[0]], (h, hs.pop()), emb_rows, geom, ctx_kv, P)
-            h, geom = self._run_seq(items[1:], h, emb_rows, geom, ctx_kv, P)
+            skip, skip_st = hs.pop()
+            pair_st = (st, skip_st) if (st is not None and skip_st is not None) else None
+            h, st, geom = self._run_seq([items[0]], (h, skip), pair_st, emb_rows, geom, ctx_kv, P)
+            h, st, geom = self._run_seq(items[1:], h, st, emb_rows, geom, ctx_kv, P)
         gn, w, bias = P["out"]
         c = h.shape[-1]
-        hn = ops.groupnorm(h.view(-1, c), gn[0], gn[1], rows_per_sample=geom[2] * geom[3], eps=gn[2], silu=True)
+        hn = ops.groupnorm(h.view(-1, c), gn[0], gn[1], rows_per_sample=geom[2] * geom[3], eps=gn[2], silu=True, chan_sums=st)
         y = ops.conv3x3(hn.view(b * t, geom[2], geom[3], c), w, bias, bias_div=b * t)
         return ops.frames_to_bcthw(y, b, self.out_channels, x.dtype)

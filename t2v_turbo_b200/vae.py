@@ -83,6 +83,24 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
+class _StatsPool:
+    """Zeroed fp32 workspace for the per-frame channel sums the GEMM epilogues accumulate (one memset per decode)."""
+
+    def __init__(self, device, nfloats):
+        self.buf = torch.zeros((nfloats,), device=device, dtype=torch.float32)
+        self.cur = 0
+
+    def take(self, frames, channels, k_total, grid):
+        if not ops.gn_fuse_producer(k_total, grid):
+            return None
+        n = frames * channels * 2
+        if self.cur + n > self.buf.numel():
+            raise RuntimeError("AutoencoderKL(B200): statistics workspace exhausted")
+        v = self.buf[self.cur:self.cur + n].view(frames, channels, 2)
+        self.cur += (n + 3) // 4 * 4
+        return v
+
+
 def _w2d(w):
     return w.detach().reshape(w.shape[0], -1).to(BF16).contiguous()
 
@@ -151,22 +169,26 @@ class AutoencoderKL(nn.Module):
         return self
 
     # ------------------------------------------------------------------ pieces
+    # Every conv / projection accumulates the per-frame channel sums of its output in its epilogue (`stats`), so each
+    # GroupNorm ("Normalize", ae_modules.py:16-19) runs only its apply pass.  `pool` hands out zeroed fp32 slices.
     @staticmethod
-    def _res(pr: _PRes, h):
+    def _res(pr: _PRes, h, hs, pool):
         n, hh, ww, c = h.shape
         hw = hh * ww
-        t = ops.groupnorm(h.view(-1, c), pr.gn1[0], pr.gn1[1], rows_per_sample=hw, eps=1e-6, silu=True)
-        t = ops.conv3x3(t.view(n, hh, ww, c), pr.w1, pr.b1, bias_div=n)
-        t = ops.groupnorm(t.view(-1, pr.cout), pr.gn2[0], pr.gn2[1], rows_per_sample=hw, eps=1e-6, silu=True)
+        t = ops.groupnorm(h.view(-1, c), pr.gn1[0], pr.gn1[1], rows_per_sample=hw, eps=1e-6, silu=True, chan_sums=hs)
+        s1 = pool.take(n, pr.cout, 9 * c, (ww, hh, n, 1))
+        t = ops.conv3x3(t.view(n, hh, ww, c), pr.w1, pr.b1, bias_div=n, stats=s1)
+        t = ops.groupnorm(t.view(-1, pr.cout), pr.gn2[0], pr.gn2[1], rows_per_sample=hw, eps=1e-6, silu=True, chan_sums=s1)
         res = h if pr.w_nin is None else ops.linear(h.view(-1, c), pr.w_nin, pr.b_nin).view(n, hh, ww, pr.cout)
-        return ops.conv3x3(t.view(n, hh, ww, pr.cout), pr.w2, pr.b2, bias_div=n, residual=res)
+        s2 = pool.take(n, pr.cout, 9 * pr.cout, (ww, hh, n, 1))
+        return ops.conv3x3(t.view(n, hh, ww, pr.cout), pr.w2, pr.b2, bias_div=n, residual=res, stats=s2), s2
 
     @staticmethod
-    def _attn(pa, h):
+    def _attn(pa, h, hs, pool):
         n, hh, ww, c = h.shape
         hw = hh * ww
         x = h.view(-1, c)
-        xn = ops.groupnorm(x, pa["gn"][0], pa["gn"][1], rows_per_sample=hw, eps=1e-6, silu=False)
+        xn = ops.groupnorm(x, pa["gn"][0], pa["gn"][1], rows_per_sample=hw, eps=1e-6, silu=False, chan_sums=hs)
         qk = ops.linear(xn, pa["w_qk"], pa["b_qk"])                      # [n*hw, 2c]
         q = qk[:, :c].view(n, hw, c)                                      # strided views of the fused projection
         k = qk[:, c:].view(n, hw, c)
@@ -175,7 +197,8 @@ class AutoencoderKL(nn.Module):
         # V^T for all frames in one GEMM: [c, n*hw] = W_v @ xn^T
         vt = ops.linear(pa["w_v"], xn, None)                              # A = W_v [c, c], B = xn [n*hw, c]
         o = ops.bmm_nt(s, vt.view(c, n, hw).permute(1, 0, 2))             # [n, hw, c] = P @ V (V^T read in place)
-        return ops.linear(o.view(-1, c), pa["w_o"], pa["b_o"], residual=x).view(n, hh, ww, c)
+        so = pool.take(n, c, c, (hw, n, 1, 1))
+        return ops.linear_frames(o.view(-1, c), pa["w_o"], pa["b_o"], hw=hw, residual=x, stats=so).view(n, hh, ww, c), so
 
     # ------------------------------------------------------------------ API
     @torch.no_grad()
@@ -194,17 +217,20 @@ class AutoencoderKL(nn.Module):
                     fr.data_ptr(), b, c, t, hh, ww, float(scale), P["pq_w"].data_ptr(), P["pq_b"].data_ptr(), stream_ptr())
         w, bias, cout = P["conv_in"]
         h = ops.conv3x3_small_cin(fr, w, bias, cout)
-        h = self._res(P["mid1"], h)
-        h = self._attn(P["attn"], h)
-        h = self._res(P["mid2"], h)
+        pool = _StatsPool(z.device, b * t * 512 * 2 * 48)
+        h, hs = self._res(P["mid1"], h, None, pool)       # (conv_in is a direct 4-channel conv: no sums for the first norm)
+        h, hs = self._attn(P["attn"], h, hs, pool)
+        h, hs = self._res(P["mid2"], h, hs, pool)
         for i_level in reversed(range(len(P["up"]))):
             blocks, ups = P["up"][i_level]
             for pr in blocks:
-                h = self._res(pr, h)
+                h, hs = self._res(pr, h, hs, pool)
             if ups is not None:
-                h = ops.upconv3x3(h, ups[0], ups[1])
+                hs = pool.take(h.shape[0], ups[0].shape[1], ups[0].shape[2], (h.shape[2], h.shape[1], h.shape[0], 1))
+                h = ops.upconv3x3(h, ups[0], ups[1], stats=hs)
         n, hh2, ww2, ch = h.shape
-        hn = ops.groupnorm(h.view(-1, ch), P["norm_out"][0], P["norm_out"][1], rows_per_sample=hh2 * ww2, eps=1e-6, silu=True)
+        hn = ops.groupnorm(h.view(-1, ch), P["norm_out"][0], P["norm_out"][1], rows_per_sample=hh2 * ww2, eps=1e-6, silu=True,
+                           chan_sums=hs)
         w, bias, cout = P["conv_out"]
         y = ops.conv3x3(hn.view(n, hh2, ww2, ch), w, bias, bias_div=n)
         return ops.frames_to_bcthw(y, b, cout, z.dtype)

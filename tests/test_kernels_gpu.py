@@ -308,6 +308,95 @@ def test_conv_small_cin(cuda_device):
 
 
 # ----------------------------------------------------------------------------- norms
+# GroupNorm statistics accumulated by the producing GEMM's epilogue (col_accum) and consumed by t2v_groupnorm (chan_sums)
+def _chan_sums_ref(y, n_samples):
+    yf = y.float().reshape(n_samples, -1, y.shape[-1])
+    return torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 8, 16, 64, 64), (16, 10, 16, 128, 320), (16, 5, 8, 128, 128), (2, 40, 64, 64, 320)])
+def test_conv3x3_groupnorm_stats(cuda_device, n, h, w, cin, cout):
+    ops = _ops()
+    x = rnd(n, h, w, cin, seed=70).to(BF16)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=71).to(BF16)
+    b = rnd(1, cout, seed=72)
+    res = (rnd(n, h, w, cout, seed=73) + 0.3).to(BF16)
+    stats = torch.zeros(n, cout, 2, device=x.device)
+    y = ops.conv3x3(x, ops.pack_conv_weight(wt), b, bias_div=n, residual=res, stats=stats)
+    ref = _chan_sums_ref(y, n)
+    torch.testing.assert_close(stats, ref, rtol=2e-3, atol=2e-2)
+    g = rnd(cout, seed=74) * 0.2 + 1
+    be = rnd(cout, seed=75) * 0.2
+    out = ops.groupnorm(y.view(-1, cout), g, be, rows_per_sample=h * w, eps=1e-5, silu=True, chan_sums=stats)
+    gn = F.silu(F.group_norm(y.float().permute(0, 3, 1, 2), 32, g, be, 1e-5)).permute(0, 2, 3, 1).reshape(-1, cout)
+    assert_close(out, gn, what="groupnorm from producer sums")
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1,cout,t", [(8, 8, 8, 64, 64, 64, 4), (4, 4, 4, 64, 0, 128, 4), (16, 40, 64, 64, 64, 320, 16)])
+def test_conv3x3_groupnorm_stats_no_residual(cuda_device, n, h, w, c0, c1, cout, t):
+    """ResBlock in_layers conv: concatenated input, per-batch-element bias rows (emb), no residual."""
+    ops = _ops()
+    xa = rnd(n, h, w, c0, seed=90).to(BF16)
+    xb = rnd(n, h, w, c1, seed=91).to(BF16) if c1 else None
+    cin = c0 + c1
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=92).to(BF16)
+    bias = rnd(n // t, cout, seed=93)
+    stats = torch.zeros(n, cout, 2, device=xa.device)
+    y = ops.conv3x3((xa, xb) if xb is not None else xa, ops.pack_conv_weight(wt), bias, bias_div=t, stats=stats)
+    xin = torch.cat([xa, xb], -1) if xb is not None else xa
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), wt.float(), None, padding=1).permute(0, 2, 3, 1) + bias.repeat_interleave(t, 0)[:, None, None, :]
+    assert_close(y, ref, what="conv3x3 (stats, no residual)")
+    torch.testing.assert_close(stats, _chan_sums_ref(y, n), rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(8, 16, 16, 64, 64), (4, 8, 8, 64, 128), (16, 40, 64, 64, 320)])
+def test_conv3x3_s2_groupnorm_stats(cuda_device, n, h, w, cin, cout):
+    ops = _ops()
+    x = rnd(n, h, w, cin, seed=94).to(BF16)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=95).to(BF16)
+    stats = torch.zeros(n, cout, 2, device=x.device)
+    y = ops.conv3x3_s2(x, ops.pack_conv_weight(wt), rnd(cout, seed=96), stats=stats)
+    torch.testing.assert_close(stats, _chan_sums_ref(y, n), rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("b,t,hw,c", [(1, 16, 40, 128), (2, 4, 160, 64)])
+def test_tconv3_groupnorm_stats_temporal(cuda_device, b, t, hw, c):
+    """per-frame sums from the (3,1,1) conv, consumed by a GroupNorm over (t, hw) per batch element (chan_group = t)."""
+    ops = _ops()
+    x = rnd(b, t, hw, c, seed=76).to(BF16)
+    wt = rnd(c, c, 3, 1, 1, scale=(3 * c) ** -0.5, seed=77).to(BF16)
+    stats = torch.zeros(b * t, c, 2, device=x.device)
+    y = ops.tconv3(x, ops.pack_conv_weight(wt), rnd(c, seed=78), stats=stats)
+    torch.testing.assert_close(stats, _chan_sums_ref(y, b * t), rtol=2e-3, atol=2e-2)
+    g = rnd(c, seed=79) * 0.2 + 1
+    be = rnd(c, seed=80) * 0.2
+    out = ops.groupnorm(y.view(-1, c), g, be, rows_per_sample=t * hw, eps=1e-5, silu=True, chan_sums=stats, chan_group=t)
+    gn = F.silu(F.group_norm(y.float().view(b, t * hw, c).permute(0, 2, 1), 32, g, be, 1e-5)).permute(0, 2, 1).reshape(-1, c)
+    assert_close(out, gn, what="temporal groupnorm from per-frame sums")
+
+
+@pytest.mark.parametrize("nf,hw,k,n,split_k", [(16, 160, 320, 320, 0), (16, 40, 1280, 1280, 0), (4, 640, 128, 640, 0), (16, 40, 2048, 128, 4)])
+def test_linear_frames_groupnorm_stats_concat(cuda_device, nf, hw, k, n, split_k):
+    """proj_out (+residual) tiled per frame; its sums feed a GroupNorm over the concatenation with a second tensor."""
+    ops = _ops()
+    x = rnd(nf * hw, k, seed=81).to(BF16)
+    w = rnd(n, k, scale=k ** -0.5, seed=82).to(BF16)
+    res = rnd(nf * hw, n, seed=83).to(BF16)
+    stats = torch.zeros(nf, n, 2, device=x.device)
+    y = ops.linear_frames(x, w, rnd(n, seed=84), hw=hw, residual=res, stats=stats, split_k=split_k)
+    assert_close(y, x.float() @ w.float().t() + rnd(n, seed=84) + res.float(), what="linear_frames")
+    torch.testing.assert_close(stats, _chan_sums_ref(y, nf), rtol=2e-3, atol=2e-2)
+    skip = (rnd(nf * hw, 64, seed=85) * 2).to(BF16)
+    s2 = _chan_sums_ref(skip, nf).contiguous()
+    c = n + 64
+    g = rnd(c, seed=86) * 0.2 + 1
+    be = rnd(c, seed=87) * 0.2
+    out = ops.groupnorm((y, skip), g, be, rows_per_sample=hw, eps=1e-5, silu=True, chan_sums=(stats, s2))
+    cat = torch.cat([y, skip], 1).float().view(nf, hw, c).permute(0, 2, 1)
+    gn = F.silu(F.group_norm(cat, 32, g, be, 1e-5)).permute(0, 2, 1).reshape(-1, c)
+    assert_close(out, gn, what="concat groupnorm from producer sums")
+
+
 # mode 1 = statistics + apply kernel pair, mode 2 = single-kernel cluster path (must not fall back), 0 = automatic
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("n,hw,c,rps_mult,silu", [(4, 160, 320, 1, True), (2, 40, 1280, 2, True), (6, 64, 128, 3, False),
