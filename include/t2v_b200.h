@@ -243,6 +243,10 @@ int t2v_conv3x3_small_cin(const void* in, const void* w, const float* bias, void
 /* [B,C,T,H,W] (any float dtype given by in_dtype: 0 bf16, 1 fp16, 2 fp32) -> [B*T,H,W,C] bf16, times scale */
 int t2v_bcthw_to_frames(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
                         int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t stream);
+/* same with the channel count padded to c_pad (<= 8) by zero channels: RGB video -> 4-channel frames for the
+ * encoder's direct small-Cin conv (ae_modules.py:411-413) */
+int t2v_bcthw_to_frames_pad(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c, int32_t c_pad,
+                            int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t stream);
 /* same, followed by a per-pixel channel mix out[o] = sum_c mix[o][c] * scale * in[c] + bias[o]  (c <= 8):
  * `1/scale_factor * z` + post_quant_conv 1x1 (ddpm3d.py:669, autoencoder.py:111). mix/bias: fp32 device arrays */
 int t2v_bcthw_to_frames_mix(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
@@ -273,6 +277,12 @@ int t2v_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t row_stride, fl
 int t2v_lcm_step(const void* x, const void* eps, const void* noise, void* prev, void* denoised,
                  int64_t n, int32_t dtype, float inv_sqrt_alpha_t, float sqrt_beta_t, float c_skip,
                  float c_out, float sqrt_alpha_prev, float sqrt_beta_prev, t2v_stream_t stream);
+
+/* KL-VAE posterior (lvdm/distributions.py:24-42 + ddpm3d.py:558-567): moments fp32 channels-last
+ * [B*T, H, W, 2*zc] = (mean | logvar) -> out [B, zc, T, H, W] (out_dtype 0 bf16 / 1 fp16 / 2 fp32)
+ * = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise); noise fp32 [B*T, zc, H, W] or NULL (posterior mode). */
+int t2v_gaussian_sample(const float* moments, const float* noise, void* out, int32_t out_dtype, int32_t b,
+                        int32_t t, int32_t h, int32_t w, int32_t zc, float scale, t2v_stream_t stream);
 
 /* Weight packing helpers (device-side, run once at load). */
 /* conv weight [Cout][Cin][kh*kw] (torch OIHW / OIDHW flattened taps) -> [Cout][taps][Cin] bf16 */

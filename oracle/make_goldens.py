@@ -76,6 +76,35 @@ def gen_vae(name):
     torch.save({"name": name, "z": z, "output": out}, os.path.join(GOLD, f"vae_{name}.pt"))
 
 
+def gen_vae_enc(name):
+    """Encode path: reference Encoder + quant_conv + DiagonalGaussianDistribution.sample with a seeded
+    noise tensor (the reference draws it on the CPU, distributions.py:38-41), times scale_factor (ddpm3d.py:558-567)."""
+    from lvdm.modules.networks.ae_modules import Encoder
+    from lvdm.distributions import DiagonalGaussianDistribution
+    spec = VAE_CONFIGS[name]
+    dd = spec["ddconfig"]
+    enc = Encoder(**dd).eval()
+    qc = torch.nn.Conv2d(2 * dd["z_channels"], 2 * spec["embed_dim"], 1)
+    template = {f"encoder.{k}": v for k, v in enc.state_dict().items()}
+    template.update({f"quant_conv.{k}": v for k, v in qc.state_dict().items()})
+    sd = seeded_state_dict(template, spec["weight_seed"] + 100)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")})
+    qc.load_state_dict({k[len("quant_conv."):]: v for k, v in sd.items() if k.startswith("quant_conv.")})
+    g = torch.Generator().manual_seed(spec["input_seed"] + 100)
+    b, _, t, hz, wz = spec["z_shape"]
+    f = 2 ** (len(dd["ch_mult"]) - 1)   # spatial reduction of the encoder
+    x = torch.randn((b, 3, t, hz * f, wz * f), generator=g)
+    noise = torch.randn((b * t, spec["embed_dim"], hz, wz), generator=g)
+    with torch.no_grad():
+        frames = x.permute(0, 2, 1, 3, 4).reshape(b * t, 3, hz * f, wz * f)
+        post = DiagonalGaussianDistribution(qc(enc(frames)))
+        z = 0.18215 * post.sample(noise=noise)
+        zm = 0.18215 * post.mode()
+        back = lambda v: v.reshape(b, t, *v.shape[1:]).permute(0, 2, 1, 3, 4).contiguous()
+    print(f"  vae_enc {name}: z std {z.std():.4f} absmax {z.abs().max():.4f}; moments absmax {post.parameters.abs().max():.3f}")
+    torch.save({"name": name, "x": x, "noise": noise, "z_sample": back(z), "z_mode": back(zm)}, os.path.join(GOLD, f"vae_enc_{name}.pt"))
+
+
 def gen_scheduler():
     from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
     s = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
@@ -161,13 +190,15 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "pipeline"] + (["unet_full", "vae_full"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "pipeline"] + (["unet_full", "vae_full", "vae_enc_full"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
             gen_scheduler()
         elif item.startswith("unet_"):
             gen_unet(item[5:])
+        elif item.startswith("vae_enc_"):
+            gen_vae_enc(item[8:])
         elif item.startswith("vae_"):
             gen_vae(item[4:])
         elif item == "pipeline":

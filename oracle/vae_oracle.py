@@ -70,3 +70,43 @@ def decode_first_stage_2dae(sd, ddconfig, z, scale_factor=0.18215):
         zi = F.conv2d(z[:, :, i], sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])  # autoencoder.py:111
         frames.append(decoder_forward(sd, ddconfig, zi).unsqueeze(2))
     return torch.cat(frames, dim=2)
+
+
+# ------------------------------------------------------------------------------------------ encode path
+def encoder_forward(sd, ddconfig, x, prefix="encoder"):
+    """ae_modules.py:470-503 `Encoder.forward` (attn_resolutions=[], temb=None).  Downsample (ae_modules.py:87-105):
+    zero-pad right/bottom by one, then a stride-2 3x3 conv without padding."""
+    nres = len(ddconfig["ch_mult"])
+    nrb = ddconfig["num_res_blocks"]
+    h = F.conv2d(x, sd[f"{prefix}.conv_in.weight"], sd[f"{prefix}.conv_in.bias"], padding=1)
+    for i_level in range(nres):
+        for i_block in range(nrb):
+            h = resnet_block(sd, f"{prefix}.down.{i_level}.block.{i_block}", h)
+        if i_level != nres - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = F.conv2d(h, sd[f"{prefix}.down.{i_level}.downsample.conv.weight"],
+                         sd[f"{prefix}.down.{i_level}.downsample.conv.bias"], stride=2)
+    h = resnet_block(sd, f"{prefix}.mid.block_1", h)
+    h = attn_block(sd, f"{prefix}.mid.attn_1", h)
+    h = resnet_block(sd, f"{prefix}.mid.block_2", h)
+    h = _swish(_norm(sd, f"{prefix}.norm_out", h))
+    return F.conv2d(h, sd[f"{prefix}.conv_out.weight"], sd[f"{prefix}.conv_out.bias"], padding=1)
+
+
+def encode_moments(sd, ddconfig, x):
+    """autoencoder.py:103-107: moments = quant_conv(encoder(x)); x [n, 3, H, W] -> [n, 2*embed_dim, H/8, W/8]."""
+    return F.conv2d(encoder_forward(sd, ddconfig, x), sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def encode_first_stage(sd, ddconfig, x, noise=None, scale_factor=0.18215):
+    """ddpm3d.py:558-584: x [b, 3, t, H, W] -> scale_factor * (mean + std * noise), [b, c, t, H/8, W/8].
+    distributions.py:24-42: logvar clamped to [-30, 20], std = exp(logvar / 2); noise=None -> posterior mode (mean)."""
+    b, _, t = x.shape[:3]
+    frames = x.permute(0, 2, 1, 3, 4).reshape(b * t, *x.shape[1:2], *x.shape[3:])
+    mom = encode_moments(sd, ddconfig, frames)
+    mean, logvar = torch.chunk(mom, 2, dim=1)
+    z = mean
+    if noise is not None:
+        z = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+    z = scale_factor * z
+    return z.reshape(b, t, *z.shape[1:]).permute(0, 2, 1, 3, 4)

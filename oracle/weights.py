@@ -31,3 +31,14 @@ def seeded_state_dict(template: dict, seed: int) -> dict:
             v = 0.05 * torch.randn(shape, generator=g)
         out[name] = v
     return out
+
+
+def vae_state_dict(module_sd: dict, seed: int) -> dict:
+    """AutoencoderKL weights for the parity tests, identical to what oracle/make_goldens.py loaded into the reference:
+    the decode side (`decoder.*`, `post_quant_conv.*`) from `seed`, the encode side (`encoder.*`, `quant_conv.*`)
+    from `seed + 100`, each generated over its own sorted key set."""
+    dec = {k: v for k, v in module_sd.items() if k.startswith(("decoder.", "post_quant_conv."))}
+    enc = {k: v for k, v in module_sd.items() if k.startswith(("encoder.", "quant_conv."))}
+    out = seeded_state_dict(dec, seed)
+    out.update(seeded_state_dict(enc, seed + 100))
+    return out

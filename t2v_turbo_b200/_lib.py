@@ -138,11 +138,13 @@ SYMBOLS = {
     "t2v_sinusoidal_embedding": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_conv3x3_small_cin": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "t2v_bcthw_to_frames": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "t2v_bcthw_to_frames_pad": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "t2v_bcthw_to_frames_mix": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "t2v_frames_to_bcthw": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "t2v_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_concat_channels": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "t2v_softmax_rows": (C.c_int, [_vp, _i64, _i32, _i64, _f32, _vp]),
+    "t2v_gaussian_sample": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "t2v_lcm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "t2v_pack_conv_weight": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp]),
     "t2v_pack_geglu_rows": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),

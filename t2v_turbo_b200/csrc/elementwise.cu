@@ -203,6 +203,20 @@ __global__ void bcthw_to_frames_mix_kernel(const void* in, int in_dtype, __nv_bf
     }
   }
 }
+// [B,C,T,H,W] -> [B*T,H,W,c_pad] bf16 with channels c..c_pad-1 zero (RGB -> 4-channel frames for the small-Cin conv)
+__global__ void bcthw_to_frames_pad_kernel(const void* in, int in_dtype, __nv_bfloat16* out, int b, int c, int c_pad,
+                                           int t, int h, int w, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = int64_t(b) * t * h * w;
+  const int64_t plane = int64_t(t) * h * w;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t bi = i / plane, rem = i % plane;
+    for (int o = 0; o < c_pad; ++o)
+      out[i * c_pad + o] = __float2bfloat16_rn(o < c ? load_as_float(in, (bi * c + o) * plane + rem, in_dtype) * scale : 0.f);
+  }
+}
 __global__ void frames_to_bcthw_kernel(const __nv_bfloat16* in, int c_pad, void* out, int out_dtype,
                                        int b, int c, int t, int h, int w) {
   pdl_launch_dependents();
@@ -271,6 +285,34 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* x, int
   const float inv = 1.0f / sum;
   for (int c = threadIdx.x; c < cols; c += blockDim.x)
     row[c] = __float2bfloat16_rn(__expf(__bfloat162float(row[c]) * scale - mx) * inv);
+}
+
+// ------------------------------------------------------------------ posterior sample of the KL-VAE encoder
+// moments: fp32 channels-last [B*T, H, W, 2*zc] (mean | logvar); noise: fp32 [B*T, zc, H, W] (the reference's layout,
+// may be null = posterior mode); out: [B, zc, T, H, W] in out_dtype = scale * (mean + exp(0.5 clamp(logvar,-30,20)) * noise)
+__global__ void gaussian_sample_kernel(const float* __restrict__ mom, const float* __restrict__ noise, void* out,
+                                       int out_dtype, int b, int t, int h, int w, int zc, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t plane = int64_t(h) * w;
+  const int64_t total = int64_t(b) * t * plane * zc;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    // i indexes the output [b][zc][t][h*w]
+    const int64_t px = i % plane;
+    int64_t r = i / plane;
+    const int ti = int(r % t);
+    r /= t;
+    const int c = int(r % zc);
+    const int bi = int(r / zc);
+    const int64_t f = int64_t(bi) * t + ti;
+    const float* m = mom + (f * plane + px) * (2 * zc);
+    float z = m[c];
+    if (noise != nullptr) {
+      const float lv = fminf(fmaxf(m[zc + c], -30.f), 20.f);
+      z = fmaf(expf(0.5f * lv), noise[(f * zc + c) * plane + px], z);
+    }
+    store_from_float(out, i, out_dtype, scale * z);
+  }
 }
 
 // ------------------------------------------------------------------ fused LCM step
@@ -423,6 +465,16 @@ extern "C" int t2v_bcthw_to_frames_mix(const void* in, int32_t in_dtype, void* o
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_bcthw_to_frames_mix launch");
 }
 
+extern "C" int t2v_bcthw_to_frames_pad(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c, int32_t c_pad,
+                                       int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t s) {
+  if (!in || !out) return fail(-1, "t2v_bcthw_to_frames_pad: null pointer");
+  if (c < 1 || c_pad < c || c_pad > 8) return fail(-2, "t2v_bcthw_to_frames_pad: need 1 <= c <= c_pad <= 8");
+  const int64_t total = int64_t(b) * t * h * w;
+  launch_kernel(bcthw_to_frames_pad_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(s), in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, c_pad, t, h, w, scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_bcthw_to_frames_pad launch");
+}
+
 extern "C" int t2v_frames_to_bcthw(const void* in, int32_t c_pad, void* out, int32_t out_dtype, int32_t b,
                                    int32_t c, int32_t t, int32_t h, int32_t w, t2v_stream_t s) {
   if (!in || !out) return fail(-1, "t2v_frames_to_bcthw: null pointer");
@@ -456,6 +508,17 @@ extern "C" int t2v_softmax_rows(void* x, int64_t rows, int32_t cols, int64_t row
   launch_kernel(softmax_rows_kernel, dim3(unsigned(rows)), dim3(256), 0, static_cast<cudaStream_t>(s), static_cast<__nv_bfloat16*>(x), cols, row_stride, scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_softmax_rows launch");
+}
+
+extern "C" int t2v_gaussian_sample(const float* moments, const float* noise, void* out, int32_t out_dtype, int32_t b,
+                                   int32_t t, int32_t h, int32_t w, int32_t zc, float scale, t2v_stream_t s) {
+  if (!moments || !out || b < 1 || t < 1 || h < 1 || w < 1 || zc < 1) return fail(-1, "t2v_gaussian_sample: bad argument");
+  if (out_dtype < 0 || out_dtype > 2) return fail(-2, "t2v_gaussian_sample: dtype must be 0 (bf16), 1 (fp16) or 2 (fp32)");
+  const int64_t total = int64_t(b) * t * h * w * zc;
+  launch_kernel(gaussian_sample_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(s), moments, noise, out,
+                out_dtype, b, t, h, w, zc, scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_gaussian_sample launch");
 }
 
 extern "C" int t2v_lcm_step(const void* x, const void* eps, const void* noise, void* prev, void* denoised,

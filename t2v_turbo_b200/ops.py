@@ -283,7 +283,7 @@ _TAPS_3X3 = [(kx - 1, ky - 1, 0, 0) for ky in range(3) for kx in range(3)]
 _TAPS_T3 = [(0, kt - 1, 0, 0) for kt in range(3)]
 
 
-def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, split_k=0, stats=None):
+def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, split_k=0, stats=None, out_f32=False):
     """3x3 / pad 1 / stride 1 conv over [N,H,W,C] (or a channel-concatenated pair).
     w: [Cout, 9*C] packed (tap-major); bias: fp32 [rows, Cout], row = frame // bias_div.
     stats: fp32 [N, Cout, 2] (zeroed): per-frame per-channel (sum, sum of squares) of the output for the next GroupNorm."""
@@ -294,7 +294,7 @@ def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, 
     cout = w.shape[0]
     assert w.shape[1] == 9 * (c0 + c1), (w.shape, c0, c1)
     if out is None:
-        out = torch.empty((n, h, wd, cout), device=x0.device, dtype=BF16)
+        out = torch.empty((n, h, wd, cout), device=x0.device, dtype=torch.float32 if out_f32 else BF16)
     box = plan_box((wd, h, n, 1))
     return _gemm_raw(
         a=(x0, x1), a_ch=(c0, c1), a_ch_total=(c0, c1), a_size=(wd, h, n, 1),
@@ -302,13 +302,15 @@ def conv3x3(x, w, bias=None, *, bias_div=1, residual=None, out=None, block_n=0, 
         box=box, taps=_TAPS_3X3, tap_ch_off=None, w=w, n_rows=cout, out=out,
         o_size=(wd, h, n, 1), o_stride=(cout, wd * cout, h * wd * cout, 0), n_out=cout, bias=bias,
         bias_row_stride=cout if bias is not None else 0, bias_dim=2, bias_div=bias_div,
-        residual=residual, block_n=block_n, split_k=split_k,
+        residual=residual, block_n=block_n, split_k=split_k, flags=_lib.EPI_OUT_F32 if out_f32 else 0,
         col_accum=(stats, (0, 0, 1, 0)) if stats is not None else None)
 
 
-def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0, stats=None):
-    """3x3 / pad 1 / stride 2 conv (Downsample, openaimodel3d.py:65-72).  The input is read through a
-    parity view [N, H/2, 2, W/2, 2*C] so every tap is a plain box load."""
+def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0, stats=None, pad="sym"):
+    """3x3 / stride 2 conv.  pad="sym": padding 1 on every side (UNet Downsample, openaimodel3d.py:65-72);
+    pad="br": zero-pad right / bottom by one only, no other padding (KL-VAE Downsample, ae_modules.py:87-105).
+    The input is read through a parity view [N, H/2, 2, W/2, 2*C] so every tap is a plain box load and the padding
+    is TMA out-of-bounds zero fill."""
     _check_act(x)
     n, h, wd, c = x.shape
     assert h % 2 == 0 and wd % 2 == 0
@@ -318,10 +320,13 @@ def conv3x3_s2(x, w, bias=None, *, out=None, block_n=0, stats=None):
     if out is None:
         out = torch.empty((n, h2, w2, cout), device=x.device, dtype=BF16)
     taps, choff = [], []
+    assert pad in ("sym", "br")
+    # source row of output row y and tap k: sym 2y+k-1, br 2y+k  ->  (parity, offset in half-resolution rows)
+    src = {0: (1, -1), 1: (0, 0), 2: (1, 0)} if pad == "sym" else {0: (0, 0), 1: (1, 0), 2: (0, 1)}
     for ky in range(3):
-        hpar, dh = (0, 0) if ky == 1 else (1, -1 if ky == 0 else 0)
+        hpar, dh = src[ky]
         for kx in range(3):
-            wpar, dw = (0, 0) if kx == 1 else (1, -1 if kx == 0 else 0)
+            wpar, dw = src[kx]
             taps.append((dw, hpar, dh, 0))
             choff.append(wpar * c)
     b = plan_box((w2, 1, h2, n), fixed=(None, 1, None, None))
@@ -618,6 +623,19 @@ def lcm_step(x, eps, noise, *, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqr
                              x.numel(), _lib.DTYPE_CODE[x.dtype], inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out,
                              sqrt_alpha_prev, sqrt_beta_prev, stream_ptr())
     return prev, den
+
+
+def gaussian_sample(moments, noise, *, b, t, zc, scale, dtype):
+    """KL posterior sample / mode (distributions.py:24-42) from fp32 channels-last moments [b*t, h, w, 2*zc]."""
+    n, h, w, c2 = moments.shape
+    assert n == b * t and c2 == 2 * zc and moments.dtype == torch.float32 and moments.is_contiguous()
+    out = torch.empty((b, zc, t, h, w), device=moments.device, dtype=dtype)
+    if noise is not None:
+        noise = noise.to(device=moments.device, dtype=torch.float32).contiguous()
+        assert noise.shape == (n, zc, h, w)
+    _launch("gaussian_sample", 0, lib().t2v_gaussian_sample, moments.data_ptr(), ptr(noise), out.data_ptr(),
+            _lib.DTYPE_CODE[dtype], b, t, h, w, zc, float(scale), stream_ptr())
+    return out
 
 
 # ----------------------------------------------------------------------------- weight packing

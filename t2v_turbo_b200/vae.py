@@ -1,4 +1,4 @@
-"""Drop-in KL-VAE decode path on B200: `AutoencoderKL.decode` / `decode_first_stage_2DAE`.
+"""Drop-in KL-VAE on B200: `AutoencoderKL.decode` / `decode_first_stage_2DAE` and `AutoencoderKL.encode`.
 
 Mirrors lvdm/models/autoencoder.py:110-113 and lvdm/modules/networks/ae_modules.py:506-641 (Decoder,
 ResnetBlock :146-203, AttnBlock :29-73, Upsample :108-122): same constructor config (`ddconfig`,
@@ -6,7 +6,10 @@ ResnetBlock :146-203, AttnBlock :29-73, Upsample :108-122): same constructor con
 `decoder.up.{i}.block.{j}.*`, `decoder.up.{i}.upsample.conv.*`, ...).  The nn modules are parameter
 containers; the arithmetic is libt2v_b200.so kernels over channels-last bf16 with ALL frames batched
 (the reference decodes frame by frame in a Python loop, ddpm3d.py:671-677).
-The encoder (training only) is out of scope this round.
+The encode side (training only: autoencoder.py:103-108, Encoder ae_modules.py:381-503, DiagonalGaussian
+distributions.py:24-42) uses the same kernels: `encoder.*` / `quant_conv.*` keys, Downsample as a stride-2 conv over a
+parity view with the reference's right/bottom zero padding, conv_out and quant_conv folded into one GEMM with fp32
+moments, posterior sample / mode in one elementwise kernel.
 """
 from __future__ import annotations
 
@@ -50,6 +53,45 @@ class UpsampleConv(nn.Module):
         self.conv = nn.Conv2d(ch, ch, 3, padding=1)
 
 
+class DownsampleConv(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=0)
+
+
+class Encoder(nn.Module):
+    """Parameter container with the reference's key layout (ae_modules.py:381-468)."""
+
+    def __init__(self, *, ch, out_ch=None, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions=(), dropout=0.0,
+                 resamp_with_conv=True, in_channels=3, resolution=256, z_channels, double_z=True, **ignored):
+        super().__init__()
+        if len(attn_resolutions) or not resamp_with_conv:
+            raise NotImplementedError("Encoder(B200): attn_resolutions / resamp_with_conv=False are not used by VC2")
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, padding=1)
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            down = nn.Module()
+            down.block = nn.ModuleList()
+            down.attn = nn.ModuleList()
+            for _ in range(num_res_blocks):
+                down.block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+            if i_level != self.num_resolutions - 1:
+                down.downsample = DownsampleConv(block_in)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        self.norm_out = _norm(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, 3, padding=1)
+
+
 class Decoder(nn.Module):
     def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions=(), dropout=0.0,
                  resamp_with_conv=True, in_channels=3, resolution=256, z_channels, **ignored):
@@ -84,15 +126,17 @@ def _f32(t):
 
 
 class _StatsPool:
-    """Zeroed fp32 workspace for the per-frame channel sums the GEMM epilogues accumulate (one memset per decode)."""
+    """Zeroed fp32 workspace for the per-frame channel sums the GEMM epilogues accumulate (one memset per call;
+    allocated on first use — nothing when the fusion is off, see ops.GN_FUSE)."""
 
     def __init__(self, device, nfloats):
-        self.buf = torch.zeros((nfloats,), device=device, dtype=torch.float32)
-        self.cur = 0
+        self.device, self.nfloats, self.buf, self.cur = device, nfloats, None, 0
 
     def take(self, frames, channels, k_total, grid):
         if not ops.gn_fuse_producer(k_total, grid):
             return None
+        if self.buf is None:
+            self.buf = torch.zeros((self.nfloats,), device=self.device, dtype=torch.float32)
         n = frames * channels * 2
         if self.cur + n > self.buf.numel():
             raise RuntimeError("AutoencoderKL(B200): statistics workspace exhausted")
@@ -117,22 +161,70 @@ class _PRes:
 
 
 class AutoencoderKL(nn.Module):
-    """Decode-side AutoencoderKL (reference ctor: ddconfig, lossconfig, embed_dim; lossconfig ignored)."""
+    """AutoencoderKL (reference ctor: ddconfig, lossconfig, embed_dim; lossconfig ignored): decode and encode."""
 
     def __init__(self, ddconfig, embed_dim, lossconfig=None, **ignored):
         super().__init__()
         self.ddconfig, self.embed_dim = dict(ddconfig), embed_dim
+        self.encoder = Encoder(**ddconfig)
         self.decoder = Decoder(**ddconfig)
+        self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self._packed = None
+        self._packed_enc = None
 
     def _apply(self, fn, *a, **k):
-        self._packed = None
+        self._packed = self._packed_enc = None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed = None
+        self._packed = self._packed_enc = None
         return super().load_state_dict(*a, **k)
+
+    @staticmethod
+    def _pack_attn(a):
+        c = a.in_channels
+        wo = a.proj_out.weight.detach().float().reshape(c, c)
+        # v bias folded through the softmax (rows sum to 1) into the output projection bias
+        return dict(gn=(_f32(a.norm.weight), _f32(a.norm.bias)),
+                    w_qk=torch.cat([_w2d(a.q.weight), _w2d(a.k.weight)], 0).contiguous(),
+                    b_qk=torch.cat([_f32(a.q.bias), _f32(a.k.bias)], 0).contiguous(),
+                    w_v=_w2d(a.v.weight), w_o=_w2d(a.proj_out.weight),
+                    b_o=(_f32(a.proj_out.bias) + wo @ _f32(a.v.bias)).contiguous(), c=c)
+
+    @torch.no_grad()
+    def pack_encoder(self):
+        e = self.encoder
+        dev = e.conv_in.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("AutoencoderKL(B200) runs on a CUDA device only (no CPU fallback)")
+        P = {}
+        cin = e.conv_in.weight.shape[1]
+        if cin > 4:
+            raise NotImplementedError("Encoder(B200): more than 4 input channels")
+        # RGB frames are padded to 4 channels (zero weights for the 4th) so the direct small-Cin conv kernel applies
+        w_in = torch.zeros(e.conv_in.weight.shape[0], 4, 3, 3, device=dev, dtype=torch.float32)
+        w_in[:, :cin] = e.conv_in.weight.detach().float()
+        P["conv_in"] = (ops.pack_conv_weight(w_in), _f32(e.conv_in.bias), w_in.shape[0])
+        P["down"] = []
+        for i_level in range(e.num_resolutions):
+            dn = e.down[i_level]
+            blocks = [_PRes(b) for b in dn.block]
+            ds = None
+            if i_level != e.num_resolutions - 1:
+                ds = (ops.pack_conv_weight(dn.downsample.conv.weight.detach()), _f32(dn.downsample.conv.bias))
+            P["down"].append((blocks, ds))
+        P["mid1"], P["mid2"] = _PRes(e.mid.block_1), _PRes(e.mid.block_2)
+        P["attn"] = self._pack_attn(e.mid.attn_1)
+        P["norm_out"] = (_f32(e.norm_out.weight), _f32(e.norm_out.bias))
+        # quant_conv (1x1) composed with conv_out: moments = (Wq Wc) * x + (Wq bc + bq)
+        wq = self.quant_conv.weight.detach().float().reshape(self.quant_conv.weight.shape[0], -1)
+        wc = e.conv_out.weight.detach().float()
+        w_fold = torch.einsum("oc,cikl->oikl", wq, wc)
+        b_fold = wq @ e.conv_out.bias.detach().float() + self.quant_conv.bias.detach().float()
+        P["conv_out"] = (ops.pack_conv_weight(w_fold), b_fold.view(1, -1).contiguous(), w_fold.shape[0])
+        self._packed_enc = P
+        return self
 
     @torch.no_grad()
     def pack(self):
@@ -146,15 +238,7 @@ class AutoencoderKL(nn.Module):
         P["pq_b"] = _f32(self.post_quant_conv.bias)
         P["conv_in"] = (ops.pack_conv_weight(d.conv_in.weight.detach()), _f32(d.conv_in.bias), d.conv_in.weight.shape[0])
         P["mid1"], P["mid2"] = _PRes(d.mid.block_1), _PRes(d.mid.block_2)
-        a = d.mid.attn_1
-        c = a.in_channels
-        wo = a.proj_out.weight.detach().float().reshape(c, c)
-        # v bias folded through the softmax (rows sum to 1) into the output projection bias
-        P["attn"] = dict(gn=(_f32(a.norm.weight), _f32(a.norm.bias)),
-                         w_qk=torch.cat([_w2d(a.q.weight), _w2d(a.k.weight)], 0).contiguous(),
-                         b_qk=torch.cat([_f32(a.q.bias), _f32(a.k.bias)], 0).contiguous(),
-                         w_v=_w2d(a.v.weight), w_o=_w2d(a.proj_out.weight),
-                         b_o=(_f32(a.proj_out.bias) + wo @ _f32(a.v.bias)).contiguous(), c=c)
+        P["attn"] = self._pack_attn(d.mid.attn_1)
         P["up"] = []
         for i_level in range(d.num_resolutions):
             up = d.up[i_level]
@@ -234,6 +318,48 @@ class AutoencoderKL(nn.Module):
         w, bias, cout = P["conv_out"]
         y = ops.conv3x3(hn.view(n, hh2, ww2, ch), w, bias, bias_div=n)
         return ops.frames_to_bcthw(y, b, cout, z.dtype)
+
+    @torch.no_grad()
+    def encode_frames(self, x, noise=None, scale=1.0, sample=True):
+        """x: [B, 3, T, H, W] video (any float dtype) -> scale * posterior sample (or mode) [B, zc, T, H/f, W/f] in
+        x.dtype, all B*T frames batched (ddpm3d.py:558-584).  noise: fp32 [B*T, zc, h, w] (the reference draws it
+        with torch.randn on the CPU, distributions.py:38-41 — done here the same way when omitted and sample=True)."""
+        if not x.is_cuda:
+            raise RuntimeError("AutoencoderKL(B200): input must be a CUDA tensor (no CPU fallback)")
+        if self._packed_enc is None:
+            self.pack_encoder()
+        P = self._packed_enc
+        b, c, t, hh, ww = x.shape
+        x = x.contiguous()
+        fr = torch.empty((b * t, hh, ww, 4), device=x.device, dtype=BF16)
+        ops._launch("bcthw_to_frames_pad", 0, lib().t2v_bcthw_to_frames_pad, x.data_ptr(), DTYPE_CODE[x.dtype],
+                    fr.data_ptr(), b, c, 4, t, hh, ww, 1.0, stream_ptr())
+        w, bias, cout = P["conv_in"]
+        h = ops.conv3x3_small_cin(fr, w, bias, cout)
+        pool = _StatsPool(x.device, b * t * 512 * 2 * 48)
+        hs = None
+        for blocks, ds in P["down"]:
+            for pr in blocks:
+                h, hs = self._res(pr, h, hs, pool)
+            if ds is not None:
+                hs = pool.take(h.shape[0], ds[0].shape[0], ds[0].shape[1], (h.shape[2] // 2, 1, h.shape[1] // 2, h.shape[0]))
+                h = ops.conv3x3_s2(h, ds[0], ds[1], pad="br", stats=hs)
+        h, hs = self._res(P["mid1"], h, hs, pool)
+        h, hs = self._attn(P["attn"], h, hs, pool)
+        h, hs = self._res(P["mid2"], h, hs, pool)
+        n, h2, w2, ch = h.shape
+        hn = ops.groupnorm(h.view(-1, ch), P["norm_out"][0], P["norm_out"][1], rows_per_sample=h2 * w2, eps=1e-6, silu=True,
+                           chan_sums=hs)
+        w, bias, cout = P["conv_out"]
+        moments = ops.conv3x3(hn.view(n, h2, w2, ch), w, bias, bias_div=n, out_f32=True)   # fp32 [n, h, w, 2*embed]
+        zc = cout // 2
+        if sample and noise is None:
+            noise = torch.randn((n, zc, h2, w2))
+        return ops.gaussian_sample(moments, noise if sample else None, b=b, t=t, zc=zc, scale=scale, dtype=x.dtype)
+
+    def encode(self, x, noise=None, sample=True, **kwargs):
+        """autoencoder.py:103-108 + posterior.sample()/mode(): x [N, 3, H, W] -> z [N, zc, H/f, W/f]."""
+        return self.encode_frames(x.unsqueeze(2), noise=noise, scale=1.0, sample=sample).squeeze(2)
 
     def decode(self, z, **kwargs):
         """autoencoder.py:110-113: z [N, C, h, w] -> [N, 3, 8h, 8w]."""

@@ -275,6 +275,38 @@ def test_upconv3x3(cuda_device, n, h, w, cin, cout):
     assert_close(out, ref, what="upconv3x3")
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 16, 64, 64), (3, 20, 32, 128, 128), (1, 40, 64, 128, 128)])
+def test_conv3x3_s2_pad_bottom_right(cuda_device, n, h, w, cin, cout):
+    """KL-VAE Downsample (ae_modules.py:87-105): F.pad(x, (0, 1, 0, 1)) then a stride-2 3x3 conv without padding."""
+    ops = _ops()
+    x = rnd(n, h, w, cin, seed=97).to(BF16)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=98).to(BF16)
+    b = rnd(cout, seed=99)
+    out = ops.conv3x3_s2(x, ops.pack_conv_weight(wt), b, pad="br")
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xp, wt.float(), b, stride=2).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert_close(out, ref, what="conv3x3 s2 (pad bottom/right)")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, BF16])
+def test_gaussian_sample(cuda_device, dtype):
+    """distributions.py:24-42 + ddpm3d.py:558-567: scale * (mean + exp(0.5 clamp(logvar)) * noise), and the mode."""
+    ops = _ops()
+    b, t, h, w, zc = 2, 3, 5, 8, 4
+    mom = (rnd(b * t, h, w, 2 * zc, seed=100) * 20).float().contiguous()     # logvar beyond the clamp range too
+    noise = rnd(b * t, zc, h, w, seed=101).float()
+    z = ops.gaussian_sample(mom, noise, b=b, t=t, zc=zc, scale=0.18215, dtype=dtype)
+    zm = ops.gaussian_sample(mom, None, b=b, t=t, zc=zc, scale=0.18215, dtype=dtype)
+    m = mom.permute(0, 3, 1, 2)
+    mean, logvar = m[:, :zc], torch.clamp(m[:, zc:], -30.0, 20.0)
+    ref = 0.18215 * (mean + torch.exp(0.5 * logvar) * noise)
+    back = lambda v: v.reshape(b, t, zc, h, w).permute(0, 2, 1, 3, 4)
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(z.float(), back(ref), **tol)
+    torch.testing.assert_close(zm.float(), back(0.18215 * mean), **tol)
+
+
 @pytest.mark.parametrize("b,t,hw,c", [(1, 16, 40, 128), (2, 4, 160, 64), (1, 16, 640, 64)])
 def test_tconv3(cuda_device, b, t, hw, c):
     ops = _ops()
