@@ -105,6 +105,32 @@ def gen_vae_enc(name):
     torch.save({"name": name, "x": x, "noise": noise, "z_sample": back(z), "z_mode": back(zm)}, os.path.join(GOLD, f"vae_enc_{name}.pt"))
 
 
+def gen_lora(name="small"):
+    """LoRA wire format + merge: the reference injects LoRA below the UNetModel
+    (utils/lora.py:387-486), the flat [up, down, ...] list is filled with seeded values, collapse_lora (:793-830) merges
+    it.  Stored: per target layer its name, the shapes of up / down and a digest (sum, abs-sum) of the merged weight."""
+    from utils import lora as rlora
+    spec = UNET_CONFIGS[name]
+    m = ref_unet(spec["cfg"], spec["weight_seed"])
+    rlora.inject_trainable_lora_extended(m, target_replace_module={"UNetModel"}, r=64)
+    g = torch.Generator().manual_seed(4242)
+    ups_downs = list(rlora.extract_lora_ups_down(m, target_replace_module={"UNetModel"}))
+    flat = []
+    for up, down in ups_downs:
+        up.weight.data = torch.randn(up.weight.shape, generator=g) * 0.05
+        down.weight.data = torch.randn(down.weight.shape, generator=g) * 0.05
+        flat += [up.weight.data.clone(), down.weight.data.clone()]
+    rlora.collapse_lora(m, {"UNetModel"})
+    rlora.monkeypatch_remove_lora(m)
+    layers = [(n, mod) for n, mod in m.named_modules() if mod.__class__ in (torch.nn.Linear, torch.nn.Conv2d, torch.nn.Conv3d)]
+    assert len(layers) * 2 == len(flat)
+    rec = [dict(name=n, up=tuple(flat[2 * i].shape), down=tuple(flat[2 * i + 1].shape),
+                sum=mod.weight.double().sum().item(), abs=mod.weight.double().abs().sum().item())
+           for i, (n, mod) in enumerate(layers)]
+    print(f"  lora {name}: {len(layers)} layers, {sum(t.numel() for t in flat)} LoRA parameters")
+    torch.save({"name": name, "seed": 4242, "layers": rec}, os.path.join(GOLD, f"lora_{name}.pt"))
+
+
 def gen_scheduler():
     from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
     s = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
@@ -190,13 +216,15 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "pipeline"] + (["unet_full", "vae_full", "vae_enc_full"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline"] + (["unet_full", "vae_full", "vae_enc_full"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
             gen_scheduler()
         elif item.startswith("unet_"):
             gen_unet(item[5:])
+        elif item.startswith("lora_"):
+            gen_lora(item[5:])
         elif item.startswith("vae_enc_"):
             gen_vae_enc(item[8:])
         elif item.startswith("vae_"):
