@@ -35,6 +35,30 @@ class LatentVideoModel(nn.Module):
         """ddpm3d.py:666-679: z [b, c, t, h, w] -> [b, 3, t, 8h, 8w]; all frames in one batched decode."""
         return self.first_stage_model.decode_frames(z, 1.0 / self.scale_factor)
 
+    @torch.no_grad()
+    def encode_first_stage(self, x, noise=None):
+        """ddpm3d.py:558-584 (`get_first_stage_encoding` of the posterior sample): video x [b, 3, t, H, W] ->
+        scale_factor * z [b, c, t, H/8, W/8]; all frames in one batched encode.  noise: fp32 [b*t, c, h, w]
+        (drawn with torch.randn on the CPU like the reference, distributions.py:38-41, when omitted)."""
+        return self.first_stage_model.encode_frames(x, noise=noise, scale=self.scale_factor)
+
+    encode_first_stage_2DAE = encode_first_stage      # ddpm3d.py:586-600: same result, frame loop in the reference
+
+    def load_vc2_checkpoint(self, ckpt, strict_unet=True):
+        """VideoCrafter2 `model.ckpt` key space (common_utils.py:399-411): {"state_dict": {...}} or the bare dict with
+        `model.diffusion_model.*`, `first_stage_model.*`, `cond_stage_model.*` and the DDPM schedule buffers.  Loads the
+        UNet and the KL-VAE; returns the keys that were not consumed (text encoder, schedule buffers, loss weights)."""
+        sd = torch.load(ckpt, map_location="cpu", weights_only=True) if not isinstance(ckpt, dict) else ckpt
+        sd = sd.get("state_dict", sd)
+        unet_sd = {k[len("model.diffusion_model."):]: v for k, v in sd.items() if k.startswith("model.diffusion_model.")}
+        vae_keys = tuple(self.first_stage_model.state_dict().keys())
+        vae_sd = {k[len("first_stage_model."):]: v for k, v in sd.items()
+                  if k.startswith("first_stage_model.") and k[len("first_stage_model."):] in vae_keys}
+        self.model.diffusion_model.load_state_dict(unet_sd, strict=strict_unet)
+        self.first_stage_model.load_state_dict(vae_sd, strict=True)
+        used = {"model.diffusion_model." + k for k in unet_sd} | {"first_stage_model." + k for k in vae_sd}
+        return sorted(k for k in sd if k not in used)
+
 
 class _GraphedCall:
     """Capture fn(*static_inputs) once per input signature; replay with inputs copied into static buffers."""
