@@ -126,19 +126,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
     const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
     mbar_wait(q_full, 0);
-    for (int j = 0; j < n_kv; ++j) {
+    // Issue order per key tile j:  [p_full(j)]  S(j+1)  PV(j).  S(j+1) only needs the S columns (free once softmax(j)
+    // has arrived on p_full) and K(j+1), so it is issued BEFORE PV(j): softmax(j+1) starts while PV(j) still runs and
+    // the PV latency leaves the per-tile critical path.  (P(j+1) may only be written after PV(j) completed: the
+    // softmax warps wait for pv_done(j) right before their first P store.)
+    auto issue_s = [&](int j) {
       const int s = j % kKvStages;
-      const uint32_t ph = (j / kKvStages) & 1;
-      // S = Q K_j^T   (S is free: the softmax of tile j-1 finished reading it before p_full(j-1))
-      mbar_wait(&k_full[s], ph);
+      mbar_wait(&k_full[s], (j / kKvStages) & 1);
       tc_fence_after();
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + s * kKBytes));
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_ss(tmem_base, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
       umma_commit(&k_empty[s]);
       umma_commit(s_full);
-      // O += P_j V_j
+    };
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % kKvStages;
+      const uint32_t ph = (j / kKvStages) & 1;
       mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (j + 1 < n_kv) issue_s(j + 1);
+      // O += P_j V_j
       mbar_wait(&v_full[s], ph);
       tc_fence_after();
       const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + s * kKBytes));
@@ -189,6 +198,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float rs = 0.f, raw_max = -INFINITY;
       // One pass over the 128 scores of this row: the TMEM load of the next 32-column chunk is in flight while the
       // current chunk is exponentiated and written to the P tile.
+      bool p_free = (j == 0);  // the P buffer (and O) may be touched once PV(j-1) has completed
       auto exp_chunk = [&](const uint32_t (&v)[32], int c0, float nref) {
         uint32_t pk[16];
         if (c0 + 32 <= kv_left) {
@@ -213,6 +223,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             rs += e0 + e1;
             pk[i >> 1] = pack_bf16(e0, e1);
           }
+        }
+        if (!p_free) {
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          p_free = true;
         }
         // 32 keys = 4 chunks of 16 bytes; chunk index within the 128-key row: c0/8 + q
         uint8_t* sub = p_row + (c0 >> 6) * (kTile * 128);
@@ -240,7 +255,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_wait_ld();
         exp_chunk(vb, 96, nref);
       };
-      // (the P buffer is free: PV(j-1) completion was observed at the end of the previous iteration)
       exp_pass(m_ref);
       const float tile_max = raw_max * p.scale_log2;
       if (__any_sync(0xffffffffu, tile_max > m_ref + kLazy)) {
@@ -267,10 +281,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async();  // P stores (generic proxy) -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
-      // wait for PV(j): O is updated and the P buffer may be overwritten
-      mbar_wait(pv_done, j & 1);
-      tc_fence_after();
     }
+    // the last PV must have landed before O is read
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
     // epilogue: O / l -> bf16 -> global
     const int qi = q0 + r;
     const float inv_l = 1.0f / l_run;

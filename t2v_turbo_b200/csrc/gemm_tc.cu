@@ -1096,7 +1096,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   const int64_t pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
   // measured: +10 % at K >= 1024 (1441 TFLOP/s on 512->512 3x3 convs = the cuBLAS sustained level), a loss at small K
   const bool pair = staged && !(d->tune & 0x800) && d->b_batch_dim < 0 && bn >= 128 && m_tiles >= 2 &&
-                    pair_tiles >= sms / 2 && p.total_kb >= 16;
+                    pair_tiles >= sms / 2 && p.total_kb >= (((d->tune >> 16) & 0xff) ? ((d->tune >> 16) & 0xff) : 15);
   if (pair) {
     p.n_tiles_mn = int(pair_tiles);
     p.num_tiles = int(pair_tiles);
