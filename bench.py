@@ -44,7 +44,7 @@ def peaks():
 def ncu_gemm_traffic():
     """DRAM bytes (read + write) per gemm_tc launch, averaged over the launches of one pipeline step, from the committed
     ncu capture of scripts/profile_step.py (profiles/README.md); None when the summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r01_launches_step_v5_summary.json")
+    p = os.path.join(ROOT, "profiles", "r01_launches_step_final_summary.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))

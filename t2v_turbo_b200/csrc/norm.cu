@@ -52,12 +52,6 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 
 constexpr int kGnThreads = 256;
 
-__global__ void gn_zero_kernel(float* ws, int n) {
-  pdl_launch_dependents();
-  pdl_wait();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) ws[i] = 0.f;
-}
-
 // grid: (blocks_per_sample, n_samples)
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) {
   pdl_launch_dependents();
