@@ -28,6 +28,14 @@ CASES = {
     "big1280": ("linear", 40960, 1280, 1280, dict(res=True)),
     "tconv1280_l3": ("tconv", (1, 16, 40, 1280), 0, 1280, dict()),
 }
+CASES.update({
+    "qkv640": ("linear", 10240, 640, 1920, dict()),
+    "qkv1280": ("linear", 2560, 1280, 3840, dict()),
+    "q640": ("linear", 10240, 640, 640, dict()),
+    "ff2_640": ("linear", 10240, 2560, 640, dict(res=True)),
+    "ff2_1280": ("linear", 2560, 5120, 1280, dict(res=True)),
+})
+BN = int(os.environ.get("BN", "0"))   # force a tile width (experiments)
 names = sys.argv[1:] or list(CASES)
 for name in names:
     kind, M, K, N, ex = CASES[name]
@@ -39,7 +47,7 @@ for name in names:
         n_out = N // 2 if ex.get("geglu") else N
         res = torch.randn(M, n_out, device=dev, generator=g).to(BF16) if ex.get("res") else None
         out = torch.empty(M, n_out, device=dev, dtype=BF16)
-        fn = lambda: ops.linear(x, w, b, residual=res, geglu=bool(ex.get("geglu")), out=out)
+        fn = lambda: ops.linear(x, w, b, residual=res, geglu=bool(ex.get("geglu")), out=out, block_n=BN)
         flops = 2 * M * K * N
     elif kind == "conv":
         n, h, wd, c = M
@@ -48,7 +56,7 @@ for name in names:
         b = torch.randn(1, N, device=dev, generator=g)
         res = torch.randn(n, h, wd, N, device=dev, generator=g).to(BF16)
         out = torch.empty(n, h, wd, N, device=dev, dtype=BF16)
-        fn = lambda: ops.conv3x3(x, w, b, bias_div=n, residual=res, out=out)
+        fn = lambda: ops.conv3x3(x, w, b, bias_div=n, residual=res, out=out, block_n=BN)
         flops = 2 * n * h * wd * 9 * c * N
     else:
         bb, t, hw, c = M
@@ -56,7 +64,7 @@ for name in names:
         w = (torch.randn(N, 3 * c, device=dev, generator=g) * (3 * c) ** -0.5).to(BF16)
         b = torch.randn(N, device=dev, generator=g)
         out = torch.empty(bb, t, hw, N, device=dev, dtype=BF16)
-        fn = lambda: ops.tconv3(x, w, b, out=out)
+        fn = lambda: ops.tconv3(x, w, b, out=out, block_n=BN)
         flops = 2 * bb * t * hw * 3 * c * N
     for _ in range(3):
         fn()

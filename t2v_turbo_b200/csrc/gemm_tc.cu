@@ -937,7 +937,8 @@ static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu, 
     const int64_t waves = (tiles + sms - 1) / sms;
     const double eff_w = tiles >= sms ? double(tiles) / double(waves * sms) : 1.0;  // small grids use split-K
     // wide tiles halve the shared-memory / L2 operand traffic per flop
-    const double eff_t = bn >= 256 ? 1.0 : bn >= 160 ? 0.95 : bn >= 128 ? 0.90 : bn >= 64 ? 0.70 : 0.45;
+    // (measured on the UNet's shapes, scripts/gemm_bench.py with BN=...: N = 960 prefers 256-wide tiles over 160)
+    const double eff_t = bn >= 256 ? 1.0 : bn >= 160 ? 0.88 : bn >= 128 ? 0.86 : bn >= 64 ? 0.70 : 0.45;
     const double score = eff_n * eff_w * eff_t;
     if (score > best) {
       best = score;
