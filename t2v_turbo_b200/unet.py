@@ -298,6 +298,7 @@ class UNetModel(nn.Module):
         self._packed = None
         self._ctx_cache = None
         self._ln_state = None
+        self._ln_states = {}     # per input geometry: captured CUDA graphs keep pointing at their workspace
 
     # ------------------------------------------------------------------ packing
     def invalidate_packed(self):
@@ -430,11 +431,14 @@ class UNetModel(nn.Module):
     # buffer that a single memset zeroes at the start of a forward.  The first forward of a geometry sizes the buffer
     # (individually zeroed tensors).
     def _ln_begin(self, key):
-        st = self._ln_state
-        if st is None or st["key"] != key:
-            st = self._ln_state = dict(key=key, buf=None, need=0, cursor=0)
+        st = self._ln_states.get(key)
+        if st is None:
+            st = self._ln_states[key] = dict(key=key, buf=None, need=0, cursor=0)
+            self._ln_state = st
         elif st["buf"] is None and st["need"] > 0:
+            self._ln_state = st
             st["buf"] = torch.empty((st["need"],), device=key[-1], dtype=torch.float32)
+        self._ln_state = st
         if st["buf"] is not None:
             st["buf"].zero_()
             st["cursor"] = 0
