@@ -69,3 +69,32 @@ def test_gn_fuse_policy_defaults_off():
     assert ops.GN_FUSE in ("off", "conv", "all")
     if ops.GN_FUSE == "off":
         assert not ops.gn_fuse_producer(1 << 20, (64, 40, 16, 1))
+
+
+def test_unet_statistics_workspace_per_geometry():
+    """UNetModel keeps one statistics workspace per input geometry (captured CUDA graphs hold raw pointers into it):
+    sizing pass -> one buffer -> reuse with a single zeroing; another geometry gets its own buffer."""
+    from oracle.configs import UNET_CONFIGS
+    from t2v_turbo_b200.unet import UNetModel
+    m = UNetModel(**UNET_CONFIGS["small"]["cfg"])
+    dev = torch.device("cpu")
+
+    def fwd(key, rows):
+        m._ln_begin(key)
+        outs = [m._ln_slice(r, dev) for r in rows]
+        for o in outs:
+            o += 1.0
+        return outs
+
+    ka, kb = (1, 4, 8, 8, dev), (2, 4, 8, 8, dev)
+    fwd(ka, [10, 20, 30])
+    assert m._ln_states[ka]["buf"] is None and m._ln_states[ka]["need"] == 120
+    a2 = fwd(ka, [10, 20, 30])
+    buf_a = m._ln_states[ka]["buf"]
+    assert buf_a.numel() == 120 and float(buf_a.sum()) == 120.0
+    assert a2[1].data_ptr() == buf_a.data_ptr() + 20 * 4
+    fwd(kb, [16])
+    fwd(kb, [16])
+    fwd(ka, [10, 20, 30])
+    assert m._ln_states[ka]["buf"] is buf_a and float(buf_a.sum()) == 120.0
+    assert m._ln_states[kb]["buf"] is not None and m._ln_states[kb]["buf"] is not buf_a
