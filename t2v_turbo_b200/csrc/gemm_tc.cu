@@ -75,7 +75,7 @@ struct GemmParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kEpiWGs = 3;                            // epilogue warpgroups (128 threads = 128 accumulator rows each)
+constexpr int kEpiWGs = 2;                            // epilogue warpgroups (128 threads = 128 accumulator rows each); 3 measured: no gain, one pipeline stage less
 constexpr int kThreads = 128 + 128 * kEpiWGs;
 constexpr int kEpiWarps = 4 * kEpiWGs;
 constexpr int kEpiBufBytes = 128 * 64;               // 128 rows x 32 bf16 columns, 64-byte swizzle
