@@ -994,8 +994,21 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   if (sms <= 0) return fail(-110, "t2v_gemm: no CUDA device");
   int bn = d->block_n;
   const int ln_mode = d->row_stats ? 1 : (d->row_accum ? 2 : (d->col_accum ? 3 : 0));
-  if (bn == 0) bn = choose_block_n(d->b_rows, m_tiles, sms, geglu, ln_mode != 0);
-  if (ln_mode != 0 && bn < 128) return fail(-19, "t2v_gemm: LayerNorm-aware GEMMs need block_n >= 128");
+  bool narrow_no_split = false;
+  if (bn == 0) {
+    bn = choose_block_n(d->b_rows, m_tiles, sms, geglu, ln_mode != 0);
+    // Small-M layers (level 3: M = 640): when wide tiles cannot fill the SMs, 64-wide tiles over the full K beat
+    // split-K (one launch instead of zero + GEMM + finalize) as long as K is short: Linear 640x1280x1280 8.0 us vs
+    // 19.0 us, (3,1,1) conv 15.0 vs 20.6 us; 3x3 convs (K >= 11520) stay on split-K (30 vs 37 us).
+    const int64_t tiles_wide = m_tiles * ((d->b_rows + bn - 1) / bn);
+    if (d->split_k == 0 && !geglu && ln_mode != 3 && d->b_batch_dim < 0 && tiles_wide * 2 <= sms && K / 64 >= 16 && K / 64 <= 64 &&
+        d->b_rows >= 64) {
+      bn = 64;
+      narrow_no_split = true;
+    }
+  }
+  if (ln_mode != 0 && bn < 128 && !(bn == 64 && ln_mode != 3))
+    return fail(-19, "t2v_gemm: LayerNorm-aware GEMMs need block_n >= 128 (or 64 for the row-statistics modes)");
   if (bn != 32 && bn != 64 && bn != 128 && bn != 160 && bn != 256) return fail(-13, "t2v_gemm: block_n=%d unsupported", bn);
   p.n_tiles_n = int((d->b_rows + bn - 1) / bn);
   const int64_t tiles_mn = m_tiles * p.n_tiles_n;
@@ -1005,7 +1018,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   if (split < 0) return fail(-15, "t2v_gemm: split_k must be >= 0");
   if (split == 0) {
     split = 1;
-    if (!geglu && d->b_batch_dim < 0 && d->workspace && tiles_mn * 2 <= sms && p.total_kb >= 16 &&
+    if (!narrow_no_split && !geglu && d->b_batch_dim < 0 && d->workspace && tiles_mn * 2 <= sms && p.total_kb >= 16 &&
         d->workspace_bytes >= n_points * d->b_rows * 4) {
       split = int(sms / tiles_mn);
       if (split > p.total_kb / 8) split = p.total_kb / 8;
@@ -1172,7 +1185,11 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
       else T2V_GEMM_CASE(256, false, LN_);                                       \
     }                                                                            \
   } while (0)
-  if (ln_mode == 1) {
+  if (ln_mode == 1 && bn == 64) {
+    T2V_GEMM_CASE(64, false, 1);
+  } else if (ln_mode == 2 && bn == 64) {
+    T2V_GEMM_CASE(64, false, 2);
+  } else if (ln_mode == 1) {
     T2V_GEMM_WIDE(1);
   } else if (ln_mode == 2) {
     T2V_GEMM_WIDE(2);
