@@ -34,6 +34,8 @@ CASES.update({
     "q640": ("linear", 10240, 640, 640, dict()),
     "ff2_640": ("linear", 10240, 2560, 640, dict(res=True)),
     "ff2_1280": ("linear", 2560, 5120, 1280, dict(res=True)),
+    "tconv1280": ("tconv", (1, 16, 160, 1280), 0, 1280, dict()),
+    "conv1280_cat": ("conv", (16, 10, 16, 2560), 0, 1280, dict(res=True)),
 })
 BN = int(os.environ.get("BN", "0"))   # force a tile width (experiments)
 names = sys.argv[1:] or list(CASES)

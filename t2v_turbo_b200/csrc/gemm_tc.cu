@@ -923,7 +923,7 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   return 0;
 }
 
-static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu, bool wide_only) {
+static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu, bool wide_only, int64_t total_kb) {
   const int cands[5] = {256, 160, 128, 64, 32};
   double best = -1.0;
   int best_bn = 128;
@@ -944,6 +944,14 @@ static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu, 
       best = score;
       best_bn = bn;
     }
+  }
+  // An under-filled single wave of 256-wide tiles (level 2: 20 x 5 = 100 tiles on 148 SMs) loses to 128-wide CTA pairs
+  // when K is long enough for the pair mode to pay (measured: conv 2560x1280x11520 72 -> 63.5 us, ff.net.2
+  // 2560x1280x5120 37.0 -> 32.8 us, (3,1,1) conv 27.5 -> 25.5 us; K = 1280 prefers the wide tiles).
+  if (best_bn == 256 && !geglu && total_kb >= 48 && m_tiles >= 2) {
+    const int64_t t256 = m_tiles * ((n_rows + 255) / 256);
+    const int64_t pair128 = ((m_tiles + 1) / 2) * ((n_rows + 127) / 128);
+    if (t256 < sms && pair128 >= sms / 2 && n_rows % 128 == 0) best_bn = 128;
   }
   return best_bn;
 }
@@ -996,7 +1004,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   const int ln_mode = d->row_stats ? 1 : (d->row_accum ? 2 : (d->col_accum ? 3 : 0));
   bool narrow_no_split = false;
   if (bn == 0) {
-    bn = choose_block_n(d->b_rows, m_tiles, sms, geglu, ln_mode != 0);
+    bn = choose_block_n(d->b_rows, m_tiles, sms, geglu, ln_mode != 0, K / 64);
     // Small-M layers (level 3: M = 640): when wide tiles cannot fill the SMs, 64-wide tiles over the full K beat
     // split-K (one launch instead of zero + GEMM + finalize) as long as K is short: Linear 640x1280x1280 8.0 us vs
     // 19.0 us, (3,1,1) conv 15.0 vs 20.6 us; 3x3 convs (K >= 11520) stay on split-K (30 vs 37 us).
