@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import functools
 import math
+import os as _os
 
 import torch
 
@@ -21,7 +22,7 @@ from ._lib import (AttnDesc, GemmDesc, GroupNormDesc, LayerNormDesc, ShortAttnDe
 BF16 = torch.bfloat16
 
 # ----------------------------------------------------------------------------- launch accounting
-KERNELS_PER_CALL = {"groupnorm": 2}     # stats + apply (plus one memset node)
+KERNELS_PER_CALL = {"groupnorm": 2}     # stats + apply (the cluster path and split-K GEMMs are counted as one: a lower bound)
 LAUNCHES = 0                            # kernels of libt2v_b200.so enqueued so far (incl. during graph capture)
 _PROF = None                            # list of (family, flops, ev_start, ev_end) while profiling
 _FLOPS: dict = {}
@@ -171,7 +172,6 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     return out
 
 
-import os as _os
 # GroupNorm statistics in the producing GEMM's epilogue (T2VGemmDesc.col_accum -> T2VGroupNormDesc.chan_sums): built,
 # parity-tested, and measured SLOWER on B200 than the statistics kernel it removes (bench: 151.0 frames/s off, 140.7
 # with every K >= 1152 producer fused, 147.1 with K >= 2304): the per-chunk column reduction adds ~130 instructions
