@@ -171,10 +171,31 @@ def run_reference(args, rank, world):
                 config=dict(workload="T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet + KL-VAE decode, bs=1 per GPU"),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=desc),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    _emit(line)
+
+
+_RESULT_FD = None
+
+
+def _reserve_stdout():
+    """Contract: exactly ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the result line is
+    written to the saved descriptor at the end."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
 
 
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -299,7 +320,7 @@ def main():
             tcpu = run()
             line["cpu_baseline"] = dict(value=FRAMES / (tcpu * PIPE_TFLOP / sample_tflop), unit="frames/s", cores=threads,
                                         kind="port", sample=desc + f"; sample took {tcpu:.1f} s")
-        print(json.dumps(line))
+        _emit(line)
     t2v_dist.shutdown()
 
 
