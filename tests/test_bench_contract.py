@@ -45,6 +45,6 @@ def test_reference_arm_line():
 
 
 def test_two_gpu_line_is_weak_scaling_aggregate():
-    one, two = _load("r01_bench_final.json"), _load("r01_bench_v7_2gpu.json")
+    one, two = _load("r01_bench_final.json"), _load("r01_bench_final_2gpu.json")
     assert two["n_gpus"] == 2 and two["scaling"] == "weak"
     assert 1.8 < two["value"] / one["value"] < 2.2
