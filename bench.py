@@ -9,10 +9,10 @@ synthetic inputs (random prompt embeddings, random-init weights of the VC2 archi
           host memory (H2D each step) and the decoded video copied back to pinned host memory (D2H).
   roofline     : tensor-core roofline of the dominant kernel family (gemm_tc: every Linear / conv),
                  algorithmic FLOPs / CUDA-event time of those launches, measured live in an eager pass.
-  cpu_baseline : the oracle port of the reference UNet (plain fp32 torch, naive attention) timed on the
-                 host cores on a bounded sample, extrapolated by FLOPs.
-`--impl reference` runs only that CPU arm (the reference is pure Python with no GPU kernels of its
-own; /root/reference does not exist on the GPU box, so the oracle port stands in for it).
+  cpu_baseline : the unmodified reference UNetModel + Decoder timed on the host cores on a bounded sample of the
+                 same config (one full UNet forward + one decoded frame; video = 4 forwards + 16 frames).
+`--impl reference` runs only that CPU arm: the UNMODIFIED reference modules from the git-ignored snapshot
+oracle/_ref/ (made by oracle/build_ref.py; it travels to the GPU box), full config, or the oracle port if absent.
 Multi-GPU (torchrun): replicas only — each rank samples its own videos; no data-path collective.
 """
 import argparse
@@ -118,58 +118,158 @@ def build_pipeline(device, use_graph=True):
     return pipe
 
 
-def cpu_sample(threads, t_frames=4):
-    """One bounded sample of the CPU path: the oracle UNet forward (fp32, naive attention) on t_frames of the 16 frames."""
+WORKLOAD = "T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet (1.41B) + KL-VAE decode, bs=%d per GPU"
+
+
+def _fill_random(module, seed=0):
+    """Random-init weights of the bench (same recipe as build_pipeline) for a module created on the meta device."""
     import torch
-    from t2v_turbo_b200.configs import VC2_UNET
-    from oracle.unet_oracle import unet_forward, guidance_scale_embedding
-    from t2v_turbo_b200.unet import UNetModel
-    torch.set_num_threads(threads)
+    module.to_empty(device="cpu")
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0, 0.6 / p[0].numel() ** 0.5, generator=g)
+            elif name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.zero_()
+    return module.eval()
+
+
+def reference_sample():
+    """The UNMODIFIED reference (oracle/_ref snapshot made by oracle/build_ref.py; /root/reference in the authoring
+    container) on the host cores, full BASELINE config: one step = ONE `UNetModel.forward` on the full 1x4x16x40x64
+    latent + 77x1024 context (naive attention: xformers is not installed, attention.py:128-144) and ONE decoded 320x512
+    frame through `Decoder`; a 4-step 16-frame video costs 4 * t_unet + 16 * t_frame (the reference decodes frame by
+    frame, ddpm3d.py:671-677).  dtype and thread count are whichever is fastest on this host (probed on the frame
+    decode before the timed region).  Returns None when no copy of the reference is available."""
+    import torch
+    from oracle import ref_loader
+    if ref_loader.enable() is None:
+        return None
+    from t2v_turbo_b200.configs import VC2_UNET, VC2_VAE_DDCONFIG
+    from lvdm.modules.networks.openaimodel3d import UNetModel as RefUNet
+    from lvdm.modules.networks.ae_modules import Decoder as RefDecoder
     with torch.device("meta"):
-        shapes = {k: v.shape for k, v in UNetModel(**VC2_UNET).state_dict().items()}
+        unet, dec = RefUNet(**VC2_UNET), RefDecoder(**VC2_VAE_DDCONFIG)
+    unet, dec = _fill_random(unet, 0), _fill_random(dec, 1)
     g = torch.Generator().manual_seed(0)
-    sd = {}
-    for k, shp in shapes.items():
-        if len(shp) >= 2:
-            fan_in = 1
-            for s in shp[1:]:
-                fan_in *= s
-            sd[k] = torch.empty(shp).normal_(0, 0.6 / fan_in ** 0.5, generator=g)
-        elif k.endswith("weight"):
-            sd[k] = torch.ones(shp)
-        else:
-            sd[k] = torch.zeros(shp)
-    x = torch.randn(1, 4, t_frames, HEIGHT // 8, WIDTH // 8, generator=g)
+    z = torch.randn(1, 4, HEIGHT // 8, WIDTH // 8, generator=g)
+    ncpu = os.cpu_count() or 1
+    forced_t, forced_d = os.environ.get("T2V_REF_THREADS"), os.environ.get("T2V_REF_DTYPE")
+    cands_t = [int(forced_t)] if forced_t else sorted({min(ncpu, n) for n in (16, 32, 64, ncpu)})
+    cands_d = [dict(f32=torch.float32, bf16=torch.bfloat16)[forced_d]] if forced_d else [torch.float32, torch.bfloat16]
+    best, probe = None, {}
+    for dt in cands_d:
+        dec.to(dt)
+        zz = z.to(dt)
+        for nt in cands_t:
+            torch.set_num_threads(nt)
+            with torch.no_grad():
+                dec(zz)   # warm (allocator, oneDNN primitive cache)
+                t0 = time.perf_counter()
+                dec(zz)
+                dtm = time.perf_counter() - t0
+            probe[f"{str(dt).split('.')[-1]}/{nt}"] = round(dtm, 2)
+            if best is None or dtm < best[0]:
+                best = (dtm, dt, nt)
+    _, dt, nt = best
+    torch.set_num_threads(nt)
+    unet.to(dt)
+    unet.dtype = dt            # what app.py:143 does
+    dec.to(dt)
+    x = torch.randn(1, 4, FRAMES, HEIGHT // 8, WIDTH // 8, generator=g).to(dt)
+    ctx = torch.randn(1, 77, 1024, generator=g).to(dt)
+    from oracle.unet_oracle import guidance_scale_embedding
+    w = guidance_scale_embedding(torch.tensor([7.5]), 256).to(dt)
+    ts = torch.tensor([999])
+    zz = z.to(dt)
+
+    def run():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            unet(x, ts, context=ctx, fps=16, timestep_cond=w)
+            t1 = time.perf_counter()
+            dec(zz)
+            t2 = time.perf_counter()
+        return STEPS * (t1 - t0) + FRAMES * (t2 - t1), (t1 - t0, t2 - t1)
+    desc = (f"unmodified reference UNetModel.forward (1x4x16x40x64, 77x1024 context, naive attention) + Decoder on one 320x512 "
+            f"frame per step, {str(dt).split('.')[-1]}, {nt} threads of {ncpu}; video time = 4*t_unet + 16*t_frame; "
+            f"probe (frame decode s per dtype/threads): {probe}")
+    return run, "reference", nt, str(dt).split(".")[-1].replace("float32", "f32").replace("bfloat16", "bf16"), desc
+
+
+def port_sample():
+    """Fallback when no copy of the reference travels with the repo: the oracle port of UNetModel.forward (fp32)."""
+    import torch
+    from t2v_turbo_b200.configs import VC2_UNET, VC2_VAE_DDCONFIG
+    from oracle.unet_oracle import unet_forward, guidance_scale_embedding
+    from oracle.vae_oracle import decode_first_stage_2dae
+    from t2v_turbo_b200.unet import UNetModel
+    from t2v_turbo_b200.vae import AutoencoderKL
+    nt = min(os.cpu_count() or 1, 16)
+    torch.set_num_threads(nt)
+
+    def rand_sd(shapes, seed):
+        g = torch.Generator().manual_seed(seed)
+        sd = {}
+        for k, shp in shapes.items():
+            if len(shp) >= 2:
+                fan_in = 1
+                for v in shp[1:]:
+                    fan_in *= v
+                sd[k] = torch.empty(shp).normal_(0, 0.6 / fan_in ** 0.5, generator=g)
+            else:
+                sd[k] = torch.ones(shp) if k.endswith("weight") else torch.zeros(shp)
+        return sd
+    with torch.device("meta"):
+        ushapes = {k: v.shape for k, v in UNetModel(**VC2_UNET).state_dict().items()}
+        vshapes = {k: v.shape for k, v in AutoencoderKL(VC2_VAE_DDCONFIG, 4).state_dict().items()}
+    usd, vsd = rand_sd(ushapes, 0), rand_sd(vshapes, 1)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, FRAMES, HEIGHT // 8, WIDTH // 8, generator=g)
     ctx = torch.randn(1, 77, 1024, generator=g)
     w = guidance_scale_embedding(torch.tensor([7.5]), 256)
     ts = torch.tensor([999])
 
     def run():
-        t0 = time.perf_counter()
         with torch.no_grad():
-            unet_forward(sd, VC2_UNET, x, ts, ctx, fps=16, timestep_cond=w)
-        return time.perf_counter() - t0
-    sample_tflop = UNET_TFLOP * t_frames / FRAMES
-    desc = (f"oracle port of UNetModel.forward, fp32, naive attention, {t_frames} of {FRAMES} frames at 40x64 "
-            f"({sample_tflop:.2f} of {PIPE_TFLOP:.2f} TFLOP per video; frames/s extrapolated by FLOPs)")
-    return run, sample_tflop, desc
+            t0 = time.perf_counter()
+            unet_forward(usd, VC2_UNET, x, ts, ctx, fps=16, timestep_cond=w)
+            t1 = time.perf_counter()
+            decode_first_stage_2dae(vsd, VC2_VAE_DDCONFIG, x[:, :, :1])
+            t2 = time.perf_counter()
+        return STEPS * (t1 - t0) + FRAMES * (t2 - t1), (t1 - t0, t2 - t1)
+    desc = (f"oracle PORT (oracle/_ref absent) of UNetModel.forward (full 1x4x16x40x64) + one decoded frame per step, fp32, "
+            f"{nt} threads; video time = 4*t_unet + 16*t_frame")
+    return run, "port", nt, "f32", desc
+
+
+def cpu_arm():
+    return reference_sample() or port_sample()
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path, on this arm's config / metric / unit.
+    Rank 0 alone runs; K timed steps after W warm-ups, each step one bounded sample (see reference_sample)."""
     if rank != 0:
         return
-    threads = min(os.cpu_count() or 1, 16)   # measured on the 128-core box: 16 threads 1.8 s/frame, 32: 3.4 s, 64: 3.0 s
-    run, sample_tflop, desc = cpu_sample(threads)
+    run, kind, threads, dtype, desc = cpu_arm()
     for _ in range(args.warmup):
         run()
-    times = [run() for _ in range(args.steps)]
-    t = sum(times) / len(times)
-    fps = FRAMES / (t * PIPE_TFLOP / sample_tflop)
+    recs = [run() for _ in range(args.steps)]
+    t_video = sum(r[0] for r in recs) / len(recs)
+    t_unet = sum(r[1][0] for r in recs) / len(recs)
+    t_frame = sum(r[1][1] for r in recs) / len(recs)
+    fps = FRAMES / t_video
     line = dict(impl="reference", metric="4-step 16x320x512 frames/sec", value=fps, unit="frames/s", n_gpus=args.gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet + KL-VAE decode, bs=1 per GPU"),
-                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=desc),
+                steps=args.steps, warmup=args.warmup, ms_per_step=(t_unet + t_frame) * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype=dtype, data="synthetic", config=dict(workload=WORKLOAD % args.batch),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind=kind,
+                                  sample=desc + f"; measured t_unet {t_unet:.2f} s, t_frame {t_frame:.2f} s per step "
+                                                f"(ms_per_step = t_unet + t_frame, the wall time of one step; value = 16 frames / "
+                                                f"(4*t_unet + 16*t_frame) = {t_video:.1f} s per video)"),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     _emit(line)
 
@@ -305,7 +405,7 @@ def main():
         line = dict(metric="4-step 16x320x512 frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic",
-                    config=dict(workload="T2VTurboVC2Pipeline 4-step, 16x320x512, VC2 UNet (1.41B) + KL-VAE decode, bs=%d per GPU" % bs,
+                    config=dict(workload=WORKLOAD % bs,
                                 parallelism=f"replicas x{world} (no data-path collective)", cuda_graph=not args.no_graph,
                                 l2="working set per step (2.83 GB weights x4 + activations) >> 126 MB L2; no flush needed",
                                 algorithmic_tflop_per_step=PIPE_TFLOP * bs, output_finite=finite),
@@ -315,11 +415,11 @@ def main():
                     gpu_launches=launches_per_step * args.steps, roofline=roofline,
                     tensor_frac_of_step=PIPE_TFLOP * bs / (ms / args.steps * 1e-3) / pk["tflops"])
         if world == 1 and not args.no_cpu_baseline:
-            threads = min(os.cpu_count() or 1, 16)
-            run, sample_tflop, desc = cpu_sample(threads)
-            tcpu = run()
-            line["cpu_baseline"] = dict(value=FRAMES / (tcpu * PIPE_TFLOP / sample_tflop), unit="frames/s", cores=threads,
-                                        kind="port", sample=desc + f"; sample took {tcpu:.1f} s")
+            torch.cuda.synchronize()
+            run, kind, threads, cdt, desc = cpu_arm()
+            tv, (tu, tf) = run()
+            line["cpu_baseline"] = dict(value=FRAMES / tv, unit="frames/s", cores=threads, kind=kind, dtype=cdt,
+                                        sample=desc + f"; one sample: t_unet {tu:.1f} s, t_frame {tf:.1f} s")
         _emit(line)
     t2v_dist.shutdown()
 

@@ -278,6 +278,16 @@ int t2v_lcm_step(const void* x, const void* eps, const void* noise, void* prev, 
                  int64_t n, int32_t dtype, float inv_sqrt_alpha_t, float sqrt_beta_t, float c_skip,
                  float c_out, float sqrt_alpha_prev, float sqrt_beta_prev, t2v_stream_t stream);
 
+/*
+ * out[r, i] = rnd( rnd(a[r] * x[r, i]) + rnd(b[r] * y[r, i]) ) over [rows, row_len] tensors of one dtype (0 bf16,
+ * 1 fp16, 2 fp32), a / b fp32 per-row scalars on the device, rnd = round to the tensor dtype after every tensor op as
+ * torch does.  T2VTurboScheduler.add_noise (scheduler/t2v_turbo_scheduler.py:470-495, rows = samples), and the DDIM
+ * solver / predicted-x0 lines of the distillation step (ode_solver/ddim_solver.py:67-87, utils/common_utils.py:87-133).
+ * y (and b) may be NULL: out = rnd(a[r] * x).
+ */
+int t2v_scale_add_rows(const void* x, const void* y, const float* a, const float* b, void* out, int64_t rows,
+                       int64_t row_len, int32_t dtype, t2v_stream_t stream);
+
 /* KL-VAE posterior (lvdm/distributions.py:24-42 + ddpm3d.py:558-567): moments fp32 channels-last
  * [B*T, H, W, 2*zc] = (mean | logvar) -> out [B, zc, T, H, W] (out_dtype 0 bf16 / 1 fp16 / 2 fp32)
  * = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise); noise fp32 [B*T, zc, H, W] or NULL (posterior mode). */

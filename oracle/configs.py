@@ -17,6 +17,17 @@ UNET_CONFIGS = {
     # BASELINE.json config 1: full VC2 UNet, 1x4x16x40x64 latent, 77x1024 text embedding
     "full": dict(cfg=dict(VC2_UNET), x_shape=(1, 4, 16, 40, 64), ctx_len=77, weight_seed=9, input_seed=1234,
                  timesteps=[999]),
+    # the same model at the later sampling timesteps of the 4-step schedule, and at batch 2 with a different timestep
+    # per sample (round 2; separate fixtures so the round-1 golden stays untouched)
+    "full_t": dict(cfg=dict(VC2_UNET), x_shape=(1, 4, 16, 40, 64), ctx_len=77, weight_seed=9, input_seed=1236,
+                   timesteps=[759, 279]),
+    "full_b2": dict(cfg=dict(VC2_UNET), x_shape=(2, 4, 16, 40, 64), ctx_len=77, weight_seed=9, input_seed=1237,
+                    timesteps=[(519, 279)]),
+    # v2 models (BASELINE config 3): motion_cond_proj_dim=256 adds motion_cond_proj / combine_proj (openaimodel3d.py:690-697)
+    "small_motion": dict(cfg={**VC2_UNET, "model_channels": 64, "attention_resolutions": [2, 1], "num_res_blocks": 1,
+                              "channel_mult": [1, 2], "context_dim": 128, "temporal_length": 4, "motion_cond_proj_dim": 256},
+                         x_shape=(2, 4, 4, 8, 8), ctx_len=77, weight_seed=17, input_seed=1238, timesteps=[(999, 519)],
+                         motion_gs=(0.05, 0.0)),
 }
 
 VAE_CONFIGS = {
@@ -34,4 +45,8 @@ def unet_inputs(spec, timestep):
     x = torch.randn(spec["x_shape"], generator=g)
     ctx = torch.randn(b, spec["ctx_len"], spec["cfg"]["context_dim"], generator=g)
     w_emb = guidance_scale_embedding(torch.tensor(7.5).repeat(b), 256)
-    return dict(x=x, context=ctx, timesteps=torch.full((b,), timestep, dtype=torch.long), fps=16, timestep_cond=w_emb)
+    ts = torch.tensor(timestep, dtype=torch.long) if isinstance(timestep, (tuple, list)) else torch.full((b,), timestep, dtype=torch.long)
+    out = dict(x=x, context=ctx, timesteps=ts, fps=16, timestep_cond=w_emb)
+    if "motion_gs" in spec:   # pipeline:197-204: the same sin/cos embedding of the motion guidance scale
+        out["motion_cond"] = guidance_scale_embedding(torch.tensor(spec["motion_gs"], dtype=torch.float32), 256)
+    return out

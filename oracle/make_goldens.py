@@ -148,18 +148,31 @@ def gen_scheduler():
         noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + i))
         prev, den = s.step(eps, i, t, x, generator=gen, return_dict=False)
         steps.append({"i": i, "t": int(t), "noise": noise, "prev": prev, "den": den})
+    # add_noise (:470-495), fp32 and bf16, per-sample timesteps
+    an_x, an_n = torch.randn(3, 4, 2, 5, 5, generator=g), torch.randn(3, 4, 2, 5, 5, generator=g)
+    an_t = torch.tensor([0, 519, 999])
+    add_noise = {"x": an_x, "noise": an_n, "t": an_t, "out_f32": s.add_noise(an_x, an_n, an_t),
+                 "out_bf16": s.add_noise(an_x.bfloat16(), an_n.bfloat16(), an_t)}
+    # bf16 steps (what the bf16 pipeline executes: every tensor op rounds to bf16)
+    steps_bf16 = []
+    for i, t in enumerate(s.timesteps):
+        # the reference draws its own noise (randn_tensor in the sample dtype from the generator; variance_noise is ignored)
+        noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + i), dtype=torch.bfloat16)
+        prev, den = s.step(eps.bfloat16(), i, t, x.bfloat16(), generator=torch.Generator().manual_seed(100 + i), return_dict=False)
+        steps_bf16.append({"i": i, "t": int(t), "noise": noise, "prev": prev, "den": den})
     torch.save({"alphas_cumprod": s.alphas_cumprod.clone(), "timesteps": table, "x": x, "eps": eps, "steps": steps,
+                "add_noise": add_noise, "steps_bf16": steps_bf16,
                 "scalings": {t: tuple(float(v) for v in s.get_scalings_for_boundary_condition_discrete(t)) for t in (0, 279, 999)}},
                os.path.join(GOLD, "scheduler.pt"))
     print("  scheduler: alphas_cumprod[0], [999] =", float(s.alphas_cumprod[0]), float(s.alphas_cumprod[999]))
 
 
-def gen_pipeline():
-    """4-step T2VTurboVC2Pipeline on CPU with the small UNet/VAE through the unmodified reference classes."""
+def _ref_pipeline(unet_name):
+    """The unmodified reference pipeline around a small UNet / VAE (the attributes it touches: pipeline:27-29,144,216)."""
     from pipeline.t2v_turbo_vc2_pipeline import T2VTurboVC2Pipeline
     from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
     from lvdm.modules.networks.ae_modules import Decoder
-    uspec, vspec = UNET_CONFIGS["small"], VAE_CONFIGS["small"]
+    uspec, vspec = UNET_CONFIGS[unet_name], VAE_CONFIGS["small"]
     unet = ref_unet(uspec["cfg"], uspec["weight_seed"])
     dd = vspec["ddconfig"]
     dec = Decoder(**dd).eval()
@@ -178,7 +191,7 @@ def gen_pipeline():
         def decode(self, z, **kw):
             return self.decoder(self.post_quant_conv(z))
 
-    class FakeT2V(torch.nn.Module):   # the attributes the pipeline touches (pipeline:27-29,144,216)
+    class FakeT2V(torch.nn.Module):
         def __init__(self):
             super().__init__()
             self.first_stage_model = FakeVAE()
@@ -194,19 +207,49 @@ def gen_pipeline():
 
     pipe = T2VTurboVC2Pipeline(FakeT2V(), T2VTurboScheduler(linear_start=0.00085, linear_end=0.012),
                                {"params": {"unet_config": {"params": uspec["cfg"]}}})
+    return pipe, uspec
+
+
+def _run_pipeline_cases(pipe, prompt_embeds, cases):
+    res = {}
+    for key, kw in cases.items():
+        out = {}
+        for otype, name in (("latent", "latent"), ("pt", "video")):
+            gen = torch.Generator().manual_seed(1234)
+            out[name] = pipe(prompt_embeds=prompt_embeds, height=64, width=64, frames=4, fps=16, guidance_scale=7.5,
+                             generator=gen, output_type=otype, **kw)
+        res[key] = out
+        print(f"  pipeline {key} {kw}: latent std {out['latent'].std():.4f} video std {out['video'].std():.4f}")
+    return res
+
+
+def gen_pipeline():
+    """4- and 8-step T2VTurboVC2Pipeline on CPU with the small UNet/VAE through the unmodified reference classes."""
+    pipe, uspec = _ref_pipeline("small")
     g = torch.Generator().manual_seed(5)
     prompt_embeds = torch.randn(1, 77, uspec["cfg"]["context_dim"], generator=g)
-    res = {}
-    for steps in (4, 8):
-        gen = torch.Generator().manual_seed(1234)
-        lat = pipe(prompt_embeds=prompt_embeds, height=64, width=64, frames=4, fps=16, guidance_scale=7.5,
-                   num_inference_steps=steps, lcm_origin_steps=50, generator=gen, output_type="latent")
-        gen = torch.Generator().manual_seed(1234)
-        vid = pipe(prompt_embeds=prompt_embeds, height=64, width=64, frames=4, fps=16, guidance_scale=7.5,
-                   num_inference_steps=steps, lcm_origin_steps=50, generator=gen, output_type="pt")
-        res[steps] = {"latent": lat, "video": vid}
-        print(f"  pipeline {steps} steps: latent std {lat.std():.4f} video std {vid.std():.4f}")
+    res = _run_pipeline_cases(pipe, prompt_embeds, {s: dict(num_inference_steps=s, lcm_origin_steps=50) for s in (4, 8)})
     torch.save({"prompt_embeds": prompt_embeds, "results": res}, os.path.join(GOLD, "pipeline_small.pt"))
+
+
+def gen_pipeline_v2():
+    """BASELINE config 3 (the v2 sampling path): 16 steps, lcm_origin_steps=200 (what app.py / predict.py pass), and the
+    motion-conditioned UNet with use_motion_cond=True, motion_gs=0.05, percentage=0.5 (pipeline:191-204: the motion
+    embedding switches to the embedding of 0 below t = 500), batch 2.  Each case stores its kwargs."""
+    cases_plain = {"s16_o200": dict(num_inference_steps=16, lcm_origin_steps=200),
+                   "s4_o200": dict(num_inference_steps=4, lcm_origin_steps=200)}
+    pipe, uspec = _ref_pipeline("small")
+    g = torch.Generator().manual_seed(6)
+    pe = torch.randn(1, 77, uspec["cfg"]["context_dim"], generator=g)
+    out = {"plain": {"prompt_embeds": pe, "cases": cases_plain, "results": _run_pipeline_cases(pipe, pe, cases_plain)}}
+    cases_motion = {"s16_o200_motion": dict(num_inference_steps=16, lcm_origin_steps=200, use_motion_cond=True, motion_gs=0.05,
+                                            percentage=0.5),
+                    "s8_o50_motion": dict(num_inference_steps=8, lcm_origin_steps=50, use_motion_cond=True, motion_gs=0.05,
+                                          percentage=0.5)}
+    pipe, uspec = _ref_pipeline("small_motion")
+    pe2 = torch.randn(2, 77, uspec["cfg"]["context_dim"], generator=g)
+    out["motion"] = {"prompt_embeds": pe2, "cases": cases_motion, "results": _run_pipeline_cases(pipe, pe2, cases_motion)}
+    torch.save(out, os.path.join(GOLD, "pipeline_small_v2.pt"))
 
 
 if __name__ == "__main__":
@@ -216,7 +259,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline"] + (["unet_full", "vae_full", "vae_enc_full"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -231,3 +274,5 @@ if __name__ == "__main__":
             gen_vae(item[4:])
         elif item == "pipeline":
             gen_pipeline()
+        elif item == "pipeline_v2":
+            gen_pipeline_v2()

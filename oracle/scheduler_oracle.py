@@ -42,3 +42,9 @@ class SchedulerOracle:
         else:
             prev = den
         return prev, den
+
+    def add_noise(self, original_samples, noise, timesteps):
+        """scheduler/t2v_turbo_scheduler.py:470-495: the alpha table is cast to the sample dtype before the square roots."""
+        ac = self.alphas_cumprod.to(dtype=original_samples.dtype)[timesteps]
+        shape = (-1,) + (1,) * (original_samples.dim() - 1)
+        return (ac ** 0.5).view(shape) * original_samples + ((1 - ac) ** 0.5).view(shape) * noise

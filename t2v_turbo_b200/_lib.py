@@ -145,6 +145,7 @@ SYMBOLS = {
     "t2v_concat_channels": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "t2v_softmax_rows": (C.c_int, [_vp, _i64, _i32, _i64, _f32, _vp]),
     "t2v_gaussian_sample": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "t2v_scale_add_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "t2v_lcm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "t2v_pack_conv_weight": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp]),
     "t2v_pack_geglu_rows": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
@@ -154,13 +155,18 @@ _lib = None
 
 
 def lib() -> C.CDLL:
-    """Load the shared library (built by t2v_turbo_b200.build). Fails loudly when absent."""
+    """Load the shared library; a fresh clone builds it on first use (nvcc, ~2 min).  Fails loudly when it can be
+    neither found nor built: there is no CPU / PyTorch fallback for the hot path."""
     global _lib
     if _lib is None:
         if not LIB_PATH.exists():
-            raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m t2v_turbo_b200.build` "
-                "(there is no CPU / PyTorch fallback for the hot path)")
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:   # no nvcc, compile error, read-only tree ...
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing and could not be built ({e}); build it with "
+                    "`python -m t2v_turbo_b200.build` (there is no CPU / PyTorch fallback for the hot path)") from e
         l = C.CDLL(str(LIB_PATH))
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)  # AttributeError if the symbol is not exported

@@ -315,6 +315,20 @@ __global__ void gaussian_sample_kernel(const float* __restrict__ mom, const floa
   }
 }
 
+// ------------------------------------------------------------------ per-row scaled sum (add_noise, DDIM solver lines)
+__global__ void scale_add_rows_kernel(const void* x, const void* y, const float* __restrict__ a, const float* __restrict__ b,
+                                      void* out, int64_t rows, int64_t row_len, int dt) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t n = rows * row_len;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / row_len;
+    float v = round_to(__ldg(a + r) * load_as_float(x, i, dt), dt);
+    if (y != nullptr) v = round_to(v + round_to(__ldg(b + r) * load_as_float(y, i, dt), dt), dt);
+    store_from_float(out, i, dt, v);
+  }
+}
+
 // ------------------------------------------------------------------ fused LCM step
 __global__ void lcm_step_kernel(const void* x, const void* eps, const void* noise, void* prev, void* den,
                                 int64_t n, int dt, float sa_inv, float sb, float c_skip, float c_out,
@@ -519,6 +533,16 @@ extern "C" int t2v_gaussian_sample(const float* moments, const float* noise, voi
                 out_dtype, b, t, h, w, zc, scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_gaussian_sample launch");
+}
+
+extern "C" int t2v_scale_add_rows(const void* x, const void* y, const float* a, const float* b, void* out, int64_t rows,
+                                  int64_t row_len, int32_t dtype, t2v_stream_t s) {
+  if (!x || !a || !out || rows < 1 || row_len < 1 || (y && !b)) return fail(-1, "t2v_scale_add_rows: bad argument");
+  if (dtype < 0 || dtype > 2) return fail(-2, "t2v_scale_add_rows: dtype must be 0 (bf16), 1 (fp16) or 2 (fp32)");
+  launch_kernel(scale_add_rows_kernel, dim3(grid_for(rows * row_len)), dim3(256), 0, static_cast<cudaStream_t>(s), x, y, a, b, out,
+                rows, row_len, dtype);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_scale_add_rows launch");
 }
 
 extern "C" int t2v_lcm_step(const void* x, const void* eps, const void* noise, void* prev, void* denoised,

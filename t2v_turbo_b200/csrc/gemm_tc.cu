@@ -327,6 +327,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t res_bytes = uint32_t(p.rows_in_box) * 64u;
     const int sw = (r >> 1) & 3;
     uint32_t q = 0;  // chunks processed so far by this warpgroup (buffer = q % 3)
+    float* cs_tab = bias_smem + 512;  // LN == 3: [BN columns][sum, sum of squares] (the folded-LayerNorm vectors' slot)
+    if (LN == 3) {
+      for (int i = et; i < 2 * BN; i += 128 * kEpiWGs) cs_tab[i] = 0.f;
+      named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
+    }
     int it = 0;
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
@@ -384,29 +389,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       float acc_sum = 0.f, acc_sq = 0.f;  // LN == 2: this thread's row, this tile
-      // LN == 3: this thread reduces channel pair (r & 15) over rows [16 (r >> 4), +16) in two half-blocks of 8 rows;
-      // a half-block never straddles samples (host: box[0] % 8 == 0, cs_mult[0] == 0)
-      int64_t cs_off[2] = {0, 0};
+      // LN == 3: this thread reduces channel pair (r & 15) over rows [16 (r >> 4), +16) in two half-blocks of 8 rows
+      // (host: box[0] % 8 == 0 and the whole tile lies in ONE sample: box[j] == 1 wherever cs_mult[j] != 0).  The
+      // column sums of every chunk go to a per-CTA shared-memory table and reach global memory once per tile.
+      int64_t cs_off = -1;    // offset of this tile's sample in col_accum, -1: tile outside the output
       int cs_nv[2] = {0, 0};  // valid rows (0..8) of each half-block: rows run along dim 0, the box may overhang the tensor
       if (LN == 3) {
+        bool tile_ok = true;
+        int64_t smp = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tile_ok = tile_ok && (int64_t(o[j]) < p.o_size[j]);
+          smp += int64_t(o[j]) * p.cs_mult[j];
+        }
+        if (tile_ok) cs_off = smp * int64_t(p.n_rows_b) * 2;
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
           int rr = (r >> 4) * 16 + hb * 8;
-          bool ok = rr < p.rows_in_box;
-          int64_t smp = 0;
+          bool ok = tile_ok && rr < p.rows_in_box;
+          const int i0 = rr % p.box[0];
+          rr /= p.box[0];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 1; j < 4; ++j) {
             const int ij = rr % p.box[j];
             rr /= p.box[j];
-            const int64_t xj = int64_t(o[j]) + ij;
-            ok = ok && (xj < p.o_size[j]);
-            smp += xj * p.cs_mult[j];
+            ok = ok && (int64_t(o[j]) + ij < p.o_size[j]);
           }
-          const int i0 = ((r >> 4) * 16 + hb * 8) % p.box[0];
           int64_t nv = p.o_size[0] - (int64_t(o[0]) + i0);
           nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
           cs_nv[hb] = ok ? int(nv) : 0;
-          cs_off[hb] = smp * int64_t(p.n_rows_b) * 2;
         }
       }
       if (has_res && lead_warp && elect_one()) {
@@ -578,26 +589,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           named_bar_sync(1 + g, 128);
         }
         if (LN == 3) {
-          // column sums of this 128 x 32 chunk from the staged bf16 rows (exactly the values GroupNorm will read)
+          // column sums of this 128 x 32 chunk from the staged bf16 rows (exactly the values GroupNorm will read):
+          // packed fp32x2 accumulation of the channel pair, lanes l / l+16 combined by a shuffle, then one
+          // shared-memory reduction per (channel, statistic) and warp into the CTA's table
           const int cp = r & 15;  // channel pair: 4 bytes at word (cp & 3) of 16-byte chunk (cp >> 2)
           const uint8_t* cbase = ebuf + buf * kEpiBufBytes + (cp & 3) * 4;
+          float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
             const int r0 = (r >> 4) * 16 + hb * 8;
-            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int ii = i ^ ((lane >> 4) & 1);  // the two half-warps read rows of opposite parity: no bank conflict
               const int rw = r0 + ii;
               uint32_t u = *reinterpret_cast<const uint32_t*>(cbase + rw * 64 + ((((cp >> 2) ^ (rw >> 1)) & 3) << 4));
               if (ii >= cs_nv[hb]) u = 0u;
-              const float lo = bf16_lo(u), hi = bf16_hi(u);
-              s0 += lo;
-              q0 = fmaf(lo, lo, q0);
-              s1 += hi;
-              q1 = fmaf(hi, hi, q1);
+              const float2 v2 = make_float2(bf16_lo(u), bf16_hi(u));
+              s2 = add_f32x2(s2, v2);
+              q2 = fma_f32x2(v2, v2, q2);
             }
-            if (cs_nv[hb] > 0 && oc0 + 2 * cp < p.n_out) red_add_v4(p.col_accum + cs_off[hb] + (oc0 + 2 * cp) * 2, s0, q0, s1, q1);
+          }
+          s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 16);
+          s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 16);
+          q2.x += __shfl_xor_sync(0xffffffffu, q2.x, 16);
+          q2.y += __shfl_xor_sync(0xffffffffu, q2.y, 16);
+          if (lane < 16) {
+            float* tab = cs_tab + (c * 32 + 2 * cp) * 2;
+            atomicAdd(tab + 0, s2.x);
+            atomicAdd(tab + 1, q2.x);
+            atomicAdd(tab + 2, s2.y);
+            atomicAdd(tab + 3, q2.y);
           }
         }
         if (lead_warp && elect_one()) {
@@ -629,6 +650,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (LN == 2) {
         const int64_t m = int64_t(o[0]) + r;
         if (m < p.o_size[0] && g < chunks_per_tile && n_base + g * acc_cw < p.n_rows_b) red_add_v2(p.row_accum + 2 * m, acc_sum, acc_sq);
+      }
+      if (LN == 3) {
+        // flush this warpgroup's columns of the table (chunks c = g, g + 2, ...) to the sample's global sums and clear
+        // them; the clears are ordered before the next tile's reductions by that tile's staging barriers
+        named_bar_sync(1 + g, 128);
+        const int c = g + kEpiWGs * (r >> 4);
+        if (c < chunks_per_tile && n_base + c * 32 < p.n_rows_b) {
+          float4* t4 = reinterpret_cast<float4*>(cs_tab + (c * 32 + 2 * (r & 15)) * 2);
+          const float4 tv = *t4;
+          *t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cs_off >= 0) red_add_v4(p.col_accum + cs_off + (n_base + c * 32 + 2 * (r & 15)) * 2, tv.x, tv.y, tv.z, tv.w);
+        }
       }
     }
     if (lead_warp && elect_one()) bulk_wait_group_read<0>();
@@ -1084,6 +1117,9 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     if (geglu || (d->flags & T2V_EPI_OUT_F32) || d->b_rows % 32 || d->n_out != d->b_rows || d->box[0] % 8 || d->cs_mult[0] != 0 ||
         d->b_batch_dim >= 0 || (reinterpret_cast<uintptr_t>(d->col_accum) & 15))
       return fail(-20, "t2v_gemm: col_accum needs bf16 output, N %% 32 == 0, box[0] %% 8 == 0, cs_mult[0] == 0, no batched B");
+    for (int j = 1; j < 4; ++j)
+      if (d->cs_mult[j] != 0 && d->box[j] != 1)
+        return fail(-20, "t2v_gemm: col_accum needs every tile inside one sample (box[%d] = %d spans samples)", j, d->box[j]);
   }
   if (d->row_stats && d->row_accum) return fail(-19, "t2v_gemm: row_stats and row_accum are mutually exclusive");
   if (d->row_stats && d->ln_raw && d->ln_channels <= 0) return fail(-19, "t2v_gemm: ln_raw needs ln_channels");

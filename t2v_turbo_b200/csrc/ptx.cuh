@@ -350,6 +350,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- packed fp32x2 arithmetic (sm_100: one FP instruction for two lanes)
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  uint64_t ua = (uint64_t(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
+  uint64_t ub = (uint64_t(__float_as_uint(b.y)) << 32) | __float_as_uint(b.x);
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ua), "l"(ub));
+  return make_float2(__uint_as_float(uint32_t(r)), __uint_as_float(uint32_t(r >> 32)));
+}
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  uint64_t ua = (uint64_t(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
+  uint64_t ub = (uint64_t(__float_as_uint(b.y)) << 32) | __float_as_uint(b.x);
+  uint64_t uc = (uint64_t(__float_as_uint(c.y)) << 32) | __float_as_uint(c.x);
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(ua), "l"(ub), "l"(uc));
+  return make_float2(__uint_as_float(uint32_t(r)), __uint_as_float(uint32_t(r >> 32)));
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -172,22 +172,26 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     return out
 
 
-# GroupNorm statistics in the producing GEMM's epilogue (T2VGemmDesc.col_accum -> T2VGroupNormDesc.chan_sums): built,
-# parity-tested, and measured SLOWER on B200 than the statistics kernel it removes (bench: 151.0 frames/s off, 140.7
-# with every K >= 1152 producer fused, 147.1 with K >= 2304): the per-chunk column reduction adds ~130 instructions
-# and, worse, every tile issues its reductions to the same few (frame, channel) addresses — 21 M vector atomics onto
-# 16 KB for one VAE conv.  It therefore stays OFF by default; the next step is a per-CTA shared-memory table flushed on
-# frame change.  T2V_GN_FUSE = off | conv (producers with K >= T2V_GN_FUSE_MIN_K, per-frame consumers) | all.
-GN_FUSE = _os.environ.get("T2V_GN_FUSE", "off")
+# GroupNorm statistics in the producing GEMM's epilogue (T2VGemmDesc.col_accum -> T2VGroupNormDesc.chan_sums).  The
+# epilogue reduces each staged 128 x 32 bf16 chunk over its rows into a per-CTA shared-memory table and flushes the
+# table to the (sample, channel) sums once per tile (round 1 issued a global vector atomic per 8 rows: 21 M atomics
+# onto 16 KB for one VAE conv, slower than the statistics pass it removed).  Requires every tile to lie inside one
+# sample (large images: VAE, UNet levels 0-1); other geometries keep the statistics kernel.
+# T2V_GN_FUSE = off | conv (producers with K >= T2V_GN_FUSE_MIN_K, per-frame consumers) | all.
+GN_FUSE = _os.environ.get("T2V_GN_FUSE", "conv")
 GN_FUSE_MIN_K = int(_os.environ.get("T2V_GN_FUSE_MIN_K", "1152"))
 
 
-def gn_fuse_producer(k_total, grid=None, fixed=(None, None, None, None)):
+def gn_fuse_producer(k_total, grid=None, fixed=(None, None, None, None), sample_dims=()):
     """Should a GEMM with reduction length k_total over the output point grid `grid` accumulate GroupNorm statistics
-    for its consumer?  (The epilogue reduces rows in runs of 8 along dim 0: the tile box must allow that.)"""
+    for its consumer?  (The epilogue reduces rows in runs of 8 along dim 0 and keeps one sample per tile: the tile box
+    must allow that — box[0] % 8 == 0 and box[j] == 1 for the dims that index samples.)"""
     if GN_FUSE == "off" or (GN_FUSE == "conv" and k_total < GN_FUSE_MIN_K):
         return False
-    return grid is None or plan_box(tuple(int(v) for v in grid), fixed)[0] % 8 == 0
+    if grid is None:
+        return True
+    box = plan_box(tuple(int(v) for v in grid), fixed)
+    return box[0] % 8 == 0 and all(box[j] == 1 for j in sample_dims)
 
 
 def gn_fuse_temporal():
@@ -200,8 +204,9 @@ SPLITK_WS_BYTES = 32 << 20
 
 
 def _splitk_workspace(device):
-    """Persistent fp32 scratch for split-K partial sums (per device and stream; zeroed by each call that uses it)."""
-    key = (device, torch.cuda.current_stream().cuda_stream)
+    """Persistent fp32 scratch for split-K partial sums, one per device (zeroed by each call that uses it; calls on
+    one device are stream-ordered by the host mirror, which runs a model on one stream at a time)."""
+    key = device
     ws = _SPLITK_WS.get(key)
     if ws is None:
         ws = torch.empty(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
@@ -416,12 +421,15 @@ _GN_WS: dict = {}
 
 
 def _gn_workspace(device, n):
-    key = (device, torch.cuda.current_stream().cuda_stream)
-    ws = _GN_WS.get(key)
-    if ws is None or ws.numel() < n:
-        ws = torch.zeros(max(n, 4096), device=device, dtype=torch.float32)   # zero once: t2v_groupnorm leaves it clean
-        _GN_WS[key] = ws
-    return ws
+    """Zeroed fp32 statistics scratch of the two-kernel GroupNorm, one per device (self-cleaning: t2v_groupnorm leaves it
+    zeroed).  Outgrown buffers are kept alive: captured CUDA graphs may still point at them."""
+    ws = _GN_WS.get(device)
+    if ws is None or ws[-1].numel() < n:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("t2v_turbo_b200: GroupNorm workspace must be allocated before CUDA-graph capture (run a warm-up call)")
+        _GN_WS.setdefault(device, []).append(torch.zeros(max(n, 1 << 16), device=device, dtype=torch.float32))
+        ws = _GN_WS[device]
+    return ws[-1]
 
 
 def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None, mode=0, chan_sums=None, chan_group=1):
@@ -623,6 +631,19 @@ def lcm_step(x, eps, noise, *, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqr
                              x.numel(), _lib.DTYPE_CODE[x.dtype], inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out,
                              sqrt_alpha_prev, sqrt_beta_prev, stream_ptr())
     return prev, den
+
+
+def scale_add_rows(x, a, y=None, b=None):
+    """out[r] = rnd(rnd(a[r] * x[r]) + rnd(b[r] * y[r])) with per-row (= per-sample) fp32 scalars a, b on the device;
+    x / y: contiguous tensors of one dtype whose leading dim indexes the rows."""
+    assert x.is_cuda and x.is_contiguous() and a.dtype == torch.float32 and a.numel() == x.shape[0]
+    rows = x.shape[0]
+    out = torch.empty_like(x)
+    if y is not None:
+        assert y.shape == x.shape and y.dtype == x.dtype and y.is_contiguous() and b.dtype == torch.float32 and b.numel() == rows
+    _launch("scale_add_rows", 0, lib().t2v_scale_add_rows, x.data_ptr(), ptr(y), a.data_ptr(), ptr(b), out.data_ptr(), rows,
+            x.numel() // rows, _lib.DTYPE_CODE[x.dtype], stream_ptr())
+    return out
 
 
 def gaussian_sample(moments, noise, *, b, t, zc, scale, dtype):

@@ -7,7 +7,11 @@ driving the B200 UNet, scheduler-step kernel and batched VAE decode.
 
 B200-first additions (all optional, none change results): the UNet forward of a sampling loop is
 captured once into a CUDA graph (static shapes; ~1.3k kernel launches replayed per step) and the
-decode is a second graph; text-context K/V projections are computed once per call, not per step.
+decode is a second graph.  The text-context K/V projection of all 16 cross-attention layers is ONE GEMM on 77 rows;
+in graph mode it is part of the captured forward (replayed each step), in eager mode it is cached per context tensor.
+Graphs are keyed on everything that changes what they would replay — input signature, fps, motion / no motion,
+`unet.dtype`, and the weight generation of the UNet / VAE (bumped by `load_state_dict`, `.to()`, `merge_lora`,
+`invalidate_packed`) — so a weight update never replays kernels that point at freed packed weights.
 """
 from __future__ import annotations
 
@@ -44,35 +48,61 @@ class LatentVideoModel(nn.Module):
 
     encode_first_stage_2DAE = encode_first_stage      # ddpm3d.py:586-600: same result, frame loop in the reference
 
-    def load_vc2_checkpoint(self, ckpt, strict_unet=True):
+    # parameters T2V-Turbo ADDS to the VC2 UNet; absent from `model.ckpt`, filled by the LoRA / unet.pt load (app.py:245-247)
+    _T2V_TURBO_EXTRA = ("time_cond_proj.", "motion_cond_proj.", "combine_proj.")
+
+    def load_vc2_checkpoint(self, ckpt, strict_unet=False):
         """VideoCrafter2 `model.ckpt` key space (common_utils.py:399-411): {"state_dict": {...}} or the bare dict with
         `model.diffusion_model.*`, `first_stage_model.*`, `cond_stage_model.*` and the DDPM schedule buffers.  Loads the
-        UNet and the KL-VAE; returns the keys that were not consumed (text encoder, schedule buffers, loss weights)."""
+        UNet and the KL-VAE; returns the keys that were not consumed (text encoder, schedule buffers, loss weights).
+        Like the reference (`load_state_dict(..., strict=False)`, app.py:245-247) the UNet load tolerates the missing
+        T2V-Turbo additions (`time_cond_proj`, `motion_cond_proj`, `combine_proj`) — and nothing else: any other
+        missing or unexpected key raises.  strict_unet=True demands those too."""
         sd = torch.load(ckpt, map_location="cpu", weights_only=True) if not isinstance(ckpt, dict) else ckpt
         sd = sd.get("state_dict", sd)
         unet_sd = {k[len("model.diffusion_model."):]: v for k, v in sd.items() if k.startswith("model.diffusion_model.")}
         vae_keys = tuple(self.first_stage_model.state_dict().keys())
         vae_sd = {k[len("first_stage_model."):]: v for k, v in sd.items()
                   if k.startswith("first_stage_model.") and k[len("first_stage_model."):] in vae_keys}
-        self.model.diffusion_model.load_state_dict(unet_sd, strict=strict_unet)
+        res = self.model.diffusion_model.load_state_dict(unet_sd, strict=strict_unet)
+        if not strict_unet:
+            bad = [k for k in res.missing_keys if not k.startswith(self._T2V_TURBO_EXTRA)] + list(res.unexpected_keys)
+            if bad:
+                raise RuntimeError(f"load_vc2_checkpoint: UNet keys missing / unexpected beyond the T2V-Turbo additions: {bad[:8]}"
+                                   f"{' ...' if len(bad) > 8 else ''}")
         self.first_stage_model.load_state_dict(vae_sd, strict=True)
         used = {"model.diffusion_model." + k for k in unet_sd} | {"first_stage_model." + k for k in vae_sd}
         return sorted(k for k in sd if k not in used)
 
 
-class _GraphedCall:
-    """Capture fn(*static_inputs) once per input signature; replay with inputs copied into static buffers."""
+_WARMUP_STREAM: dict = {}
 
-    def __init__(self, fn):
+
+def _warmup_stream(device):
+    """One reusable side stream per device for graph warm-ups (a fresh stream per capture would make every
+    stream-keyed cache downstream grow without bound)."""
+    s = _WARMUP_STREAM.get(device)
+    if s is None:
+        s = _WARMUP_STREAM[device] = torch.cuda.Stream(device=device)
+    return s
+
+
+class _GraphedCall:
+    """Capture fn(*static_inputs) once per input signature; replay with inputs copied into static buffers.
+    clone_out: hand the caller a copy of the graph's static output (outputs that escape the pipeline must not alias
+    the buffer the next replay overwrites)."""
+
+    def __init__(self, fn, clone_out=False):
         self.fn = fn
         self.cache = {}
+        self.clone_out = clone_out
 
     def __call__(self, *tensors):
         key = tuple((tuple(t.shape), t.dtype) for t in tensors)
         ent = self.cache.get(key)
         if ent is None:
             static_in = [t.clone() for t in tensors]
-            s = torch.cuda.Stream()
+            s = _warmup_stream(tensors[0].device)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):      # warm-up: lazy packing, workspace allocation, kernel attributes
@@ -88,7 +118,7 @@ class _GraphedCall:
         for dst, src in zip(static_in, tensors):
             dst.copy_(src)
         g.replay()
-        return static_out
+        return static_out.clone() if self.clone_out else static_out
 
 
 class T2VTurboVC2Pipeline:
@@ -159,21 +189,23 @@ class T2VTurboVC2Pipeline:
     def _unet_call(self, latents, ts, ctx, w_emb, motion, fps):
         if not self.use_cuda_graph:
             return self.unet(latents, ts, context=ctx, fps=fps, timestep_cond=w_emb, motion_cond=motion)
-        if self._unet_graph is None or self._unet_graph[0] != (fps, motion is None):
+        key = (fps, motion is None, self.unet.dtype, getattr(self.unet, "weight_generation", 0))
+        if self._unet_graph is None or self._unet_graph[0] != key:
             if motion is None:
                 fn = lambda x, t, c, w: self.unet(x, t, context=c, fps=fps, timestep_cond=w)  # noqa: E731
             else:
                 fn = lambda x, t, c, w, m: self.unet(x, t, context=c, fps=fps, timestep_cond=w, motion_cond=m)  # noqa: E731
-            self._unet_graph = ((fps, motion is None), _GraphedCall(fn))
+            self._unet_graph = (key, _GraphedCall(fn))   # model_pred is consumed by scheduler.step before the next replay
         args = (latents, ts, ctx, w_emb) if motion is None else (latents, ts, ctx, w_emb, motion)
         return self._unet_graph[1](*args)
 
     def _decode(self, denoised):
         if not self.use_cuda_graph:
             return self.pretrained_t2v.decode_first_stage_2DAE(denoised)
-        if self._vae_graph is None:
-            self._vae_graph = _GraphedCall(lambda z: self.pretrained_t2v.decode_first_stage_2DAE(z))
-        return self._vae_graph(denoised)
+        key = getattr(self.vae, "weight_generation", 0)
+        if self._vae_graph is None or self._vae_graph[0] != key:
+            self._vae_graph = (key, _GraphedCall(lambda z: self.pretrained_t2v.decode_first_stage_2DAE(z), clone_out=True))
+        return self._vae_graph[1](denoised)
 
     @torch.no_grad()
     def __call__(self, prompt: Union[str, List[str]] = None, height: Optional[int] = 320, width: Optional[int] = 512,

@@ -105,15 +105,17 @@ class T2VTurboScheduler:
         return T2VTurboSchedulerOutput(prev_sample=prev_sample, denoised=denoised)
 
     def add_noise(self, original_samples, noise, timesteps):
-        """Reference :470-495 (training-time helper; plain torch: not on the inference hot path)."""
+        """Reference :470-495.  The per-sample coefficients are computed exactly as the reference does (the alpha table
+        cast to the sample dtype, then `** 0.5` in that dtype: a [b]-element gather on the device); the tensor
+        arithmetic `sqrt_a * x0 + sqrt(1 - a) * noise` is one kernel (t2v_scale_add_rows)."""
+        if not original_samples.is_cuda:
+            raise RuntimeError("T2VTurboScheduler(B200).add_noise: samples must be CUDA tensors (no CPU fallback)")
         alphas_cumprod = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
         timesteps = timesteps.to(original_samples.device)
-        sqrt_alpha_prod = alphas_cumprod[timesteps] ** 0.5
-        sqrt_one_minus = (1 - alphas_cumprod[timesteps]) ** 0.5
-        while len(sqrt_alpha_prod.shape) < len(original_samples.shape):
-            sqrt_alpha_prod = sqrt_alpha_prod.unsqueeze(-1)
-            sqrt_one_minus = sqrt_one_minus.unsqueeze(-1)
-        return sqrt_alpha_prod * original_samples + sqrt_one_minus * noise
+        sqrt_alpha_prod = (alphas_cumprod[timesteps] ** 0.5).flatten().float().contiguous()
+        sqrt_one_minus = ((1 - alphas_cumprod[timesteps]) ** 0.5).flatten().float().contiguous()
+        return ops.scale_add_rows(original_samples.contiguous(), sqrt_alpha_prod,
+                                  noise.to(original_samples.dtype).contiguous(), sqrt_one_minus)
 
     def __len__(self):
         return self.config.num_train_timesteps

@@ -297,6 +297,7 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(_gn(ch), nn.SiLU(), out_conv)
         self._packed = None
         self._ctx_cache = None
+        self.weight_generation = 0   # bumped whenever the packed weights are dropped: CUDA graphs key on it
         self._ln_state = None
         self._ln_states = {}     # per input geometry: captured CUDA graphs keep pointing at their workspace
 
@@ -304,6 +305,7 @@ class UNetModel(nn.Module):
     def invalidate_packed(self):
         self._packed = None
         self._ctx_cache = None
+        self.weight_generation = getattr(self, "weight_generation", 0) + 1
 
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.half() change the parameters -> repack lazily
         self.invalidate_packed()
@@ -458,10 +460,10 @@ class UNetModel(nn.Module):
     def _ln_slice(self, rows, device):
         return self._ws_alloc(rows * 2, device)[:rows * 2].view(rows, 2)
 
-    def _gn_slice(self, frames, channels, device, k_total, tag="", grid=None, fixed=(None, None, None, None)):
+    def _gn_slice(self, frames, channels, device, k_total, tag="", grid=None, fixed=(None, None, None, None), sdims=()):
         """Channel-sum slice for a producer GEMM with reduction length k_total, or None when the fusion does not pay
         (ops.gn_fuse_producer): the consuming GroupNorm then runs its own statistics pass."""
-        if not ops.gn_fuse_producer(k_total, grid, fixed) or (_DBG_TAGS is not None and tag not in _DBG_TAGS):
+        if not ops.gn_fuse_producer(k_total, grid, fixed, sdims) or (_DBG_TAGS is not None and tag not in _DBG_TAGS):
             return None
         return self._ws_alloc(frames * channels * 2, device)[:frames * channels * 2].view(frames, channels, 2)
 
@@ -512,7 +514,7 @@ class UNetModel(nn.Module):
         acc1 = self._ln_slice(xn.shape[0], xn.device)
         x = ops.linear(xn, pt.w_in, pt.b_in, row_accum=acc1)
         x = self._block(pt.blk, x, acc1, geom, pt.temporal, ctx_kv, pt.kv_slice)
-        so = self._gn_slice(b * t, c, h.device, c, "tr", (hh * ww, b * t, 1, 1))
+        so = self._gn_slice(b * t, c, h.device, c, "tr", (hh * ww, b * t, 1, 1), sdims=(1,))
         out = ops.linear_frames(x, pt.w_out, pt.b_out, hw=hh * ww, residual=x_in, stats=so)
         return out.view(b * t, hh, ww, c), so
 
@@ -528,7 +530,7 @@ class UNetModel(nn.Module):
         hn = ops.groupnorm(x, pr.gn1[0], pr.gn1[1], rows_per_sample=hw, eps=pr.gn1[2], silu=True, chan_sums=x_stats)
         off, cout = pr.emb_slice
         rowbias = emb_rows[:, off:off + cout].contiguous()
-        s1 = self._gn_slice(nf, cout, dev, 9 * cin, "res1", (ww, hh, nf, 1))
+        s1 = self._gn_slice(nf, cout, dev, 9 * cin, "res1", (ww, hh, nf, 1), sdims=(2,))
         h = ops.conv3x3(hn.view(nf, hh, ww, cin), pr.w1, rowbias, bias_div=t, stats=s1)
         hn2 = ops.groupnorm(h.view(-1, cout), pr.gn2[0], pr.gn2[1], rows_per_sample=hw, eps=pr.gn2[2], silu=True, chan_sums=s1)
         if pr.w_skip is None:
@@ -537,7 +539,7 @@ class UNetModel(nn.Module):
             xa = x0.view(-1, x0.shape[-1])
             xb = x1.view(-1, x1.shape[-1]) if x1 is not None else None
             res = ops.linear((xa, xb) if xb is not None else xa, pr.w_skip, pr.b_skip).view(nf, hh, ww, cout)
-        s2 = self._gn_slice(nf, cout, dev, 9 * cout, "res2", (ww, hh, nf, 1))
+        s2 = self._gn_slice(nf, cout, dev, 9 * cout, "res2", (ww, hh, nf, 1), sdims=(2,))
         h = ops.conv3x3(hn2.view(nf, hh, ww, cout), pr.w2, pr.b2, bias_div=nf, residual=res, stats=s2)
         if pr.tconv is not None:
             ident = h.view(b, t, hw, cout)
@@ -545,7 +547,7 @@ class UNetModel(nn.Module):
             for i, (gn, w, bias) in enumerate(pr.tconv):
                 yn = ops.groupnorm(y.view(-1, cout), gn[0], gn[1], rows_per_sample=t * hw, eps=gn[2], silu=True,
                                    chan_sums=ys if ops.gn_fuse_temporal() else None, chan_group=t)
-                ys = self._gn_slice(nf, cout, dev, 3 * cout, "tconv", (hw, t, b, 1))
+                ys = self._gn_slice(nf, cout, dev, 3 * cout, "tconv", (hw, t, b, 1), sdims=(1, 2))
                 y = ops.tconv3(yn.view(b, t, hw, cout), w, bias, residual=ident if i == 3 else None, stats=ys)
             h, s2 = y.view(nf, hh, ww, cout), ys
         return h, s2
@@ -559,12 +561,12 @@ class UNetModel(nn.Module):
             elif kind in ("st", "tt"):
                 h, h_stats = self._transformer(pk, h, h_stats, geom, ctx_kv)
             elif kind == "down":
-                h_stats = self._gn_slice(b * t, pk[0].shape[0], h.device, pk[0].shape[1], "down", (ww // 2, 1, hh // 2, b * t), (None, 1, None, None))
+                h_stats = self._gn_slice(b * t, pk[0].shape[0], h.device, pk[0].shape[1], "down", (ww // 2, 1, hh // 2, b * t), (None, 1, None, None), sdims=(3,))
                 h = ops.conv3x3_s2(h, pk[0], pk[1], stats=h_stats)
                 hh, ww = hh // 2, ww // 2
                 geom = (b, t, hh, ww)
             elif kind == "up":
-                h_stats = self._gn_slice(b * t, pk[0].shape[1], h.device, pk[0].shape[2], "up", (ww, hh, b * t, 1))
+                h_stats = self._gn_slice(b * t, pk[0].shape[1], h.device, pk[0].shape[2], "up", (ww, hh, b * t, 1), sdims=(2,))
                 h = ops.upconv3x3(h, pk[0], pk[1], stats=h_stats)
                 hh, ww = hh * 2, ww * 2
                 geom = (b, t, hh, ww)

@@ -132,8 +132,8 @@ class _StatsPool:
     def __init__(self, device, nfloats):
         self.device, self.nfloats, self.buf, self.cur = device, nfloats, None, 0
 
-    def take(self, frames, channels, k_total, grid):
-        if not ops.gn_fuse_producer(k_total, grid):
+    def take(self, frames, channels, k_total, grid, sdims=(2,)):
+        if not ops.gn_fuse_producer(k_total, grid, sample_dims=sdims):
             return None
         if self.buf is None:
             self.buf = torch.zeros((self.nfloats,), device=self.device, dtype=torch.float32)
@@ -160,6 +160,66 @@ class _PRes:
         self.b_nin = _f32(rb.nin_shortcut.bias) if self.cin != self.cout else None
 
 
+class DiagonalGaussianDistribution:
+    """The reference's posterior object (lvdm/distributions.py:24-72) over the fp32 channels-last moments
+    [N, h, w, 2*zc] the encoder GEMM wrote.  `sample` / `mode` are one elementwise kernel (t2v_gaussian_sample) and return
+    NCHW in the dtype of the encoded frames; the attribute views (`mean`, `logvar`, `std`, `var`, `parameters`) and
+    `kl` / `nll` (loss-side helpers outside the hot path) are plain torch on the moments."""
+
+    def __init__(self, moments_nhwc, dtype, deterministic=False):
+        self._m, self._dtype, self.deterministic = moments_nhwc, dtype, deterministic
+        self._zc = moments_nhwc.shape[-1] // 2
+
+    def _out(self, noise):
+        n, h, w, _ = self._m.shape
+        return ops.gaussian_sample(self._m, noise, b=n, t=1, zc=self._zc, scale=1.0, dtype=self._dtype).squeeze(2)
+
+    def sample(self, noise=None):
+        if self.deterministic:
+            return self.mode()
+        if noise is None:   # the reference draws on the CPU and moves the tensor (distributions.py:38-41)
+            n, h, w, _ = self._m.shape
+            noise = torch.randn((n, self._zc, h, w))
+        return self._out(noise)
+
+    def mode(self):
+        return self._out(None)
+
+    @property
+    def parameters(self):
+        return self._m.permute(0, 3, 1, 2).to(self._dtype)
+
+    @property
+    def mean(self):
+        return self._m[..., :self._zc].permute(0, 3, 1, 2).to(self._dtype)
+
+    @property
+    def logvar(self):
+        return torch.clamp(self._m[..., self._zc:], -30.0, 20.0).permute(0, 3, 1, 2).to(self._dtype)
+
+    @property
+    def std(self):
+        return torch.zeros_like(self.mean) if self.deterministic else torch.exp(0.5 * self.logvar)
+
+    @property
+    def var(self):
+        return torch.zeros_like(self.mean) if self.deterministic else torch.exp(self.logvar)
+
+    def kl(self, other=None):
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0 - self.logvar
+                               + other.logvar, dim=[1, 2, 3])
+
+    def nll(self, sample, dims=(1, 2, 3)):
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        import math
+        return 0.5 * torch.sum(math.log(2.0 * math.pi) + self.logvar + torch.pow(sample - self.mean, 2) / self.var, dim=list(dims))
+
+
 class AutoencoderKL(nn.Module):
     """AutoencoderKL (reference ctor: ddconfig, lossconfig, embed_dim; lossconfig ignored): decode and encode."""
 
@@ -172,13 +232,18 @@ class AutoencoderKL(nn.Module):
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self._packed = None
         self._packed_enc = None
+        self.weight_generation = 0   # bumped whenever the packed weights are dropped: CUDA graphs key on it
+
+    def invalidate_packed(self):
+        self._packed = self._packed_enc = None
+        self.weight_generation = getattr(self, "weight_generation", 0) + 1
 
     def _apply(self, fn, *a, **k):
-        self._packed = self._packed_enc = None
+        self.invalidate_packed()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed = self._packed_enc = None
+        self.invalidate_packed()
         return super().load_state_dict(*a, **k)
 
     @staticmethod
@@ -281,7 +346,7 @@ class AutoencoderKL(nn.Module):
         # V^T for all frames in one GEMM: [c, n*hw] = W_v @ xn^T
         vt = ops.linear(pa["w_v"], xn, None)                              # A = W_v [c, c], B = xn [n*hw, c]
         o = ops.bmm_nt(s, vt.view(c, n, hw).permute(1, 0, 2))             # [n, hw, c] = P @ V (V^T read in place)
-        so = pool.take(n, c, c, (hw, n, 1, 1))
+        so = pool.take(n, c, c, (hw, n, 1, 1), sdims=(1,))
         return ops.linear_frames(o.view(-1, c), pa["w_o"], pa["b_o"], hw=hw, residual=x, stats=so).view(n, hh, ww, c), so
 
     # ------------------------------------------------------------------ API
@@ -320,10 +385,9 @@ class AutoencoderKL(nn.Module):
         return ops.frames_to_bcthw(y, b, cout, z.dtype)
 
     @torch.no_grad()
-    def encode_frames(self, x, noise=None, scale=1.0, sample=True):
-        """x: [B, 3, T, H, W] video (any float dtype) -> scale * posterior sample (or mode) [B, zc, T, H/f, W/f] in
-        x.dtype, all B*T frames batched (ddpm3d.py:558-584).  noise: fp32 [B*T, zc, h, w] (the reference draws it
-        with torch.randn on the CPU, distributions.py:38-41 — done here the same way when omitted and sample=True)."""
+    def _encode_moments(self, x):
+        """x: [B, 3, T, H, W] -> fp32 channels-last moments [B*T, H/f, W/f, 2*embed] (mean | logvar) of the posterior:
+        Encoder (ae_modules.py:470-503) and quant_conv (autoencoder.py:105-106), all frames batched."""
         if not x.is_cuda:
             raise RuntimeError("AutoencoderKL(B200): input must be a CUDA tensor (no CPU fallback)")
         if self._packed_enc is None:
@@ -342,7 +406,7 @@ class AutoencoderKL(nn.Module):
             for pr in blocks:
                 h, hs = self._res(pr, h, hs, pool)
             if ds is not None:
-                hs = pool.take(h.shape[0], ds[0].shape[0], ds[0].shape[1], (h.shape[2] // 2, 1, h.shape[1] // 2, h.shape[0]))
+                hs = pool.take(h.shape[0], ds[0].shape[0], ds[0].shape[1], (h.shape[2] // 2, 1, h.shape[1] // 2, h.shape[0]), sdims=(3,))
                 h = ops.conv3x3_s2(h, ds[0], ds[1], pad="br", stats=hs)
         h, hs = self._res(P["mid1"], h, hs, pool)
         h, hs = self._attn(P["attn"], h, hs, pool)
@@ -351,19 +415,26 @@ class AutoencoderKL(nn.Module):
         hn = ops.groupnorm(h.view(-1, ch), P["norm_out"][0], P["norm_out"][1], rows_per_sample=h2 * w2, eps=1e-6, silu=True,
                            chan_sums=hs)
         w, bias, cout = P["conv_out"]
-        moments = ops.conv3x3(hn.view(n, h2, w2, ch), w, bias, bias_div=n, out_f32=True)   # fp32 [n, h, w, 2*embed]
-        zc = cout // 2
+        return ops.conv3x3(hn.view(n, h2, w2, ch), w, bias, bias_div=n, out_f32=True)   # fp32 [n, h, w, 2*embed]
+
+    @torch.no_grad()
+    def encode_frames(self, x, noise=None, scale=1.0, sample=True):
+        """x: [B, 3, T, H, W] video (any float dtype) -> scale * posterior sample (or mode) [B, zc, T, H/f, W/f] in
+        x.dtype, all B*T frames batched (ddpm3d.py:558-584).  noise: fp32 [B*T, zc, h, w] (the reference draws it
+        with torch.randn on the CPU, distributions.py:38-41 — done here the same way when omitted and sample=True)."""
+        b, _, t = x.shape[:3]
+        moments = self._encode_moments(x)
+        n, h2, w2, c2 = moments.shape
+        zc = c2 // 2
         if sample and noise is None:
             noise = torch.randn((n, zc, h2, w2))
         return ops.gaussian_sample(moments, noise if sample else None, b=b, t=t, zc=zc, scale=scale, dtype=x.dtype)
 
-    def encode(self, x, noise=None, sample=True, **kwargs):
-        """autoencoder.py:103-108 + posterior.sample()/mode(): x [N, 3, H, W] -> z [N, zc, H/f, W/f]."""
-        return self.encode_frames(x.unsqueeze(2), noise=noise, scale=1.0, sample=sample).squeeze(2)
+    def encode(self, x, **kwargs):
+        """autoencoder.py:103-108: x [N, 3, H, W] -> the posterior; callers do `.sample()` / `.mode()`
+        (train_t2v_turbo_v1_lora.py:958-965, ddpm3d.py:558-567)."""
+        return DiagonalGaussianDistribution(self._encode_moments(x.unsqueeze(2)), x.dtype)
 
     def decode(self, z, **kwargs):
         """autoencoder.py:110-113: z [N, C, h, w] -> [N, 3, 8h, 8w]."""
         return self.decode_frames(z.unsqueeze(2), 1.0).squeeze(2)
-
-    def encode(self, x, **kwargs):
-        raise NotImplementedError("AutoencoderKL(B200): the encoder (training-time only) is not built in this round")
