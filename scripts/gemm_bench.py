@@ -25,6 +25,8 @@ CASES = {
     "conv1280_l3": ("conv", (16, 5, 8, 1280), 0, 1280, dict(res=True)),
     "tconv320": ("tconv", (1, 16, 2560, 320), 0, 320, dict()),
     "vae512": ("conv", (16, 80, 128, 512), 0, 512, dict(res=True)),
+    "vae128": ("conv", (16, 320, 512, 128), 0, 128, dict(res=True)),
+    "vae256": ("conv", (16, 160, 256, 256), 0, 256, dict(res=True)),
     "big1280": ("linear", 40960, 1280, 1280, dict(res=True)),
     "tconv1280_l3": ("tconv", (1, 16, 40, 1280), 0, 1280, dict()),
 }
@@ -38,6 +40,7 @@ CASES.update({
     "conv1280_cat": ("conv", (16, 10, 16, 2560), 0, 1280, dict(res=True)),
 })
 BN = int(os.environ.get("BN", "0"))   # force a tile width (experiments)
+STATS = int(os.environ.get("STATS", "0"))   # conv / tconv: also accumulate the GroupNorm statistics in the epilogue
 names = sys.argv[1:] or list(CASES)
 for name in names:
     kind, M, K, N, ex = CASES[name]
@@ -58,7 +61,8 @@ for name in names:
         b = torch.randn(1, N, device=dev, generator=g)
         res = torch.randn(n, h, wd, N, device=dev, generator=g).to(BF16)
         out = torch.empty(n, h, wd, N, device=dev, dtype=BF16)
-        fn = lambda: ops.conv3x3(x, w, b, bias_div=n, residual=res, out=out, block_n=BN)
+        st = torch.zeros(n, N, 2, device=dev) if STATS else None
+        fn = lambda: ops.conv3x3(x, w, b, bias_div=n, residual=res, out=out, block_n=BN, stats=st)
         flops = 2 * n * h * wd * 9 * c * N
     else:
         bb, t, hw, c = M
@@ -66,7 +70,8 @@ for name in names:
         w = (torch.randn(N, 3 * c, device=dev, generator=g) * (3 * c) ** -0.5).to(BF16)
         b = torch.randn(N, device=dev, generator=g)
         out = torch.empty(bb, t, hw, N, device=dev, dtype=BF16)
-        fn = lambda: ops.tconv3(x, w, b, out=out, block_n=BN)
+        st = torch.zeros(bb * t, N, 2, device=dev) if STATS else None
+        fn = lambda: ops.tconv3(x, w, b, out=out, block_n=BN, stats=st)
         flops = 2 * bb * t * hw * 3 * c * N
     for _ in range(3):
         fn()

@@ -59,6 +59,7 @@ struct GemmParams {
   int32_t bias_vec_ok;
   uint32_t a_tile_bytes;
   float* ws;  // split-K workspace [points][N] fp32
+  uint32_t* tile_cnt;  // split-K: per output tile arrival counters (zero on entry, self-resetting); nullptr = legacy 3-launch path
   int32_t epi_mode;  // 0 = direct row stores, 1 = smem-staged TMA store (+ TMA residual load)
   int32_t n_stages;  // pipeline stages in use
   const float2* row_stats;  // folded LayerNorm: per input row (rstd, -rstd*mean); nullptr = off
@@ -119,6 +120,61 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
+}
+
+// split-K epilogue of 4 consecutive output columns [n0, n0 + 4) of one output point from the fp32 partial sums `wp`
+// (shared by the in-kernel fix-up phase and the legacy finalize kernel).  `clear`: zero the partial sums after reading.
+__device__ __forceinline__ void splitk_finalize_quad(const GemmParams& p, float* wp, int64_t point, int64_t out_off,
+                                                     int64_t res_off, int64_t bias_row, int64_t smp, int n0, bool clear) {
+  const bool out_f32 = (p.flags & T2V_EPI_OUT_F32) != 0;
+  const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
+  float fsum = 0.f, fsq = 0.f;
+  float cv[4] = {0.f, 0.f, 0.f, 0.f};
+  float rs = 1.f, rm = 0.f;
+  if (p.row_stats) {  // folded LayerNorm (A is a plain [M, K] matrix: point == row)
+    const float2 st = __ldcg(p.row_stats + point);
+    rs = st.x, rm = st.y;
+    if (p.ln_raw) {
+      const float mean = st.x * p.ln_inv_c;
+      rs = rsqrtf(fmaxf(fmaf(st.y, p.ln_inv_c, -mean * mean), 0.f) + p.ln_eps);
+      rm = -rs * mean;
+    }
+  }
+  float w4[4];
+  if (n0 + 3 < p.n_rows_b && (p.n_rows_b & 3) == 0) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(wp));
+    w4[0] = t.x, w4[1] = t.y, w4[2] = t.z, w4[3] = t.w;
+    if (clear) *reinterpret_cast<float4*>(wp) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w4[j] = n0 + j < p.n_rows_b ? __ldcg(wp + j) : 0.f;
+      if (clear && n0 + j < p.n_rows_b) wp[j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (n0 + j < p.n_rows_b) {
+      float v = w4[j];
+      if (p.row_stats) v = fmaf(rs, v, rm * __ldg(p.col_sum + n0 + j));
+      if (p.bias) v += p.bias[bias_row * p.bias_row_stride + n0 + j];
+      if (gelu) v = gelu_erf(v);
+      if (p.residual) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + n0 + j]);
+      if (out_f32)
+        reinterpret_cast<float*>(p.out)[out_off + n0 + j] = v;
+      else
+        reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + n0 + j] = __float2bfloat16_rn(v);
+      fsum += v;
+      fsq = fmaf(v, v, fsq);
+      cv[j] = out_f32 ? v : __bfloat162float(__float2bfloat16_rn(v));
+    }
+  }
+  if (p.row_accum) red_add_v2(p.row_accum + 2 * point, fsum, fsq);
+  if (p.col_accum && n0 + 3 < p.n_rows_b) {
+    float* ca = p.col_accum + (smp * p.n_rows_b + n0) * 2;
+    red_add_v4(ca, cv[0], cv[0] * cv[0], cv[1], cv[1] * cv[1]);
+    red_add_v4(ca + 4, cv[2], cv[2] * cv[2], cv[3], cv[3] * cv[3]);
+  }
 }
 
 // LN: 0 = plain epilogue; 1 = this GEMM CONSUMES a LayerNorm (folded: per-row statistics applied in the epilogue);
@@ -588,8 +644,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           fence_proxy_async();
           named_bar_sync(1 + g, 128);
         }
+        if (lead_warp && elect_one()) {
+          if (!(p.dbg & 1)) tma_store_5d(&tmOut, ebuf + buf * kEpiBufBytes, oc0, o[0], o[1], o[2], o[3]);
+          bulk_commit_group();
+          bulk_wait_group_read<1>();  // every store but the one just issued has finished reading smem
+          if (has_res) {
+            const int c2 = c + 2 * kEpiWGs;
+            if (c2 < chunks_per_tile && n_base + c2 * acc_cw < p.n_rows_b) {
+              const uint32_t buf2 = (q + 2) % kEpiBufs;
+              mbar_expect_tx(&rbar[buf2], res_bytes);
+              tma_load_5d(ebuf + buf2 * kEpiBufBytes, &tmRes, &rbar[buf2], (n_base + c2 * acc_cw) / (acc_cw / 32), o[0],
+                          o[1], o[2], o[3]);
+            }
+          }
+        }
         if (LN == 3) {
-          // column sums of this 128 x 32 chunk from the staged bf16 rows (exactly the values GroupNorm will read):
+          // column sums of this 128 x 32 chunk from the staged bf16 rows (exactly the values GroupNorm will read; issued AFTER
+          // the chunk's TMA store so the store / residual pipeline is not delayed — both only read the buffer):
           // packed fp32x2 accumulation of the channel pair, lanes l / l+16 combined by a shuffle, then one
           // shared-memory reduction per (channel, statistic) and warp into the CTA's table
           const int cp = r & 15;  // channel pair: 4 bytes at word (cp & 3) of 16-byte chunk (cp >> 2)
@@ -619,20 +690,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             atomicAdd(tab + 1, q2.x);
             atomicAdd(tab + 2, s2.y);
             atomicAdd(tab + 3, q2.y);
-          }
-        }
-        if (lead_warp && elect_one()) {
-          if (!(p.dbg & 1)) tma_store_5d(&tmOut, ebuf + buf * kEpiBufBytes, oc0, o[0], o[1], o[2], o[3]);
-          bulk_commit_group();
-          bulk_wait_group_read<1>();  // every store but the one just issued has finished reading smem
-          if (has_res) {
-            const int c2 = c + 2 * kEpiWGs;
-            if (c2 < chunks_per_tile && n_base + c2 * acc_cw < p.n_rows_b) {
-              const uint32_t buf2 = (q + 2) % kEpiBufs;
-              mbar_expect_tx(&rbar[buf2], res_bytes);
-              tma_load_5d(ebuf + buf2 * kEpiBufBytes, &tmRes, &rbar[buf2], (n_base + c2 * acc_cw) / (acc_cw / 32), o[0],
-                          o[1], o[2], o[3]);
-            }
           }
         }
         ++q;
@@ -835,6 +892,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             else
               mbar_arrive(&tempty_bar[acc]);
           }
+      if (split && p.tile_cnt != nullptr) {
+        // this K slice's partial sums are in the workspace: publish (release) one arrival for the output tile
+        __threadfence();
+        named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
+        if (ew == 0 && lane == 0) atomicAdd(p.tile_cnt + mn, 1u);
+      }
+    }
+    if (split && p.tile_cnt != nullptr) {
+      // ---------------------------------------------------------- split-K fix-up, in the same launch
+      // Every CTA of this grid is resident (grid <= SMs, one CTA per SM) and none of them waits before all of its own
+      // partial sums are published, so waiting here cannot deadlock.  Once the `split_k` slices of a tile have arrived
+      // the CTA that computed slice ks applies the epilogue to rows [ks * rpt, (ks + 1) * rpt) of the tile straight
+      // from the workspace and clears what it read: no zero kernel before and no finalize kernel after the GEMM.
+      const int et = ew * 32 + lane;
+      const int rpt = (p.rows_in_box + p.split_k - 1) / p.split_k;
+      const int nq = BN / 4;
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+        const int ks = tile / p.n_tiles_mn;
+        const int mn = tile - ks * p.n_tiles_mn;
+        const int n_tile = mn % p.n_tiles_n;
+        const int m_tile0 = mn / p.n_tiles_n;
+        if (et == 0) {
+          uint32_t spins = 0;
+          while (ld_acquire_gpu_u32(p.tile_cnt + mn) < uint32_t(p.split_k)) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();
+          }
+        }
+        named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
+        const int r_begin = ks * rpt;
+        const int r_end = min(r_begin + rpt, p.rows_in_box);
+        for (int i = et; i < (r_end - r_begin) * nq; i += 128 * kEpiWGs) {
+          const int row = r_begin + i / nq;
+          const int n0 = n_tile * BN + (i % nq) * 4;
+          if (n0 >= p.n_rows_b) continue;
+          int m_tile = m_tile0, rr = row;
+          bool valid = true;
+          int64_t out_off = 0, res_off = 0, point = 0, pmul = 1, bias_row = 0, smp = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int oj = (j < 3 ? m_tile % p.ntile[j] : m_tile) * p.box[j];
+            m_tile /= p.ntile[j];
+            const int64_t x = oj + rr % p.box[j];
+            rr /= p.box[j];
+            valid = valid && (x < p.o_size[j]);
+            out_off += x * p.o_stride[j];
+            res_off += x * p.r_stride[j];
+            point += x * pmul;
+            pmul *= p.o_size[j];
+            smp += x * p.cs_mult[j];
+            if (j == p.bias_dim) bias_row = x / p.bias_div;
+          }
+          if (valid) splitk_finalize_quad(p, p.ws + point * p.n_rows_b + n0, point, out_off, res_off, bias_row, smp, n0, true);
+        }
+        // second round of arrivals: the last CTA to finish with this tile resets its counter for the next launch
+        __threadfence();
+        named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
+        if (et == 0) {
+          const uint32_t old = atomicAdd(p.tile_cnt + mn, 1u);
+          if (old == 2u * uint32_t(p.split_k) - 1u) atomicExch(p.tile_cnt + mn, 0u);
+        }
+      }
     }
   }
 
@@ -863,61 +982,20 @@ __global__ void __launch_bounds__(256) gemm_finalize_kernel(const GemmParams p, 
   pdl_wait();
   const int nq = (p.n_rows_b + 3) >> 2;
   const int64_t total = n_points * nq;
-  const bool out_f32 = (p.flags & T2V_EPI_OUT_F32) != 0;
-  const bool gelu = (p.flags & T2V_EPI_GELU) != 0;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t point = i / nq;
     const int n0 = int(i - point * nq) * 4;
-    int64_t rem = point, out_off = 0, res_off = 0, bias_row = 0;
+    int64_t rem = point, out_off = 0, res_off = 0, bias_row = 0, smp = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t x = rem % p.o_size[j];
       rem /= p.o_size[j];
       out_off += x * p.o_stride[j];
       res_off += x * p.r_stride[j];
+      smp += x * p.cs_mult[j];
       if (j == p.bias_dim) bias_row = x / p.bias_div;
     }
-    const float* wp = p.ws + point * p.n_rows_b + n0;
-    float fsum = 0.f, fsq = 0.f;
-    float cv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (n0 + j < p.n_rows_b) {
-        float v = wp[j];
-        if (p.row_stats) {  // folded LayerNorm (A is a plain [M, K] matrix: point == row)
-          const float2 st = __ldcg(p.row_stats + point);
-          float rs = st.x, rm = st.y;
-          if (p.ln_raw) {
-            const float mean = st.x * p.ln_inv_c;
-            rs = rsqrtf(fmaxf(fmaf(st.y, p.ln_inv_c, -mean * mean), 0.f) + p.ln_eps);
-            rm = -rs * mean;
-          }
-          v = fmaf(rs, v, rm * __ldg(p.col_sum + n0 + j));
-        }
-        if (p.bias) v += p.bias[bias_row * p.bias_row_stride + n0 + j];
-        if (gelu) v = gelu_erf(v);
-        if (p.residual) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[res_off + n0 + j]);
-        if (out_f32)
-          reinterpret_cast<float*>(p.out)[out_off + n0 + j] = v;
-        else
-          reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + n0 + j] = __float2bfloat16_rn(v);
-        fsum += v;
-        fsq = fmaf(v, v, fsq);
-        cv[j] = out_f32 ? v : __bfloat162float(__float2bfloat16_rn(v));
-      }
-    }
-    if (p.row_accum) red_add_v2(p.row_accum + 2 * point, fsum, fsq);
-    if (p.col_accum && n0 + 3 < p.n_rows_b) {
-      int64_t rem2 = point, smp = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        smp += (rem2 % p.o_size[j]) * p.cs_mult[j];
-        rem2 /= p.o_size[j];
-      }
-      float* ca = p.col_accum + (smp * p.n_rows_b + n0) * 2;
-      red_add_v4(ca, cv[0], cv[0] * cv[0], cv[1], cv[1] * cv[1]);
-      red_add_v4(ca + 4, cv[2], cv[2] * cv[2], cv[3], cv[3] * cv[3]);
-    }
+    splitk_finalize_quad(p, p.ws + point * p.n_rows_b + n0, point, out_off, res_off, bias_row, smp, n0, (p.flags & T2V_WS_CLEAN) != 0);
   }
 }
 
@@ -1209,7 +1287,13 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     int rc = make_tmap_bf16(&tmB, d->b, 3, dims, strides, box, "t2v_gemm B");
     if (rc) return rc;
   }
-  if (split > 1) {
+  // split-K in ONE launch (the CTAs fix up the tiles themselves) whenever the whole grid is resident and the workspace
+  // holds the tile counters behind the partial sums; the workspace must be zero on entry and is left zeroed.
+  const int64_t ws_sum_bytes = ((n_points * d->b_rows * 4 + 15) / 16) * 16;
+  const bool fixup = split > 1 && !(d->tune & 0x1000000) && num_tiles <= sms && (d->flags & T2V_WS_CLEAN) &&
+                     d->workspace_bytes >= ws_sum_bytes + tiles_mn * 4;
+  p.tile_cnt = fixup ? reinterpret_cast<uint32_t*>(static_cast<char*>(d->workspace) + ws_sum_bytes) : nullptr;
+  if (split > 1 && !fixup) {
     const int64_t n4 = (n_points * d->b_rows + 3) / 4;  // workspace is a multiple of 16 bytes
     int64_t zg = (n4 + 255) / 256;
     if (zg > sms * 4) zg = sms * 4;
@@ -1249,7 +1333,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
 #undef T2V_GEMM_WIDE
 #undef T2V_GEMM_CASE
   if (rc) return rc;
-  if (split > 1) {
+  if (split > 1 && !fixup) {
     const int64_t total = n_points * ((d->b_rows + 3) / 4);
     int64_t grid = (total + 255) / 256;
     if (grid > sms * 8) grid = sms * 8;

@@ -367,6 +367,12 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
   return make_float2(__uint_as_float(uint32_t(r)), __uint_as_float(uint32_t(r >> 32)));
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -148,7 +148,7 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     d.residual = ptr(residual)
     _fill(d.r_stride, r_stride if r_stride is not None else o_stride)
     d.alpha = alpha
-    d.flags = flags
+    d.flags = flags | _lib.WS_CLEAN
     d.block_n = block_n
     d.split_k = split_k
     d.tune = GEMM_TUNE
@@ -204,12 +204,15 @@ SPLITK_WS_BYTES = 32 << 20
 
 
 def _splitk_workspace(device):
-    """Persistent fp32 scratch for split-K partial sums, one per device (zeroed by each call that uses it; calls on
-    one device are stream-ordered by the host mirror, which runs a model on one stream at a time)."""
+    """Persistent fp32 scratch for split-K partial sums + tile counters, one per device.  Zeroed ONCE here: every
+    split-K call finds it zeroed and leaves it zeroed (T2V_WS_CLEAN: the CTAs fix up their tiles in the same launch and
+    clear what they read).  Calls on one device are stream-ordered by the host mirror (one stream at a time)."""
     key = device
     ws = _SPLITK_WS.get(key)
     if ws is None:
-        ws = torch.empty(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("t2v_turbo_b200: split-K workspace must be allocated before CUDA-graph capture (run a warm-up call)")
+        ws = torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
         _SPLITK_WS[key] = ws
     return ws
 
@@ -466,6 +469,8 @@ def groupnorm(x, gamma, beta, *, rows_per_sample, eps, silu, groups=32, out=None
         d.chan_sums[0] = cs0.data_ptr()
         d.chan_sums[1] = ptr(cs1)
         d.chan_group = chan_group
+    if _PROF is not None:
+        _TAG["groupnorm"] = f"rows={rows} C={c0 + c1} rps={rows_per_sample} sums={int(chan_sums is not None)}"
     _launch("groupnorm", _FLOPS.pop("groupnorm", 0), lib().t2v_groupnorm, C.byref(d), stream_ptr())
     return out
 
@@ -550,6 +555,8 @@ def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None):
         setattr(d, f"{name}_stride_h", 64)
     d.scale = scale
     _FLOPS["attn_short_fwd"] = 4 * b * hw * heads * t * t * 64
+    if _PROF is not None:
+        _TAG["attn_short_fwd"] = f"b={b} hw={hw} H={heads} t={t}"
     _launch("attn_short_fwd", _FLOPS.pop("attn_short_fwd", 0), lib().t2v_attn_short_fwd, C.byref(d), stream_ptr())
     return out
 

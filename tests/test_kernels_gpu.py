@@ -21,13 +21,17 @@ def rnd(*shape, scale=1.0, seed=0, device="cuda"):
     return (torch.randn(*shape, generator=g) * scale).to(device)
 
 
-def assert_close(got, ref, rtol=1.6e-2, atol_scale=8e-3, what=""):
+def assert_close(got, ref, rtol=8e-3, atol_scale=4e-3, what=""):
+    """|got - ref| <= atol_scale * max|ref| + rtol * |ref| elementwise: 2 bf16 ulps of the element plus 1 bf16 ulp of the
+    output scale (round 2: half of round 1's bound; the observed worst err / tol ratio is printed with -s and stays
+    below 0.5 for every kernel, i.e. the bound is ~2x the observed error)."""
     got = got.float()
     ref = ref.float()
     scale = ref.abs().max().item() + 1e-6
     err = (got - ref).abs()
     tol = atol_scale * scale + rtol * ref.abs()
     bad = err > tol
+    print(f"[tol] {what}: worst err/tol {(err / tol).max().item():.3f}, max err {err.max().item():.3e}, scale {scale:.3e}")
     assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} mismatches, max err {err.max().item():.4g} "
                            f"(scale {scale:.4g}), first bad idx {bad.nonzero()[0].tolist()}")
     assert torch.isfinite(got).all(), f"{what}: non-finite output"
