@@ -33,8 +33,8 @@ typedef void* t2v_stream_t; /* cudaStream_t */
 #define T2V_EPI_GEGLU 1u   /* out[m,j] = (acc[m,v_j]+b) * gelu_erf(acc[m,g_j]+b); weights packed by t2v_pack_geglu_rows */
 #define T2V_EPI_OUT_F32 2u /* write fp32 instead of bf16 */
 #define T2V_EPI_GELU 4u    /* out = gelu_erf(acc) (unused by VC2; kept for FeedForward(glu=False)) */
-#define T2V_WS_CLEAN 8u    /* the caller guarantees `workspace` is all-zero on entry (and accepts it zeroed on return):
-                              split-K then runs as ONE launch with an in-kernel fix-up instead of zero + GEMM + finalize */
+#define T2V_WS_CLEAN 8u    /* the caller guarantees `workspace` is all-zero on entry (and gets it back zeroed): split-K then
+                              skips its zero kernel — the finalize kernel clears the partial sums as it reads them */
 
 int t2v_version(void);
 const char* t2v_last_error(void);

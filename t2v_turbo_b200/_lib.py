@@ -19,7 +19,7 @@ MAX_TAPS = 9
 EPI_GEGLU = 1
 EPI_OUT_F32 = 2
 EPI_GELU = 4
-WS_CLEAN = 8      # the split-K workspace is all-zero on entry (and is left zeroed): one-launch split-K with in-kernel fix-up
+WS_CLEAN = 8      # the split-K workspace is all-zero on entry and is left zeroed: no zero kernel before a split-K GEMM
 
 
 class GemmDesc(C.Structure):

@@ -14,6 +14,7 @@
 //                     fp32 (exp2 with the scale folded in), P -> bf16 -> 128B-swizzled smem,
 //                     lazy rescale of the O accumulator in TMEM, final 1/l scaling and store.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/t2v_b200.h"
@@ -316,6 +317,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// attn_fwd2.cu: the two-Q-tile kernel (P in TMEM, part of the exponentials on the FMA pipe)
+int launch_attn_fwd2(const T2VAttnDesc* d, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t stream);
+
 }  // namespace t2v
 
 extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
@@ -351,6 +355,9 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
     rc = make_tmap_bf16(&tv, d->v, 4, dims, strv, box, "t2v_attn_fwd V");
     if (rc) return rc;
   }
+  // default: the two-Q-tile kernel; T2V_ATTN_V1=1 selects the round-1 single-tile kernel (A/B measurements)
+  static const int use_v1 = (getenv("T2V_ATTN_V1") != nullptr && getenv("T2V_ATTN_V1")[0] == '1') ? 1 : 0;
+  if (!use_v1) return launch_attn_fwd2(d, tq, tk, tv, stream);
   AttnParams p;
   p.heads = d->heads;
   p.len_q = d->len_q;

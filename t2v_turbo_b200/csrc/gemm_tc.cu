@@ -59,7 +59,6 @@ struct GemmParams {
   int32_t bias_vec_ok;
   uint32_t a_tile_bytes;
   float* ws;  // split-K workspace [points][N] fp32
-  uint32_t* tile_cnt;  // split-K: per output tile arrival counters (zero on entry, self-resetting); nullptr = legacy 3-launch path
   int32_t epi_mode;  // 0 = direct row stores, 1 = smem-staged TMA store (+ TMA residual load)
   int32_t n_stages;  // pipeline stages in use
   const float2* row_stats;  // folded LayerNorm: per input row (rstd, -rstd*mean); nullptr = off
@@ -69,6 +68,7 @@ struct GemmParams {
   float* row_accum;         // LN == 2: fp32 [M][2], += (sum, sum of squares) of each output row
   float* col_accum;         // LN == 3: fp32 [samples][N][2], += per-channel (sum, sum of squares) of the output rows
   int32_t cs_mult[4];       // LN == 3: sample index of an output point = sum_j coord[j] * cs_mult[j]
+  int32_t cs_direct;        // LN == 3: tiles span several samples -> per-half-block global reductions instead of the CTA table
   uint32_t smem_epi_off;  // offset of the epilogue staging buffers
   int32_t dbg;              // timing experiments only (results are wrong when non-zero)
 };
@@ -383,9 +383,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t res_bytes = uint32_t(p.rows_in_box) * 64u;
     const int sw = (r >> 1) & 3;
     uint32_t q = 0;  // chunks processed so far by this warpgroup (buffer = q % 3)
-    float* cs_tab = bias_smem + 512;  // LN == 3: [BN columns][sum, sum of squares] (the folded-LayerNorm vectors' slot)
+    // LN == 3: [4 warps of a warpgroup][BN columns][sum, sum of squares], behind the barrier / bias block
+    float* cs_tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bias_smem + 1024) + 15) & ~uintptr_t(15));
     if (LN == 3) {
-      for (int i = et; i < 2 * BN; i += 128 * kEpiWGs) cs_tab[i] = 0.f;
+      for (int i = et; i < 8 * BN; i += 128 * kEpiWGs) cs_tab[i] = 0.f;
       named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
     }
     int it = 0;
@@ -448,7 +449,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // LN == 3: this thread reduces channel pair (r & 15) over rows [16 (r >> 4), +16) in two half-blocks of 8 rows
       // (host: box[0] % 8 == 0 and the whole tile lies in ONE sample: box[j] == 1 wherever cs_mult[j] != 0).  The
       // column sums of every chunk go to a per-CTA shared-memory table and reach global memory once per tile.
-      int64_t cs_off = -1;    // offset of this tile's sample in col_accum, -1: tile outside the output
+      int64_t cs_off = -1;    // offset of this tile's (first) sample in col_accum, -1: tile outside the output
+      int64_t cs_hb_off[2] = {0, 0};  // cs_direct: offset of the sample of each of this thread's two half-blocks
       int cs_nv[2] = {0, 0};  // valid rows (0..8) of each half-block: rows run along dim 0, the box may overhang the tensor
       if (LN == 3) {
         bool tile_ok = true;
@@ -465,15 +467,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           bool ok = tile_ok && rr < p.rows_in_box;
           const int i0 = rr % p.box[0];
           rr /= p.box[0];
+          int64_t rel = 0;
 #pragma unroll
           for (int j = 1; j < 4; ++j) {
             const int ij = rr % p.box[j];
             rr /= p.box[j];
             ok = ok && (int64_t(o[j]) + ij < p.o_size[j]);
+            rel += int64_t(ij) * p.cs_mult[j];
           }
           int64_t nv = p.o_size[0] - (int64_t(o[0]) + i0);
           nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
           cs_nv[hb] = ok ? int(nv) : 0;
+          cs_hb_off[hb] = (smp + rel) * int64_t(p.n_rows_b) * 2;
         }
       }
       if (has_res && lead_warp && elect_one()) {
@@ -660,14 +665,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (LN == 3) {
           // column sums of this 128 x 32 chunk from the staged bf16 rows (exactly the values GroupNorm will read; issued AFTER
-          // the chunk's TMA store so the store / residual pipeline is not delayed — both only read the buffer):
-          // packed fp32x2 accumulation of the channel pair, lanes l / l+16 combined by a shuffle, then one
-          // shared-memory reduction per (channel, statistic) and warp into the CTA's table
+          // the chunk's TMA store so the store / residual pipeline is not delayed — both only read the buffer): packed fp32x2
+          // accumulation of the channel pair over this thread's two 8-row half-blocks.
           const int cp = r & 15;  // channel pair: 4 bytes at word (cp & 3) of 16-byte chunk (cp >> 2)
           const uint8_t* cbase = ebuf + buf * kEpiBufBytes + (cp & 3) * 4;
-          float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+          float2 s2[2], q2[2];
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
+            s2[hb] = make_float2(0.f, 0.f);
+            q2[hb] = make_float2(0.f, 0.f);
             const int r0 = (r >> 4) * 16 + hb * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -676,20 +682,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               uint32_t u = *reinterpret_cast<const uint32_t*>(cbase + rw * 64 + ((((cp >> 2) ^ (rw >> 1)) & 3) << 4));
               if (ii >= cs_nv[hb]) u = 0u;
               const float2 v2 = make_float2(bf16_lo(u), bf16_hi(u));
-              s2 = add_f32x2(s2, v2);
-              q2 = fma_f32x2(v2, v2, q2);
+              s2[hb] = add_f32x2(s2[hb], v2);
+              q2[hb] = fma_f32x2(v2, v2, q2[hb]);
             }
           }
-          s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 16);
-          s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 16);
-          q2.x += __shfl_xor_sync(0xffffffffu, q2.x, 16);
-          q2.y += __shfl_xor_sync(0xffffffffu, q2.y, 16);
-          if (lane < 16) {
-            float* tab = cs_tab + (c * 32 + 2 * cp) * 2;
-            atomicAdd(tab + 0, s2.x);
-            atomicAdd(tab + 1, q2.x);
-            atomicAdd(tab + 2, s2.y);
-            atomicAdd(tab + 3, q2.y);
+          if (p.cs_direct) {
+            // tiles that span several samples (small images): one vector reduction per half-block straight to the sample's sums
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb)
+              if (cs_nv[hb] > 0 && oc0 + 2 * cp < p.n_out)
+                red_add_v4(p.col_accum + cs_hb_off[hb] + (oc0 + 2 * cp) * 2, s2[hb].x, q2[hb].x, s2[hb].y, q2[hb].y);
+          } else {
+            // one sample per tile: lanes l / l + 16 combined by a shuffle, then lanes 0..15 add their channel pair into THIS
+            // WARP's slice of the CTA's table (no atomics: each (warp, column) entry has exactly one writer)
+            float4 t4 = make_float4(s2[0].x + s2[1].x, q2[0].x + q2[1].x, s2[0].y + s2[1].y, q2[0].y + q2[1].y);
+            t4.x += __shfl_xor_sync(0xffffffffu, t4.x, 16);
+            t4.y += __shfl_xor_sync(0xffffffffu, t4.y, 16);
+            t4.z += __shfl_xor_sync(0xffffffffu, t4.z, 16);
+            t4.w += __shfl_xor_sync(0xffffffffu, t4.w, 16);
+            if (lane < 16) {
+              float4* tab = reinterpret_cast<float4*>(cs_tab + (lg * BN + c * 32 + 2 * cp) * 2);
+              float4 a4 = *tab;
+              a4.x += t4.x, a4.y += t4.y, a4.z += t4.z, a4.w += t4.w;
+              *tab = a4;
+            }
           }
         }
         ++q;
@@ -708,15 +724,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int64_t m = int64_t(o[0]) + r;
         if (m < p.o_size[0] && g < chunks_per_tile && n_base + g * acc_cw < p.n_rows_b) red_add_v2(p.row_accum + 2 * m, acc_sum, acc_sq);
       }
-      if (LN == 3) {
-        // flush this warpgroup's columns of the table (chunks c = g, g + 2, ...) to the sample's global sums and clear
-        // them; the clears are ordered before the next tile's reductions by that tile's staging barriers
+      if (LN == 3 && !p.cs_direct) {
+        // flush this warpgroup's columns (chunks c = g, g + 2, ...): sum the four warps' slices, one vector reduction per channel
+        // pair to the sample's global sums, clear; the clears are ordered before the next tile's updates by its staging barriers
         named_bar_sync(1 + g, 128);
         const int c = g + kEpiWGs * (r >> 4);
         if (c < chunks_per_tile && n_base + c * 32 < p.n_rows_b) {
-          float4* t4 = reinterpret_cast<float4*>(cs_tab + (c * 32 + 2 * (r & 15)) * 2);
-          const float4 tv = *t4;
-          *t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            float4* t4 = reinterpret_cast<float4*>(cs_tab + (w * BN + c * 32 + 2 * (r & 15)) * 2);
+            const float4 x = *t4;
+            *t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            tv.x += x.x, tv.y += x.y, tv.z += x.z, tv.w += x.w;
+          }
           if (cs_off >= 0) red_add_v4(p.col_accum + cs_off + (n_base + c * 32 + 2 * (r & 15)) * 2, tv.x, tv.y, tv.z, tv.w);
         }
       }
@@ -892,68 +913,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             else
               mbar_arrive(&tempty_bar[acc]);
           }
-      if (split && p.tile_cnt != nullptr) {
-        // this K slice's partial sums are in the workspace: publish (release) one arrival for the output tile
-        __threadfence();
-        named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
-        if (ew == 0 && lane == 0) atomicAdd(p.tile_cnt + mn, 1u);
-      }
-    }
-    if (split && p.tile_cnt != nullptr) {
-      // ---------------------------------------------------------- split-K fix-up, in the same launch
-      // Every CTA of this grid is resident (grid <= SMs, one CTA per SM) and none of them waits before all of its own
-      // partial sums are published, so waiting here cannot deadlock.  Once the `split_k` slices of a tile have arrived
-      // the CTA that computed slice ks applies the epilogue to rows [ks * rpt, (ks + 1) * rpt) of the tile straight
-      // from the workspace and clears what it read: no zero kernel before and no finalize kernel after the GEMM.
-      const int et = ew * 32 + lane;
-      const int rpt = (p.rows_in_box + p.split_k - 1) / p.split_k;
-      const int nq = BN / 4;
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-        const int ks = tile / p.n_tiles_mn;
-        const int mn = tile - ks * p.n_tiles_mn;
-        const int n_tile = mn % p.n_tiles_n;
-        const int m_tile0 = mn / p.n_tiles_n;
-        if (et == 0) {
-          uint32_t spins = 0;
-          while (ld_acquire_gpu_u32(p.tile_cnt + mn) < uint32_t(p.split_k)) {
-            __nanosleep(64);
-            if (++spins > (1u << 24)) __trap();
-          }
-        }
-        named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
-        const int r_begin = ks * rpt;
-        const int r_end = min(r_begin + rpt, p.rows_in_box);
-        for (int i = et; i < (r_end - r_begin) * nq; i += 128 * kEpiWGs) {
-          const int row = r_begin + i / nq;
-          const int n0 = n_tile * BN + (i % nq) * 4;
-          if (n0 >= p.n_rows_b) continue;
-          int m_tile = m_tile0, rr = row;
-          bool valid = true;
-          int64_t out_off = 0, res_off = 0, point = 0, pmul = 1, bias_row = 0, smp = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int oj = (j < 3 ? m_tile % p.ntile[j] : m_tile) * p.box[j];
-            m_tile /= p.ntile[j];
-            const int64_t x = oj + rr % p.box[j];
-            rr /= p.box[j];
-            valid = valid && (x < p.o_size[j]);
-            out_off += x * p.o_stride[j];
-            res_off += x * p.r_stride[j];
-            point += x * pmul;
-            pmul *= p.o_size[j];
-            smp += x * p.cs_mult[j];
-            if (j == p.bias_dim) bias_row = x / p.bias_div;
-          }
-          if (valid) splitk_finalize_quad(p, p.ws + point * p.n_rows_b + n0, point, out_off, res_off, bias_row, smp, n0, true);
-        }
-        // second round of arrivals: the last CTA to finish with this tile resets its counter for the next launch
-        __threadfence();
-        named_bar_sync(kEpiWGs + 1, 128 * kEpiWGs);
-        if (et == 0) {
-          const uint32_t old = atomicAdd(p.tile_cnt + mn, 1u);
-          if (old == 2u * uint32_t(p.split_k) - 1u) atomicExch(p.tile_cnt + mn, 0u);
-        }
-      }
     }
   }
 
@@ -1023,9 +982,11 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   if (stages > kMaxStages) stages = kMaxStages;
   if (p.n_stages > 0 && p.n_stages < stages) stages = p.n_stages;
   if (stages < 2) return fail(-111, "gemm_tc: shared memory layout leaves %d pipeline stages", stages);
+  constexpr size_t kCsTabBytes = (LN == 3) ? size_t(4 * BN * 2 * 4 + 16) : 0;  // per-warp GroupNorm-statistics tables
+  while (stages > 2 && size_t(stages) * Cfg::kStageBytes + kEpiBytes + Cfg::kBarBytes + 1024 + kCsTabBytes > size_t(kSmemLimit)) --stages;
   pp.n_stages = stages;
   pp.smem_epi_off = uint32_t(stages) * uint32_t(Cfg::kStageBytes);
-  const size_t smem_bytes = size_t(pp.smem_epi_off) + kEpiBytes + Cfg::kBarBytes + 1024;
+  const size_t smem_bytes = size_t(pp.smem_epi_off) + kEpiBytes + Cfg::kBarBytes + 1024 + kCsTabBytes;
   if (smem_bytes > size_t(kSmemLimit)) return fail(-112, "gemm_tc: %zu bytes of shared memory needed", smem_bytes);
   launch_kernel_cluster(gemm_tc_kernel<BN, PAIR, LN>, dim3(grid), dim3(kThreads), smem_bytes, stream, PAIR ? 2u : 1u, a0, a1, b,
                         to, tr, pp);
@@ -1196,8 +1157,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
         d->b_batch_dim >= 0 || (reinterpret_cast<uintptr_t>(d->col_accum) & 15))
       return fail(-20, "t2v_gemm: col_accum needs bf16 output, N %% 32 == 0, box[0] %% 8 == 0, cs_mult[0] == 0, no batched B");
     for (int j = 1; j < 4; ++j)
-      if (d->cs_mult[j] != 0 && d->box[j] != 1)
-        return fail(-20, "t2v_gemm: col_accum needs every tile inside one sample (box[%d] = %d spans samples)", j, d->box[j]);
+      if (d->cs_mult[j] != 0 && d->box[j] != 1) p.cs_direct = 1;  // a tile spans samples (small images)
   }
   if (d->row_stats && d->row_accum) return fail(-19, "t2v_gemm: row_stats and row_accum are mutually exclusive");
   if (d->row_stats && d->ln_raw && d->ln_channels <= 0) return fail(-19, "t2v_gemm: ln_raw needs ln_channels");
@@ -1287,13 +1247,9 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
     int rc = make_tmap_bf16(&tmB, d->b, 3, dims, strides, box, "t2v_gemm B");
     if (rc) return rc;
   }
-  // split-K in ONE launch (the CTAs fix up the tiles themselves) whenever the whole grid is resident and the workspace
-  // holds the tile counters behind the partial sums; the workspace must be zero on entry and is left zeroed.
-  const int64_t ws_sum_bytes = ((n_points * d->b_rows * 4 + 15) / 16) * 16;
-  const bool fixup = split > 1 && !(d->tune & 0x1000000) && num_tiles <= sms && (d->flags & T2V_WS_CLEAN) &&
-                     d->workspace_bytes >= ws_sum_bytes + tiles_mn * 4;
-  p.tile_cnt = fixup ? reinterpret_cast<uint32_t*>(static_cast<char*>(d->workspace) + ws_sum_bytes) : nullptr;
-  if (split > 1 && !fixup) {
+  // T2V_WS_CLEAN: the workspace is zero on entry and the finalize kernel clears what it reads, so the zero kernel is
+  // skipped (tune bit 0x1000000 forces it, for A/B measurements)
+  if (split > 1 && (!(d->flags & T2V_WS_CLEAN) || (d->tune & 0x1000000))) {
     const int64_t n4 = (n_points * d->b_rows + 3) / 4;  // workspace is a multiple of 16 bytes
     int64_t zg = (n4 + 255) / 256;
     if (zg > sms * 4) zg = sms * 4;
@@ -1333,7 +1289,7 @@ extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
 #undef T2V_GEMM_WIDE
 #undef T2V_GEMM_CASE
   if (rc) return rc;
-  if (split > 1 && !fixup) {
+  if (split > 1) {
     const int64_t total = n_points * ((d->b_rows + 3) / 4);
     int64_t grid = (total + 255) / 256;
     if (grid > sms * 8) grid = sms * 8;

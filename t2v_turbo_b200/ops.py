@@ -173,25 +173,23 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
 
 
 # GroupNorm statistics in the producing GEMM's epilogue (T2VGemmDesc.col_accum -> T2VGroupNormDesc.chan_sums).  The
-# epilogue reduces each staged 128 x 32 bf16 chunk over its rows into a per-CTA shared-memory table and flushes the
-# table to the (sample, channel) sums once per tile (round 1 issued a global vector atomic per 8 rows: 21 M atomics
-# onto 16 KB for one VAE conv, slower than the statistics pass it removed).  Requires every tile to lie inside one
-# sample (large images: VAE, UNet levels 0-1); other geometries keep the statistics kernel.
+# epilogue reduces each staged 128 x 32 bf16 chunk over its rows; tiles inside one sample (large images: VAE, UNet
+# levels 0-1) accumulate in per-warp shared-memory tables flushed once per tile, tiles spanning samples (small images)
+# reduce 8-row blocks straight to the global sums.  (Round 1 issued a global vector atomic per 8 rows everywhere: 21 M
+# atomics onto 16 KB for one VAE conv, slower than the statistics pass it removed.)  Measured on B200 (scripts/
+# gemm_bench.py STATS=0/1): the reduction costs the epilogue-bound GEMMs more than the statistics kernel it replaces.
 # T2V_GN_FUSE = off | conv (producers with K >= T2V_GN_FUSE_MIN_K, per-frame consumers) | all.
 GN_FUSE = _os.environ.get("T2V_GN_FUSE", "conv")
-GN_FUSE_MIN_K = int(_os.environ.get("T2V_GN_FUSE_MIN_K", "1152"))
+GN_FUSE_MIN_K = int(_os.environ.get("T2V_GN_FUSE_MIN_K", "2304"))
 
 
 def gn_fuse_producer(k_total, grid=None, fixed=(None, None, None, None), sample_dims=()):
     """Should a GEMM with reduction length k_total over the output point grid `grid` accumulate GroupNorm statistics
-    for its consumer?  (The epilogue reduces rows in runs of 8 along dim 0 and keeps one sample per tile: the tile box
-    must allow that — box[0] % 8 == 0 and box[j] == 1 for the dims that index samples.)"""
+    for its consumer?  (The epilogue reduces rows in runs of 8 along dim 0: the tile box must allow that.  sample_dims
+    names the dims that index samples; tiles spanning them use the direct-reduction mode.)"""
     if GN_FUSE == "off" or (GN_FUSE == "conv" and k_total < GN_FUSE_MIN_K):
         return False
-    if grid is None:
-        return True
-    box = plan_box(tuple(int(v) for v in grid), fixed)
-    return box[0] % 8 == 0 and all(box[j] == 1 for j in sample_dims)
+    return grid is None or plan_box(tuple(int(v) for v in grid), fixed)[0] % 8 == 0
 
 
 def gn_fuse_temporal():
@@ -205,8 +203,8 @@ SPLITK_WS_BYTES = 32 << 20
 
 def _splitk_workspace(device):
     """Persistent fp32 scratch for split-K partial sums + tile counters, one per device.  Zeroed ONCE here: every
-    split-K call finds it zeroed and leaves it zeroed (T2V_WS_CLEAN: the CTAs fix up their tiles in the same launch and
-    clear what they read).  Calls on one device are stream-ordered by the host mirror (one stream at a time)."""
+    split-K call finds it zeroed and leaves it zeroed (T2V_WS_CLEAN: the finalize kernel clears what it reads, so no
+    zero kernel runs).  Calls on one device are stream-ordered by the host mirror (one stream at a time)."""
     key = device
     ws = _SPLITK_WS.get(key)
     if ws is None:

@@ -345,12 +345,6 @@ def test_conv_small_cin(cuda_device):
 
 # ----------------------------------------------------------------------------- norms
 # GroupNorm statistics accumulated by the producing GEMM's epilogue (col_accum) and consumed by t2v_groupnorm (chan_sums)
-def _one_sample_per_tile(grid, sdims, fixed=(None, None, None, None)):
-    """The fused statistics need every GEMM tile inside one sample (ops.gn_fuse_producer); other geometries are refused."""
-    box = _ops().plan_box(tuple(grid), fixed)
-    return box[0] % 8 == 0 and all(box[j] == 1 for j in sdims)
-
-
 def _chan_sums_ref(y, n_samples):
     yf = y.float().reshape(n_samples, -1, y.shape[-1])
     return torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1)
@@ -365,10 +359,6 @@ def test_conv3x3_groupnorm_stats(cuda_device, n, h, w, cin, cout):
     b = rnd(1, cout, seed=72)
     res = (rnd(n, h, w, cout, seed=73) + 0.3).to(BF16)
     stats = torch.zeros(n, cout, 2, device=x.device)
-    if not _one_sample_per_tile((w, h, n, 1), (2,)):
-        with pytest.raises(RuntimeError, match="inside one sample"):
-            ops.conv3x3(x, ops.pack_conv_weight(wt), b, bias_div=n, residual=res, stats=stats)
-        return
     y = ops.conv3x3(x, ops.pack_conv_weight(wt), b, bias_div=n, residual=res, stats=stats)
     ref = _chan_sums_ref(y, n)
     torch.testing.assert_close(stats, ref, rtol=2e-3, atol=2e-2)
@@ -388,28 +378,25 @@ def test_conv3x3_groupnorm_stats_no_residual(cuda_device, n, h, w, c0, c1, cout,
     cin = c0 + c1
     wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=92).to(BF16)
     bias = rnd(n // t, cout, seed=93)
-    stats = torch.zeros(n, cout, 2, device=xa.device) if _one_sample_per_tile((w, h, n, 1), (2,)) else None
+    stats = torch.zeros(n, cout, 2, device=xa.device)
     y = ops.conv3x3((xa, xb) if xb is not None else xa, ops.pack_conv_weight(wt), bias, bias_div=t, stats=stats)
     xin = torch.cat([xa, xb], -1) if xb is not None else xa
     ref = F.conv2d(xin.float().permute(0, 3, 1, 2), wt.float(), None, padding=1).permute(0, 2, 3, 1) + bias.repeat_interleave(t, 0)[:, None, None, :]
     assert_close(y, ref, what="conv3x3 (stats, no residual)")
-    if stats is not None:
-        torch.testing.assert_close(stats, _chan_sums_ref(y, n), rtol=2e-3, atol=2e-2)
+    torch.testing.assert_close(stats, _chan_sums_ref(y, n), rtol=2e-3, atol=2e-2)
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(8, 32, 32, 64, 64), (4, 16, 64, 64, 128), (16, 40, 64, 64, 320), (3, 80, 128, 64, 128)])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(8, 16, 16, 64, 64), (4, 8, 8, 64, 128), (8, 32, 32, 64, 64), (16, 40, 64, 64, 320), (3, 80, 128, 64, 128)])
 def test_conv3x3_s2_groupnorm_stats(cuda_device, n, h, w, cin, cout):
     ops = _ops()
     x = rnd(n, h, w, cin, seed=94).to(BF16)
     wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=95).to(BF16)
     stats = torch.zeros(n, cout, 2, device=x.device)
-    if not _one_sample_per_tile((w // 2, 1, h // 2, n), (3,), (None, 1, None, None)):
-        pytest.skip("tile spans samples: producer statistics refused (covered by test_conv3x3_groupnorm_stats)")
     y = ops.conv3x3_s2(x, ops.pack_conv_weight(wt), rnd(cout, seed=96), stats=stats)
     torch.testing.assert_close(stats, _chan_sums_ref(y, n), rtol=2e-3, atol=2e-2)
 
 
-@pytest.mark.parametrize("b,t,hw,c", [(1, 16, 128, 128), (2, 4, 640, 64), (1, 3, 2560, 64)])
+@pytest.mark.parametrize("b,t,hw,c", [(1, 16, 40, 128), (2, 4, 160, 64), (1, 16, 128, 128), (2, 4, 640, 64), (1, 3, 2560, 64)])
 def test_tconv3_groupnorm_stats_temporal(cuda_device, b, t, hw, c):
     """per-frame sums from the (3,1,1) conv, consumed by a GroupNorm over (t, hw) per batch element (chan_group = t)."""
     ops = _ops()
@@ -425,7 +412,8 @@ def test_tconv3_groupnorm_stats_temporal(cuda_device, b, t, hw, c):
     assert_close(out, gn, what="temporal groupnorm from per-frame sums")
 
 
-@pytest.mark.parametrize("nf,hw,k,n,split_k", [(16, 256, 320, 320, 0), (6, 2560, 320, 320, 0), (4, 640, 128, 640, 0), (2, 128, 2048, 128, 4)])
+@pytest.mark.parametrize("nf,hw,k,n,split_k", [(16, 160, 320, 320, 0), (16, 40, 1280, 1280, 0), (16, 256, 320, 320, 0), (6, 2560, 320, 320, 0),
+                                               (4, 640, 128, 640, 0), (16, 40, 2048, 128, 4)])
 def test_linear_frames_groupnorm_stats_concat(cuda_device, nf, hw, k, n, split_k):
     """proj_out (+residual) tiled per frame; its sums feed a GroupNorm over the concatenation with a second tensor."""
     ops = _ops()
@@ -519,6 +507,7 @@ def _sdpa_ref(q, k, v, heads, scale):
 
 @pytest.mark.parametrize("b,lq,lk,heads,rep", [
     (2, 256, 256, 2, 1), (1, 128, 128, 1, 1), (2, 160, 160, 3, 1), (4, 40, 40, 2, 1), (4, 640, 77, 2, 4), (1, 2560, 2560, 5, 1),
+    (2, 320, 300, 2, 1), (3, 100, 513, 1, 1), (2, 640, 640, 10, 1), (1, 257, 129, 2, 1),
 ])
 def test_attention(cuda_device, b, lq, lk, heads, rep):
     ops = _ops()
@@ -529,6 +518,24 @@ def test_attention(cuda_device, b, lq, lk, heads, rep):
     out = ops.attention(q, k, v, heads=heads, scale=0.125, kv_batch_div=rep)
     ref = _sdpa_ref(q, k, v, heads, 0.125)
     assert_close(out, ref, what=f"attention b{b} lq{lq} lk{lk} h{heads}")
+
+
+def test_attention_reference_raise_slow_path(cuda_device):
+    """Later key tiles whose scores exceed the first tile's row maximum by far more than 2^100: the exponent reference
+    fixed by the first tile must be raised and l / O rescaled exactly (the rare slow path of the two-tile kernel)."""
+    ops = _ops()
+    b, lq, lk, heads = 2, 256, 512, 2
+    inner = heads * 64
+    q = rnd(b, lq, inner, seed=144).to(BF16)
+    k = rnd(b, lk, inner, seed=145)
+    k[:, 300:340] *= 40.0      # tile 2 holds scores ~ +-250 in the log2 domain; tiles 0, 1 stay O(1)
+    k[:, 450:452] *= 90.0      # and tile 3 raises the reference a second time for some rows
+    k = k.to(BF16)
+    v = rnd(b, lk, inner, seed=146).to(BF16)
+    out = ops.attention(q, k, v, heads=heads, scale=0.125)
+    ref = _sdpa_ref(q, k, v, heads, 0.125)
+    assert torch.isfinite(out.float()).all()
+    assert_close(out, ref, what="attention, exponent reference raised mid-sequence")
 
 
 def test_attention_strided_qkv(cuda_device):
