@@ -296,6 +296,53 @@ int t2v_scale_add_rows(const void* x, const void* y, const float* a, const float
 int t2v_gaussian_sample(const float* moments, const float* noise, void* out, int32_t out_dtype, int32_t b,
                         int32_t t, int32_t h, int32_t w, int32_t zc, float scale, t2v_stream_t stream);
 
+/* ------------------------------------------------------------------ consistency-distillation step (LoRA training)
+ * Backward twins of the LoRA-injected layers (utils/lora.py:19-230: y = W x + b + scale * dropout(U (D x))):
+ *   dgrad  — dx = dy W (+ d(Dx) D): the forward t2v_gemm on pre-transposed / tap-rotated weights (host packing);
+ *   wgrad  — the LoRA weight gradients, accumulated into the caller's fp32 gradient ARENA by t2v_wgrad:
+ *            out[j, c, tap] += alpha * sum_points A[point + off(tap), c] * B[point, j],  c < a_ch, j < b_cols <= 64
+ *            (lora_down: A = layer input, B = d(Dx), taps of the base kernel; lora_up: A = scale * mask * dy, B = Dx).
+ * A / B are channels-last bf16 read in place as MN-major tensor-core operands (no transposed copies, no im2col; a tap
+ * is a coordinate offset, conv padding is TMA zero fill).  out is ACCUMULATED into (zero the arena once per step):
+ * element (j, c, tap) lives at out[j * out_j_stride + c * out_c_stride + tap * out_tap_stride]. */
+typedef struct T2VWgradDesc {
+  const void* a;                        /* bf16 [points..][a_ch] channels-last (point grid a_size, strides a_stride) */
+  int32_t a_ch;                         /* multiple of 8 */
+  int64_t a_size[T2V_MAX_DIMS];
+  int64_t a_stride[T2V_MAX_DIMS];
+  const void* b;                        /* bf16 [points..][b_cols] over the OUTPUT point grid o_size, strides b_stride */
+  int32_t b_cols;                       /* multiple of 8, <= 64 (the LoRA rank) */
+  int64_t o_size[T2V_MAX_DIMS];
+  int64_t b_stride[T2V_MAX_DIMS];
+  int32_t box[T2V_MAX_DIMS];            /* point tile: product a multiple of 16, <= 128 */
+  int32_t n_taps;
+  int32_t tap_off[T2V_MAX_TAPS][T2V_MAX_DIMS];
+  float* out;                           /* fp32 gradient arena slice (accumulated into) */
+  int64_t out_j_stride, out_c_stride, out_tap_stride;
+  float alpha;
+} T2VWgradDesc;
+
+int t2v_wgrad(const T2VWgradDesc* desc, t2v_stream_t stream);
+
+/* out[i] = x[i] * scale * (mask ? mask[i] : 1)  (bf16; mask is a uint8 keep-mask): the `dropout(...) * scale` of the LoRA
+ * branch in the forward (applied to U(Dx) before the add) and its adjoint on dy in the backward (utils/lora.py:45-50). */
+int t2v_scale_mask(const void* x, const uint8_t* mask, void* out, int64_t n, float scale, t2v_stream_t stream);
+
+/* Fused AdamW over the flat fp32 LoRA parameter / gradient arenas (torch.optim.AdamW semantics, one launch for all 575
+ * layers; train_t2v_turbo_v1_lora.py:897-906,1193): grad is multiplied by grad_scale first (1/world for the DDP mean
+ * and the gradient-clipping factor folded in). step >= 1. */
+int t2v_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale, t2v_stream_t stream);
+
+/* out[0] += sum_i x[i]^2 over n fp32 values (gradient-norm clipping, accelerator.clip_grad_norm_, :1191); out is
+ * accumulated into (zero it first). */
+int t2v_sum_squares(const float* x, int64_t n, float* out, t2v_stream_t stream);
+
+/* mean-squared-error loss and its gradient (F.mse_loss(model_pred.float(), target.float()), :1183-1186):
+ * loss[0] += sum (a - b)^2 / n ; grad[i] = 2 (a[i] - b[i]) / n * grad_scale in the dtype of a (0 bf16, 1 fp16, 2 fp32). */
+int t2v_mse_loss_grad(const void* a, const void* b, void* grad, float* loss, int64_t n, int32_t dtype, float grad_scale,
+                      t2v_stream_t stream);
+
 /* Weight packing helpers (device-side, run once at load). */
 /* conv weight [Cout][Cin][kh*kw] (torch OIHW / OIDHW flattened taps) -> [Cout][taps][Cin] bf16 */
 int t2v_pack_conv_weight(const void* w, int32_t w_dtype, void* out, int32_t cout, int32_t cin,

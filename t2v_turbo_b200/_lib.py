@@ -124,6 +124,21 @@ class SmallLinearDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("a_ch", C.c_int32),
+        ("a_size", C.c_int64 * MAX_DIMS), ("a_stride", C.c_int64 * MAX_DIMS),
+        ("b", C.c_void_p), ("b_cols", C.c_int32),
+        ("o_size", C.c_int64 * MAX_DIMS), ("b_stride", C.c_int64 * MAX_DIMS),
+        ("box", C.c_int32 * MAX_DIMS),
+        ("n_taps", C.c_int32),
+        ("tap_off", (C.c_int32 * MAX_DIMS) * MAX_TAPS),
+        ("out", C.c_void_p),
+        ("out_j_stride", C.c_int64), ("out_c_stride", C.c_int64), ("out_tap_stride", C.c_int64),
+        ("alpha", C.c_float),
+    ]
+
+
 # every symbol include/t2v_b200.h declares: (name, restype, argtypes)
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 SYMBOLS = {
@@ -146,6 +161,11 @@ SYMBOLS = {
     "t2v_concat_channels": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "t2v_softmax_rows": (C.c_int, [_vp, _i64, _i32, _i64, _f32, _vp]),
     "t2v_gaussian_sample": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "t2v_wgrad": (C.c_int, [C.POINTER(WgradDesc), _vp]),
+    "t2v_scale_mask": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
+    "t2v_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
+    "t2v_sum_squares": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "t2v_mse_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
     "t2v_scale_add_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "t2v_lcm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "t2v_pack_conv_weight": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp]),

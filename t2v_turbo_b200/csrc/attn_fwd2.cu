@@ -15,11 +15,15 @@
 //     guard against overflow (a rare slow path raises the reference and rescales l / O exactly).  Softmax is shift
 //     invariant and P / l / O carry the same factor, so results are unchanged.
 // TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
-//   warp 0    : TMA producer — Q0 / Q1 once, K / V tiles (128 keys) through 3-stage rings, read in place from the
-//               projection outputs via 4-D tensor maps {64, head, token, batch} (no head-split copy)
-//   warp 1    : MMA issuer (one elected thread): per key tile and Q tile t: [P_t(j) ready] S_t(j+1) then PV_t(j)
-//   warp 2    : TMEM allocator
-//   warps 4-7 : softmax of Q tile 0 (thread = query row);  warps 8-11 : softmax of Q tile 1
+//   warps 0-15 : softmax.  Warp w works on Q tile t = w / 8, key-column half hh = (w / 4) % 2 and rows 32 (w % 4) + lane:
+//                TWO threads per query row (64 of the 128 keys each), four softmax warps per scheduler — one warp per
+//                scheduler and tile (thread = whole row) left the kernel latency bound at 31 % tensor pipe.  The two halves
+//                of a row share only the exponent reference: they exchange their row maxima once (first key tile) and
+//                meet at one named barrier per key tile, where a rare overflow flag is checked.
+//   warp 16    : TMA producer — Q0 / Q1 once, K / V tiles (128 keys) through 3-stage rings, read in place from the
+//                projection outputs via 4-D tensor maps {64, head, token, batch} (no head-split copy)
+//   warp 17    : MMA issuer (one elected thread): per key tile and Q tile t: [P_t(j) ready] S_t(j+1) then PV_t(j)
+//   warp 18    : TMEM allocator
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,11 +34,11 @@
 
 namespace t2v {
 
-constexpr int kA2Threads = 384;
+constexpr int kA2Threads = 608;
 constexpr int kA2Stages = 3;
 constexpr int kA2Tile = 128;
 constexpr int kA2TileBytes = kA2Tile * 64 * 2;  // 16 KB: 128 rows x 64 bf16
-constexpr int kA2Smem = 2 * kA2TileBytes + 2 * kA2Stages * kA2TileBytes + 512;
+constexpr int kA2Smem = 2 * kA2TileBytes + 2 * kA2Stages * kA2TileBytes + 512 + 2 * 2 * 128 * 4 + 64;
 constexpr int kA2PolyPairs = 7;  // of the 16 column pairs of every 32-column chunk: exp2 on the FMA pipe
 
 struct Attn2Params {
@@ -86,6 +90,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* p_full = s_full + 2;              // 2, 128 arrivals each
   uint64_t* pv_done = p_full + 2;             // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint32_t* ovf_flag = tmem_slot + 2;                       // [2] per Q tile: some row of the tile overflowed its reference
+  float* s_xchg = reinterpret_cast<float*>(bars) + 128;   // [2 tiles][2 halves][128 rows]: row maxima of the halves
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);  // provably warp-uniform: lean TMA / MMA issue code
   const int lane = threadIdx.x & 31;
@@ -97,12 +103,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int kvb = b / p.kv_batch_div;
   const int q0 = q_pair * 2 * kA2Tile;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 17 && lane == 0) {
+    ovf_flag[0] = ovf_flag[1] = 0u;
     mbar_init(q_full, 1);
     for (int s = 0; s < kA2Stages; ++s) {
       mbar_init(&k_full[s], 1);
@@ -112,12 +119,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t], 256);
       mbar_init(&pv_done[t], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 18) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -129,7 +136,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   pdl_wait();
   const int n_kv = p.n_kv_tiles;
 
-  if (warp == 0 && elect_one()) {
+  if (warp == 16 && elect_one()) {
     // ------------------------------------------------------------ TMA producer
     mbar_expect_tx(q_full, 2 * kA2TileBytes);
     tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
@@ -144,7 +151,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_expect_tx(&v_full[s], kA2TileBytes);
       tma_load_4d(sV + s * kA2TileBytes, &tmV, &v_full[s], 0, h, j * kA2Tile, kvb);
     }
-  } else if (warp == 1 && elect_one()) {
+  } else if (warp == 17 && elect_one()) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (TMEM, K-major) x V (MN-major)
@@ -191,26 +198,30 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma_commit(&pv_done[t]);
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ softmax / epilogue: warps 4-7 tile 0, warps 8-11 tile 1
-    const int t = (warp - 4) >> 2;
-    const int ew = (warp - 4) & 3;
+  } else if (warp < 16) {
+    // ------------------------------------------------------------ softmax / epilogue
+    const int t = warp >> 3;         // Q tile
+    const int hh = (warp >> 2) & 1;  // key-column half of every 128-key tile
+    const int ew = warp & 3;         // TMEM lane group
     const int r = ew * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(ew * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_addr + t * 128;
-    const uint32_t p_addr = tmem_base + lane_addr + 256 + t * 64;
-    const uint32_t o_addr = tmem_base + lane_addr + 384 + t * 64;
+    const uint32_t s_addr = tmem_base + lane_addr + t * 128 + hh * 64;
+    const uint32_t p_addr = tmem_base + lane_addr + 256 + t * 64 + hh * 32;
+    const uint32_t o_addr = tmem_base + lane_addr + 384 + t * 64 + hh * 32;   // this thread rescales / stores 32 of the 64 columns
+    float* my_x = s_xchg + (t * 2 + hh) * 128 + r;
+    const float* other_x = s_xchg + (t * 2 + (hh ^ 1)) * 128 + r;
     const float c_log2 = p.scale_log2;
     float m_ref = 0.f;   // exponent reference (log2 domain, scale folded in), fixed by the first key tile
-    float l_run = 0.f;
+    float l_run = 0.f;   // this half's share of the row sum
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      const int kv_left = p.len_k - j * kA2Tile;  // valid keys in this tile (>= 1)
+      const int kv_left = p.len_k - j * kA2Tile - hh * 64;  // valid keys of this half (may be <= 0 in the last tile)
+      // exact row maximum over both halves (first tile; slow path): own 64 columns, exchange through shared memory
       auto row_max = [&]() {
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kA2Tile; c0 += 32) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(s_addr + c0, v);
           tmem_wait_ld();
@@ -218,6 +229,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int i = 0; i < 32; ++i)
             if (c0 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
+        *my_x = mx;
+        named_bar_sync(1 + t, 256);
+        mx = fmaxf(mx, *other_x);
+        named_bar_sync(1 + t, 256);   // the slots may be rewritten
         return mx;
       };
       if (j == 0) m_ref = row_max() * c_log2;
@@ -266,26 +281,23 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_32x32(s_addr + 32, vb);
         exp_chunk(va, 0, nref);
         tmem_wait_ld();
-        tmem_ld_32x32(s_addr + 64, va);
         exp_chunk(vb, 32, nref);
-        tmem_wait_ld();
-        tmem_ld_32x32(s_addr + 96, vb);
-        exp_chunk(va, 64, nref);
-        tmem_wait_ld();
-        exp_chunk(vb, 96, nref);
         return rs2.x + rs2.y;
       };
       float rs = exp_pass(m_ref);
-      if (__any_sync(0xffffffffu, !(rs < 1e30f))) {
-        // rare: a row's scores exceed the reference by ~2^100: raise the reference for the rows that need it, rescale l and O
-        // exactly, redo this tile's P (S_t(j) is still intact: S and P do not alias)
+      if (__any_sync(0xffffffffu, !(rs < 1e30f)) && lane == 0) atomicOr(ovf_flag + t, 1u);
+      named_bar_sync(1 + t, 256);   // the two halves of every row of this tile meet once per key tile
+      if (*reinterpret_cast<volatile uint32_t*>(ovf_flag + t) != 0u) {
+        // rare: a row's scores exceed the reference by ~2^100: all 256 threads of the tile raise the reference for the rows
+        // that need it, rescale l and O exactly and redo this tile's P (S_t(j) is still intact: S and P do not alias)
         const float new_ref = fmaxf(m_ref, row_max() * c_log2);
         const float alpha = ex2_mufu(m_ref - new_ref);  // 1 for rows that keep their reference
         l_run *= alpha;
+        if (warp == (t << 3) && lane == 0) ovf_flag[t] = 0u;   // (every thread of the tile is past its read: row_max synchronised twice)
         if (j > 0) {
-          // (p_free is already true: exp_pass waited for PV_t(j-1))
+          // (p_free is already true: exp_pass waited for PV_t(j-1)); each half rescales its 32 columns of O
 #pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 16) {
+          for (int c0 = 0; c0 < 32; c0 += 16) {
             uint32_t ov[16];
             tmem_ld_32x16(o_addr + c0, ov);
             tmem_wait_ld();
@@ -302,35 +314,36 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&p_full[t]);
     }
+    // total row sum = the two halves' shares
+    *my_x = l_run;
+    named_bar_sync(1 + t, 256);
+    l_run += *other_x;
     // the last PV must have landed before O is read
     mbar_wait(&pv_done[t], (n_kv - 1) & 1);
     tc_fence_after();
-    // epilogue: O / l -> bf16 -> global
+    // epilogue: O / l -> bf16 -> global; this thread stores columns [32 hh, 32 hh + 32) of its row
     const int qi = q0 + t * kA2Tile + r;
     const float inv_l = 1.0f / l_run;
-    __nv_bfloat16* orow = p.o + int64_t(b) * p.o_stride_b + int64_t(qi) * p.o_stride_t + int64_t(h) * p.o_stride_h;
+    __nv_bfloat16* orow = p.o + int64_t(b) * p.o_stride_b + int64_t(qi) * p.o_stride_t + int64_t(h) * p.o_stride_h + hh * 32;
+    uint32_t ov[32];
+    tmem_ld_32x32(o_addr, ov);
+    tmem_wait_ld();
+    if (qi < p.len_q) {
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      uint32_t ov[32];
-      tmem_ld_32x32(o_addr + c0, ov);
-      tmem_wait_ld();
-      if (qi < p.len_q) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
-          pk.y = pack_bf16(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
-          pk.z = pack_bf16(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
-          pk.w = pack_bf16(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c0 + q * 8) = pk;
-        }
+      for (int q = 0; q < 4; ++q) {
+        uint4 pk;
+        pk.x = pack_bf16(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
+        pk.y = pack_bf16(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
+        pk.z = pack_bf16(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
+        pk.w = pack_bf16(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + q * 8) = pk;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 18) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -176,10 +176,13 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
 # epilogue reduces each staged 128 x 32 bf16 chunk over its rows; tiles inside one sample (large images: VAE, UNet
 # levels 0-1) accumulate in per-warp shared-memory tables flushed once per tile, tiles spanning samples (small images)
 # reduce 8-row blocks straight to the global sums.  (Round 1 issued a global vector atomic per 8 rows everywhere: 21 M
-# atomics onto 16 KB for one VAE conv, slower than the statistics pass it removed.)  Measured on B200 (scripts/
-# gemm_bench.py STATS=0/1): the reduction costs the epilogue-bound GEMMs more than the statistics kernel it replaces.
+# atomics onto 16 KB for one VAE conv, slower than the statistics pass it removed.)  Measured on B200 in round 2 (scripts/
+# gemm_bench.py STATS=0/1, profiles/r02_gn_fusion.txt): +1 us on the MMA-bound convs (K >= 2304) but +5 us on the K = 960
+# temporal convs and +29 % on the epilogue-bound 128-channel VAE convs; whole-step frames/s off 158.6 / conv 153.8 / all
+# 147.3 under the 1 kW power cap.  The standalone statistics pass already streams at 5.6-5.9 TB/s on the tensors that
+# matter, so the fusion stays OFF by default.
 # T2V_GN_FUSE = off | conv (producers with K >= T2V_GN_FUSE_MIN_K, per-frame consumers) | all.
-GN_FUSE = _os.environ.get("T2V_GN_FUSE", "conv")
+GN_FUSE = _os.environ.get("T2V_GN_FUSE", "off")
 GN_FUSE_MIN_K = int(_os.environ.get("T2V_GN_FUSE_MIN_K", "2304"))
 
 
