@@ -131,6 +131,42 @@ def gen_lora(name="small"):
     torch.save({"name": name, "seed": 4242, "layers": rec}, os.path.join(GOLD, f"lora_{name}.pt"))
 
 
+LORA_LAYER_CASES = {
+    # kind: (ctor kwargs of the reference module, input shape in the reference layout)
+    "linear": (dict(in_features=128, out_features=192, bias=True), (3, 100, 128)),
+    "conv2d": (dict(in_channels=64, out_channels=128, kernel_size=3, padding=1), (2, 64, 12, 16)),
+    "conv3d": (dict(in_channels=64, out_channels=64, kernel_size=(3, 1, 1), padding=(1, 0, 0)), (1, 64, 4, 6, 8)),
+}
+
+
+def gen_lora_layers():
+    """Forward + backward of the reference's LoraInjectedLinear / Conv2d / Conv3d (utils/lora.py:19-230), r = 64, dropout 0,
+    scale 0.7, seeded weights / input / upstream gradient: y, dx, d lora_up.weight, d lora_down.weight."""
+    from utils import lora as rlora
+    out = {}
+    g = torch.Generator().manual_seed(777)
+    for kind, (kw, xs) in LORA_LAYER_CASES.items():
+        cls = dict(linear=rlora.LoraInjectedLinear, conv2d=rlora.LoraInjectedConv2d, conv3d=rlora.LoraInjectedConv3d)[kind]
+        m = cls(**kw, r=64, dropout_p=0.0, scale=0.7)
+        base = m.linear if kind == "linear" else m.conv
+        with torch.no_grad():
+            for prm in (base.weight, base.bias, m.lora_up.weight, m.lora_down.weight):
+                if prm is not None:
+                    fan = prm[0].numel() if prm.dim() > 1 else 1
+                    prm.copy_(torch.randn(prm.shape, generator=g) * (0.3 if prm.dim() == 1 else 0.8 / fan ** 0.5))
+        x = torch.randn(xs, generator=g).requires_grad_(True)
+        y = m(x)
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        out[kind] = dict(w=base.weight.detach().clone(), b=base.bias.detach().clone() if base.bias is not None else None,
+                         up=m.lora_up.weight.detach().clone(), down=m.lora_down.weight.detach().clone(), x=x.detach().clone(), dy=dy,
+                         y=y.detach().clone(), dx=x.grad.clone(), d_up=m.lora_up.weight.grad.clone(), d_down=m.lora_down.weight.grad.clone(),
+                         scale=0.7)
+        print(f"  lora layer {kind}: y std {y.std():.3f}, dx std {x.grad.std():.3f}, d_up std {m.lora_up.weight.grad.std():.3f}, "
+              f"d_down std {m.lora_down.weight.grad.std():.3f}")
+    torch.save(out, os.path.join(GOLD, "lora_layers.pt"))
+
+
 def gen_scheduler():
     from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
     s = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
@@ -259,13 +295,15 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
             gen_scheduler()
         elif item.startswith("unet_"):
             gen_unet(item[5:])
+        elif item == "lora_layers":
+            gen_lora_layers()
         elif item.startswith("lora_"):
             gen_lora(item[5:])
         elif item.startswith("vae_enc_"):
@@ -276,3 +314,5 @@ if __name__ == "__main__":
             gen_pipeline()
         elif item == "pipeline_v2":
             gen_pipeline_v2()
+        elif item == "lora_layers":
+            gen_lora_layers()

@@ -89,7 +89,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_full = v_empty + kA2Stages;     // 2 (per Q tile)
   uint64_t* p_full = s_full + 2;              // 2, 128 arrivals each
   uint64_t* pv_done = p_full + 2;             // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_free = pv_done + 2;             // 2, 256 arrivals each: S_t(j) is in registers, its TMEM columns may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
   uint32_t* ovf_flag = tmem_slot + 2;                       // [2] per Q tile: some row of the tile overflowed its reference
   float* s_xchg = reinterpret_cast<float*>(bars) + 128;   // [2 tiles][2 halves][128 rows]: row maxima of the halves
 
@@ -120,6 +121,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 256);
+      mbar_init(&s_free[t], 256);
       mbar_init(&pv_done[t], 1);
     }
     fence_mbar_init();
@@ -176,13 +178,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < n_kv; ++j) {
       const int s = j % kA2Stages;
       const uint32_t ph = (j / kA2Stages) & 1;
+      // The softmax threads pull S_t(j) into registers first thing and release its columns (s_free): the next score tile
+      // is computed WHILE they exponentiate, so softmax_t(j+1) never waits for the tensor pipe.
+      if (j + 1 < n_kv) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&s_free[t], j & 1);
+          tc_fence_after();
+          issue_s(t, j + 1);
+        }
+      }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        // P_t(j) is in TMEM and S_t(j) has been consumed: the next score tile goes first, so that softmax_t(j+1) can start
-        // while PV_t(j) still runs
-        mbar_wait(&p_full[t], j & 1);
+        mbar_wait(&p_full[t], j & 1);   // P_t(j) is in TMEM
         tc_fence_after();
-        if (j + 1 < n_kv) issue_s(t, j + 1);
         if (t == 0) {
           mbar_wait(&v_full[s], ph);
           tc_fence_after();
@@ -217,17 +226,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       const int kv_left = p.len_k - j * kA2Tile - hh * 64;  // valid keys of this half (may be <= 0 in the last tile)
+      // S_t(j), this thread's 64 columns, into registers; then the TMEM columns are released for S_t(j+1)
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(s_addr, va);
+      tmem_ld_32x32(s_addr + 32, vb);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);
       // exact row maximum over both halves (first tile; slow path): own 64 columns, exchange through shared memory
       auto row_max = [&]() {
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c0, v);
-          tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (i < kv_left) mx = fmaxf(mx, __uint_as_float(va[i]));
+          if (32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(vb[i]));
         }
         *my_x = mx;
         named_bar_sync(1 + t, 256);
@@ -274,14 +286,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       };
       auto exp_pass = [&](float ref) {
         rs2 = make_float2(0.f, 0.f);
-        const float nref = -ref;
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(s_addr, va);
-        tmem_wait_ld();
-        tmem_ld_32x32(s_addr + 32, vb);
-        exp_chunk(va, 0, nref);
-        tmem_wait_ld();
-        exp_chunk(vb, 32, nref);
+        exp_chunk(va, 0, -ref);
+        exp_chunk(vb, 32, -ref);
         return rs2.x + rs2.y;
       };
       float rs = exp_pass(m_ref);
@@ -289,7 +295,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       named_bar_sync(1 + t, 256);   // the two halves of every row of this tile meet once per key tile
       if (*reinterpret_cast<volatile uint32_t*>(ovf_flag + t) != 0u) {
         // rare: a row's scores exceed the reference by ~2^100: all 256 threads of the tile raise the reference for the rows
-        // that need it, rescale l and O exactly and redo this tile's P (S_t(j) is still intact: S and P do not alias)
+        // that need it, rescale l and O exactly and redo this tile's P from the scores still held in registers
         const float new_ref = fmaxf(m_ref, row_max() * c_log2);
         const float alpha = ex2_mufu(m_ref - new_ref);  // 1 for rows that keep their reference
         l_run *= alpha;

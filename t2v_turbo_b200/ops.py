@@ -667,6 +667,87 @@ def gaussian_sample(moments, noise, *, b, t, zc, scale, dtype):
     return out
 
 
+# ----------------------------------------------------------------------------- training (LoRA) ops
+def wgrad(a, b, out, *, taps=None, out_strides, alpha=1.0, a_grid=None):
+    """out[j, c, tap] += alpha * sum_points a[point + off(tap), c] * b[point, j] (t2v_wgrad).
+    a: channels-last bf16 [x4.., x1, C] (any leading point dims, up to 4) or [M, C]; b: bf16 [same points.., r];
+    out: fp32 tensor (a slice of the gradient arena) addressed by out_strides = (j_stride, c_stride, tap_stride)."""
+    _check_act(a, "a")
+    _check_act(b, "b")
+    assert out.dtype == torch.float32 and out.is_cuda
+    pts = tuple(a.shape[:-1])
+    assert tuple(b.shape[:-1]) == pts and len(pts) <= 4
+    c, r = a.shape[-1], b.shape[-1]
+    if math.prod(pts) < 16:   # fewer points than one MMA k-step (embedding layers, M = batch): zero rows add nothing
+        assert len(pts) == 1 and taps is None
+        a = torch.cat([a, a.new_zeros(16 - pts[0], c)])
+        b = torch.cat([b, b.new_zeros(16 - pts[0], r)])
+        pts = (16,)
+    grid = tuple(reversed(pts)) + (1,) * (4 - len(pts))       # x1 fastest
+    d = _lib.WgradDesc()
+    d.a, d.a_ch, d.b, d.b_cols = a.data_ptr(), c, b.data_ptr(), r
+    astr, bstr, acc = [], [], 1
+    for g in grid:
+        astr.append(acc * c)
+        bstr.append(acc * r)
+        acc *= g
+    _fill(d.a_size, grid)
+    _fill(d.o_size, grid)
+    _fill(d.a_stride, astr)
+    _fill(d.b_stride, bstr)
+    box = plan_box(grid)
+    if math.prod(box) % 16:
+        box = plan_box(grid, fixed=(16 if grid[0] % 16 == 0 else None, None, None, None))
+    assert math.prod(box) % 16 == 0, f"wgrad: no 16-row tile box for point grid {grid}"
+    _fill(d.box, box)
+    taps = taps if taps is not None else [(0, 0, 0, 0)]
+    d.n_taps = len(taps)
+    for t, off in enumerate(taps):
+        _fill(d.tap_off[t], off)
+    d.out = out.data_ptr()
+    d.out_j_stride, d.out_c_stride, d.out_tap_stride = (int(v) for v in out_strides)
+    d.alpha = alpha
+    _launch("wgrad", 2 * math.prod(grid) * c * r * len(taps), lib().t2v_wgrad, C.byref(d), stream_ptr())
+    return out
+
+
+def scale_mask(x, scale, mask=None, out=None):
+    """out = x * scale * mask (bf16; mask uint8 keep-mask or None): the LoRA branch's dropout(...) * scale and its adjoint."""
+    assert x.is_cuda and x.dtype == BF16 and x.is_contiguous() and x.numel() % 8 == 0
+    if out is None:
+        out = torch.empty_like(x)
+    if mask is not None:
+        assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() == x.numel()
+    _launch("scale_mask", 0, lib().t2v_scale_mask, x.data_ptr(), ptr(mask), out.data_ptr(), x.numel(), float(scale), stream_ptr())
+    return out
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, step, grad_scale=1.0):
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    _launch("adamw_step", 0, lib().t2v_adamw_step, param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+            float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), stream_ptr())
+
+
+def sum_squares(x, out=None):
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.zeros(1, device=x.device, dtype=torch.float32)
+    _launch("sum_squares", 0, lib().t2v_sum_squares, x.data_ptr(), x.numel(), out.data_ptr(), stream_ptr())
+    return out
+
+
+def mse_loss_grad(a, b, *, want_grad=True, grad_scale=1.0):
+    """(mean((a - b)^2) as a 1-element fp32 tensor, d loss / d a * grad_scale in a's dtype)."""
+    assert a.is_cuda and a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
+    loss = torch.zeros(1, device=a.device, dtype=torch.float32)
+    grad = torch.empty_like(a) if want_grad else None
+    _launch("mse_loss_grad", 0, lib().t2v_mse_loss_grad, a.data_ptr(), b.data_ptr(), ptr(grad), loss.data_ptr(), a.numel(),
+            _lib.DTYPE_CODE[a.dtype], float(grad_scale), stream_ptr())
+    return loss, grad
+
+
 # ----------------------------------------------------------------------------- weight packing
 def pack_conv_weight(w):
     """torch conv weight [Cout, Cin, *k] -> bf16 [Cout, taps*Cin] (tap-major K)."""
