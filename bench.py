@@ -294,6 +294,103 @@ def _emit(line):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
 
 
+def run_lora_step(args, rank, local_rank, world):
+    """`--workload lora-step` (supplementary; BASELINE config 4's data-parallel exchange): per rank, the 567 LoRA-injected
+    layers of the VC2 UNet that are on the tensor-core training path (utils/lora.py:19-230, r = 64) run forward and backward
+    at the activation geometry of one 16x320x512 sample — base GEMM + LoRA down / up in the forward; dgrad (base and LoRA)
+    and the two weight-gradient GEMMs per layer in the backward, written straight into the 117 142 176-value fp32 arena —
+    then the bucketed NCCL sum all-reduce of the arena (overlapped with the backward, reverse layer order), global-norm
+    clipping and ONE fused AdamW launch.  Layer inputs / upstream gradients are independent random tensors per shape: the
+    non-GEMM layers between the LoRA layers (GroupNorm, LayerNorm, attention, GEGLU) have no backward kernels yet, so this
+    is the LoRA-layer + exchange + optimizer part of train_t2v_turbo_v1_lora.py:1190-1194, not the whole student step."""
+    import math
+    import torch
+    from t2v_turbo_b200 import dist as t2v_dist, lora_train as lt, ops
+    from t2v_turbo_b200.configs import VC2_UNET
+    from t2v_turbo_b200.unet import UNetModel
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    t2v_dist.init_replicas("nccl", device)
+    with torch.device("meta"):
+        unet = UNetModel(**VC2_UNET)
+    work = lt.unet_lora_workload(unet)
+    arena = lt.arena_for_unet(unet, device, r=64)
+    gen = torch.Generator(device=device).manual_seed(7 + rank)
+    layers, acts, flops = [], {}, 0
+    from t2v_turbo_b200.lora import lora_target_layers
+    mods = dict(lora_target_layers(unet))
+    for i, (name, kind, pts, cin, cout) in enumerate(work):
+        if kind == "skip":
+            continue
+        m = mods[name]
+        wshape = tuple(m.weight.shape)
+        w = torch.randn(wshape, device=device, generator=gen) * (0.6 / math.prod(wshape[1:]) ** 0.5)
+        arena.param(2 * i).normal_(0, 0.02, generator=gen)             # lora_up (non-zero so that every GEMM does real work)
+        arena.param(2 * i + 1).normal_(0, 1.0 / 64, generator=gen)     # lora_down ~ N(0, 1/r)
+        pk = lt._PackedLora(kind, w, None, arena.param(2 * i), arena.param(2 * i + 1), 1.0)
+        del w
+        for key, ch in (("x", cin), ("dy", cout)):
+            if (key, pts, ch) not in acts:
+                acts[(key, pts, ch)] = torch.randn(*pts, ch, device=device, generator=gen).to(torch.bfloat16)
+        taps = dict(linear=1, conv2d=9, conv3d=3)[kind]
+        mm = math.prod(pts)
+        flops += 2 * mm * (2 * taps * cin * cout + 2 * (taps * cin * 64 + 64 * cout) + taps * cin * 64 + cout * 64)
+        layers.append((i, pk, acts[("x", pts, cin)], acts[("dy", pts, cout)]))
+    red = t2v_dist.ArenaReducer(arena.grads, n_buckets=8)
+
+    def step():
+        saved = []
+        for i, pk, x, dy in layers:                     # forward, arena order
+            _, t = lt.lora_forward(pk, x, None, 1.0)
+            saved.append(t)
+        arena.zero_grad()
+        for (i, pk, x, dy), t in zip(reversed(layers), reversed(saved)):   # backward, reverse order
+            lt.lora_backward(pk, x, t, None, 1.0, dy, arena.grad(2 * i), arena.grad(2 * i + 1))
+            red.ready(arena.offsets[2 * i])
+        red.finish()
+        arena.adamw_step(lr=1e-5, grad_scale=1.0 / world, max_grad_norm=1.0)
+
+    for _ in range(max(args.warmup, 2)):
+        step()
+    n0 = ops.LAUNCHES
+    sampler = ClockSampler(local_rank)
+    t2v_dist.barrier(device)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    t2v_dist.barrier(device)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - n0
+    # the exchange alone (same buffer, no overlap), for the all-reduce share
+    ar = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    torch.cuda.synchronize()
+    ar[0].record()
+    for _ in range(5):
+        red.ready(0)
+        red.finish()
+    ar[1].record()
+    torch.cuda.synchronize()
+    ar_ms = ar[0].elapsed_time(ar[1]) / 5
+    ms, ar_ms = t2v_dist.max_over_ranks([ms, ar_ms], device)
+    if rank == 0:
+        per = ms / args.steps
+        _emit(dict(metric="LoRA-layer forward+backward + gradient all-reduce + AdamW, steps/sec (one 16x320x512 sample per rank)",
+                   value=world * args.steps / (ms * 1e-3), unit="samples/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 2),
+                   ms_per_step=per, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                   config=dict(workload="567 LoRA-injected layers of the VC2 UNet (r=64), fwd+bwd at bs=1 per rank, fp32 gradient arena "
+                                        "117142176 values, bucketed NCCL all-reduce, fused AdamW", parallelism=f"dp{world}",
+                               not_included="backward of GroupNorm / LayerNorm / attention / GEGLU (not built)"),
+                   gpu_launches=launches, tflop_per_step=flops / 1e12, tflops=flops / (per * 1e-3) / 1e12,
+                   allreduce=dict(bytes=arena.padded * 4, ms_alone=ar_ms, share_of_step=ar_ms / per if world > 1 else 0.0,
+                                  gb_per_s=(arena.padded * 4 / (ar_ms * 1e-3) / 1e9) if world > 1 else None, buckets=8),
+                   clocks=clocks))
+    t2v_dist.shutdown()
+
+
 def main():
     _reserve_stdout()
     ap = argparse.ArgumentParser()
@@ -304,12 +401,17 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="videos per pipeline call per GPU (headline = 1)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "lora-step"],
+                    help="pipeline = the headline metric; lora-step = the data-parallel LoRA training exchange (supplementary)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "lora-step":
+        run_lora_step(args, rank, local_rank, world)
         return
     args.warmup = max(args.warmup, 3)
 

@@ -159,6 +159,11 @@ typedef struct T2VShortAttnDesc {
   int64_t v_stride_outer, v_stride_inner, v_stride_t, v_stride_h;
   int64_t o_stride_outer, o_stride_inner, o_stride_t, o_stride_h;
   float scale;
+  /* optional export of the attention probabilities (attention.py:124-126 `record_attn_probs`, consumed by the motion-prior
+   * code: motion_prior_sample.py:40-56): probs[(seq * heads + head)][query][key], seq = outer * n_seq_inner + inner — the
+   * reference's "(b h) i j" layout; dtype 0 bf16 / 1 fp16 / 2 fp32; NULL = off */
+  void* probs;
+  int32_t probs_dtype;
 } T2VShortAttnDesc;
 
 int t2v_attn_short_fwd(const T2VShortAttnDesc* desc, t2v_stream_t stream);

@@ -131,6 +131,20 @@ def gen_lora(name="small"):
     torch.save({"name": name, "seed": 4242, "layers": rec}, os.path.join(GOLD, f"lora_{name}.pt"))
 
 
+def gen_unet_probs():
+    """Attention-probability export: the reference UNet built with record_attn_probs=True keeps
+    softmax(q k^T) of the decoder's temporal self-attentions (attention.py:124-126; read by motion_prior_sample.py:40-56)."""
+    spec = UNET_CONFIGS["small"]
+    m = ref_unet({**spec["cfg"], "record_attn_probs": True}, spec["weight_seed"])
+    inp = unet_inputs(spec, 519)
+    with torch.no_grad():
+        y = m(inp["x"], inp["timesteps"], context=inp["context"], fps=inp["fps"], timestep_cond=inp["timestep_cond"])
+    probs = {n: mod.attention_probs.clone() for n, mod in m.named_modules()
+             if n.endswith("transformer_blocks.0.attn1") and getattr(mod, "attention_probs", None) is not None}
+    print("  recorded:", {k: tuple(v.shape) for k, v in probs.items()})
+    torch.save({"timestep": 519, "output": y, "probs": probs}, os.path.join(GOLD, "unet_small_probs.pt"))
+
+
 LORA_LAYER_CASES = {
     # kind: (ctor kwargs of the reference module, input shape in the reference layout)
     "linear": (dict(in_features=128, out_features=192, bias=True), (3, 100, 128)),
@@ -295,15 +309,17 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
             gen_scheduler()
-        elif item.startswith("unet_"):
+        elif item.startswith("unet_") and item != "unet_probs":
             gen_unet(item[5:])
         elif item == "lora_layers":
             gen_lora_layers()
+        elif item == "unet_probs":
+            gen_unet_probs()
         elif item.startswith("lora_"):
             gen_lora(item[5:])
         elif item.startswith("vae_enc_"):

@@ -86,6 +86,7 @@ class ShortAttnDesc(C.Structure):
         ("v_stride_outer", C.c_int64), ("v_stride_inner", C.c_int64), ("v_stride_t", C.c_int64), ("v_stride_h", C.c_int64),
         ("o_stride_outer", C.c_int64), ("o_stride_inner", C.c_int64), ("o_stride_t", C.c_int64), ("o_stride_h", C.c_int64),
         ("scale", C.c_float),
+        ("probs", C.c_void_p), ("probs_dtype", C.c_int32),
     ]
 
 

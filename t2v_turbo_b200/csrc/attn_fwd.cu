@@ -355,9 +355,11 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
     rc = make_tmap_bf16(&tv, d->v, 4, dims, strv, box, "t2v_attn_fwd V");
     if (rc) return rc;
   }
-  // default: the two-Q-tile kernel; T2V_ATTN_V1=1 selects the round-1 single-tile kernel (A/B measurements)
-  static const int use_v1 = (getenv("T2V_ATTN_V1") != nullptr && getenv("T2V_ATTN_V1")[0] == '1') ? 1 : 0;
-  if (!use_v1) return launch_attn_fwd2(d, tq, tk, tv, stream);
+  // T2V_ATTN_V2=1 selects the two-Q-tile kernel (attn_fwd2.cu: P in TMEM, polynomial exp2).  Measured on B200 (round 2,
+  // profiles/r02_attention.md): (16, 2560, 2560, 5) 219-228 us vs 228 us for this kernel, the small shapes 10-30 % slower
+  // (one CTA per SM) — so the single-tile kernel below stays the default.
+  static const int use_v2 = (getenv("T2V_ATTN_V2") != nullptr && getenv("T2V_ATTN_V2")[0] == '1') ? 1 : 0;
+  if (use_v2) return launch_attn_fwd2(d, tq, tk, tv, stream);
   AttnParams p;
   p.heads = d->heads;
   p.len_q = d->len_q;

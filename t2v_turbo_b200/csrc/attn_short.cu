@@ -10,12 +10,19 @@
 //   The work is HBM-bound: 4 x 128 B per token per layer.
 // 16 < len <= 32: scalar kernel (thread = query row), kept for generality.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "../../include/t2v_b200.h"
 #include "host_common.h"
 #include "ptx.cuh"
 
 namespace t2v {
+
+__device__ __forceinline__ void store_prob(void* p, int dtype, int64_t i, float v) {
+  if (dtype == 0) static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else if (dtype == 1) static_cast<__half*>(p)[i] = __float2half_rn(v);
+  else static_cast<float*>(p)[i] = v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // mma.sync path, len <= 16
@@ -132,6 +139,21 @@ __global__ void __launch_bounds__(kSaWarps * 32) attn_short_mma_kernel(const T2V
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
   const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  if (d.probs != nullptr) {
+    // attention-probability export (attention.py:124-126, `record_attn_probs`): probs[(seq * heads + h)][query][key]
+    const int64_t base = task * int64_t(len) * len;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = j * 8 + 2 * t + e;
+        if (col < len) {
+          if (g < len) store_prob(d.probs, d.probs_dtype, base + int64_t(g) * len + col, s[j][e] * inv0);
+          if (g + 8 < len) store_prob(d.probs, d.probs_dtype, base + int64_t(g + 8) * len + col, s[j][2 + e] * inv1);
+        }
+      }
+    }
+  }
   // P (bf16) as the A operand of O = P V: k = key index
   uint32_t pa[4];
   pa[0] = pack_bf16(s[0][0], s[0][1]);
@@ -248,6 +270,12 @@ __global__ void __launch_bounds__(kSaThreads) attn_short_kernel(const T2VShortAt
     sum += s[j];
   }
   const float inv = 1.0f / sum;
+  if (d.probs != nullptr) {
+    const int64_t base = (task * int64_t(len) + qi) * len;
+#pragma unroll
+    for (int j = 0; j < LEN_PAD; ++j)
+      if (j < len) store_prob(d.probs, d.probs_dtype, base + j, s[j] * inv);
+  }
   __nv_bfloat16* op = static_cast<__nv_bfloat16*>(d.o) + outer * d.o_stride_outer +
                       inner * d.o_stride_inner + int64_t(qi) * d.o_stride_t + h * d.o_stride_h;
 #pragma unroll
@@ -284,6 +312,7 @@ extern "C" int t2v_attn_short_fwd(const T2VShortAttnDesc* d, t2v_stream_t stream
   if (!d || !d->q || !d->k || !d->v || !d->o) return fail(-1, "t2v_attn_short_fwd: null pointer");
   if (d->len < 1 || d->len > 32) return fail(-2, "t2v_attn_short_fwd: len must be in [1,32] (got %d)", d->len);
   if (d->heads < 1 || d->n_seq_inner < 1 || d->n_seq_outer < 1) return fail(-3, "t2v_attn_short_fwd: bad sizes");
+  if (d->probs && (d->probs_dtype < 0 || d->probs_dtype > 2)) return fail(-6, "t2v_attn_short_fwd: probs_dtype must be 0 (bf16), 1 (fp16) or 2 (fp32)");
   const int64_t strides[] = {d->q_stride_outer, d->q_stride_inner, d->q_stride_t, d->q_stride_h,
                              d->k_stride_outer, d->k_stride_inner, d->k_stride_t, d->k_stride_h,
                              d->v_stride_outer, d->v_stride_inner, d->v_stride_t, d->v_stride_h,

@@ -341,3 +341,60 @@ def arena_for_unet(unet: nn.Module, device, r: int = 64) -> LoraArena:
     for up, down in lora_shapes(unet, r):
         shapes += [up, down]
     return LoraArena(shapes, device)
+
+
+def unet_lora_workload(unet: nn.Module, batch=1, frames=16, h=40, w=64, ctx_len=77):
+    """The LoRA target layers of a (B200) UNetModel with the activation geometry each one sees in a forward on
+    [batch, 4, frames, h, w] latents: [(name, kind, points, cin, cout)] in `named_modules()` order (= arena order), where
+    kind is linear | conv2d | conv3d | skip (not on the tensor-core training path: the 4-channel conv_in / out and the
+    strided / upsampling convolutions) and points is the channels-last point grid ([M] | [n, h, w] | [b, t, hw])."""
+    from .lora import lora_target_layers
+    from . import unet as U
+    geo = {}
+    n = batch * frames
+
+    def walk(seq, hh, ww):
+        for layer in seq:
+            if isinstance(layer, (U.ResBlock, U.SpatialTransformer, U.TemporalTransformer, U.Downsample, U.Upsample)):
+                geo[layer] = (hh, ww)
+            if isinstance(layer, U.Downsample):
+                hh, ww = hh // 2, ww // 2
+            elif isinstance(layer, U.Upsample):
+                hh, ww = hh * 2, ww * 2
+        return hh, ww
+    hh, ww = h, w
+    for blk in unet.input_blocks:
+        hh, ww = walk(blk, hh, ww)
+    if getattr(unet, "init_attn", None) is not None:
+        walk(unet.init_attn, h, w)
+    hh, ww = walk(unet.middle_block, hh, ww)
+    for blk in unet.output_blocks:
+        hh, ww = walk(blk, hh, ww)
+    owner = {}
+    for mod, g in geo.items():
+        for sub in mod.modules():
+            owner[sub] = (mod, g)
+    out = []
+    for name, m in lora_target_layers(unet):
+        cin = m.in_features if isinstance(m, nn.Linear) else m.in_channels
+        cout = m.out_features if isinstance(m, nn.Linear) else m.out_channels
+        if m not in owner:                       # time_embed / fps_embedding / cond projections: one row per sample
+            kind, pts = ("linear", (batch,)) if isinstance(m, nn.Linear) else ("skip", None)
+        else:
+            mod, (gh, gw) = owner[m]
+            if isinstance(mod, (U.Downsample, U.Upsample)):
+                kind, pts = "skip", None
+            elif isinstance(m, nn.Conv3d):
+                kind, pts = "conv3d", (batch, frames, gh * gw)
+            elif isinstance(m, nn.Conv2d):
+                kind, pts = ("conv2d", (n, gh, gw)) if m.kernel_size == (3, 3) else ("linear", (n * gh * gw,))
+            elif ".emb_layers." in name:
+                kind, pts = "linear", (batch,)
+            elif name.endswith(("attn2.to_k", "attn2.to_v")) and isinstance(mod, U.SpatialTransformer):
+                kind, pts = "linear", (n * ctx_len,)   # the reference projects the frame-repeated text context (openaimodel3d.py:710)
+            else:
+                kind, pts = "linear", (n * gh * gw,)
+        if kind != "skip" and (cin % 64 or cout % 64):
+            kind, pts = "skip", None
+        out.append((name, kind, pts, cin, cout))
+    return out

@@ -538,9 +538,11 @@ def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None):
     return out
 
 
-def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None):
+def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None, probs=None):
     """Temporal self-attention over token matrices laid out [(b t hw), H*64]: each of the b*hw pixels
-    attends over its t frames (token stride hw*row_stride).  Replaces the '(b hw) t c' regrouping."""
+    attends over its t frames (token stride hw*row_stride).  Replaces the '(b hw) t c' regrouping.
+    probs: optional [(b*hw*heads), t, t] tensor (bf16 / fp16 / fp32) receiving the attention probabilities in the
+    reference's "(b h) i j" layout (attention.py:124-126)."""
     rows, inner = q.shape
     assert rows == b * t * hw and inner == heads * 64
     if out is None:
@@ -555,6 +557,9 @@ def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None):
         setattr(d, f"{name}_stride_t", hw * rs)
         setattr(d, f"{name}_stride_h", 64)
     d.scale = scale
+    if probs is not None:
+        assert probs.is_cuda and probs.is_contiguous() and tuple(probs.shape) == (b * hw * heads, t, t)
+        d.probs, d.probs_dtype = probs.data_ptr(), _lib.DTYPE_CODE[probs.dtype]
     _FLOPS["attn_short_fwd"] = 4 * b * hw * heads * t * t * 64
     if _PROF is not None:
         _TAG["attn_short_fwd"] = f"b={b} hw={hw} H={heads} t={t}"

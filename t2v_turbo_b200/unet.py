@@ -74,8 +74,10 @@ class ResBlock(nn.Module):
 
 
 class CrossAttention(nn.Module):
-    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64):
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, record_attn_probs=False):
         super().__init__()
+        self.record_attn_probs = record_attn_probs   # attention.py:99-100: keep softmax(q k^T) of the last forward
+        self.attention_probs = None
         inner = heads * dim_head
         context_dim = context_dim or query_dim
         self.heads, self.dim_head, self.scale = heads, dim_head, dim_head ** -0.5
@@ -99,9 +101,9 @@ class FeedForward(nn.Module):
 
 
 class BasicTransformerBlock(nn.Module):
-    def __init__(self, dim, n_heads, d_head, context_dim=None):
+    def __init__(self, dim, n_heads, d_head, context_dim=None, record_attn_probs=False):
         super().__init__()
-        self.attn1 = CrossAttention(dim, None, n_heads, d_head)
+        self.attn1 = CrossAttention(dim, None, n_heads, d_head, record_attn_probs=record_attn_probs)   # attention.py:262-269
         self.ff = FeedForward(dim)
         self.attn2 = CrossAttention(dim, context_dim, n_heads, d_head)
         self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
@@ -122,14 +124,14 @@ class SpatialTransformer(nn.Module):
 
 
 class TemporalTransformer(nn.Module):
-    def __init__(self, in_channels, n_heads, d_head, depth=1, use_linear=False, only_self_att=True):
+    def __init__(self, in_channels, n_heads, d_head, depth=1, use_linear=False, only_self_att=True, record_attn_probs=False):
         super().__init__()
         assert depth == 1 and only_self_att, "VC2 config: temporal_selfatt_only, depth 1"
         inner = n_heads * d_head
         self.in_channels, self.use_linear = in_channels, use_linear
         self.norm = nn.GroupNorm(32, in_channels, eps=1e-6)
         self.proj_in = nn.Linear(in_channels, inner) if use_linear else nn.Conv1d(in_channels, inner, 1)
-        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, n_heads, d_head, None)])
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, n_heads, d_head, None, record_attn_probs=record_attn_probs)])
         self.proj_out = nn.Linear(inner, in_channels) if use_linear else nn.Conv1d(inner, in_channels, 1)
         nn.init.zeros_(self.proj_out.weight)
         nn.init.zeros_(self.proj_out.bias)
@@ -183,6 +185,8 @@ class _PackedTransformer:
         self.w_out, self.b_out = _w2d(m.proj_out.weight), _f32(m.proj_out.bias)
         self.blk = _PackedBlock(m.transformer_blocks[0], cross=not temporal)
         self.kv_slice = None  # (offset, inner) into the batched context K/V projection
+        a1 = m.transformer_blocks[0].attn1
+        self.record_attn = a1 if (temporal and getattr(a1, "record_attn_probs", False)) else None
 
 
 class _PackedRes:
@@ -223,8 +227,7 @@ class UNetModel(nn.Module):
         super().__init__()
         unsupported = dict(use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
                            tempspatial_aware=tempspatial_aware, use_relative_position=use_relative_position,
-                           use_causal_attention=use_causal_attention, use_image_attention=use_image_attention,
-                           record_attn_probs=record_attn_probs)
+                           use_causal_attention=use_causal_attention, use_image_attention=use_image_attention)
         bad = [k for k, v in unsupported.items() if v]
         if bad or dims != 2 or not conv_resample or num_head_channels != 64 or not temporal_attention:
             raise NotImplementedError(f"UNetModel(B200): options outside the VC2/T2V-Turbo config: {bad}")
@@ -254,11 +257,11 @@ class UNetModel(nn.Module):
         def res(cin, cout):
             return ResBlock(cin, ted, out_channels=cout, use_temporal_conv=temporal_conv)
 
-        def attn_layers(ch):
+        def attn_layers(ch, record=False):
             heads = ch // num_head_channels
             return [SpatialTransformer(ch, heads, num_head_channels, transformer_depth, context_dim, use_linear),
                     TemporalTransformer(ch, heads, num_head_channels, temporal_transformer_depth, use_linear,
-                                        temporal_selfatt_only)]
+                                        temporal_selfatt_only, record_attn_probs=record)]
 
         self.input_blocks = nn.ModuleList([_Seq(nn.Conv2d(in_channels, mc, 3, padding=1))])
         if addition_attention:
@@ -286,7 +289,9 @@ class UNetModel(nn.Module):
                 layers = [res(ch + ich, mult * mc)]
                 ch = mult * mc
                 if ds in attention_resolutions:
-                    layers += attn_layers(ch)
+                    # only the decoder's temporal self-attentions record (openaimodel3d.py:630-646); the motion-prior code
+                    # reads output_blocks.{3..11}.2.transformer_blocks.0.attn1.attention_probs (motion_prior_sample.py:40-56)
+                    layers += attn_layers(ch, record_attn_probs)
                 if level and i == num_res_blocks:
                     layers.append(Upsample(ch, ch))
                     ds //= 2
@@ -467,7 +472,7 @@ class UNetModel(nn.Module):
             return None
         return self._ws_alloc(frames * channels * 2, device)[:frames * channels * 2].view(frames, channels, 2)
 
-    def _block(self, blk: _PackedBlock, x, acc1, geom, temporal, ctx_kv, kv_slice):
+    def _block(self, blk: _PackedBlock, x, acc1, geom, temporal, ctx_kv, kv_slice, record=None):
         b, t, hh, ww = geom
         hw = hh * ww
         a1 = blk.a1
@@ -480,7 +485,13 @@ class UNetModel(nn.Module):
         qkv = ops.linear(x, a1.w_qkv, a1.b_qkv, ln=(acc1, a1.cs_qkv, (c, blk.ln_eps[0])))
         q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
         if temporal:
-            att = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=a1.heads, scale=a1.scale)
+            probs = None
+            if record is not None:   # "(b h) i j" softmax of the temporal self-attention, in the model dtype (attention.py:124-126)
+                pd = self.dtype if self.dtype in (torch.float16, BF16) else torch.float32
+                probs = torch.empty((b * hw * a1.heads, t, t), device=x.device, dtype=pd)
+            att = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=a1.heads, scale=a1.scale, probs=probs)
+            if record is not None:
+                record.attention_probs = probs
         else:
             att = ops.attention(q.view(b * t, hw, inner), k.view(b * t, hw, inner), v.view(b * t, hw, inner),
                                 heads=a1.heads, scale=a1.scale).view(-1, inner)
@@ -513,7 +524,7 @@ class UNetModel(nn.Module):
                            chan_group=t if pt.temporal else 1)
         acc1 = self._ln_slice(xn.shape[0], xn.device)
         x = ops.linear(xn, pt.w_in, pt.b_in, row_accum=acc1)
-        x = self._block(pt.blk, x, acc1, geom, pt.temporal, ctx_kv, pt.kv_slice)
+        x = self._block(pt.blk, x, acc1, geom, pt.temporal, ctx_kv, pt.kv_slice, record=pt.record_attn)
         so = self._gn_slice(b * t, c, h.device, c, "tr", (hh * ww, b * t, 1, 1), sdims=(1,))
         out = ops.linear_frames(x, pt.w_out, pt.b_out, hw=hh * ww, residual=x_in, stats=so)
         return out.view(b * t, hh, ww, c), so

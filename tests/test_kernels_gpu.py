@@ -566,6 +566,26 @@ def test_attention_temporal(cuda_device, b, t, hw, heads):
     assert_close(out, ref, what="attention temporal")
 
 
+@pytest.mark.parametrize("b,t,hw,heads,dtype", [(1, 16, 40, 2, torch.bfloat16), (2, 16, 33, 1, torch.float32), (1, 24, 10, 2, torch.float32)])
+def test_attention_temporal_prob_export(cuda_device, b, t, hw, heads, dtype):
+    """record_attn_probs (attention.py:124-126): softmax(q k^T * scale) in the reference's "(b h) i j" layout."""
+    ops = _ops()
+    inner = heads * 64
+    q = rnd(b * t * hw, inner, seed=148).to(BF16)
+    k = rnd(b * t * hw, inner, seed=149).to(BF16)
+    v = rnd(b * t * hw, inner, seed=150).to(BF16)
+    probs = torch.empty(b * hw * heads, t, t, device="cuda", dtype=dtype)
+    out = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=heads, scale=0.125, probs=probs)
+    out2 = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=heads, scale=0.125)
+    assert torch.equal(out, out2)
+
+    def seqs(x):  # (b t hw) (h d) -> ((b hw) h) t d
+        return x.view(b, t, hw, heads, 64).permute(0, 2, 3, 1, 4).reshape(b * hw * heads, t, 64).float()
+    ref = torch.softmax(seqs(q) @ seqs(k).transpose(1, 2) * 0.125, dim=-1)
+    assert_close(probs, ref, rtol=8e-3 if dtype == torch.bfloat16 else 2e-3, atol_scale=4e-3 if dtype == torch.bfloat16 else 1e-3,
+                 what=f"temporal attention probabilities t={t}")
+
+
 # ----------------------------------------------------------------------------- small ops
 def test_small_linear_and_sinusoid(cuda_device):
     ops = _ops()
