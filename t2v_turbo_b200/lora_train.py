@@ -126,7 +126,8 @@ class _PackedLora:
         if self.cin % 64 or self.cout % 64 or self.r % 64:
             raise NotImplementedError(f"LoRA layer {self.cin} -> {self.cout} (rank {self.r}): the tensor-core path needs channel "
                                       "counts and rank in multiples of 64 (every VC2 layer except the 4-channel conv_in / out)")
-        if kind == "linear":
+        if kind == "linear":   # nn.Linear, or a 1x1 convolution (ResBlock skip_connection) run as a per-pixel Linear
+            wd = wd.reshape(wd.shape[0], -1)
             self.w = wd.to(BF16).contiguous()                                   # [N, K]
             self.w_t = wd.t().to(BF16).contiguous()                             # [K, N]: dgrad operand
         else:
@@ -141,6 +142,7 @@ class _PackedLora:
         self.u = up.reshape(self.cout, self.r).to(BF16).contiguous()            # [N, r]
         self.u_t = up.reshape(self.cout, self.r).t().to(BF16).contiguous()      # [r, N]
         if self.kind == "linear":
+            down = down.reshape(self.r, -1)
             self.d = down.to(BF16).contiguous()                                 # [r, K]
             self.d_t = down.t().to(BF16).contiguous()                           # [K, r]
         else:
