@@ -141,6 +141,8 @@ typedef struct T2VAttnDesc {
   int64_t o_stride_b, o_stride_t, o_stride_h;
   int32_t kv_batch_div;                 /* kv batch index = q batch index / kv_batch_div (>= 1) */
   float scale;
+  int32_t causal;                       /* 1: key j is visible to query i iff j <= i (the CLIP text tower's attn_mask,
+                                           lvdm/modules/encoders/condition.py:262-266); 0 = no mask (the UNet) */
 } T2VAttnDesc;
 
 int t2v_attn_fwd(const T2VAttnDesc* desc, t2v_stream_t stream);
@@ -294,6 +296,15 @@ int t2v_lcm_step(const void* x, const void* eps, const void* noise, void* prev, 
  */
 int t2v_scale_add_rows(const void* x, const void* y, const float* a, const float* b, void* out, int64_t rows,
                        int64_t row_len, int32_t dtype, t2v_stream_t stream);
+
+/* Steps either side of the denoising path.
+ * out[i, :] = table[ids[i], :] + pos[i % ctx, :] as bf16: token + positional embedding of the OpenCLIP text tower
+ * (condition.py:262-263); table / pos dtype 0 bf16 / 1 fp16 / 2 fp32; ids int64. */
+int t2v_embedding_gather(const void* table, const void* pos, int32_t dtype, const int64_t* ids, void* out, int64_t n, int32_t width,
+                         int32_t ctx, int32_t vocab, t2v_stream_t stream);
+/* video [B, 3, T, H, W] (dtype 0 / 1 / 2) -> uint8 [B, T, H, W, 3] = trunc((clamp(v, -1, 1) + 1) / 2 * 255): the tensor
+ * post-processing of app.py:90-94 in one pass (the h264 encode that follows is host code, out of scope). */
+int t2v_video_to_uint8(const void* video, int32_t dtype, uint8_t* out, int32_t b, int32_t t, int32_t h, int32_t w, t2v_stream_t stream);
 
 /* KL-VAE posterior (lvdm/distributions.py:24-42 + ddpm3d.py:558-567): moments fp32 channels-last
  * [B*T, H, W, 2*zc] = (mean | logvar) -> out [B, zc, T, H, W] (out_dtype 0 bf16 / 1 fp16 / 2 fp32)

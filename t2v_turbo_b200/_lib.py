@@ -73,7 +73,7 @@ class AttnDesc(C.Structure):
         ("k_stride_b", C.c_int64), ("k_stride_t", C.c_int64), ("k_stride_h", C.c_int64),
         ("v_stride_b", C.c_int64), ("v_stride_t", C.c_int64), ("v_stride_h", C.c_int64),
         ("o_stride_b", C.c_int64), ("o_stride_t", C.c_int64), ("o_stride_h", C.c_int64),
-        ("kv_batch_div", C.c_int32), ("scale", C.c_float),
+        ("kv_batch_div", C.c_int32), ("scale", C.c_float), ("causal", C.c_int32),
     ]
 
 
@@ -167,6 +167,8 @@ SYMBOLS = {
     "t2v_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "t2v_sum_squares": (C.c_int, [_vp, _i64, _vp, _vp]),
     "t2v_mse_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "t2v_embedding_gather": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "t2v_video_to_uint8": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_scale_add_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "t2v_lcm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "t2v_pack_conv_weight": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp]),

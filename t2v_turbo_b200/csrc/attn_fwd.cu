@@ -35,6 +35,7 @@ constexpr int kOCol = 128;
 
 struct AttnParams {
   int32_t heads, len_q, len_k, n_q_tiles, n_kv_tiles, kv_batch_div;
+  int32_t causal;  // key j visible to query i iff j <= i (CLIP text tower); 0 = no mask
   float scale_log2;
   __nv_bfloat16* o;
   int64_t o_stride_b, o_stride_t, o_stride_h;
@@ -181,7 +182,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kv_left = p.len_k - j * kTile;  // valid keys in this tile (>= 1)
+      int kv_left = p.len_k - j * kTile;  // valid keys in this tile (>= 1)
+      if (p.causal) kv_left = min(kv_left, q0 + r - j * kTile + 1);  // per query row: keys up to the diagonal (may be <= 0)
       if (j == 0) {
         // first tile: exact row max
         float mx = -INFINITY;
@@ -359,7 +361,7 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
   // profiles/r02_attention.md): (16, 2560, 2560, 5) 219-228 us vs 228 us for this kernel, the small shapes 10-30 % slower
   // (one CTA per SM) — so the single-tile kernel below stays the default.
   static const int use_v2 = (getenv("T2V_ATTN_V2") != nullptr && getenv("T2V_ATTN_V2")[0] == '1') ? 1 : 0;
-  if (use_v2) return launch_attn_fwd2(d, tq, tk, tv, stream);
+  if (use_v2 && !d->causal) return launch_attn_fwd2(d, tq, tk, tv, stream);
   AttnParams p;
   p.heads = d->heads;
   p.len_q = d->len_q;
@@ -367,6 +369,7 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
   p.n_q_tiles = (d->len_q + kTile - 1) / kTile;
   p.n_kv_tiles = (d->len_k + kTile - 1) / kTile;
   p.kv_batch_div = d->kv_batch_div;
+  p.causal = d->causal ? 1 : 0;
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.o = static_cast<__nv_bfloat16*>(d->o);
   p.o_stride_b = d->o_stride_b;

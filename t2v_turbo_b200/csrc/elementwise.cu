@@ -315,6 +315,43 @@ __global__ void gaussian_sample_kernel(const float* __restrict__ mom, const floa
   }
 }
 
+// ------------------------------------------------------------------ text-tower token + positional embedding, video -> uint8
+__global__ void embedding_gather_kernel(const void* table, const void* pos, int dt, const int64_t* __restrict__ ids,
+                                        __nv_bfloat16* out, int64_t n, int width, int ctx, int vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = n * width;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = i / width;
+    const int c = int(i - row * width);
+    int64_t id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    float v = load_as_float(table, id * width + c, dt);
+    if (pos != nullptr) v = round_to(v + load_as_float(pos, (row % ctx) * int64_t(width) + c, dt), dt);   // x + positional_embedding in the model dtype
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void video_to_uint8_kernel(const void* video, int dt, uint8_t* out, int b, int t, int h, int w) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t plane = int64_t(h) * w;
+  const int64_t total = int64_t(b) * t * plane * 3;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    // i indexes the output [b][t][h*w][3]
+    const int c = int(i % 3);
+    int64_t r = i / 3;
+    const int64_t px = r % plane;
+    r /= plane;
+    const int ti = int(r % t);
+    const int bi = int(r / t);
+    float v = load_as_float(video, ((int64_t(bi) * 3 + c) * t + ti) * plane + px, dt);
+    v = fminf(fmaxf(v, -1.0f), 1.0f);
+    v = (v + 1.0f) / 2.0f;
+    out[i] = static_cast<uint8_t>(v * 255.0f);   // truncation, like torch's .to(torch.uint8)
+  }
+}
+
 // ------------------------------------------------------------------ per-row scaled sum (add_noise, DDIM solver lines)
 __global__ void scale_add_rows_kernel(const void* x, const void* y, const float* __restrict__ a, const float* __restrict__ b,
                                       void* out, int64_t rows, int64_t row_len, int dt) {
@@ -533,6 +570,25 @@ extern "C" int t2v_gaussian_sample(const float* moments, const float* noise, voi
                 out_dtype, b, t, h, w, zc, scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_gaussian_sample launch");
+}
+
+extern "C" int t2v_embedding_gather(const void* table, const void* pos, int32_t dtype, const int64_t* ids, void* out, int64_t n,
+                                    int32_t width, int32_t ctx, int32_t vocab, t2v_stream_t s) {
+  if (!table || !ids || !out || n < 1 || width < 1 || ctx < 1 || vocab < 1 || dtype < 0 || dtype > 2)
+    return fail(-1, "t2v_embedding_gather: bad argument");
+  launch_kernel(embedding_gather_kernel, dim3(grid_for(n * width)), dim3(256), 0, static_cast<cudaStream_t>(s), table, pos, dtype, ids,
+                static_cast<__nv_bfloat16*>(out), n, width, ctx, vocab);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_embedding_gather launch");
+}
+
+extern "C" int t2v_video_to_uint8(const void* video, int32_t dtype, uint8_t* out, int32_t b, int32_t t, int32_t h, int32_t w,
+                                  t2v_stream_t s) {
+  if (!video || !out || b < 1 || t < 1 || h < 1 || w < 1 || dtype < 0 || dtype > 2) return fail(-1, "t2v_video_to_uint8: bad argument");
+  launch_kernel(video_to_uint8_kernel, dim3(grid_for(int64_t(b) * t * h * w * 3)), dim3(256), 0, static_cast<cudaStream_t>(s), video, dtype,
+                out, b, t, h, w);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_video_to_uint8 launch");
 }
 
 extern "C" int t2v_scale_add_rows(const void* x, const void* y, const float* a, const float* b, void* out, int64_t rows,

@@ -513,7 +513,7 @@ def fold_layernorm(w, bias, gamma, beta):
     return wp, bp.contiguous(), wp.float().sum(1).contiguous()
 
 
-def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None):
+def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None, causal=False):
     """q: [Bq, Lq, H*64] view, k/v: [Bk, Lk, H*64] views (last dim contiguous; token/batch strides free).
     Returns o: [Bq, Lq, H*64]."""
     bq, lq, inner = q.shape
@@ -531,6 +531,7 @@ def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None):
     d.o_stride_b, d.o_stride_t, d.o_stride_h = out.stride(0), out.stride(1), 64
     d.kv_batch_div = kv_batch_div
     d.scale = scale
+    d.causal = 1 if causal else 0
     _FLOPS["attn_fwd"] = 4 * bq * heads * lq * lk * 64
     if _PROF is not None:
         _TAG["attn_fwd"] = f"B={bq} H={heads} Lq={lq} Lk={lk}"
@@ -644,6 +645,30 @@ def lcm_step(x, eps, noise, *, inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqr
                              x.numel(), _lib.DTYPE_CODE[x.dtype], inv_sqrt_alpha_t, sqrt_beta_t, c_skip, c_out,
                              sqrt_alpha_prev, sqrt_beta_prev, stream_ptr())
     return prev, den
+
+
+def embedding_gather(table, ids, pos=None):
+    """bf16 [n, W] = table[ids] (+ pos[i % ctx]): token + positional embedding (condition.py:262-263)."""
+    assert table.is_cuda and table.is_contiguous() and ids.dtype == torch.int64 and ids.is_cuda
+    ids = ids.contiguous().view(-1)
+    n, width = ids.numel(), table.shape[1]
+    out = torch.empty((n, width), device=table.device, dtype=BF16)
+    ctx = pos.shape[0] if pos is not None else 1
+    if pos is not None:
+        assert pos.dtype == table.dtype and pos.is_contiguous() and pos.shape[1] == width
+    _launch("embedding_gather", 0, lib().t2v_embedding_gather, table.data_ptr(), ptr(pos), _lib.DTYPE_CODE[table.dtype], ids.data_ptr(),
+            out.data_ptr(), n, width, ctx, table.shape[0], stream_ptr())
+    return out
+
+
+def video_to_uint8(video):
+    """[B, 3, T, H, W] in [-1, 1] -> uint8 [B, T, H, W, 3] (app.py:90-94: clamp, (v + 1) / 2 * 255, truncate, channels last)."""
+    assert video.is_cuda and video.is_contiguous() and video.dim() == 5 and video.shape[1] == 3
+    b, _, t, h, w = video.shape
+    out = torch.empty((b, t, h, w, 3), device=video.device, dtype=torch.uint8)
+    _launch("video_to_uint8", 0, lib().t2v_video_to_uint8, video.data_ptr(), _lib.DTYPE_CODE[video.dtype], out.data_ptr(), b, t, h, w,
+            stream_ptr())
+    return out
 
 
 def scale_add_rows(x, a, y=None, b=None):
