@@ -344,16 +344,46 @@ def run_lora_step(args, rank, local_rank, world):
         flops += 2 * mm * (2 * taps * cin * cout + 2 * (taps * cin * 64 + 64 * cout) + taps * cin * 64 + cout * 64)
         layers.append((i, pk, acts[("x", pts, cin)], acts[("dy", pts, cout)]))
     red = t2v_dist.ArenaReducer(arena.grads, n_buckets=8)
+    saved = [None] * len(layers)
+
+    def forward_all():
+        for k, (i, pk, x, dy) in enumerate(layers):                     # arena order
+            _, saved[k] = lt.lora_forward(pk, x, None, 1.0)
+
+    def backward_range(k_hi, k_lo):                                     # layers k_hi-1 .. k_lo, reverse order
+        for k in range(k_hi - 1, k_lo - 1, -1):
+            i, pk, x, dy = layers[k]
+            lt.lora_backward(pk, x, saved[k], None, 1.0, dy, arena.grad(2 * i), arena.grad(2 * i + 1))
+
+    # The backward is cut where the gradients cross a bucket boundary of the reducer: after segment s every gradient of
+    # bucket s is final and its all-reduce is issued while the next segment's GEMMs run.  Each segment (and the forward)
+    # is ONE CUDA graph — the step is ~5 700 small launches, host-bound when issued one by one through ctypes.
+    cuts, k_hi = [], len(layers)
+    for a, _ in reversed(red.bounds):
+        k_lo = min(next((k for k, (i, *_r) in enumerate(layers) if arena.offsets[2 * i] >= a), len(layers)), k_hi)
+        # after this segment every gradient at or above the first parameter of layer k_lo is final
+        cuts.append((k_hi, k_lo, arena.offsets[2 * layers[k_lo][0]] if k_lo < len(layers) else arena.padded))
+        k_hi = k_lo
+    use_graph = not args.no_graph
+
+    def capture(fn):
+        fn()                                                            # warm-up: lazy allocations, kernel attributes
+        torch.cuda.synchronize()
+        if not use_graph:
+            return fn
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g.replay
+    fwd = capture(forward_all)
+    segs = [(capture(lambda hi=hi, lo=lo: backward_range(hi, lo)), a) for hi, lo, a in cuts]
 
     def step():
-        saved = []
-        for i, pk, x, dy in layers:                     # forward, arena order
-            _, t = lt.lora_forward(pk, x, None, 1.0)
-            saved.append(t)
+        fwd()
         arena.zero_grad()
-        for (i, pk, x, dy), t in zip(reversed(layers), reversed(saved)):   # backward, reverse order
-            lt.lora_backward(pk, x, t, None, 1.0, dy, arena.grad(2 * i), arena.grad(2 * i + 1))
-            red.ready(arena.offsets[2 * i])
+        for run, a in segs:
+            run()
+            red.ready(a)
         red.finish()
         arena.adamw_step(lr=1e-5, grad_scale=1.0 / world, max_grad_norm=1.0)
 
@@ -390,7 +420,7 @@ def run_lora_step(args, rank, local_rank, world):
                    ms_per_step=per, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                    config=dict(workload="567 LoRA-injected layers of the VC2 UNet (r=64), fwd+bwd at bs=1 per rank, fp32 gradient arena "
                                         "117142176 values, bucketed NCCL all-reduce, fused AdamW", parallelism=f"dp{world}",
-                               not_included="backward of GroupNorm / LayerNorm / attention / GEGLU (not built)"),
+                               cuda_graph=use_graph, not_included="backward of GroupNorm / LayerNorm / attention / GEGLU (not built)"),
                    gpu_launches=launches, tflop_per_step=flops / 1e12, tflops=flops / (per * 1e-3) / 1e12,
                    allreduce=dict(bytes=arena.padded * 4, ms_alone=ar_ms, share_of_step=ar_ms / per if world > 1 else 0.0,
                                   gb_per_s=(arena.padded * 4 / (ar_ms * 1e-3) / 1e9) if world > 1 else None, buckets=8),
