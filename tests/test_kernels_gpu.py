@@ -333,12 +333,14 @@ def test_bmm_nt(cuda_device):
     assert_close(out, ref, what="bmm_nt")
 
 
-def test_conv_small_cin(cuda_device):
+@pytest.mark.parametrize("n,h,w,cout", [(3, 10, 16, 64), (2, 7, 10, 64), (16, 40, 64, 320), (2, 40, 64, 512), (1, 5, 4, 8)])
+def test_conv_small_cin(cuda_device, n, h, w, cout):
+    """4-channel latent conv: the 4-pixels-per-thread path (width % 4 == 0) and the one-pixel path (ragged width)."""
     ops = _ops()
-    x = rnd(3, 10, 16, 4, seed=31).to(BF16)
-    wt = rnd(64, 4, 3, 3, scale=1 / 6, seed=32).to(BF16)
-    b = rnd(64, seed=33)
-    out = ops.conv3x3_small_cin(x, ops.pack_conv_weight(wt), b, 64)
+    x = rnd(n, h, w, 4, seed=31).to(BF16)
+    wt = rnd(cout, 4, 3, 3, scale=1 / 6, seed=32).to(BF16)
+    b = rnd(cout, seed=33)
+    out = ops.conv3x3_small_cin(x, ops.pack_conv_weight(wt), b, cout)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1).permute(0, 2, 3, 1)
     assert_close(out, ref, what="conv small cin")
 
