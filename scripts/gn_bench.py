@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from t2v_turbo_b200 import ops
 dev = "cuda"
-CASES = [(16, 163840, 128), (16, 40960, 512)] if "big" in sys.argv[1:] else [(16, 2560, 320), (16, 2560, 640), (16, 640, 640), (16, 640, 1280), (16, 640, 1920), (16, 160, 1280), (16, 160, 2560), (16, 40, 1280), (16, 40, 2560)]
+CASES = [(16, 163840, 128), (16, 40960, 512), (128, 2560, 320), (128, 640, 640), (128, 160, 1280), (128, 40960, 256), (8, 40960, 320), (8, 10240, 1280)] if "big" in sys.argv[1:] else [(16, 2560, 320), (16, 2560, 640), (16, 640, 640), (16, 640, 1280), (16, 640, 1920), (16, 160, 1280), (16, 160, 2560), (16, 40, 1280), (16, 40, 2560)]
 for n, hw, c in CASES:
     x = torch.randn(n * hw, c, device=dev).bfloat16()
     g = torch.randn(c, device=dev); b = torch.randn(c, device=dev)
@@ -26,4 +26,4 @@ for n, hw, c in CASES:
             res.append(float("nan"))
     mb = n * hw * c * 2 / 1e6
     res = res + [float("nan")] * (2 - len(res))
-    print(f"n={n} hw={hw} c={c} ({mb:.1f} MB): two-kernel {res[0]:.1f} us ({3 * mb / res[0] * 1e-3:.2f} TB/s of 3 passes), cluster {res[1]:.1f} us", flush=True)
+    print(f"n={n} hw={hw} c={c} ({mb:.1f} MB): two-kernel {res[0]:.1f} us ({3 * mb / res[0]:.2f} TB/s of 3 passes), cluster {res[1]:.1f} us", flush=True)

@@ -121,7 +121,14 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
 // The statistics workspace is SELF-CLEANING: every apply block copies its sample's sums to shared memory, then
 // takes a ticket; the block that draws the last ticket knows every block has read the sums and zeroes them (and
 // the ticket counter), so the next GroupNorm call finds a zeroed workspace without a memset / zero kernel.
-__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) {
+//
+// SiLU(y) = y * sigmoid(y) = h + h * tanh(h) with h = y / 2: the 1/2 is folded into the per-channel scale / shift, so an
+// element costs FFMA + MUFU.TANH + FFMA (was FFMA, FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL: the XU pipe sat at 64 % and
+// the kernel at 4.4 TB/s of the 6.5 TB/s the statistics pass reaches; profiles/r02_groupnorm.md).  tanh.approx is good
+// to 2^-11 relative, i.e. an absolute error <= |h| * 4.9e-4 -- below the bf16 rounding of the output for y > -3 and
+// under 1.3e-3 absolute in the negative tail.
+template <bool kSilu, int kMinBlocks>
+__global__ void __launch_bounds__(kGnThreads, kMinBlocks) gn_apply_kernel(const GnParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_ws[2 * 64];
@@ -184,9 +191,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) 
       float var = ws[2 * g + 1] * inv_n - mean * mean;
       var = var < 0.f ? 0.f : var;
       const float rstd = rsqrtf(var + p.eps);
-      const float ga = __ldg(p.gamma + c);
+      const float ga = __ldg(p.gamma + c) * (kSilu ? 0.5f : 1.0f);
       sc[j] = rstd * ga;
-      sh[j] = __ldg(p.beta + c) - mean * rstd * ga;
+      sh[j] = __ldg(p.beta + c) * (kSilu ? 0.5f : 1.0f) - mean * rstd * ga;
     }
     const bool src1 = cv >= p.ncv0;
     const __nv_bfloat16* xp = src1 ? p.x1 + (cv - p.ncv0) * 8 : p.x0 + cv * 8;
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float y = fmaf(f[j], sc[j], sh[j]);
-            if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+            if (kSilu) y = fmaf(y, tanh_approx(y), y);
             f[j] = y;
           }
           uint4 o;
@@ -330,9 +337,10 @@ __global__ void __launch_bounds__(kGcThreads) gn_cluster_kernel(const GnParams p
       float var = s_tot[2 * g + 1] * inv_n - mean * mean;
       var = var < 0.f ? 0.f : var;
       const float rstd = rsqrtf(var + p.eps);
-      const float ga = __ldg(p.gamma + c);
+      const float half = p.silu ? 0.5f : 1.0f;  // SiLU through tanh of y / 2, as gn_apply_kernel
+      const float ga = __ldg(p.gamma + c) * half;
       sc[j] = rstd * ga;
-      sh[j] = __ldg(p.beta + c) - mean * rstd * ga;
+      sh[j] = __ldg(p.beta + c) * half - mean * rstd * ga;
     }
     __nv_bfloat16* op = p.out + cv * 8 + base_row * p.out_rs;
     for (int r = rr; r < nrows; r += rpp) {
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(kGcThreads) gn_cluster_kernel(const GnParams p
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float y = fmaf(f[j], sc[j], sh[j]);
-        if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+        if (p.silu) y = fmaf(y, tanh_approx(y), y);
         f[j] = y;
       }
       uint4 o;
@@ -552,7 +560,9 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   }
   const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;
   const int rpp = kGnThreads / tpr;
-  int64_t want_blocks = (int64_t(sms) * 4 + n_samples - 1) / n_samples;
+  static const int bps_knob = getenv("T2V_GN_BPS") ? atoi(getenv("T2V_GN_BPS")) : 4;   // experiment knobs
+  static const int regs_knob = getenv("T2V_GN_MINB") ? atoi(getenv("T2V_GN_MINB")) : 4;
+  int64_t want_blocks = (int64_t(sms) * bps_knob + n_samples - 1) / n_samples;
   if (want_blocks < 1) want_blocks = 1;
   int64_t rpb = (d->rows_per_sample + want_blocks - 1) / want_blocks;
   const int64_t min_rpb = int64_t(rpp) * 4;
@@ -565,7 +575,9 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   cudaError_t e;
   dim3 grid((unsigned)bps, (unsigned)n_samples);
   if (!have_sums) launch_kernel(gn_stats_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
-  launch_kernel(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
+  if (!p.silu) launch_kernel(gn_apply_kernel<false, 4>, dim3(grid), dim3(kGnThreads), 0, stream, p);
+  else if (regs_knob >= 5) launch_kernel(gn_apply_kernel<true, 5>, dim3(grid), dim3(kGnThreads), 0, stream, p);
+  else launch_kernel(gn_apply_kernel<true, 4>, dim3(grid), dim3(kGnThreads), 0, stream, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "t2v_groupnorm launch");
   return 0;
