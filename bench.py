@@ -272,7 +272,7 @@ def run_reference(args, rank, world):
     fps = FRAMES / t_video
     line = dict(impl="reference", metric="4-step 16x320x512 frames/sec", value=fps, unit="frames/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=(t_unet + t_frame) * 1e3, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype=dtype, data="synthetic", config=dict(workload=WORKLOAD % args.batch),
+                vs_baseline=None, dtype=dtype, data="synthetic", config=dict(workload=WORKLOAD % args.batch, videos_per_step=args.batch),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind=kind,
                                   sample=desc + f"; measured t_unet {t_unet:.2f} s, t_frame {t_frame:.2f} s per step "
                                                 f"(ms_per_step = t_unet + t_frame, the wall time of one step; value = 16 frames / "
@@ -548,7 +548,7 @@ def main():
         line = dict(metric="4-step 16x320x512 frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic",
-                    config=dict(workload=WORKLOAD % bs,
+                    config=dict(workload=WORKLOAD % bs, videos_per_step=bs,
                                 parallelism=f"replicas x{world} (no data-path collective)", cuda_graph=not args.no_graph,
                                 l2="working set per step (2.83 GB weights x4 + activations) >> 126 MB L2; no flush needed",
                                 batch_note="throughput configuration: bs videos per pipeline call (bs=1 latency numbers: unet_fwd_ms, "

@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
 // the kernel at 4.4 TB/s of the 6.5 TB/s the statistics pass reaches; profiles/r02_groupnorm.md).  tanh.approx is good
 // to 2^-11 relative, i.e. an absolute error <= |h| * 4.9e-4 -- below the bf16 rounding of the output for y > -3 and
 // under 1.3e-3 absolute in the negative tail.
-template <bool kSilu, int kMinBlocks>
-__global__ void __launch_bounds__(kGnThreads, kMinBlocks) gn_apply_kernel(const GnParams p) {
+template <bool kSilu>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_ws[2 * 64];
@@ -560,9 +560,9 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   }
   const int tpr = p.ncv < kGnThreads ? p.ncv : kGnThreads;
   const int rpp = kGnThreads / tpr;
-  static const int bps_knob = getenv("T2V_GN_BPS") ? atoi(getenv("T2V_GN_BPS")) : 4;   // experiment knobs
-  static const int regs_knob = getenv("T2V_GN_MINB") ? atoi(getenv("T2V_GN_MINB")) : 4;
-  int64_t want_blocks = (int64_t(sms) * bps_knob + n_samples - 1) / n_samples;
+  // 8 blocks per SM (two waves of the 4 resident ones): measured 1-12 % faster than one wave on every shape of the
+  // bs = 8 step; 48-register variants (5 resident blocks) spill and lose 15-20 % (profiles/r02_groupnorm.md)
+  int64_t want_blocks = (int64_t(sms) * 8 + n_samples - 1) / n_samples;
   if (want_blocks < 1) want_blocks = 1;
   int64_t rpb = (d->rows_per_sample + want_blocks - 1) / want_blocks;
   const int64_t min_rpb = int64_t(rpp) * 4;
@@ -575,9 +575,8 @@ extern "C" int t2v_groupnorm(const T2VGroupNormDesc* d, t2v_stream_t stream_) {
   cudaError_t e;
   dim3 grid((unsigned)bps, (unsigned)n_samples);
   if (!have_sums) launch_kernel(gn_stats_kernel, dim3(grid), dim3(kGnThreads), 0, stream, p);
-  if (!p.silu) launch_kernel(gn_apply_kernel<false, 4>, dim3(grid), dim3(kGnThreads), 0, stream, p);
-  else if (regs_knob >= 5) launch_kernel(gn_apply_kernel<true, 5>, dim3(grid), dim3(kGnThreads), 0, stream, p);
-  else launch_kernel(gn_apply_kernel<true, 4>, dim3(grid), dim3(kGnThreads), 0, stream, p);
+  if (p.silu) launch_kernel(gn_apply_kernel<true>, dim3(grid), dim3(kGnThreads), 0, stream, p);
+  else launch_kernel(gn_apply_kernel<false>, dim3(grid), dim3(kGnThreads), 0, stream, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "t2v_groupnorm launch");
   return 0;

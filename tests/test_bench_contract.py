@@ -16,7 +16,7 @@ def _load(name):
 
 
 def test_device_arm_line():
-    d = _load("r01_bench_final.json")
+    d = _load("r02_bench_default.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -24,10 +24,12 @@ def test_device_arm_line():
     assert d["dtype"] == "bf16" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["warmup"] >= 3 and d["gpu_launches"] > 0
-    # value = 16 frames per step per GPU / device time
-    assert abs(d["value"] - 16 * d["n_gpus"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    # value = 16 frames per video x videos per step per GPU / device time
+    bs = d["config"].get("videos_per_step") or int(d["config"]["workload"].split("bs=")[1].split()[0])
+    assert abs(d["value"] - 16 * bs * d["n_gpus"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
     e = d["e2e"]
-    assert e["unit"] == "frames/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 16 * 3 * 320 * 512 * 2
+    assert e["unit"] == "frames/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == bs * 16 * 3 * 320 * 512 * 2
+    assert e["value"] < d["value"]  # copies inside the timed region: never just a repeat of the device-timed number
     r = d["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] is None or r["traffic"] > 0
@@ -38,13 +40,14 @@ def test_device_arm_line():
 
 
 def test_reference_arm_line():
-    d = _load("r01_bench_v7_reference_arm.json")
+    d = _load("r02_bench_reference_arm.json")
     assert d["impl"] == "reference" and d["metric"] == "4-step 16x320x512 frames/sec" and d["unit"] == "frames/s"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["config"]["workload"] == _load("r02_bench_default.json")["config"]["workload"]   # the same workload as our arm
 
 
 def test_two_gpu_line_is_weak_scaling_aggregate():
-    one, two = _load("r01_bench_final.json"), _load("r01_bench_final_2gpu.json")
+    one, two = _load("r02_bench_default.json"), _load("r02_bench_2gpu.json")
     assert two["n_gpus"] == 2 and two["scaling"] == "weak"
     assert 1.8 < two["value"] / one["value"] < 2.2
