@@ -143,6 +143,8 @@ typedef struct T2VAttnDesc {
   float scale;
   int32_t causal;                       /* 1: key j is visible to query i iff j <= i (the CLIP text tower's attn_mask,
                                            lvdm/modules/encoders/condition.py:262-266); 0 = no mask (the UNet) */
+  float* lse2;                          /* optional fp32 [batch][heads][len_q]: log2(sum_j exp2(scale*log2e * q.k_j)) per row, kept
+                                           for t2v_attn_bwd; NULL = not written */
 } T2VAttnDesc;
 
 int t2v_attn_fwd(const T2VAttnDesc* desc, t2v_stream_t stream);
@@ -358,6 +360,91 @@ int t2v_sum_squares(const float* x, int64_t n, float* out, t2v_stream_t stream);
  * loss[0] += sum (a - b)^2 / n ; grad[i] = 2 (a[i] - b[i]) / n * grad_scale in the dtype of a (0 bf16, 1 fp16, 2 fp32). */
 int t2v_mse_loss_grad(const void* a, const void* b, void* grad, float* loss, int64_t n, int32_t dtype, float grad_scale,
                       t2v_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Student backward (train_t2v_turbo_v1_lora.py:1190 `accelerator.backward(distill_loss)` through the LoRA-injected UNet):
+ * adjoints of the non-GEMM layers.  Only the LoRA weights train, so none of these produces gamma / beta / bias gradients.
+ * Gradients are channels-last bf16 like the activations; arithmetic and statistics fp32. */
+
+/* GroupNorm (+SiLU) backward (adjoint of t2v_groupnorm; basics.py:78-89, openaimodel3d.py:155-159,179-184,275-295):
+ * dx = rstd * (dyh - mean_g(dyh) - xh * mean_g(dyh * xh)) (+ dx_add), dyh = dy * act'(xh * gamma + beta) * gamma.
+ * workspace: fp32 [n_samples * groups * 4], ZERO on entry (left holding the statistics). */
+typedef struct T2VGroupNormBwdDesc {
+  const void* x; int64_t x_row_stride;       /* forward input, bf16 [rows, channels] */
+  const void* dy; int64_t dy_row_stride;     /* gradient of the forward output */
+  const void* dx_add; int64_t dx_add_row_stride; /* optional: added to dx (a second gradient path into x); may be NULL */
+  void* dx; int64_t dx_row_stride;
+  const float* gamma; const float* beta;
+  int64_t rows, rows_per_sample;
+  int32_t channels, groups; float eps; int32_t silu;
+  float* workspace;
+} T2VGroupNormBwdDesc;
+int t2v_groupnorm_bwd(const T2VGroupNormBwdDesc* desc, t2v_stream_t stream);
+
+/* LayerNorm backward (attention.py:279-281,300-311), one warp per row, statistics recomputed: channels in
+ * {64, 128, 320, 640, 1024, 1280}; dx_add (optional) is the residual-path gradient summed into dx. */
+int t2v_layernorm_bwd(const void* x, int64_t x_row_stride, const void* dy, int64_t dy_row_stride, const void* dx_add,
+                      int64_t dx_add_row_stride, void* dx, int64_t dx_row_stride, const float* gamma, int64_t rows,
+                      int32_t channels, float eps, t2v_stream_t stream);
+
+/* GEGLU (attention.py:516-523), unfused for training: pre = [a | gate] bf16 [rows, 2*inner].
+ * dout == NULL: out[rows, inner] = a * gelu_erf(gate);  else: out[rows, 2*inner] = d(pre) given dout[rows, inner]. */
+int t2v_geglu(const void* pre, int64_t pre_row_stride, const void* dout, int64_t dout_row_stride, void* out,
+              int64_t out_row_stride, int64_t rows, int32_t inner, t2v_stream_t stream);
+
+/* Row-strided elementwise bf16 [rows, channels]: op 0 out = a + b (gradient accumulation at a fan-out);
+ * op 1 out = silu(a); op 2 out = b * silu'(a) (the SiLU of emb_layers / time_embed, openaimodel3d.py:172-178,403-411). */
+int t2v_ew2d(int32_t op, const void* a, int64_t a_row_stride, const void* b, int64_t b_row_stride, void* out,
+             int64_t out_row_stride, int64_t rows, int32_t channels, t2v_stream_t stream);
+
+/* out[s, c] += sum of x[row, c] over the rows of sample s (fp32 [rows / rows_per_sample, channels], accumulated into):
+ * adjoint of the broadcast timestep-embedding add h + emb_out[:, :, None, None] (openaimodel3d.py:237-246). */
+int t2v_colsum_samples(const void* x, int64_t x_row_stride, float* out, int64_t rows, int64_t rows_per_sample,
+                       int32_t channels, t2v_stream_t stream);
+
+/* 2x resampling of [n, h, w, channels] frames; (h_out, w_out) are the OUTPUT extents.
+ * mode 0: out[y, x] = in[2y, 2x] (a stride-2 / pad-1 conv is the stride-1 conv subsampled: Downsample, openaimodel3d.py:104-111);
+ * mode 1: zero stuffing out[2y, 2x] = in[y, x], 0 elsewhere (adjoint of mode 0);
+ * mode 2: out[y, x] = sum of the 2x2 block of in (adjoint of the nearest 2x upsampling, openaimodel3d.py:65-72). */
+int t2v_resample2x(int32_t mode, const void* in, void* out, int64_t n, int32_t h_out, int32_t w_out, int32_t channels,
+                   t2v_stream_t stream);
+
+/* delta[b, h, i] = sum_d dO[b,i,h,d] * O[b,i,h,d] (fp32 [batch][heads][len]): the row term of the softmax Jacobian. */
+int t2v_attn_delta(const void* o, int64_t o_stride_b, int64_t o_stride_t, int64_t o_stride_h, const void* d_o,
+                   int64_t do_stride_b, int64_t do_stride_t, int64_t do_stride_h, float* delta, int32_t batch, int32_t heads,
+                   int32_t len, t2v_stream_t stream);
+
+/* Flash-attention backward on tcgen05 (adjoint of t2v_attn_fwd, head_dim 64, no mask; attention.py:121-149,198-224):
+ *   P = exp2(scale*log2e * Q K^T - lse2),  dP = dO V^T,  dS = P * (dP - delta) * scale
+ *   dQ = dS K,   dK = dS^T Q,   dV = P^T dO
+ * lse2[b][h][i] = log2-domain log-sum-exp of row i (written by t2v_attn_fwd when T2VAttnDesc.lse2 is set), delta from
+ * t2v_attn_delta.  Two launches of one kernel: row tiles over queries (dQ) and row tiles over keys (dK, dV; the query
+ * batches sharing a K/V batch are looped inside the CTA, no atomics).  Any of dq / (dk, dv) may be NULL to skip that half. */
+typedef struct T2VAttnBwdDesc {
+  const void* q; const void* k; const void* v; const void* d_o;
+  const float* lse2; const float* delta;
+  void* dq; void* dk; void* dv;
+  int32_t batch, heads, len_q, len_k;
+  int64_t q_stride_b, q_stride_t, q_stride_h;       /* q, d_o, dq share the query geometry but have their own strides */
+  int64_t k_stride_b, k_stride_t, k_stride_h;
+  int64_t v_stride_b, v_stride_t, v_stride_h;
+  int64_t do_stride_b, do_stride_t, do_stride_h;
+  int64_t dq_stride_b, dq_stride_t, dq_stride_h;
+  int64_t dk_stride_b, dk_stride_t, dk_stride_h;
+  int64_t dv_stride_b, dv_stride_t, dv_stride_h;
+  int32_t kv_batch_div;
+  float scale;
+} T2VAttnBwdDesc;
+int t2v_attn_bwd(const T2VAttnBwdDesc* desc, t2v_stream_t stream);
+
+/* Short-sequence attention backward (adjoint of t2v_attn_short_fwd; temporal self-attention, attention.py:471-513):
+ * one warp per (sequence, head), probabilities recomputed; d_o / dq / dk / dv use the strides of o / q / k / v. */
+typedef struct T2VShortAttnBwdDesc {
+  T2VShortAttnDesc fwd;                 /* q, k, v and their strides, o strides (o itself unused), scale; probs ignored */
+  const void* d_o;                      /* gradient of o, o's strides */
+  void* dq; void* dk; void* dv;         /* q's / k's / v's strides */
+} T2VShortAttnBwdDesc;
+int t2v_attn_short_bwd(const T2VShortAttnBwdDesc* desc, t2v_stream_t stream);
 
 /* Weight packing helpers (device-side, run once at load). */
 /* conv weight [Cout][Cin][kh*kw] (torch OIHW / OIDHW flattened taps) -> [Cout][taps][Cin] bf16 */

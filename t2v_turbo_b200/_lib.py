@@ -74,6 +74,7 @@ class AttnDesc(C.Structure):
         ("v_stride_b", C.c_int64), ("v_stride_t", C.c_int64), ("v_stride_h", C.c_int64),
         ("o_stride_b", C.c_int64), ("o_stride_t", C.c_int64), ("o_stride_h", C.c_int64),
         ("kv_batch_div", C.c_int32), ("scale", C.c_float), ("causal", C.c_int32),
+        ("lse2", C.c_void_p),
     ]
 
 
@@ -140,6 +141,34 @@ class WgradDesc(C.Structure):
     ]
 
 
+class GroupNormBwdDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_row_stride", C.c_int64),
+        ("dy", C.c_void_p), ("dy_row_stride", C.c_int64),
+        ("dx_add", C.c_void_p), ("dx_add_row_stride", C.c_int64),
+        ("dx", C.c_void_p), ("dx_row_stride", C.c_int64),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("rows", C.c_int64), ("rows_per_sample", C.c_int64),
+        ("channels", C.c_int32), ("groups", C.c_int32), ("eps", C.c_float), ("silu", C.c_int32),
+        ("workspace", C.c_void_p),
+    ]
+
+
+class AttnBwdDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("d_o", C.c_void_p),
+        ("lse2", C.c_void_p), ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("len_q", C.c_int32), ("len_k", C.c_int32),
+    ] + [(f"{n}_stride_{a}", C.c_int64) for n in ("q", "k", "v", "do", "dq", "dk", "dv") for a in ("b", "t", "h")] + [
+        ("kv_batch_div", C.c_int32), ("scale", C.c_float),
+    ]
+
+
+class ShortAttnBwdDesc(C.Structure):
+    _fields_ = [("fwd", ShortAttnDesc), ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p)]
+
+
 # every symbol include/t2v_b200.h declares: (name, restype, argtypes)
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 SYMBOLS = {
@@ -167,6 +196,15 @@ SYMBOLS = {
     "t2v_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "t2v_sum_squares": (C.c_int, [_vp, _i64, _vp, _vp]),
     "t2v_mse_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "t2v_groupnorm_bwd": (C.c_int, [C.POINTER(GroupNormBwdDesc), _vp]),
+    "t2v_layernorm_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _f32, _vp]),
+    "t2v_geglu": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "t2v_ew2d": (C.c_int, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "t2v_colsum_samples": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "t2v_resample2x": (C.c_int, [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "t2v_attn_delta": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _vp]),
+    "t2v_attn_bwd": (C.c_int, [C.POINTER(AttnBwdDesc), _vp]),
+    "t2v_attn_short_bwd": (C.c_int, [C.POINTER(ShortAttnBwdDesc), _vp]),
     "t2v_embedding_gather": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "t2v_video_to_uint8": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_scale_add_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),

@@ -39,6 +39,7 @@ struct AttnParams {
   float scale_log2;
   __nv_bfloat16* o;
   int64_t o_stride_b, o_stride_t, o_stride_h;
+  float* lse2;  // optional [batch][heads][len_q]
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -291,6 +292,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // epilogue: O / l -> bf16 -> global
     const int qi = q0 + r;
     const float inv_l = 1.0f / l_run;
+    if (p.lse2 != nullptr && qi < p.len_q) p.lse2[(int64_t(b) * p.heads + h) * p.len_q + qi] = m_ref + log2f(l_run);
     __nv_bfloat16* orow = p.o + int64_t(b) * p.o_stride_b + int64_t(qi) * p.o_stride_t + int64_t(h) * p.o_stride_h;
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -361,7 +363,7 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
   // profiles/r02_attention.md): (16, 2560, 2560, 5) 219-228 us vs 228 us for this kernel, the small shapes 10-30 % slower
   // (one CTA per SM) — so the single-tile kernel below stays the default.
   static const int use_v2 = (getenv("T2V_ATTN_V2") != nullptr && getenv("T2V_ATTN_V2")[0] == '1') ? 1 : 0;
-  if (use_v2 && !d->causal) return launch_attn_fwd2(d, tq, tk, tv, stream);
+  if (use_v2 && !d->causal && !d->lse2) return launch_attn_fwd2(d, tq, tk, tv, stream);
   AttnParams p;
   p.heads = d->heads;
   p.len_q = d->len_q;
@@ -375,6 +377,7 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
   p.o_stride_b = d->o_stride_b;
   p.o_stride_t = d->o_stride_t;
   p.o_stride_h = d->o_stride_h;
+  p.lse2 = d->lse2;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem);

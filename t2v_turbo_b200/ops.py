@@ -513,9 +513,10 @@ def fold_layernorm(w, bias, gamma, beta):
     return wp, bp.contiguous(), wp.float().sum(1).contiguous()
 
 
-def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None, causal=False):
+def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None, causal=False, lse2=None):
     """q: [Bq, Lq, H*64] view, k/v: [Bk, Lk, H*64] views (last dim contiguous; token/batch strides free).
-    Returns o: [Bq, Lq, H*64]."""
+    Returns o: [Bq, Lq, H*64].  lse2: optional fp32 [Bq, H, Lq] receiving the log2-domain row log-sum-exp (kept for
+    attention_bwd)."""
     bq, lq, inner = q.shape
     bk, lk, _ = k.shape
     assert inner == heads * 64 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
@@ -532,6 +533,9 @@ def attention(q, k, v, *, heads, scale, kv_batch_div=1, out=None, causal=False):
     d.kv_batch_div = kv_batch_div
     d.scale = scale
     d.causal = 1 if causal else 0
+    if lse2 is not None:
+        assert lse2.dtype == torch.float32 and lse2.is_contiguous() and tuple(lse2.shape) == (bq, heads, lq)
+        d.lse2 = lse2.data_ptr()
     _FLOPS["attn_fwd"] = 4 * bq * heads * lq * lk * 64
     if _PROF is not None:
         _TAG["attn_fwd"] = f"B={bq} H={heads} Lq={lq} Lk={lk}"
@@ -566,6 +570,162 @@ def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None, probs=None)
         _TAG["attn_short_fwd"] = f"b={b} hw={hw} H={heads} t={t}"
     _launch("attn_short_fwd", _FLOPS.pop("attn_short_fwd", 0), lib().t2v_attn_short_fwd, C.byref(d), stream_ptr())
     return out
+
+
+# ----------------------------------------------------------------------------- student backward (non-GEMM layers)
+def _rows2d(x, name):
+    assert x.is_cuda and x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1, f"{name}: CUDA bf16 [rows, C] with contiguous channels"
+    return x
+
+
+def groupnorm_bwd(x, dy, gamma, beta, *, rows_per_sample, eps, silu, groups=32, dx_add=None, out=None):
+    """Adjoint of groupnorm (+SiLU) w.r.t. x.  x / dy: bf16 [rows, C] (row strides free); dx_add: optional second gradient
+    path summed into the result."""
+    _rows2d(x, "x"); _rows2d(dy, "dy")
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty((rows, c), device=x.device, dtype=BF16)
+    n_samples = rows // rows_per_sample
+    ws = torch.zeros((n_samples * groups * 4,), device=x.device, dtype=torch.float32)
+    d = _lib.GroupNormBwdDesc()
+    d.x, d.x_row_stride = x.data_ptr(), x.stride(0)
+    d.dy, d.dy_row_stride = dy.data_ptr(), dy.stride(0)
+    if dx_add is not None:
+        _rows2d(dx_add, "dx_add")
+        d.dx_add, d.dx_add_row_stride = dx_add.data_ptr(), dx_add.stride(0)
+    d.dx, d.dx_row_stride = out.data_ptr(), out.stride(0)
+    d.gamma, d.beta = gamma.data_ptr(), beta.data_ptr()
+    d.rows, d.rows_per_sample = rows, rows_per_sample
+    d.channels, d.groups, d.eps, d.silu = c, groups, eps, 1 if silu else 0
+    d.workspace = ws.data_ptr()
+    _launch("groupnorm_bwd", 0, lib().t2v_groupnorm_bwd, C.byref(d), stream_ptr())
+    return out
+
+
+def layernorm_bwd(x, dy, gamma, eps=1e-5, *, dx_add=None, out=None):
+    _rows2d(x, "x"); _rows2d(dy, "dy")
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty((rows, c), device=x.device, dtype=BF16)
+    if dx_add is not None:
+        _rows2d(dx_add, "dx_add")
+    _launch("layernorm_bwd", 0, lib().t2v_layernorm_bwd, x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), _lib.ptr(dx_add),
+            dx_add.stride(0) if dx_add is not None else 0, out.data_ptr(), out.stride(0), gamma.data_ptr(), rows, c, eps, stream_ptr())
+    return out
+
+
+def geglu(pre, dout=None, out=None):
+    """pre: bf16 [rows, 2*inner] = [a | gate].  dout None: a * gelu(gate) -> [rows, inner]; else d(pre) -> [rows, 2*inner]."""
+    _rows2d(pre, "pre")
+    rows, two = pre.shape
+    inner = two // 2
+    if out is None:
+        out = torch.empty((rows, inner if dout is None else two), device=pre.device, dtype=BF16)
+    if dout is not None:
+        _rows2d(dout, "dout")
+    _launch("geglu", 0, lib().t2v_geglu, pre.data_ptr(), pre.stride(0), _lib.ptr(dout), dout.stride(0) if dout is not None else 0,
+            out.data_ptr(), out.stride(0), rows, inner, stream_ptr())
+    return out
+
+
+def _ew2d(op, a, b, out):
+    _rows2d(a, "a")
+    rows, c = a.shape
+    if out is None:
+        out = torch.empty((rows, c), device=a.device, dtype=BF16)
+    if b is not None:
+        _rows2d(b, "b")
+        assert b.shape == a.shape
+    _launch("ew2d", 0, lib().t2v_ew2d, op, a.data_ptr(), a.stride(0), _lib.ptr(b), b.stride(0) if b is not None else 0, out.data_ptr(),
+            out.stride(0), rows, c, stream_ptr())
+    return out
+
+
+def add(a, b, out=None):
+    """a + b on bf16 [rows, C] views (gradient accumulation where an activation feeds two consumers)."""
+    return _ew2d(0, a, b, out)
+
+
+def silu(a, out=None):
+    return _ew2d(1, a, None, out)
+
+
+def silu_bwd(pre, dy, out=None):
+    return _ew2d(2, pre, dy, out)
+
+
+def colsum_samples(x, rows_per_sample, out=None):
+    """fp32 [rows / rows_per_sample, C]: per-sample column sums of bf16 [rows, C] (accumulated into `out` when given)."""
+    _rows2d(x, "x")
+    rows, c = x.shape
+    if out is None:
+        out = torch.zeros((rows // rows_per_sample, c), device=x.device, dtype=torch.float32)
+    _launch("colsum_samples", 0, lib().t2v_colsum_samples, x.data_ptr(), x.stride(0), out.data_ptr(), rows, rows_per_sample, c, stream_ptr())
+    return out
+
+
+def resample2x(x, mode):
+    """x: bf16 [n, h, w, C] contiguous.  mode 'sub': [n, h/2, w/2, C] = x[:, ::2, ::2]; 'stuff': [n, 2h, 2w, C] zero stuffing
+    (adjoint of 'sub'); 'pool': [n, h/2, w/2, C] 2x2 block sums (adjoint of the nearest 2x upsampling)."""
+    assert x.is_cuda and x.dtype == BF16 and x.dim() == 4 and x.is_contiguous()
+    n, h, w, c = x.shape
+    code = {"sub": 0, "stuff": 1, "pool": 2}[mode]
+    ho, wo = (2 * h, 2 * w) if mode == "stuff" else (h // 2, w // 2)
+    out = torch.empty((n, ho, wo, c), device=x.device, dtype=BF16)
+    _launch("resample2x", 0, lib().t2v_resample2x, code, x.data_ptr(), out.data_ptr(), n, ho, wo, c, stream_ptr())
+    return out
+
+
+def attention_bwd(q, k, v, o, d_o, lse2, *, heads, scale, kv_batch_div=1, need_dq=True, need_dkv=True):
+    """Adjoint of attention(): returns (dq, dk, dv) shaped like q / k / v (contiguous).  o, lse2 from the forward."""
+    bq, lq, inner = q.shape
+    bk, lk, _ = k.shape
+    assert inner == heads * 64 and bq == bk * kv_batch_div
+    for ten in (q, k, v, o, d_o):
+        assert ten.is_cuda and ten.dtype == BF16 and ten.stride(2) == 1
+    delta = torch.empty((bq, heads, lq), device=q.device, dtype=torch.float32)
+    _launch("attn_delta", 0, lib().t2v_attn_delta, o.data_ptr(), o.stride(0), o.stride(1), 64, d_o.data_ptr(), d_o.stride(0), d_o.stride(1), 64,
+            delta.data_ptr(), bq, heads, lq, stream_ptr())
+    dq = torch.empty((bq, lq, inner), device=q.device, dtype=BF16) if need_dq else None
+    dk = torch.empty((bk, lk, inner), device=q.device, dtype=BF16) if need_dkv else None
+    dv = torch.empty((bk, lk, inner), device=q.device, dtype=BF16) if need_dkv else None
+    d = _lib.AttnBwdDesc()
+    d.q, d.k, d.v, d.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
+    d.lse2, d.delta = lse2.data_ptr(), delta.data_ptr()
+    d.dq, d.dk, d.dv = _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv)
+    d.batch, d.heads, d.len_q, d.len_k = bq, heads, lq, lk
+    for name, ten in (("q", q), ("k", k), ("v", v), ("do", d_o), ("dq", dq), ("dk", dk), ("dv", dv)):
+        if ten is not None:
+            setattr(d, f"{name}_stride_b", ten.stride(0)); setattr(d, f"{name}_stride_t", ten.stride(1)); setattr(d, f"{name}_stride_h", 64)
+    d.kv_batch_div, d.scale = kv_batch_div, scale
+    flops = (6 * need_dq + 8 * need_dkv) * bq * heads * lq * lk * 64
+    _launch("attn_bwd", flops, lib().t2v_attn_bwd, C.byref(d), stream_ptr())
+    return dq, dk, dv
+
+
+def attention_temporal_bwd(q, k, v, d_o, *, b, t, hw, heads, scale):
+    """Adjoint of attention_temporal(): q / k / v / d_o are [(b t hw), H*64] views (row strides free); returns contiguous
+    (dq, dk, dv)."""
+    rows, inner = q.shape
+    assert rows == b * t * hw and inner == heads * 64
+    outs = [torch.empty((rows, inner), device=q.device, dtype=BF16) for _ in range(3)]
+    d = _lib.ShortAttnBwdDesc()
+    f = d.fwd
+    f.q, f.k, f.v, f.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
+    f.n_seq_outer, f.n_seq_inner, f.heads, f.len = b, hw, heads, t
+    for name, ten in (("q", q), ("k", k), ("v", v), ("o", d_o)):
+        rs = ten.stride(0)
+        setattr(f, f"{name}_stride_outer", t * hw * rs)
+        setattr(f, f"{name}_stride_inner", rs)
+        setattr(f, f"{name}_stride_t", hw * rs)
+        setattr(f, f"{name}_stride_h", 64)
+    f.scale = scale
+    # dq / dk / dv are written with the strides of q / k / v: the (contiguous) outputs need contiguous q / k / v
+    assert q.stride(0) == k.stride(0) == v.stride(0) == inner, "attention_temporal_bwd: q / k / v must be contiguous [rows, H*64]"
+    d.d_o = d_o.data_ptr()
+    d.dq, d.dk, d.dv = (o.data_ptr() for o in outs)
+    _launch("attn_short_bwd", 10 * b * hw * heads * t * t * 64, lib().t2v_attn_short_bwd, C.byref(d), stream_ptr())
+    return tuple(outs)
 
 
 # ----------------------------------------------------------------------------- small ops

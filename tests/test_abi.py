@@ -33,13 +33,15 @@ def test_struct_sizes_match_header(tmp_path):
     import subprocess
     from t2v_turbo_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "t2v_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "t2v_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(T2VGemmDesc),sizeof(T2VAttnDesc),sizeof(T2VShortAttnDesc),sizeof(T2VGroupNormDesc),'
-                   'sizeof(T2VLayerNormDesc),sizeof(T2VSmallLinearDesc),sizeof(T2VWgradDesc));return 0;}')
+                   'sizeof(T2VLayerNormDesc),sizeof(T2VSmallLinearDesc),sizeof(T2VWgradDesc),sizeof(T2VGroupNormBwdDesc),sizeof(T2VAttnBwdDesc),'
+                   'sizeof(T2VShortAttnBwdDesc));return 0;}')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    mirrors = [_lib.GemmDesc, _lib.AttnDesc, _lib.ShortAttnDesc, _lib.GroupNormDesc, _lib.LayerNormDesc, _lib.SmallLinearDesc, _lib.WgradDesc]
+    mirrors = [_lib.GemmDesc, _lib.AttnDesc, _lib.ShortAttnDesc, _lib.GroupNormDesc, _lib.LayerNormDesc, _lib.SmallLinearDesc, _lib.WgradDesc,
+               _lib.GroupNormBwdDesc, _lib.AttnBwdDesc, _lib.ShortAttnBwdDesc]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
