@@ -254,8 +254,8 @@ int t2v_conv3x3_small_cin(const void* in, const void* w, const float* bias, void
 /* [B,C,T,H,W] (any float dtype given by in_dtype: 0 bf16, 1 fp16, 2 fp32) -> [B*T,H,W,C] bf16, times scale */
 int t2v_bcthw_to_frames(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c,
                         int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t stream);
-/* same with the channel count padded to c_pad (<= 8) by zero channels: RGB video -> 4-channel frames for the
- * encoder's direct small-Cin conv (ae_modules.py:411-413) */
+/* same with the channel count padded to c_pad (<= 64) by zero channels: RGB video -> 4-channel frames for the
+ * encoder's direct small-Cin conv (ae_modules.py:411-413); 4-channel latents -> 64 channels for the training path's conv_in */
 int t2v_bcthw_to_frames_pad(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c, int32_t c_pad,
                             int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t stream);
 /* same, followed by a per-pixel channel mix out[o] = sum_c mix[o][c] * scale * in[c] + bias[o]  (c <= 8):

@@ -595,7 +595,7 @@ extern "C" int t2v_bcthw_to_frames_mix(const void* in, int32_t in_dtype, void* o
 extern "C" int t2v_bcthw_to_frames_pad(const void* in, int32_t in_dtype, void* out, int32_t b, int32_t c, int32_t c_pad,
                                        int32_t t, int32_t h, int32_t w, float scale, t2v_stream_t s) {
   if (!in || !out) return fail(-1, "t2v_bcthw_to_frames_pad: null pointer");
-  if (c < 1 || c_pad < c || c_pad > 8) return fail(-2, "t2v_bcthw_to_frames_pad: need 1 <= c <= c_pad <= 8");
+  if (c < 1 || c_pad < c || c_pad > 64) return fail(-2, "t2v_bcthw_to_frames_pad: need 1 <= c <= c_pad <= 64");
   const int64_t total = int64_t(b) * t * h * w;
   launch_kernel(bcthw_to_frames_pad_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(s), in, in_dtype, static_cast<__nv_bfloat16*>(out), b, c, c_pad, t, h, w, scale);
   cudaError_t e = cudaGetLastError();

@@ -151,21 +151,26 @@ class _PackedLora:
             self.d_t = ops.pack_conv_weight(down.transpose(0, 1).flip(sp).contiguous())   # [Cin, taps * r]
 
 
-def _base_op(kind, x, w, bias, residual=None):
-    """The forward implicit GEMM of the three layer kinds on channels-last bf16 (x: [M,K] | [n,h,w,C] | [b,t,hw,C])."""
+def _base_op(kind, x, w, bias, residual=None, bias_div=None):
+    """The forward implicit GEMM of the three layer kinds on channels-last bf16 (x: [M,K] | [n,h,w,C] | [b,t,hw,C]).
+    conv2d: a 2-D bias [rows, Cout] with bias_div carries a per-sample bias row (frame // bias_div): the ResBlock's
+    conv bias + timestep-embedding row (openaimodel3d.py:237-246)."""
     if kind == "linear":
         return ops.linear(x, w, bias, residual=residual)
     if kind == "conv2d":
-        return ops.conv3x3(x, w, bias.view(1, -1) if bias is not None else None, bias_div=x.shape[0], residual=residual)
+        if bias is not None and bias.dim() == 1:
+            bias, bias_div = bias.view(1, -1), x.shape[0]
+        return ops.conv3x3(x, w, bias, bias_div=bias_div or 1, residual=residual)
     return ops.tconv3(x, w, bias, residual=residual)
 
 
-def lora_forward(pk: _PackedLora, x, mask, mask_scale):
-    """-> (y, t): t = lora_down(x) is kept for the backward."""
+def lora_forward(pk: _PackedLora, x, mask, mask_scale, bias_rows=None, bias_div=None):
+    """-> (y, t): t = lora_down(x) is kept for the backward.  bias_rows / bias_div: see _base_op (conv2d only)."""
     t = _base_op(pk.kind, x, pk.d, None)                                         # [.., r]
     u = ops.linear(t.view(-1, pk.r), pk.u, None)                                 # [M, Cout]
     branch = ops.scale_mask(u, pk.scale * mask_scale, mask)
-    y = _base_op(pk.kind, x, pk.w, pk.bias, residual=branch.view(*x.shape[:-1], pk.cout))
+    bias = pk.bias if bias_rows is None else bias_rows
+    y = _base_op(pk.kind, x, pk.w, bias, residual=branch.view(*x.shape[:-1], pk.cout), bias_div=bias_div)
     return y, t
 
 

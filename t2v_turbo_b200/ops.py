@@ -765,6 +765,16 @@ def bcthw_to_frames(x, scale=1.0):
     return out
 
 
+def bcthw_to_frames_pad(x, c_pad, scale=1.0):
+    """[B, C, T, H, W] -> bf16 [B*T, H, W, c_pad] with zero channels appended (c_pad <= 64)."""
+    b, c, t, h, w = x.shape
+    x = x.contiguous()
+    out = torch.empty((b * t, h, w, c_pad), device=x.device, dtype=BF16)
+    _launch("bcthw_to_frames_pad", 0, lib().t2v_bcthw_to_frames_pad, x.data_ptr(), _lib.DTYPE_CODE[x.dtype], out.data_ptr(), b, c, c_pad, t, h, w,
+            scale, stream_ptr())
+    return out
+
+
 def frames_to_bcthw(x, b, c, dtype):
     n, h, w, cp = x.shape
     t = n // b
