@@ -382,7 +382,7 @@ typedef struct T2VGroupNormBwdDesc {
 int t2v_groupnorm_bwd(const T2VGroupNormBwdDesc* desc, t2v_stream_t stream);
 
 /* LayerNorm backward (attention.py:279-281,300-311), one warp per row, statistics recomputed: channels in
- * {64, 128, 320, 640, 1024, 1280}; dx_add (optional) is the residual-path gradient summed into dx. */
+ * {64, 128, 256, 320, 512, 640, 1024, 1280}; dx_add (optional) is the residual-path gradient summed into dx. */
 int t2v_layernorm_bwd(const void* x, int64_t x_row_stride, const void* dy, int64_t dy_row_stride, const void* dx_add,
                       int64_t dx_add_row_stride, void* dx, int64_t dx_row_stride, const float* gamma, int64_t rows,
                       int32_t channels, float eps, t2v_stream_t stream);

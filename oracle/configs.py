@@ -50,3 +50,19 @@ def unet_inputs(spec, timestep):
     if "motion_gs" in spec:   # pipeline:197-204: the same sin/cos embedding of the motion guidance scale
         out["motion_cond"] = guidance_scale_embedding(torch.tensor(spec["motion_gs"], dtype=torch.float32), 256)
     return out
+
+
+def student_loras(shapes, seed=4242):
+    """Seeded LoRA weights for the student-gradient fixture, in the reference's flat wire order [up_0, down_0, ...]: both
+    factors non-zero (the reference initialises up = 0, which would zero every lora_down gradient)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(0, len(shapes), 2):
+        up_s, down_s = shapes[i], shapes[i + 1]
+        r = up_s[1]
+        out.append(torch.randn(up_s, generator=g) * (0.5 / r ** 0.5))
+        fan = 1
+        for d in down_s[1:]:
+            fan *= d
+        out.append(torch.randn(down_s, generator=g) * (0.5 / fan ** 0.5))
+    return out

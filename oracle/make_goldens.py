@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(HERE, "shim"))
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
 
-from oracle.configs import UNET_CONFIGS, VAE_CONFIGS, unet_inputs  # noqa: E402
+from oracle.configs import UNET_CONFIGS, VAE_CONFIGS, student_loras, unet_inputs  # noqa: E402
 from oracle.weights import seeded_state_dict  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -181,6 +181,51 @@ def gen_lora_layers():
     torch.save(out, os.path.join(GOLD, "lora_layers.pt"))
 
 
+def gen_student_grads(name="small"):
+    """The student forward + backward of train_t2v_turbo_v1_lora.py:640-656,1040-1048,1190 on the UNMODIFIED reference: the UNet
+    with LoRA injected by the reference's own `inject_trainable_lora_extended` (r = 64, target {"UNetModel"}), seeded LoRA
+    weights (both up and down non-zero so every gradient is exercised), eval mode (all dropouts off: deterministic), fp32.
+    loss = sum(eps_pred * g) for a seeded g.  Stores the LoRA list (wire order), g, the output and every LoRA gradient."""
+    from utils.lora import extract_lora_ups_down, inject_trainable_lora_extended
+    spec = UNET_CONFIGS[name]
+    m = ref_unet(spec["cfg"], spec["weight_seed"])
+    m.requires_grad_(False)
+    params, _ = inject_trainable_lora_extended(m, target_replace_module={"UNetModel"}, r=64)
+    m.eval()
+    ups_downs = list(extract_lora_ups_down(m, target_replace_module={"UNetModel"}))
+    shapes = []
+    for up, down in ups_downs:
+        shapes += [tuple(up.weight.shape), tuple(down.weight.shape)]
+    loras = student_loras(shapes)
+    with torch.no_grad():
+        for i, (up, down) in enumerate(ups_downs):
+            up.weight.copy_(loras[2 * i])
+            down.weight.copy_(loras[2 * i + 1])
+            up.weight.requires_grad_(True)
+            down.weight.requires_grad_(True)
+    inp = unet_inputs(spec, spec["timesteps"][0])
+    y = m(inp["x"], inp["timesteps"], context=inp["context"], fps=inp["fps"], timestep_cond=inp["timestep_cond"])
+    d_out = torch.randn(y.shape, generator=torch.Generator().manual_seed(4243))
+    (y * d_out).sum().backward()
+    grads = []
+    for up, down in ups_downs:
+        grads += [up.weight.grad.clone(), down.weight.grad.clone()]
+    norms = torch.tensor([x.double().norm().item() for x in grads], dtype=torch.float64)
+    # the fixture keeps every norm and, to stay small, the full tensors of a fixed subset of layers (first / last three and
+    # every fifth), each as fp16 scaled by its max (5e-4 of the tensor's scale: far below the parity tolerance)
+    n_layers = len(grads) // 2
+    keep = sorted(set(range(3)) | set(range(n_layers - 3, n_layers)) | set(range(0, n_layers, 5)))
+    full = {}
+    for li in keep:
+        for j in (2 * li, 2 * li + 1):
+            sc = grads[j].abs().max().item() + 1e-30
+            full[j] = (sc, (grads[j] / sc).half())
+    print(f"  student grads {name}: {n_layers} LoRA layers, out std {y.std():.4f}, grad norm {norms.pow(2).sum().sqrt():.4f}, "
+          f"{len(keep)} layers stored in full")
+    torch.save({"name": name, "timestep": spec["timesteps"][0], "shapes": shapes, "d_out": d_out, "output": y.detach().clone(),
+                "grad_norms": norms, "grads_full": full}, os.path.join(GOLD, f"student_grads_{name}.pt"))
+
+
 def gen_scheduler():
     from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
     s = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
@@ -309,7 +354,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -318,6 +363,8 @@ if __name__ == "__main__":
             gen_unet(item[5:])
         elif item == "lora_layers":
             gen_lora_layers()
+        elif item == "student_grads":
+            gen_student_grads()
         elif item == "unet_probs":
             gen_unet_probs()
         elif item.startswith("lora_"):

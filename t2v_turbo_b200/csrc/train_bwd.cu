@@ -472,11 +472,13 @@ extern "C" int t2v_layernorm_bwd(const void* x, int64_t x_row_stride, const void
   switch (channels) {
     case 64: T2V_LN_BWD(1); break;
     case 128: T2V_LN_BWD(2); break;
+    case 256: T2V_LN_BWD(4); break;
     case 320: T2V_LN_BWD(5); break;
+    case 512: T2V_LN_BWD(8); break;
     case 640: T2V_LN_BWD(10); break;
     case 1024: T2V_LN_BWD(16); break;
     case 1280: T2V_LN_BWD(20); break;
-    default: return fail(-3, "t2v_layernorm_bwd: channels must be one of 64, 128, 320, 640, 1024, 1280 (got %d)", channels);
+    default: return fail(-3, "t2v_layernorm_bwd: channels must be one of 64, 128, 256, 320, 512, 640, 1024, 1280 (got %d)", channels);
   }
 #undef T2V_LN_BWD
   cudaError_t e = cudaGetLastError();
