@@ -211,6 +211,26 @@ def gen_student_grads(name="small"):
     for up, down in ups_downs:
         grads += [up.weight.grad.clone(), down.weight.grad.clone()]
     norms = torch.tensor([x.double().norm().item() for x in grads], dtype=torch.float64)
+    # yardstick for the tolerance: the reference's OWN bf16 forward + backward (weights, inputs and autograd in bfloat16, the
+    # precision the training script's autocast runs the student in) against its fp32 gradients above
+    m16 = m.bfloat16()
+    m16.dtype = torch.bfloat16      # app.py:143 sets the attribute the reference casts its embeddings to
+    for up, down in ups_downs:
+        up.weight.grad = None
+        down.weight.grad = None
+    y16 = m16(inp["x"].bfloat16(), inp["timesteps"], context=inp["context"].bfloat16(), fps=inp["fps"], timestep_cond=inp["timestep_cond"].bfloat16())
+    (y16 * d_out.bfloat16()).sum().backward()
+    g16 = []
+    for up, down in ups_downs:
+        g16 += [up.weight.grad.float(), down.weight.grad.float()]
+    rel16 = [((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item() for a, b in zip(g16, grads)]
+    cat16 = ((torch.cat([a.flatten() for a in g16]).double() - torch.cat([b.flatten() for b in grads]).double()).norm()
+             / torch.cat([b.flatten() for b in grads]).double().norm()).item()
+    ref_bf16 = dict(output_rel=((y16.float() - y.detach()).norm() / y.detach().norm()).item(), grad_rel_median=sorted(rel16)[len(rel16) // 2],
+                    grad_rel_worst=max(rel16), grad_rel_concat=cat16,
+                    norm_ratio=(min(a.norm().item() / (b.norm().item() + 1e-30) for a, b in zip(g16, grads)),
+                                max(a.norm().item() / (b.norm().item() + 1e-30) for a, b in zip(g16, grads))))
+    print("  reference bf16 vs its fp32:", ref_bf16)
     # the fixture keeps every norm and, to stay small, the full tensors of a fixed subset of layers (first / last three and
     # every fifth), each as fp16 scaled by its max (5e-4 of the tensor's scale: far below the parity tolerance)
     n_layers = len(grads) // 2
@@ -223,7 +243,7 @@ def gen_student_grads(name="small"):
     print(f"  student grads {name}: {n_layers} LoRA layers, out std {y.std():.4f}, grad norm {norms.pow(2).sum().sqrt():.4f}, "
           f"{len(keep)} layers stored in full")
     torch.save({"name": name, "timestep": spec["timesteps"][0], "shapes": shapes, "d_out": d_out, "output": y.detach().clone(),
-                "grad_norms": norms, "grads_full": full}, os.path.join(GOLD, f"student_grads_{name}.pt"))
+                "grad_norms": norms, "grads_full": full, "ref_bf16": ref_bf16}, os.path.join(GOLD, f"student_grads_{name}.pt"))
 
 
 def gen_scheduler():

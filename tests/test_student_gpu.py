@@ -60,9 +60,15 @@ def test_student_forward_backward_vs_reference_autograd(cuda_device):
           f"worst {rels[wj]:.3e} (tensor {wj}, shape {s.arena.shapes[wj]}, layer {s.layer_list[wj // 2].name})")
     total = _rel(torch.cat([ours[j].flatten() for j in rels]), torch.cat([(sc * t.float()).flatten() for sc, t in g["grads_full"].values()]))
     print(f"[student small] stored tensors concatenated rel-L2 {total:.3e}")
-    assert worst < 6e-2, f"gradient norm off by {worst:.3f}"
-    assert rels[wj] < 8e-2, (wj, rels[wj])
-    assert total < 4e-2, total
+    # Yardstick: the unmodified reference run in bf16 (weights, activations, autograd) against its own fp32 gradients, stored in
+    # the fixture: output 2.2e-2, gradients median 4.0e-2 / worst 6.0e-2 / concatenated 3.8e-2, norm ratio 0.975 .. 1.021.
+    # Observed on B200: output 1.9e-2, median 3.6e-2, worst 5.2e-2, concatenated 3.2e-2, norm ratio 0.985 .. 1.011.
+    rb = g["ref_bf16"]
+    print(f"[student small] reference bf16 vs its own fp32: {rb}")
+    assert e_y <= 1.15 * rb["output_rel"], (e_y, rb["output_rel"])
+    assert worst < 3e-2, f"gradient norm off by {worst:.3f}"
+    assert rels[wj] <= 1.3 * rb["grad_rel_worst"], (wj, rels[wj], rb["grad_rel_worst"])
+    assert total <= 1.15 * rb["grad_rel_concat"], (total, rb["grad_rel_concat"])
 
 
 def test_student_training_mode_and_optimizer_step(cuda_device):
