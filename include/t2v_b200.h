@@ -446,6 +446,11 @@ typedef struct T2VShortAttnBwdDesc {
 } T2VShortAttnBwdDesc;
 int t2v_attn_short_bwd(const T2VShortAttnBwdDesc* desc, t2v_stream_t stream);
 
+/* pseudo-Huber distillation loss and its gradient (huber_loss, utils/common_utils.py:302-304; --loss_type huber is the training
+ * script's default): loss[0] += mean(sqrt((a-b)^2 + c^2) - c); grad[i] = (a-b) / sqrt((a-b)^2 + c^2) / n * grad_scale. */
+int t2v_huber_loss_grad(const void* a, const void* b, void* grad, float* loss, int64_t n, int32_t dtype, float huber_c,
+                        float grad_scale, t2v_stream_t stream);
+
 /* Weight packing helpers (device-side, run once at load). */
 /* conv weight [Cout][Cin][kh*kw] (torch OIHW / OIDHW flattened taps) -> [Cout][taps][Cin] bf16 */
 int t2v_pack_conv_weight(const void* w, int32_t w_dtype, void* out, int32_t cout, int32_t cin,

@@ -246,6 +246,105 @@ def gen_student_grads(name="small"):
                 "grad_norms": norms, "grads_full": full, "ref_bf16": ref_bf16}, os.path.join(GOLD, f"student_grads_{name}.pt"))
 
 
+def distill_inputs(spec, bsz=2):
+    """Seeded inputs of the distillation-step fixture (shared with tests/test_student_gpu.py through the saved file)."""
+    g = torch.Generator().manual_seed(5151)
+    shape = (bsz,) + tuple(spec["x_shape"][1:])
+    cd = spec["cfg"]["context_dim"]
+    return dict(latents=torch.randn(shape, generator=g) * 0.8, prompt=torch.randn(bsz, spec["ctx_len"], cd, generator=g),
+                uncond=torch.randn(bsz, spec["ctx_len"], cd, generator=g) * 0.5, index=torch.tensor([37, 4][:bsz]),
+                noise=torch.randn(shape, generator=g), w=torch.tensor([6.5, 13.0][:bsz]))
+
+
+def gen_distill_step(name="small"):
+    """One consistency-distillation step (train_t2v_turbo_v1_lora.py:976-1190 with the reward terms off) composed from the
+    UNMODIFIED reference pieces: T2VTurboScheduler.add_noise, the LoRA-injected student, the teacher UNet (the same weights
+    without time_cond_proj, as :636-639 loads them), scalings_for_boundary_conditions / get_predicted_original_sample /
+    get_predicted_noise / guidance_scale_embedding / huber_loss (utils/common_utils.py) and DDIMSolver.ddim_step — fp32, eval
+    mode (dropouts off), fixed random draws.  Stores the loss, the intermediate latents and the LoRA gradients."""
+    from lvdm.modules.networks.openaimodel3d import UNetModel
+    from ode_solver.ddim_solver import DDIMSolver
+    from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
+    from utils.common_utils import (append_dims, get_predicted_noise, get_predicted_original_sample, guidance_scale_embedding, huber_loss,
+                                    scalings_for_boundary_conditions)
+    from utils.lora import extract_lora_ups_down, inject_trainable_lora_extended
+    spec = UNET_CONFIGS[name]
+    unet = ref_unet(spec["cfg"], spec["weight_seed"])
+    tcfg = dict(spec["cfg"])
+    tcfg["time_cond_proj_dim"] = None
+    teacher = UNetModel(**tcfg).eval()
+    teacher.load_state_dict({k: v for k, v in unet.state_dict().items() if not k.startswith("time_cond_proj")}, strict=True)
+    teacher.requires_grad_(False)
+    unet.requires_grad_(False)
+    inject_trainable_lora_extended(unet, target_replace_module={"UNetModel"}, r=64)
+    unet.eval()
+    ups_downs = list(extract_lora_ups_down(unet, target_replace_module={"UNetModel"}))
+    shapes = []
+    for up, down in ups_downs:
+        shapes += [tuple(up.weight.shape), tuple(down.weight.shape)]
+    loras = student_loras(shapes)
+    with torch.no_grad():
+        for i, (up, down) in enumerate(ups_downs):
+            up.weight.copy_(loras[2 * i])
+            down.weight.copy_(loras[2 * i + 1])
+            up.weight.requires_grad_(True)
+            down.weight.requires_grad_(True)
+    noise_scheduler = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
+    alpha_schedule = torch.sqrt(noise_scheduler.alphas_cumprod)
+    sigma_schedule = torch.sqrt(1 - noise_scheduler.alphas_cumprod)
+    solver = DDIMSolver(noise_scheduler.alphas_cumprod.numpy(), ddim_timesteps=50, use_scale=False)
+    inp = distill_inputs(spec)
+    latents, index, noise, w = inp["latents"], inp["index"], inp["noise"], inp["w"]
+    bsz = latents.shape[0]
+    topk, ts_scale, fps = 20, 10.0, 16
+    # ---- :976-1021
+    start_timesteps = solver.ddim_timesteps[index]
+    timesteps = start_timesteps - topk
+    timesteps = torch.where(timesteps < 0, torch.zeros_like(timesteps), timesteps)
+    c_skip_start, c_out_start = [append_dims(x, latents.ndim) for x in scalings_for_boundary_conditions(start_timesteps, timestep_scaling=ts_scale)]
+    c_skip, c_out = [append_dims(x, latents.ndim) for x in scalings_for_boundary_conditions(timesteps, timestep_scaling=ts_scale)]
+    noisy_model_input = noise_scheduler.add_noise(latents, noise, start_timesteps)
+    w_embedding = guidance_scale_embedding(w, embedding_dim=256)
+    wv = w.reshape(bsz, 1, 1, 1, 1)
+    context = {"context": inp["prompt"].float(), "fps": fps}
+    # ---- :1023-1039
+    noise_pred = unet(noisy_model_input, start_timesteps, **context, timestep_cond=w_embedding)
+    pred_x_0 = get_predicted_original_sample(noise_pred, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+    model_pred = c_skip_start * noisy_model_input + c_out_start * pred_x_0
+    # ---- :1102-1181
+    with torch.no_grad():
+        cond_teacher_output = teacher(noisy_model_input, start_timesteps, **context)
+        cond_pred_x0 = get_predicted_original_sample(cond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        cond_pred_noise = get_predicted_noise(cond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        uncond_teacher_output = teacher(noisy_model_input, start_timesteps, context=inp["uncond"])
+        uncond_pred_x0 = get_predicted_original_sample(uncond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        uncond_pred_noise = get_predicted_noise(uncond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        pred_x0 = cond_pred_x0 + wv * (cond_pred_x0 - uncond_pred_x0)
+        pred_noise = cond_pred_noise + wv * (cond_pred_noise - uncond_pred_noise)
+        x_prev = solver.ddim_step(pred_x0, pred_noise, index)
+        target_noise_pred = unet(x_prev.float(), timesteps, **context, timestep_cond=w_embedding)
+        pred_x_0_t = get_predicted_original_sample(target_noise_pred, timesteps, x_prev, "epsilon", alpha_schedule, sigma_schedule)
+        target = c_skip * x_prev + c_out * pred_x_0_t
+    distill_loss = huber_loss(model_pred, target, 0.001)
+    distill_loss.backward()
+    grads = []
+    for up, down in ups_downs:
+        grads += [up.weight.grad.clone(), down.weight.grad.clone()]
+    norms = torch.tensor([x.double().norm().item() for x in grads], dtype=torch.float64)
+    n_layers = len(grads) // 2
+    keep = sorted(set(range(2)) | set(range(n_layers - 2, n_layers)) | set(range(0, n_layers, 12)))
+    full = {}
+    for li in keep:
+        for j in (2 * li, 2 * li + 1):
+            sc = grads[j].abs().max().item() + 1e-30
+            full[j] = (sc, (grads[j] / sc).half())
+    print(f"  distill step {name}: loss {distill_loss.item():.6f}, start t {start_timesteps.tolist()}, t {timesteps.tolist()}, "
+          f"grad norm {norms.pow(2).sum().sqrt():.5f}, x_prev std {x_prev.std():.4f}")
+    torch.save({"name": name, "inputs": inp, "shapes": shapes, "loss": distill_loss.detach().clone(), "noisy": noisy_model_input,
+                "model_pred": model_pred.detach().clone(), "x_prev": x_prev, "target": target, "start_timesteps": start_timesteps,
+                "timesteps": timesteps, "grad_norms": norms, "grads_full": full}, os.path.join(GOLD, f"distill_step_{name}.pt"))
+
+
 def gen_scheduler():
     from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
     s = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
@@ -374,7 +473,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -385,6 +484,8 @@ if __name__ == "__main__":
             gen_lora_layers()
         elif item == "student_grads":
             gen_student_grads()
+        elif item == "distill_step":
+            gen_distill_step()
         elif item == "unet_probs":
             gen_unet_probs()
         elif item.startswith("lora_"):

@@ -205,6 +205,7 @@ SYMBOLS = {
     "t2v_attn_delta": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _vp]),
     "t2v_attn_bwd": (C.c_int, [C.POINTER(AttnBwdDesc), _vp]),
     "t2v_attn_short_bwd": (C.c_int, [C.POINTER(ShortAttnBwdDesc), _vp]),
+    "t2v_huber_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp]),
     "t2v_embedding_gather": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "t2v_video_to_uint8": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_scale_add_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),

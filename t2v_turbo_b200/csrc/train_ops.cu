@@ -106,15 +106,22 @@ __device__ __forceinline__ void st_any(void* p, int64_t i, int dt, float v) {
   else static_cast<float*>(p)[i] = v;
 }
 
+// huber_c < 0: mean squared error; else the pseudo-Huber loss of utils/common_utils.py:302-304, mean(sqrt(d^2 + c^2) - c)
 __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const void* a, const void* b, void* grad, float* loss, int64_t n, int dt,
-                                                            float inv_n, float gscale) {
+                                                            float inv_n, float gscale, float huber_c) {
   pdl_launch_dependents();
   pdl_wait();
   float acc = 0.f;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const float d = ld_any(a, i, dt) - ld_any(b, i, dt);
-    acc = fmaf(d, d, acc);
-    if (grad != nullptr) st_any(grad, i, dt, 2.f * d * inv_n * gscale);
+    if (huber_c < 0.f) {
+      acc = fmaf(d, d, acc);
+      if (grad != nullptr) st_any(grad, i, dt, 2.f * d * inv_n * gscale);
+    } else {
+      const float r = sqrtf(fmaf(d, d, huber_c * huber_c));
+      acc += r - huber_c;
+      if (grad != nullptr) st_any(grad, i, dt, d / r * inv_n * gscale);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -171,7 +178,17 @@ extern "C" int t2v_mse_loss_grad(const void* a, const void* b, void* grad, float
   using namespace t2v;
   if (!a || !b || !loss || n < 1 || dtype < 0 || dtype > 2) return fail(-1, "t2v_mse_loss_grad: bad argument");
   launch_kernel(mse_loss_grad_kernel, dim3(grid_1d(n)), dim3(256), 0, static_cast<cudaStream_t>(s), a, b, grad, loss, n, dtype,
-                1.0f / float(n), grad_scale);
+                1.0f / float(n), grad_scale, -1.0f);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_mse_loss_grad launch");
+}
+
+extern "C" int t2v_huber_loss_grad(const void* a, const void* b, void* grad, float* loss, int64_t n, int32_t dtype, float huber_c,
+                                   float grad_scale, t2v_stream_t s) {
+  using namespace t2v;
+  if (!a || !b || !loss || n < 1 || dtype < 0 || dtype > 2 || !(huber_c >= 0.f)) return fail(-1, "t2v_huber_loss_grad: bad argument");
+  launch_kernel(mse_loss_grad_kernel, dim3(grid_1d(n)), dim3(256), 0, static_cast<cudaStream_t>(s), a, b, grad, loss, n, dtype,
+                1.0f / float(n), grad_scale, huber_c);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_huber_loss_grad launch");
 }

@@ -948,6 +948,17 @@ def mse_loss_grad(a, b, *, want_grad=True, grad_scale=1.0):
     return loss, grad
 
 
+def huber_loss_grad(a, b, huber_c=0.001, *, want_grad=True, grad_scale=1.0):
+    """(mean(sqrt((a - b)^2 + c^2) - c) as a 1-element fp32 tensor, d loss / d a * grad_scale in a's dtype):
+    utils/common_utils.py:302-304."""
+    assert a.is_cuda and a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
+    loss = torch.zeros(1, device=a.device, dtype=torch.float32)
+    grad = torch.empty_like(a) if want_grad else None
+    _launch("huber_loss_grad", 0, lib().t2v_huber_loss_grad, a.data_ptr(), b.data_ptr(), ptr(grad), loss.data_ptr(), a.numel(),
+            _lib.DTYPE_CODE[a.dtype], float(huber_c), float(grad_scale), stream_ptr())
+    return loss, grad
+
+
 # ----------------------------------------------------------------------------- weight packing
 def pack_conv_weight(w):
     """torch conv weight [Cout, Cin, *k] -> bf16 [Cout, taps*Cin] (tap-major K)."""

@@ -536,6 +536,17 @@ class StudentUNet:
 
     __call__ = forward
 
+    def detach_tapes(self):
+        """Take the saved activations of the last forward out of the object (so that another, gradient-free forward can run
+        before the backward: the distillation step's target prediction); hand them back with restore_tapes."""
+        saved = (self._tapes_in, self._tape_mid, self._tapes_out, self._out_ctx, self._emb_ctx, self._emb_act, self._skip_ch)
+        self._tapes_in = self._tape_mid = self._tapes_out = self._out_ctx = self._emb_ctx = self._emb_act = None
+        return saved
+
+    def restore_tapes(self, saved):
+        self._tapes_in, self._tape_mid, self._tapes_out, self._out_ctx, self._emb_ctx, self._emb_act, self._skip_ch = saved
+        self._d_emb_act = None
+
     def backward(self, d_out):
         """d_out: gradient of the loss w.r.t. the forward's output [B, 4, T, H, W].  Accumulates into arena.grads."""
         gn, conv = self.s_out

@@ -97,3 +97,51 @@ def test_student_training_mode_and_optimizer_step(cuda_device):
     s.eval()
     y1 = s(*args, **kw)
     assert _rel(y1, y0) > 1e-4, "the optimizer step did not change the student's output"
+
+
+def test_distill_step_vs_reference_composition(cuda_device):
+    """One consistency-distillation step (DistillStep: add_noise, student, teacher CFG + DDIM, target, pseudo-Huber loss, student
+    backward) against the same step composed from the UNMODIFIED reference's pieces in fp32 (gen_distill_step), same draws."""
+    from oracle.configs import UNET_CONFIGS, student_loras
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200.distill import DistillStep
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.train_unet import StudentUNet
+    from t2v_turbo_b200.unet import UNetModel
+    g = torch.load(os.path.join(GOLD, "distill_step_small.pt"))
+    spec = UNET_CONFIGS["small"]
+    base = UNetModel(**spec["cfg"])
+    sd = seeded_state_dict(base.state_dict(), spec["weight_seed"])
+    base.load_state_dict(sd, strict=True)
+    tcfg = dict(spec["cfg"])
+    tcfg["time_cond_proj_dim"] = None
+    teacher = UNetModel(**tcfg)
+    teacher.load_state_dict({k: v for k, v in sd.items() if not k.startswith("time_cond_proj")}, strict=True)
+    base, teacher = base.cuda().eval(), teacher.cuda().eval()
+    s = StudentUNet(base, r=64).eval()
+    assert [tuple(x) for x in g["shapes"]] == s.arena.shapes
+    s.arena.load_list(student_loras(g["shapes"]))
+    s.pack()
+    step = DistillStep(s, teacher, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012), num_ddim_timesteps=50, topk=20,
+                       loss_type="huber", huber_c=0.001, timestep_scaling_factor=10.0)
+    inp = g["inputs"]
+    s.arena.zero_grad()
+    out = step(inp["latents"].cuda(), inp["prompt"].cuda(), inp["uncond"].cuda(),
+               fixed=dict(index=inp["index"], noise=inp["noise"].cuda(), w=inp["w"]))
+    torch.cuda.synchronize()
+    assert out["start_timesteps"].tolist() == g["start_timesteps"].tolist() and out["timesteps"].tolist() == g["timesteps"].tolist()
+    e = {k: _rel(out[k], g[k]) for k in ("model_pred", "x_prev", "target")}
+    loss, loss_ref = float(out["loss"]), float(g["loss"])
+    print(f"\n[distill small] loss {loss:.6f} vs reference {loss_ref:.6f}; rel-L2 {e}")
+    assert e["x_prev"] < 1.5e-2 and e["model_pred"] < 2.5e-2 and e["target"] < 2.5e-2, e
+    assert abs(loss - loss_ref) < 3e-2 * loss_ref, (loss, loss_ref)
+    n = len(s.arena.shapes)
+    ours = [s.arena.grad(i) for i in range(n)]
+    ratio = torch.tensor([ours[i].double().norm().item() / max(g["grad_norms"][i].item(), 1e-30) for i in range(n)])
+    rels = {j: _rel(ours[j], sc * t.float()) for j, (sc, t) in g["grads_full"].items()}
+    total = _rel(torch.cat([ours[j].flatten() for j in rels]), torch.cat([(sc * t.float()).flatten() for sc, t in g["grads_full"].values()]))
+    print(f"[distill small] grad-norm ratio min {ratio.min():.4f} max {ratio.max():.4f}; stored tensors rel-L2 median "
+          f"{sorted(rels.values())[len(rels) // 2]:.3e} worst {max(rels.values()):.3e} concatenated {total:.3e}")
+    # the gradient of the pseudo-Huber loss is sign-like (d / sqrt(d^2 + c^2), c = 1e-3): elements whose student-target
+    # difference is within bf16 noise of zero flip, so this is looser than the linear-loss fixture above
+    assert (ratio - 1).abs().max().item() < 0.15 and total < 0.25, (ratio.min().item(), ratio.max().item(), total)
