@@ -214,3 +214,15 @@ def test_attention_temporal_bwd(cuda_device, b, t, hw, heads):
         assert_close(got, unseqs(ref), what=f"attention_temporal_bwd {name} b={b} t={t} hw={hw} H={heads}")
     # forward output of the same op for reference consistency
     assert_close(ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=heads, scale=scale), unseqs(o.detach()), what="temporal fwd")
+
+
+def test_huber_loss_grad(cuda_device):
+    ops = _ops()
+    a = rnd(2, 4, 4, 8, 8, seed=1)
+    b = (a + 0.3 * rnd(2, 4, 4, 8, 8, seed=2)).contiguous()
+    ar = a.clone().requires_grad_(True)
+    ref = (torch.sqrt((ar - b) ** 2 + 0.001 ** 2) - 0.001).mean()
+    ref.backward()
+    loss, grad = ops.huber_loss_grad(a, b, 0.001)
+    assert abs(float(loss) - float(ref)) < 1e-6 * abs(float(ref)) + 1e-7
+    assert (grad - ar.grad).abs().max().item() < 1e-6 * ar.grad.abs().max().item() + 1e-9
