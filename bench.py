@@ -301,6 +301,129 @@ def _emit(line):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
 
 
+def run_train_step(args, rank, local_rank, world):
+    """`--workload train-step` (BASELINE config 4, SURVEY section 8 a22 + e): one v1 consistency-distillation step per rank on one
+    16x320x512 sample (latents 1x4x16x40x64, 77x1024 prompt embeddings): add_noise, the LoRA-injected student forward
+    (training mode: LoRA + temporal-conv dropouts), two teacher forwards (conditional / unconditional) + CFG + one DDIM step,
+    the gradient-free target forward, the pseudo-Huber loss, the hand-written backward through all 575 LoRA layers and every
+    GroupNorm / LayerNorm / attention / GEGLU between them, the bucketed NCCL all-reduce of the 117 142 176-value fp32 gradient
+    arena overlapped with that backward, global-norm clipping and ONE fused AdamW launch
+    (train_t2v_turbo_v1_lora.py:976-1194 without the reward models; random-init weights, synthetic latents)."""
+    import torch
+    from t2v_turbo_b200 import dist as t2v_dist, ops
+    from t2v_turbo_b200.configs import VC2_UNET
+    from t2v_turbo_b200.distill import DistillStep, train_step
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.train_unet import StudentUNet
+    from t2v_turbo_b200.unet import UNetModel
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    t2v_dist.init_replicas("nccl", device)
+    torch.manual_seed(1234 + rank)
+    with torch.device(device):
+        base = UNetModel(**{**VC2_UNET, "time_cond_proj_dim": 256})
+        teacher = UNetModel(**VC2_UNET)
+    with torch.no_grad():      # zero-initialised output convs would make the gradients vanish: give every parameter a value
+        for m in (base, teacher):
+            for prm in m.parameters():
+                if prm.dim() > 1 and float(prm.abs().max()) == 0.0:
+                    prm.normal_(0, 0.02)
+    base, teacher = base.eval(), teacher.eval()
+    teacher.dtype = torch.bfloat16
+    student = StudentUNet(base, r=64, dropout_p=0.1).train()
+    with torch.no_grad():
+        for i in range(0, len(student.arena.shapes), 2):
+            student.arena.param(i).normal_(0, 0.02)
+    student.pack()
+    red = t2v_dist.ArenaReducer(student.arena.grads, n_buckets=8)
+    student.on_grads_final = red.ready
+    dstep = DistillStep(student, teacher, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012))
+    g = torch.Generator(device=device).manual_seed(99 + rank)
+    latents = torch.randn(1, 4, FRAMES, HEIGHT // 8, WIDTH // 8, device=device, generator=g)
+    prompt = torch.randn(1, 77, 1024, device=device, generator=g)
+    uncond = torch.randn(1, 77, 1024, device=device, generator=g) * 0.5
+
+    use_graph = not args.no_graph
+    if use_graph:      # the whole device side of the step as a chain of CUDA graphs cut at the reducer's bucket boundaries
+        from t2v_turbo_b200.distill import GraphedDistillStep
+        student.on_grads_final = None
+        n_a = ops.LAUNCHES
+        step = GraphedDistillStep(dstep, latents, prompt, uncond, reducer=red)      # runs the device step twice: warm-up + capture
+        launches_per_step = (ops.LAUNCHES - n_a) // 2
+        student.graph_refresh()
+    else:
+        step = dstep
+
+    def one():
+        return train_step(step, latents, prompt, uncond, lr=1e-5, reducer=red, world=world)
+    for _ in range(max(args.warmup, 2)):
+        out = one()
+    torch.cuda.synchronize()
+    n0 = ops.LAUNCHES
+    sampler = ClockSampler(local_rank)
+    t2v_dist.barrier(device)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = one()
+    e1.record()
+    t2v_dist.barrier(device)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - n0
+    finite = bool(torch.isfinite(out["loss"]).all()) and bool(torch.isfinite(student.arena.params).all())
+    # GPU time of the phases (each captured as its own CUDA graph and replayed; not part of the timed region)
+    z = dstep.scheduler.add_noise(latents, torch.randn_like(latents), torch.tensor([499], device=device))
+    zb = z.bfloat16()
+    ts = torch.tensor([499], device=device)
+    w_emb = torch.zeros(1, 256, device=device)
+    d_eps = torch.randn_like(z)
+    student.on_grads_final = None
+
+    def graph_ms(fn, reps=3):
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_, capture_error_mode="thread_local"):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g_.replay()
+        a.record()
+        for _ in range(reps):
+            g_.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, g_
+    student.arena.zero_grad()
+    fwd_ms, g_f = graph_ms(lambda: student(z, ts, context=prompt, fps=16, timestep_cond=w_emb), reps=1)   # (keeps its tapes for the backward)
+    bwd_ms, g_b = graph_ms(lambda: student.backward(d_eps), reps=1)
+    tea_ms, g_t = graph_ms(lambda: teacher(zb, ts, context=prompt, fps=16))
+    phases = dict(student_forward_ms=fwd_ms, student_backward_ms=bwd_ms, teacher_forward_ms=tea_ms)
+    del g_f, g_b, g_t
+    ar = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    ar[0].record()
+    for _ in range(5):
+        red.ready(0)
+        red.finish()
+    ar[1].record()
+    torch.cuda.synchronize()
+    ar_ms = ar[0].elapsed_time(ar[1]) / 5
+    ms, ar_ms = t2v_dist.max_over_ranks([ms, ar_ms], device)
+    if rank == 0:
+        per = ms / args.steps
+        _emit(dict(metric="v1 consistency-distillation steps/sec (one 16x320x512 sample per rank; student fwd+bwd, 2 teacher fwd, target fwd, "
+                          "all-reduce, AdamW)", value=world * args.steps / (ms * 1e-3), unit="samples/s", n_gpus=world, steps=args.steps,
+                   warmup=max(args.warmup, 2), ms_per_step=per, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                   data="synthetic",
+                   config=dict(workload="train_t2v_turbo_v1_lora.py:976-1194 without the reward models: VC2 UNet (1.41B) student with 575 LoRA "
+                                        "layers (r=64, dropout 0.1) + frozen teacher, bs=1 per rank, fp32 gradient arena 117142176 values, "
+                                        "8-bucket NCCL all-reduce overlapped with the backward, fused AdamW", parallelism=f"dp{world}",
+                               cuda_graph=use_graph, graph_segments=len(step.segments) if use_graph else 0, finite=finite),
+                   gpu_launches=launches if not use_graph else launches_per_step * args.steps, phases=phases,
+                   allreduce=dict(bytes=student.arena.grads.numel() * 4, ms_alone=ar_ms, share_of_step=ar_ms / per if world > 1 else 0.0,
+                                  gb_per_s=(student.arena.grads.numel() * 4 / (ar_ms * 1e-3) / 1e9) if world > 1 else None, buckets=8),
+                   loss=float(out["loss"]), clocks=clocks))
+
+
 def run_lora_step(args, rank, local_rank, world):
     """`--workload lora-step` (supplementary; BASELINE config 4's data-parallel exchange): per rank, the 567 LoRA-injected
     layers of the VC2 UNet that are on the tensor-core training path (utils/lora.py:19-230, r = 64) run forward and backward
@@ -438,7 +561,7 @@ def main():
     ap.add_argument("--batch", type=int, default=DEFAULT_BATCH, help="videos per pipeline call per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "lora-step"],
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "lora-step", "train-step"],
                     help="pipeline = the headline metric; lora-step = the data-parallel LoRA training exchange (supplementary)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -447,6 +570,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.workload == "train-step":
+        return run_train_step(args, rank, local_rank, world)
     if args.workload == "lora-step":
         run_lora_step(args, rank, local_rank, world)
         return

@@ -60,7 +60,8 @@ class DDIMSolver:
 
 
 class DistillStep:
-    """One optimisation step's forward + backward (the caller owns the reducer / optimizer calls, see `train_step`)."""
+    """One optimisation step's forward + backward (the caller owns the reducer / optimizer calls, see `train_step`).  With a
+    data-parallel reducer: `student.on_grads_final = reducer.ready` (eager) or GraphedDistillStep(step, ..., reducer=...)."""
 
     def __init__(self, student, teacher, scheduler, *, num_ddim_timesteps=50, topk=20, w_min=5.0, w_max=15.0, loss_type="huber",
                  huber_c=0.001, timestep_scaling_factor=10.0, time_cond_proj_dim=256, fps=16):
@@ -72,73 +73,148 @@ class DistillStep:
         self.alpha, self.sigma = ac.sqrt(), (1 - ac).sqrt()                     # :682-683
         self.solver = DDIMSolver(scheduler.alphas_cumprod.cpu().numpy(), ddim_timesteps=num_ddim_timesteps)
 
-    def __call__(self, latents, prompt_embeds, uncond_prompt_embeds, *, fixed=None, generator=None):
-        """latents [B, 4, T, H, W] (already scaled by the VAE factor); returns dict(loss, model_pred, target, ...).  `fixed` may
-        pin the random draws (index [B] long, noise like latents, w [B]) — the parity test uses the reference's draws."""
+    # ---- host side: the random draws of the step and every per-sample coefficient (fp64 on the host, B floats each)
+    COEFS = ("an_a", "an_b", "k_z", "k_e", "cfg_c", "cfg_u", "x0_z", "x0_e", "dd_x", "dd_e", "tg_x", "tg_e")
+
+    def host_draws(self, bsz, fixed=None, generator=None):
+        """-> dict of CPU tensors: index, start_timesteps, timesteps, w, w_emb [B, cond_dim] and the COEFS ([B] fp32 each).
+        `fixed` may pin index [B] / w [B] (the parity test uses the reference's draws)."""
         fixed = fixed or {}
-        dev = latents.device
-        bsz = latents.shape[0]
         index = fixed.get("index")
         if index is None:
-            index = torch.randint(0, self.n_ddim, (bsz,), generator=generator)
+            index = torch.randint(0, self.n_ddim, (bsz,), generator=generator)                       # :980-982
         index = index.cpu().long()
         start_t = self.solver.ddim_timesteps[index]
-        t_n = torch.clamp(start_t - self.topk, min=0)                           # :983-987
+        t_n = torch.clamp(start_t - self.topk, min=0)                                                # :983-987
         cs_s, co_s = scalings_for_boundary_conditions(start_t.double(), timestep_scaling=self.ts_scale)
         cs_n, co_n = scalings_for_boundary_conditions(t_n.double(), timestep_scaling=self.ts_scale)
-        noise = fixed.get("noise")
-        if noise is None:
-            noise = torch.randn(latents.shape, device=dev, dtype=latents.dtype, generator=generator if (generator is not None and generator.device == dev) else None)
-        z = self.scheduler.add_noise(latents, noise.to(dev), start_t.to(dev))
         w = fixed.get("w")
         if w is None:
-            w = (self.w_max - self.w_min) * torch.rand((bsz,), generator=generator if (generator is not None and generator.device.type == "cpu") else None) + self.w_min
+            w = (self.w_max - self.w_min) * torch.rand((bsz,), generator=generator) + self.w_min      # :1009
         w = w.cpu().double()
-        w_emb = guidance_scale_embedding(w.float(), embedding_dim=self.cond_dim).to(dev)
-        f32 = lambda v: v.float().to(dev)
+        a_s, s_s, a_n, s_n = self.alpha[start_t], self.sigma[start_t], self.alpha[t_n], self.sigma[t_n]
+        a_prev = self.solver.ddim_alpha_cumprods_prev[index].double()
+        c = dict(an_a=a_s, an_b=s_s,                                      # z = alpha x + sigma noise                  (add_noise)
+                 k_z=cs_s + co_s / a_s, k_e=-co_s * s_s / a_s,            # c_skip z + c_out (z - sigma eps) / alpha   (:1030-1039)
+                 cfg_c=1.0 + w, cfg_u=-w,                                 # eps_c + w (eps_c - eps_u)                  (:1156-1158)
+                 x0_z=1.0 / a_s, x0_e=-s_s / a_s,                         # x0 of the CFG eps (linear: == x0_c + w (x0_c - x0_u))
+                 dd_x=a_prev.sqrt(), dd_e=(1.0 - a_prev).sqrt(),          # DDIMSolver.ddim_step                       (:1162)
+                 tg_x=cs_n + co_n / a_n, tg_e=-co_n * s_n / a_n)          # the target's boundary parametrisation      (:1172-1181)
+        out = {k: v.float().contiguous() for k, v in c.items()}
+        out.update(index=index, start_timesteps=start_t, timesteps=t_n, w=w,
+                   w_emb=guidance_scale_embedding(w.float(), embedding_dim=self.cond_dim))
+        return out
 
-        # ---- online student prediction (kept for the backward)
-        eps_s = self.student(z, start_t.to(dev), context=prompt_embeds, fps=self.fps, timestep_cond=w_emb)
-        a_s, s_s = self.alpha[start_t], self.sigma[start_t]
-        # c_skip z + c_out (z - sigma eps) / alpha  =  (c_skip + c_out / alpha) z  +  (-c_out sigma / alpha) eps
-        k_z, k_e = cs_s + co_s / a_s, -co_s * s_s / a_s
-        model_pred = ops.scale_add_rows(z.float(), f32(k_z), eps_s.float(), f32(k_e))
+    # ---- device side: no host synchronisation, no host-dependent control flow => CUDA-graph capturable (GraphedDistillStep)
+    def device_step(self, S, latents, noise, prompt_embeds, uncond_prompt_embeds):
+        """S: the host_draws tensors on the device.  Runs the whole step up to and including the student backward (the
+        gradient-arena hooks fire from inside it)."""
+        z = ops.scale_add_rows(latents, S["an_a"], noise, S["an_b"])
+        eps_s = self.student(z, S["start_timesteps"], context=prompt_embeds, fps=self.fps, timestep_cond=S["w_emb"])
+        model_pred = ops.scale_add_rows(z, S["k_z"], eps_s.float(), S["k_e"])
         saved = self.student.detach_tapes()
-
-        # ---- teacher CFG estimate and one DDIM step  (no grad; the frozen UNet's inference path)
+        # teacher CFG estimate and one DDIM step (no grad; the frozen UNet's inference path)
         zt = z.to(torch.bfloat16) if self.teacher.dtype == torch.bfloat16 else z
-        eps_c = self.teacher(zt, start_t.to(dev), context=prompt_embeds, fps=self.fps).float()
-        eps_u = self.teacher(zt, start_t.to(dev), context=uncond_prompt_embeds, fps=self.fps).float()
-        eps_cfg = ops.scale_add_rows(eps_c, f32(1.0 + w), eps_u, f32(-w))       # eps_c + w (eps_c - eps_u)
-        x0_cfg = ops.scale_add_rows(z.float(), f32(1.0 / a_s), eps_cfg, f32(-s_s / a_s))   # linear in eps: == x0_c + w (x0_c - x0_u)
-        x_prev = self.solver.ddim_step(x0_cfg, eps_cfg, index)
-
-        # ---- target: the student itself on x_prev at t_n, no grad (still in training mode, as the reference's unet is)
-        eps_t = self.student(x_prev, t_n.to(dev), context=prompt_embeds, fps=self.fps, timestep_cond=w_emb)
+        eps_c = self.teacher(zt, S["start_timesteps"], context=prompt_embeds, fps=self.fps).float()
+        eps_u = self.teacher(zt, S["start_timesteps"], context=uncond_prompt_embeds, fps=self.fps).float()
+        eps_cfg = ops.scale_add_rows(eps_c, S["cfg_c"], eps_u, S["cfg_u"])
+        x0_cfg = ops.scale_add_rows(z, S["x0_z"], eps_cfg, S["x0_e"])
+        x_prev = ops.scale_add_rows(x0_cfg, S["dd_x"], eps_cfg, S["dd_e"])
+        # target: the student itself on x_prev at t_n, gradient-free (still in training mode, as the reference's unet is)
+        eps_t = self.student(x_prev, S["timesteps"], context=prompt_embeds, fps=self.fps, timestep_cond=S["w_emb"])
         self.student.detach_tapes()
-        a_n, s_n = self.alpha[t_n], self.sigma[t_n]
-        target = ops.scale_add_rows(x_prev, f32(cs_n + co_n / a_n), eps_t.float(), f32(-co_n * s_n / a_n))
+        target = ops.scale_add_rows(x_prev, S["tg_x"], eps_t.float(), S["tg_e"])
         self.student.restore_tapes(saved)
-
-        # ---- loss and its gradient w.r.t. the student's eps prediction
         if self.loss_type == "l2":
             loss, d_pred = ops.mse_loss_grad(model_pred, target)
         else:
             loss, d_pred = ops.huber_loss_grad(model_pred, target, self.huber_c)
-        d_eps = ops.scale_add_rows(d_pred, f32(k_e))
-        self.student.backward(d_eps)
-        return dict(loss=loss, model_pred=model_pred, target=target, x_prev=x_prev, start_timesteps=start_t, timesteps=t_n, w=w)
+        self.student.backward(ops.scale_add_rows(d_pred, S["k_e"]))
+        return dict(loss=loss, model_pred=model_pred, target=target, x_prev=x_prev)
+
+    def __call__(self, latents, prompt_embeds, uncond_prompt_embeds, *, fixed=None, generator=None):
+        """latents [B, 4, T, H, W] fp32 (already scaled by the VAE factor); returns dict(loss, model_pred, target, x_prev, ...).
+        `fixed` may pin the random draws (index [B], noise like latents, w [B])."""
+        dev = latents.device
+        H = self.host_draws(latents.shape[0], fixed, generator)
+        noise = (fixed or {}).get("noise")
+        if noise is None:
+            noise = torch.randn(latents.shape, device=dev, dtype=torch.float32)                        # :1001
+        S = {k: (v.to(dev) if torch.is_tensor(v) and k not in ("index", "w") else v) for k, v in H.items()}
+        out = self.device_step(S, latents.float().contiguous(), noise.to(dev).float().contiguous(), prompt_embeds, uncond_prompt_embeds)
+        out.update(start_timesteps=H["start_timesteps"], timesteps=H["timesteps"], w=H["w"])
+        return out
+
+
+class GraphedDistillStep:
+    """DistillStep.device_step captured ONCE as a chain of CUDA graphs and replayed per step: the eager step is ~12 000 small
+    launches through ctypes (host bound: 350 ms per step against ~170 ms of GPU work on a B200).  The capture is cut wherever
+    the student backward reports a block of the gradient arena final (StudentUNet.on_grads_final), so the data-parallel
+    exchange keeps its overlap: after replaying segment k the reducer all-reduces the buckets that segment completed while
+    segment k+1 runs.  Per step only the host draws (a few hundred bytes) and the batch are copied into static buffers."""
+
+    def __init__(self, step: DistillStep, latents, prompt_embeds, uncond_prompt_embeds, reducer=None):
+        self.step, self.reducer = step, reducer
+        dev = latents.device
+        self.lat, self.noise = latents.float().clone(), torch.empty_like(latents, dtype=torch.float32)
+        self.prompt, self.uncond = prompt_embeds.clone(), uncond_prompt_embeds.clone()
+        H = step.host_draws(latents.shape[0])
+        self.S = {k: v.to(dev) for k, v in H.items() if torch.is_tensor(v) and k not in ("index", "w")}
+        student = step.student
+        self.noise.normal_()
+        student.on_grads_final = None
+        student.arena.zero_grad()
+        step.device_step(self.S, self.lat, self.noise, self.prompt, self.uncond)        # warm-up: lazy allocations, kernel attributes
+        torch.cuda.synchronize()
+        self.segments = []                      # [(graph, arena offset that is final after it)]
+        pool = torch.cuda.graph_pool_handle()
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            cur = [torch.cuda.CUDAGraph()]
+            cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
+
+            def cut(offset):
+                cur[0].capture_end()
+                self.segments.append((cur[0], offset))
+                cur[0] = torch.cuda.CUDAGraph()
+                cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
+            student.on_grads_final = cut
+            self.out = step.device_step(self.S, self.lat, self.noise, self.prompt, self.uncond)
+            cur[0].capture_end()
+            self.segments.append((cur[0], 0))
+        torch.cuda.current_stream().wait_stream(stream)
+        student.on_grads_final = None
+
+    def __call__(self, latents, prompt_embeds, uncond_prompt_embeds, *, fixed=None, generator=None):
+        H = self.step.host_draws(latents.shape[0], fixed, generator)
+        for k, buf in self.S.items():
+            buf.copy_(H[k], non_blocking=True)
+        self.lat.copy_(latents)
+        self.prompt.copy_(prompt_embeds)
+        self.uncond.copy_(uncond_prompt_embeds)
+        if fixed is not None and fixed.get("noise") is not None:
+            self.noise.copy_(fixed["noise"])
+        else:
+            self.noise.normal_()
+        for g, offset in self.segments:
+            g.replay()
+            if self.reducer is not None:
+                self.reducer.ready(offset)
+        out = dict(self.out)
+        out.update(start_timesteps=H["start_timesteps"], timesteps=H["timesteps"], w=H["w"])
+        return out
 
 
 def train_step(step: DistillStep, latents, prompt_embeds, uncond_prompt_embeds, *, lr, reducer=None, world=1, max_grad_norm=1.0,
                weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8, **kw):
     """zero_grad -> DistillStep -> (bucketed NCCL all-reduce) -> clip_grad_norm_ + fused AdamW -> refresh the bf16 LoRA operands."""
-    arena = step.student.arena
+    student = step.step.student if isinstance(step, GraphedDistillStep) else step.student
+    arena = student.arena
     arena.zero_grad()
-    out = step(latents, prompt_embeds, uncond_prompt_embeds, **kw)
+    out = step(latents, prompt_embeds, uncond_prompt_embeds, **kw)     # the reducer's ready() calls fire during the backward
     if reducer is not None:
-        reducer.ready(0)
         reducer.finish()
     arena.adamw_step(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=1.0 / world, max_grad_norm=max_grad_norm)
-    step.student.refresh()
+    student.refresh()
     return out

@@ -138,17 +138,23 @@ class _PackedLora:
 
     @torch.no_grad()
     def refresh(self):
+        """bf16 GEMM operands from the fp32 LoRA weights.  After the first call the operands are rewritten IN PLACE: CUDA
+        graphs captured over this layer keep reading the same buffers."""
         up, down = self.up_f32, self.down_f32
-        self.u = up.reshape(self.cout, self.r).to(BF16).contiguous()            # [N, r]
-        self.u_t = up.reshape(self.cout, self.r).t().to(BF16).contiguous()      # [r, N]
+        up2 = up.reshape(self.cout, self.r)
         if self.kind == "linear":
-            down = down.reshape(self.r, -1)
-            self.d = down.to(BF16).contiguous()                                 # [r, K]
-            self.d_t = down.t().to(BF16).contiguous()                           # [K, r]
+            down2 = down.reshape(self.r, -1)
+            vals = dict(u=up2, u_t=up2.t(), d=down2, d_t=down2.t())
         else:
             sp = tuple(range(2, down.dim()))
-            self.d = ops.pack_conv_weight(down)                                 # [r, taps * Cin]
-            self.d_t = ops.pack_conv_weight(down.transpose(0, 1).flip(sp).contiguous())   # [Cin, taps * r]
+            vals = dict(u=up2, u_t=up2.t(), d=ops.pack_conv_weight(down),                          # [r, taps * Cin]
+                        d_t=ops.pack_conv_weight(down.transpose(0, 1).flip(sp).contiguous()))      # [Cin, taps * r], taps reversed
+        for name, v in vals.items():
+            cur = getattr(self, name, None)
+            if cur is None:
+                setattr(self, name, v.to(BF16).contiguous())
+            else:
+                cur.copy_(v)
 
 
 def _base_op(kind, x, w, bias, residual=None, bias_div=None):

@@ -123,7 +123,9 @@ class _Layer:
         if not self.lora:
             return ops.linear(dy.contiguous().view(-1, dy.shape[-1]), self.w_t, None).view(*saved[0].shape) if need_dx else None
         x, t, mask, ms = saved
-        return lora_backward(self.pk, x, t, mask, ms, dy, self.g_up, self.g_down, need_dx=need_dx)
+        dx = lora_backward(self.pk, x, t, mask, ms, dy, self.g_up, self.g_down, need_dx=need_dx)
+        self.flush_padded_grads()
+        return dx
 
 
 class _Norm:
@@ -172,6 +174,14 @@ class StudentUNet:
         self._plain = {}
         self._packed = False
         self._build()
+        # first arena offset of every top-level block: once the backward has passed a block (they are visited from `out`
+        # down to the middle block in reverse arena order) every gradient at or above that offset is final -> ArenaReducer.ready
+        self._first_offset = {}
+        for lay in self.layer_list:
+            parts = lay.name.split(".")
+            key = ".".join(parts[:2]) if parts[0] in ("input_blocks", "output_blocks") else parts[0]
+            self._first_offset.setdefault(key, self.arena.offsets[lay.i_up])
+        self.on_grads_final = None      # callable(offset): the data-parallel exchange hooks in here (dist.ArenaReducer.ready)
 
     # ------------------------------------------------------------------ structure
     def _L(self, m):
@@ -239,9 +249,25 @@ class StudentUNet:
         self._packed = True
 
     def refresh(self):
-        """Re-derive the bf16 LoRA operands after `arena.adamw_step` / `arena.load_list`."""
+        """Re-derive the bf16 LoRA operands after `arena.adamw_step` / `arena.load_list` (in place; ~2 300 small device ops).
+        `graph_refresh()` captures them once as a CUDA graph, after which this is a single replay."""
+        if getattr(self, "_refresh_graph", None) is not None:
+            self._refresh_graph.replay()
+            return
         for lay in self.layer_list:
             lay.refresh()
+
+    def graph_refresh(self):
+        if not self._packed:
+            self.pack()
+        self._refresh_graph = None
+        self.refresh()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            for lay in self.layer_list:
+                lay.refresh()
+        self._refresh_graph = g
 
     def train(self, mode=True):
         self.training = mode
@@ -557,18 +583,23 @@ class StudentUNet:
         d_hn = conv.backward(oc["conv"], dy).view(-1, c)
         dh = ops.groupnorm_bwd(oc["h"], d_hn, gn.w, gn.b, rows_per_sample=hh * ww, eps=gn.eps, silu=True)
         d_skips = []
-        for tape, (c_h, c_s) in zip(reversed(self._tapes_out), reversed(self._skip_ch)):
+        n_out = len(self._tapes_out)
+        for j, (tape, (c_h, c_s)) in enumerate(zip(reversed(self._tapes_out), reversed(self._skip_ch))):
             dcat = self._seq_bwd(tape, dh)
+            if self.on_grads_final is not None:
+                self.on_grads_final(self._first_offset[f"output_blocks.{n_out - 1 - j}"])
             d2 = dcat.view(-1, c_h + c_s)
             dh = d2[:, :c_h].contiguous().view(*dcat.shape[:-1], c_h)
             d_skips.append(d2[:, c_h:])
         dh = self._seq_bwd(self._tape_mid, dh)
+        if self.on_grads_final is not None:     # (init_attn sits between input_blocks and middle_block in the arena but runs with
+            self.on_grads_final(self._first_offset["middle_block"])   # input block 0: nothing below the middle block is final yet)
         for tape in reversed(self._tapes_in):
             ds = d_skips.pop()
             dh = ops.add(dh.reshape(-1, dh.shape[-1]), ds).view(*dh.shape)
             dh = self._seq_bwd(tape, dh)
         self._emb_bwd()
-        for lay in self.layer_list:
-            lay.flush_padded_grads()
+        if self.on_grads_final is not None:
+            self.on_grads_final(0)
         # release the saved activations
         self._tapes_in = self._tape_mid = self._tapes_out = self._out_ctx = self._emb_ctx = None

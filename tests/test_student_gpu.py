@@ -148,3 +148,59 @@ def test_distill_step_vs_reference_composition(cuda_device):
     # 0.92 .. 1.10).  The backward itself is pinned by the linear-loss fixture above (3.2e-2); this test pins the step's glue:
     # timesteps, add_noise, the CFG / DDIM algebra, the boundary scalings, the loss value, and the gradient's direction.
     assert (ratio - 1).abs().max().item() < 0.15 and total < 0.40, (ratio.min().item(), ratio.max().item(), total)
+
+
+def test_graphed_distill_step_matches_eager(cuda_device):
+    """GraphedDistillStep (the device side of the step as a chain of CUDA graphs cut at the gradient-arena hooks) reproduces the
+    eager step: same loss and gradients for the same draws (eval mode: no dropout randomness), replayed twice with different
+    draws in between (the static buffers really are re-read), and the cuts report ascending-completion offsets."""
+    from oracle.configs import UNET_CONFIGS, student_loras
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200.distill import DistillStep, GraphedDistillStep
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.train_unet import StudentUNet
+    from t2v_turbo_b200.unet import UNetModel
+    g = torch.load(os.path.join(GOLD, "distill_step_small.pt"))
+    spec = UNET_CONFIGS["small"]
+    base = UNetModel(**spec["cfg"])
+    sd = seeded_state_dict(base.state_dict(), spec["weight_seed"])
+    base.load_state_dict(sd, strict=True)
+    tcfg = dict(spec["cfg"])
+    tcfg["time_cond_proj_dim"] = None
+    teacher = UNetModel(**tcfg)
+    teacher.load_state_dict({k: v for k, v in sd.items() if not k.startswith("time_cond_proj")}, strict=True)
+    base, teacher = base.cuda().eval(), teacher.cuda().eval()
+    s = StudentUNet(base, r=64).eval()
+    s.arena.load_list(student_loras(g["shapes"]))
+    s.pack()
+    step = DistillStep(s, teacher, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012))
+    inp = g["inputs"]
+    lat, pr, un = inp["latents"].cuda(), inp["prompt"].cuda(), inp["uncond"].cuda()
+    fixed = dict(index=inp["index"], noise=inp["noise"].cuda(), w=inp["w"])
+    s.arena.zero_grad()
+    out_e = step(lat, pr, un, fixed=fixed)
+    grads_e, loss_e = s.arena.grads.clone(), float(out_e["loss"])
+    seen = []
+
+    class Rec:
+        def ready(self, off):
+            seen.append(off)
+    gs = GraphedDistillStep(step, lat, pr, un, reducer=Rec())
+    assert len(gs.segments) >= 4
+    for rep in range(2):
+        s.arena.zero_grad()
+        gs(lat, pr, un, fixed=dict(index=torch.tensor([3, 44]), noise=torch.randn_like(lat), w=torch.tensor([9.0, 5.5])))   # other draws
+        s.arena.zero_grad()
+        seen.clear()
+        out_g = gs(lat, pr, un, fixed=fixed)
+        torch.cuda.synchronize()
+        assert abs(float(out_g["loss"]) - loss_e) < 1e-5 * abs(loss_e), (float(out_g["loss"]), loss_e)
+        assert _rel(s.arena.grads, grads_e) < 1e-4, _rel(s.arena.grads, grads_e)
+        assert seen == sorted(seen, reverse=True) and seen[-1] == 0, seen
+    # the in-place operand refresh under a captured graph: an optimizer step changes what the SAME graphs compute
+    s.graph_refresh()
+    s.arena.adamw_step(lr=1e-2, max_grad_norm=1.0)
+    s.refresh()
+    s.arena.zero_grad()
+    out2 = gs(lat, pr, un, fixed=fixed)
+    assert abs(float(out2["loss"]) - loss_e) > 1e-6, "the captured graphs did not see the refreshed LoRA operands"
