@@ -345,6 +345,45 @@ def gen_distill_step(name="small"):
                 "timesteps": timesteps, "grad_norms": norms, "grads_full": full}, os.path.join(GOLD, f"distill_step_{name}.pt"))
 
 
+def gen_distill_tables():
+    """Host-side tables / closed forms of the distillation step straight from the reference: DDIMSolver (ode_solver/ddim_solver.py),
+    scalings_for_boundary_conditions and guidance_scale_embedding (utils/common_utils.py), and one tensor-level composition of
+    the per-sample algebra (:1030-1039, :1108-1181) on random latents in fp64 for the coefficient-folding test."""
+    from ode_solver.ddim_solver import DDIMSolver
+    from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
+    from utils.common_utils import (append_dims, get_predicted_noise, get_predicted_original_sample, guidance_scale_embedding,
+                                    scalings_for_boundary_conditions)
+    ns = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
+    solver = DDIMSolver(ns.alphas_cumprod.numpy(), ddim_timesteps=50, use_scale=False)
+    ts = torch.tensor([0, 19, 99, 499, 759, 999])
+    cs, co = scalings_for_boundary_conditions(ts, timestep_scaling=10.0)
+    w = torch.tensor([5.0, 7.5, 14.25])
+    out = dict(ddim_timesteps=solver.ddim_timesteps.clone(), ddim_alpha_cumprods=solver.ddim_alpha_cumprods.clone(),
+               ddim_alpha_cumprods_prev=solver.ddim_alpha_cumprods_prev.clone(), scal_t=ts, c_skip=cs, c_out=co, w=w,
+               w_emb=guidance_scale_embedding(w, embedding_dim=256))
+    # tensor-level composition in fp64
+    g = torch.Generator().manual_seed(77)
+    alpha, sigma = torch.sqrt(ns.alphas_cumprod).double(), torch.sqrt(1 - ns.alphas_cumprod).double()
+    solver.ddim_alpha_cumprods_prev = solver.ddim_alpha_cumprods_prev.double()
+    index = torch.tensor([49, 7, 0])
+    start = solver.ddim_timesteps[index]
+    tn = torch.where(start - 20 < 0, torch.zeros_like(start), start - 20)
+    lat, noise, e_s, e_c, e_u, e_t = (torch.randn(3, 4, 2, 3, 3, generator=g, dtype=torch.float64) for _ in range(6))
+    z = ns.add_noise(lat, noise, start)
+    css, cos_ = [append_dims(x.double(), 5) for x in scalings_for_boundary_conditions(start, timestep_scaling=10.0)]
+    csn, con = [append_dims(x.double(), 5) for x in scalings_for_boundary_conditions(tn, timestep_scaling=10.0)]
+    model_pred = css * z + cos_ * get_predicted_original_sample(e_s, start, z, "epsilon", alpha, sigma)
+    wv = w.double().reshape(3, 1, 1, 1, 1)
+    cx0, cn = get_predicted_original_sample(e_c, start, z, "epsilon", alpha, sigma), get_predicted_noise(e_c, start, z, "epsilon", alpha, sigma)
+    ux0, un = get_predicted_original_sample(e_u, start, z, "epsilon", alpha, sigma), get_predicted_noise(e_u, start, z, "epsilon", alpha, sigma)
+    x_prev = solver.ddim_step(cx0 + wv * (cx0 - ux0), cn + wv * (cn - un), index)
+    target = csn * x_prev + con * get_predicted_original_sample(e_t, tn, x_prev, "epsilon", alpha, sigma)
+    out["compose"] = dict(index=index, w=w, lat=lat, noise=noise, e_s=e_s, e_c=e_c, e_u=e_u, e_t=e_t, z=z, model_pred=model_pred, x_prev=x_prev,
+                          target=target, start=start, tn=tn)
+    torch.save(out, os.path.join(GOLD, "distill_tables.pt"))
+    print("  distill tables: ddim_timesteps", solver.ddim_timesteps[:4].tolist(), "...", solver.ddim_timesteps[-2:].tolist())
+
+
 def gen_scheduler():
     from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
     s = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
@@ -473,7 +512,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -486,6 +525,8 @@ if __name__ == "__main__":
             gen_student_grads()
         elif item == "distill_step":
             gen_distill_step()
+        elif item == "distill_tables":
+            gen_distill_tables()
         elif item == "unet_probs":
             gen_unet_probs()
         elif item.startswith("lora_"):
