@@ -109,8 +109,8 @@ class LoraArena:
 def _keep_mask(shape, p, device, generator=None):
     if p <= 0.0:
         return None, 1.0
-    keep = torch.empty(shape, device=device, dtype=torch.float32).bernoulli_(1.0 - p, generator=generator)
-    return keep.to(torch.uint8), 1.0 / (1.0 - p)
+    keep = torch.empty(shape, device=device, dtype=torch.uint8).bernoulli_(1.0 - p, generator=generator)   # 1 byte / element
+    return keep, 1.0 / (1.0 - p)
 
 
 class _PackedLora:
@@ -126,14 +126,21 @@ class _PackedLora:
         if self.cin % 64 or self.cout % 64 or self.r % 64:
             raise NotImplementedError(f"LoRA layer {self.cin} -> {self.cout} (rank {self.r}): the tensor-core path needs channel "
                                       "counts and rank in multiples of 64 (every VC2 layer except the 4-channel conv_in / out)")
+        # dgrad: dx = dy W + dt D is ONE implicit GEMM over the channel-concatenated pair (dy | dt) — the A operand's second
+        # source — against wd_t = [W^T | D^T] concatenated along K (per tap for the convolutions): no second pass over dx.
         if kind == "linear":   # nn.Linear, or a 1x1 convolution (ResBlock skip_connection) run as a per-pixel Linear
             wd = wd.reshape(wd.shape[0], -1)
             self.w = wd.to(BF16).contiguous()                                   # [N, K]
-            self.w_t = wd.t().to(BF16).contiguous()                             # [K, N]: dgrad operand
+            self.taps = 1
+            self.wd_t = torch.empty((self.cin, self.cout + self.r), device=wd.device, dtype=BF16)     # [K, N + r]
+            self.wd_t[:, :self.cout] = wd.t()
         else:
             sp = tuple(range(2, wd.dim()))
             self.w = ops.pack_conv_weight(wd)                                   # [Cout, taps * Cin]
-            self.w_t = ops.pack_conv_weight(wd.transpose(0, 1).flip(sp).contiguous())   # [Cin, taps * Cout], taps reversed
+            self.taps = math.prod(wd.shape[2:])
+            w_t = ops.pack_conv_weight(wd.transpose(0, 1).flip(sp).contiguous())   # [Cin, taps * Cout], taps reversed
+            self.wd_t = torch.empty((self.cin, self.taps * (self.cout + self.r)), device=wd.device, dtype=BF16)
+            self.wd_t.view(self.cin, self.taps, self.cout + self.r)[:, :, :self.cout] = w_t.view(self.cin, self.taps, self.cout)
         self.refresh()
 
     @torch.no_grad()
@@ -149,6 +156,8 @@ class _PackedLora:
             sp = tuple(range(2, down.dim()))
             vals = dict(u=up2, u_t=up2.t(), d=ops.pack_conv_weight(down),                          # [r, taps * Cin]
                         d_t=ops.pack_conv_weight(down.transpose(0, 1).flip(sp).contiguous()))      # [Cin, taps * r], taps reversed
+        d_t = vals.pop("d_t")
+        self.wd_t.view(self.cin, self.taps, self.cout + self.r)[:, :, self.cout:] = d_t.reshape(self.cin, self.taps, self.r)
         for name, v in vals.items():
             cur = getattr(self, name, None)
             if cur is None:
@@ -194,8 +203,7 @@ def lora_backward(pk: _PackedLora, x, t, mask, mask_scale, dy, g_up, g_down, nee
     ops.wgrad(x, dt, g_down, taps=taps, out_strides=(pk.cin * n_taps, n_taps, 1))
     if not need_dx:
         return None
-    dx = _base_op(pk.kind, dy, pk.w_t, None)
-    return _base_op(pk.kind, dt, pk.d_t, None, residual=dx)
+    return _base_op(pk.kind, (dy.view(*x.shape[:-1], pk.cout), dt), pk.wd_t, None)
 
 
 class _LoraFn(torch.autograd.Function):

@@ -393,18 +393,20 @@ def upconv3x3(x, w_phases, bias=None, *, out=None, block_n=0, stats=None):
 
 
 def tconv3(x, w, bias=None, *, residual=None, out=None, block_n=0, split_k=0, stats=None):
-    """Conv3d (3,1,1) / pad (1,0,0) over x: [B, T, HW, C] (TemporalConvBlock, openaimodel3d.py:274-296).
-    w: [Cout, 3*C] packed."""
+    """Conv3d (3,1,1) / pad (1,0,0) over x: [B, T, HW, C] (or a channel-concatenated pair) (TemporalConvBlock,
+    openaimodel3d.py:274-296).  w: [Cout, 3*C] packed."""
+    x, x1 = _as_pair(x)
     _check_act(x)
     b, t, hw, c = x.shape
+    c1 = x1.shape[3] if x1 is not None else 0
     cout = w.shape[0]
-    assert w.shape[1] == 3 * c
+    assert w.shape[1] == 3 * (c + c1)
     if out is None:
         out = torch.empty((b, t, hw, cout), device=x.device, dtype=BF16)
     box = plan_box((hw, t, b, 1))
     return _gemm_raw(
-        a=(x, None), a_ch=(c, 0), a_ch_total=(c, 0), a_size=(hw, t, b, 1),
-        a_stride=((c, hw * c, t * hw * c, 0), None), box=box, taps=_TAPS_T3, tap_ch_off=None, w=w,
+        a=(x, x1), a_ch=(c, c1), a_ch_total=(c, c1), a_size=(hw, t, b, 1),
+        a_stride=((c, hw * c, t * hw * c, 0), (c1, hw * c1, t * hw * c1, 0) if x1 is not None else None), box=box, taps=_TAPS_T3, tap_ch_off=None, w=w,
         n_rows=cout, out=out, o_size=(hw, t, b, 1), o_stride=(cout, hw * cout, t * hw * cout, 0),
         n_out=cout, bias=bias, residual=residual, block_n=block_n, split_k=split_k,
         col_accum=(stats, (0, 1, t, 0)) if stats is not None else None)   # per-frame sums [B*T, Cout, 2]
