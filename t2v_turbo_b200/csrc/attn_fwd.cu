@@ -362,7 +362,8 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
   // T2V_ATTN_V2=1 selects the two-Q-tile kernel (attn_fwd2.cu: P in TMEM, polynomial exp2).  Measured on B200 (round 2,
   // profiles/r02_attention.md): (16, 2560, 2560, 5) 219-228 us vs 228 us for this kernel, the small shapes 10-30 % slower
   // (one CTA per SM) — so the single-tile kernel below stays the default.
-  static const int use_v2 = (getenv("T2V_ATTN_V2") != nullptr && getenv("T2V_ATTN_V2")[0] == '1') ? 1 : 0;
+  const char* v2_env = getenv("T2V_ATTN_V2");   // read per call: scripts/attn_ablate.py switches kernels inside one process
+  const int use_v2 = (v2_env != nullptr && v2_env[0] == '1') ? 1 : 0;
   if (use_v2 && !d->causal && !d->lse2) return launch_attn_fwd2(d, tq, tk, tv, stream);
   AttnParams p;
   p.heads = d->heads;

@@ -39,7 +39,8 @@ constexpr int kA2Stages = 3;
 constexpr int kA2Tile = 128;
 constexpr int kA2TileBytes = kA2Tile * 64 * 2;  // 16 KB: 128 rows x 64 bf16
 constexpr int kA2Smem = 2 * kA2TileBytes + 2 * kA2Stages * kA2TileBytes + 512 + 2 * 2 * 128 * 4 + 64;
-constexpr int kA2PolyPairs = 7;  // of the 16 column pairs of every 32-column chunk: exp2 on the FMA pipe
+constexpr int kA2SatDefault = 0;        // 1: the saturating-FMA range reduction (ex2_poly2_sat)
+constexpr int kA2PolyPairsDefault = 7;  // of the 16 column pairs of every 32-column chunk: exp2 on the FMA pipe
 
 struct Attn2Params {
   int32_t heads, len_q, len_k, n_q_pairs, n_kv_tiles, kv_batch_div;
@@ -72,6 +73,37 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return r;
 }
 
+// 2^x' for a pair, x' = 128 y - 112 with y = sat((s c + 112 - ref) / 128) already formed by ONE saturating FMA per element:
+// the saturation IS the range clamp (x' in [-112, 16]; 2^16 trips the row-sum guard), the integer part comes from one
+// packed FMA, the exponent insert is one integer multiply-add per element: 10 issue slots per pair instead of 15.
+__device__ __forceinline__ float sat_fma(float a, float b, float c) {
+  float y;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+__device__ __forceinline__ float2 ex2_poly2_sat(float2 y) {
+  constexpr float kMagicM = 12582912.f - 112.f;   // t = x' + 1.5 * 2^23: round(x') sits in the low mantissa bits
+  const float2 c128 = make_float2(128.f, 128.f);
+  const float2 t = fma_f32x2(y, c128, make_float2(kMagicM, kMagicM));
+  const float2 u = fma_f32x2(t, make_float2(-1.f, -1.f), make_float2(kMagicM, kMagicM));   // -(round(x') + 112), exact
+  const float2 fr = fma_f32x2(y, c128, u);                                                   // x' - round(x')
+  float2 p = fma_f32x2(fr, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  p = fma_f32x2(p, fr, make_float2(0.6932609677f, 0.6932609677f));
+  p = fma_f32x2(p, fr, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  uint32_t r0, r1;
+  asm("mad.lo.u32 %0, %1, 0x800000, %2;" : "=r"(r0) : "r"(__float_as_uint(t.x)), "r"(__float_as_uint(p.x)));
+  asm("mad.lo.u32 %0, %1, 0x800000, %2;" : "=r"(r1) : "r"(__float_as_uint(t.y)), "r"(__float_as_uint(p.y)));
+  r.x = __uint_as_float(r0);
+  r.y = __uint_as_float(r1);
+  return r;
+}
+
+// kA2PolyPairs: column pairs per 32-column chunk whose exp2 runs on the FMA pipe.  kAbl != 0 are TIMING ABLATIONS (wrong
+// results, scripts/attn_ablate.py only): 1 = no exponentials (P = bf16 of the shifted score), 2 = 1 + no per-tile barrier,
+// 3 = the softmax warps only run the mbarrier protocol (MMA + synchronisation floor), 4 = 3 without the PV MMAs, 5 = 3 without
+// the S MMAs.
+template <int kA2PolyPairs, int kAbl, int kSat = 0>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
@@ -169,7 +201,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + s * kA2TileBytes));
       const uint64_t qd = t ? qdesc1 : qdesc0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tmem_base + t * 128, qd + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+      for (int k = 0; k < 4; ++k)
+        if (kAbl != 5) umma_ss(tmem_base + t * 128, qd + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
       if (t == 1) umma_commit(&k_empty[s]);
       umma_commit(&s_full[t]);
     };
@@ -200,8 +233,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           // A: 16 keys = 8 TMEM columns of packed bf16 pairs; B: 16 key rows = 2048 bytes of the MN-major V tile
-          umma_ts(tmem_base + 384 + t * 64, tmem_base + 256 + t * 64 + kk * 8, vdesc + uint64_t(kk * (2048 >> 4)), idesc_o,
-                  (j | kk) != 0);
+          if (kAbl != 4)
+            umma_ts(tmem_base + 384 + t * 64, tmem_base + 256 + t * 64 + kk * 8, vdesc + uint64_t(kk * (2048 >> 4)), idesc_o,
+                    (j | kk) != 0);
         }
         if (t == 1) umma_commit(&v_empty[s]);
         umma_commit(&pv_done[t]);
@@ -225,6 +259,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      if (kAbl >= 3) {   // ablation: the barrier protocol alone (no TMEM traffic, no arithmetic)
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+        if (j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        continue;
+      }
       const int kv_left = p.len_k - j * kA2Tile - hh * 64;  // valid keys of this half (may be <= 0 in the last tile)
       // S_t(j), this thread's 64 columns, into registers; then the TMEM columns are released for S_t(j+1)
       uint32_t va[32], vb[32];
@@ -253,12 +295,21 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       auto exp_chunk = [&](const uint32_t (&v)[32], int c0, float nref) {
         uint32_t pk[16];
         const float2 c2 = make_float2(c_log2, c_log2), n2 = make_float2(nref, nref);
+        const float cs = c_log2 * (1.f / 128.f), ns = (nref + 112.f) * (1.f / 128.f);
         if (c0 + 32 <= kv_left) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float2 x = fma_f32x2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, n2);
-            float2 e;
-            if (i < kA2PolyPairs) {
+            float2 x, e;
+            if (kSat && kAbl == 0 && i < kA2PolyPairs) {
+              e = ex2_poly2_sat(make_float2(sat_fma(__uint_as_float(v[2 * i]), cs, ns), sat_fma(__uint_as_float(v[2 * i + 1]), cs, ns)));
+              rs2 = add_f32x2(rs2, e);
+              pk[i] = pack_bf16(e.x, e.y);
+              continue;
+            }
+            x = fma_f32x2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, n2);
+            if (kAbl != 0) {
+              e = x;
+            } else if (i < kA2PolyPairs) {
               e = ex2_poly2(x);
             } else {
               e.x = ex2_mufu(x.x);
@@ -291,9 +342,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         return rs2.x + rs2.y;
       };
       float rs = exp_pass(m_ref);
-      if (__any_sync(0xffffffffu, !(rs < 1e30f)) && lane == 0) atomicOr(ovf_flag + t, 1u);
-      named_bar_sync(1 + t, 256);   // the two halves of every row of this tile meet once per key tile
-      if (*reinterpret_cast<volatile uint32_t*>(ovf_flag + t) != 0u) {
+      if (kAbl != 2 && __any_sync(0xffffffffu, !(rs < (kSat ? 6e4f : 1e30f))) && lane == 0) atomicOr(ovf_flag + t, 1u);
+      if (kAbl != 2) named_bar_sync(1 + t, 256);   // the two halves of every row of this tile meet once per key tile
+      if (kAbl == 0 && *reinterpret_cast<volatile uint32_t*>(ovf_flag + t) != 0u) {
         // rare: a row's scores exceed the reference by ~2^100: all 256 threads of the tile raise the reference for the rows
         // that need it, rescale l and O exactly and redo this tile's P from the scores still held in registers
         const float new_ref = fmaxf(m_ref, row_max() * c_log2);
@@ -370,15 +421,35 @@ int launch_attn_fwd2(const T2VAttnDesc* d, const CUtensorMap& tq, const CUtensor
   p.o_stride_b = d->o_stride_b;
   p.o_stride_t = d->o_stride_t;
   p.o_stride_h = d->o_stride_h;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_fwd2)");
-    configured = true;
+  using KernelT = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, Attn2Params);
+  // T2V_ATTN_V2_VARIANT (timing experiments, scripts/attn_ablate.py): "p<N>" / "q<N>" = N polynomial pairs per chunk with the
+  // clamped / saturating-FMA range reduction, "a1" / "a2" = ablations with WRONG results.  Unset = the shipped configuration.
+  struct Variant { const char* name; KernelT fn; bool configured; };
+  static Variant variants[] = {
+      {"", attn_fwd2_kernel<kA2PolyPairsDefault, 0, kA2SatDefault>, false},
+      {"p0", attn_fwd2_kernel<0, 0, 0>, false},   {"p4", attn_fwd2_kernel<4, 0, 0>, false},
+      {"p2", attn_fwd2_kernel<2, 0, 0>, false},   {"p3", attn_fwd2_kernel<3, 0, 0>, false},
+      {"p5", attn_fwd2_kernel<5, 0, 0>, false},   {"q3", attn_fwd2_kernel<3, 0, 1>, false},
+      {"q4", attn_fwd2_kernel<4, 0, 1>, false},
+      {"p7", attn_fwd2_kernel<7, 0, 0>, false},   {"p16", attn_fwd2_kernel<16, 0, 0>, false},
+      {"q5", attn_fwd2_kernel<5, 0, 1>, false},   {"q7", attn_fwd2_kernel<7, 0, 1>, false},
+      {"q9", attn_fwd2_kernel<9, 0, 1>, false},   {"a1", attn_fwd2_kernel<7, 1, 0>, false},
+      {"a2", attn_fwd2_kernel<7, 2, 0>, false},   {"a3", attn_fwd2_kernel<7, 3, 0>, false},
+      {"a4", attn_fwd2_kernel<7, 4, 0>, false},   {"a5", attn_fwd2_kernel<7, 5, 0>, false}};
+  Variant* var = &variants[0];
+  if (const char* name = getenv("T2V_ATTN_V2_VARIANT")) {
+    for (Variant& v : variants)
+      if (!strcmp(v.name, name)) var = &v;
   }
+  if (!var->configured) {
+    cudaError_t e = cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_fwd2)");
+    var->configured = true;
+  }
+  KernelT kernel = var->fn;
   const int64_t grid = int64_t(d->batch) * d->heads * p.n_q_pairs;
   if (grid > 0x7fffffff) return fail(-5, "t2v_attn_fwd: grid too large");
-  launch_kernel(attn_fwd2_kernel, dim3(unsigned(grid)), dim3(kA2Threads), kA2Smem, stream, tq, tk, tv, p);
+  launch_kernel(kernel, dim3(unsigned(grid)), dim3(kA2Threads), kA2Smem, stream, tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_attn_fwd (two-tile kernel) launch");
 }

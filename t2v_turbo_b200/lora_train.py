@@ -10,7 +10,7 @@ arithmetic is a libt2v_b200.so kernel:
 
   forward   t = down(x) -> u = up(t) -> branch = u * mask * scale / (1 - p) -> y = base(x) + branch     3 tcgen05 GEMMs
             (the base GEMM takes `branch` as its residual operand: one pass over y)
-  backward  du = dy * mask * scale / (1 - p);  dt = du U;  dx = dy W + dt D                               4 tcgen05 GEMMs
+  backward  du = dy * mask * scale / (1 - p);  dt = du U;  dx = (dy | dt) [W^T | D^T]                     2 tcgen05 GEMMs
             dU += du^T t,  dD += dt^T x (per tap)        t2v_wgrad: MN-major operands read in place, fp32 red.add
             straight into the GRADIENT ARENA — one contiguous fp32 buffer for all layers (117 142 176 values for
             the VC2 UNet at r = 64), which `dist.allreduce_arena` reduces with ONE NCCL all-reduce and
@@ -22,10 +22,9 @@ accept the reference's layouts ([..., K] for Linear, NCHW / NCDHW for the convol
 The dropout keep-mask is drawn with torch (Bernoulli(1 - p) from the caller's RNG: same distribution as nn.Dropout,
 not the same random stream).
 
-NOT built: the backward of the non-GEMM layers between the LoRA layers (GroupNorm, LayerNorm, attention, GEGLU, SiLU)
-and of the strided / upsampling convolutions — the full student backward of train_t2v_turbo_v1_lora.py:1190 is
-therefore not available; this module covers the LoRA layers themselves, their gradient arena, the data-parallel
-reduction and the optimizer step (DESIGN.md §7 states the row status).
+The layers between the LoRA layers (GroupNorm, LayerNorm, attention, GEGLU, SiLU, the strided / upsampling convolutions)
+and the whole-UNet traversal live in `train_unet.StudentUNet`; this module is the LoRA layer pair itself, the gradient
+arena, and the reference-named `LoraInjected*` modules (autograd glue for use outside StudentUNet).
 """
 from __future__ import annotations
 
