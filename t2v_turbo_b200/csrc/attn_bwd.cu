@@ -78,7 +78,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   uint64_t* c_full = bars + 1;              // kStages
   uint64_t* c_empty = c_full + kStages;     // kStages
   uint64_t* s_full = c_empty + kStages;     // 1
-  uint64_t* p_full = s_full + 1;            // 1 (128 arrivals)
+  uint64_t* p_full = s_full + 1;            // 1 (4 arrivals: one per row warp)
   uint64_t* o_done = p_full + 1;            // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
@@ -106,7 +106,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       mbar_init(&c_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 4);   // one arrival per softmax warp
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
@@ -136,52 +136,68 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       tma_load_4d(sC1 + s * kTileBytes, &tmC1, &c_full[s], 0, h, c0, cb);
       tma_load_4d(sC2 + s * kTileBytes, &tmC2, &c_full[s], 0, h, c0, cb);
     }
-  } else if (warp == 1 && elect_one()) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    // whole-warp loop, only tcgen05.mma / commit predicated on the elected lane (uniform-datapath descriptor arithmetic:
+    // see attn_fwd2.cu for the measurement that motivated it)
+    const bool leader = elect_one();
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // K-major x K-major (reduction over the 64 channels)
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // G / Pt (K-major) x C tile (MN-major: reduction over its rows)
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t r1desc = umma_desc_sw128(smem_u32(sR1));
     const uint64_t r2desc = umma_desc_sw128(smem_u32(sR2));
     const uint64_t gdesc = umma_desc_sw128(smem_u32(sG));
     const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
+    const uint64_t c1desc0 = umma_desc_sw128(smem_u32(sC1));
+    const uint64_t c2desc0 = umma_desc_sw128(smem_u32(sC2));
+    constexpr uint64_t kTileDesc = kTileBytes >> 4;   // one ring stage further, in descriptor (16-byte) units
     mbar_wait(r_full, 0);
-    auto issue_s = [&](int it) {
-      const int s = it % kStages;
-      mbar_wait(&c_full[s], (it / kStages) & 1);
+    auto issue_s = [&](int sn, uint32_t phn) {
+      mbar_wait(&c_full[sn], phn);
       tc_fence_after();
-      const uint64_t c1desc = umma_desc_sw128(smem_u32(sC1 + s * kTileBytes));
-      const uint64_t c2desc = umma_desc_sw128(smem_u32(sC2 + s * kTileBytes));
+      const uint64_t c1desc = c1desc0 + uint64_t(sn) * kTileDesc;
+      const uint64_t c2desc = c2desc0 + uint64_t(sn) * kTileDesc;
+      if (leader) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tmem_base, r1desc + 2 * k, c1desc + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_ss(tm, r1desc + 2 * k, c1desc + 2 * k, idesc_s, k != 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tmem_base + kColU, r2desc + 2 * k, c2desc + 2 * k, idesc_s, k != 0);
-      umma_commit(s_full);
+        for (int k = 0; k < 4; ++k) umma_ss(tm + kColU, r2desc + 2 * k, c2desc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
+      }
     };
-    issue_s(0);
+    issue_s(0, 0);
+    int s = 0, sn = (kStages > 1) ? 1 : 0;            // ring stage of iteration it / it + 1
+    uint32_t phn = (kStages > 1) ? 0u : 1u;            // parity of c_full[sn]
     for (int it = 0; it < n_it; ++it) {
-      const int s = it % kStages;
       mbar_wait(p_full, it & 1);
       tc_fence_after();
-      if (it + 1 < n_it) issue_s(it + 1);   // T / U columns are free: every row thread has read them before arriving
-      const uint64_t c1desc = umma_desc_sw128(smem_u32(sC1 + s * kTileBytes));
-      const uint64_t c2desc = umma_desc_sw128(smem_u32(sC2 + s * kTileBytes));
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        // A: 16 columns = 32 bytes inside the (kk/4)-th 64-column sub-tile; B: 16 token rows of the C tile = 2048 bytes
-        const uint64_t aoff = uint64_t((kk >> 2) * (kT * 128 >> 4)) + 2 * (kk & 3);
-        const uint64_t boff = uint64_t(kk * (2048 >> 4));
-        umma_ss(tmem_base + kColO1, gdesc + aoff, c1desc + boff, idesc_o, (it | kk) != 0);
-      }
-      if (!kRowStats) {
+      if (it + 1 < n_it) issue_s(sn, phn);   // T / U columns are free: every row thread has read them before arriving
+      const uint64_t c1desc = c1desc0 + uint64_t(s) * kTileDesc;
+      const uint64_t c2desc = c2desc0 + uint64_t(s) * kTileDesc;
+      if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
+          // A: 16 columns = 32 bytes inside the (kk/4)-th 64-column sub-tile; B: 16 token rows of the C tile = 2048 bytes
           const uint64_t aoff = uint64_t((kk >> 2) * (kT * 128 >> 4)) + 2 * (kk & 3);
           const uint64_t boff = uint64_t(kk * (2048 >> 4));
-          umma_ss(tmem_base + kColO2, pdesc + aoff, c2desc + boff, idesc_o, (it | kk) != 0);
+          umma_ss(tm + kColO1, gdesc + aoff, c1desc + boff, idesc_o, (it | kk) != 0);
         }
+        if (!kRowStats) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t aoff = uint64_t((kk >> 2) * (kT * 128 >> 4)) + 2 * (kk & 3);
+            const uint64_t boff = uint64_t(kk * (2048 >> 4));
+            umma_ss(tm + kColO2, pdesc + aoff, c2desc + boff, idesc_o, (it | kk) != 0);
+          }
+        }
+        umma_commit(&c_empty[s]);
+        umma_commit(o_done);
       }
-      umma_commit(&c_empty[s]);
-      umma_commit(o_done);
+      s = sn;
+      if (++sn == kStages) {
+        sn = 0;
+        phn ^= 1u;
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ row threads
@@ -257,7 +273,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive_warp(p_full);
     }
     mbar_wait(o_done, (n_it - 1) & 1);
     tc_fence_after();

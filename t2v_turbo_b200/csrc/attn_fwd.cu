@@ -64,7 +64,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* v_full = k_empty + kKvStages;
   uint64_t* v_empty = v_full + kKvStages;
   uint64_t* s_full = v_empty + kKvStages;  // 1
-  uint64_t* p_full = s_full + 1;           // 1 (128 arrivals)
+  uint64_t* p_full = s_full + 1;           // 1 (4 arrivals: one per row warp)
   uint64_t* pv_done = p_full + 1;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
@@ -92,7 +92,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 4);   // one arrival per softmax warp
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -122,47 +122,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_expect_tx(&v_full[s], kKBytes);
       tma_load_4d(sV + s * kKBytes, &tmV, &v_full[s], 0, h, j * kTile, kvb);
     }
-  } else if (warp == 1 && elect_one()) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    // The whole warp walks the loop (uniform control flow keeps descriptor arithmetic and barrier addresses on the uniform
+    // datapath); only tcgen05.mma / commit are predicated on the elected lane.  Inside a single-thread branch the issuer
+    // needed ~12 dependent instructions per MMA and its own latency bounded the kernel (attn_fwd2.cu has the measurement).
+    const bool leader = elect_one();
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (K-major) x V (MN-major)
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
     const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
+    const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK));
+    const uint64_t vdesc0 = umma_desc_sw128(smem_u32(sV));
+    constexpr uint64_t kTileDesc = kKBytes >> 4;   // one K / V stage further, in descriptor (16-byte) units
     mbar_wait(q_full, 0);
     // Issue order per key tile j:  [p_full(j)]  S(j+1)  PV(j).  S(j+1) only needs the S columns (free once softmax(j)
     // has arrived on p_full) and K(j+1), so it is issued BEFORE PV(j): softmax(j+1) starts while PV(j) still runs and
     // the PV latency leaves the per-tile critical path.  (P(j+1) may only be written after PV(j) completed: the
     // softmax warps wait for pv_done(j) right before their first P store.)
-    auto issue_s = [&](int j) {
-      const int s = j % kKvStages;
-      mbar_wait(&k_full[s], (j / kKvStages) & 1);
+    auto issue_s = [&](int sn, uint32_t phn) {
+      mbar_wait(&k_full[sn], phn);
       tc_fence_after();
-      const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + s * kKBytes));
+      const uint64_t kdesc = kdesc0 + uint64_t(sn) * kTileDesc;
+      if (leader) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tmem_base, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-      umma_commit(&k_empty[s]);
-      umma_commit(s_full);
+        for (int k = 0; k < 4; ++k) umma_ss(tm, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&k_empty[sn]);
+        umma_commit(s_full);
+      }
     };
-    issue_s(0);
+    issue_s(0, 0);
+    int s = 0, sn = (kKvStages > 1) ? 1 : 0;            // ring stage of key tile j / j + 1
+    uint32_t ph = 0, phn = (kKvStages > 1) ? 0u : 1u;     // and their parities
     for (int j = 0; j < n_kv; ++j) {
-      const int s = j % kKvStages;
-      const uint32_t ph = (j / kKvStages) & 1;
       mbar_wait(p_full, j & 1);
       tc_fence_after();
-      if (j + 1 < n_kv) issue_s(j + 1);
+      if (j + 1 < n_kv) issue_s(sn, phn);
       // O += P_j V_j
       mbar_wait(&v_full[s], ph);
       tc_fence_after();
-      const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + s * kKBytes));
+      const uint64_t vdesc = vdesc0 + uint64_t(s) * kTileDesc;
+      if (leader) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        // A: 16 keys = 32 bytes inside the (kk/4)-th 64-key sub-tile; B: 16 key rows = 2048 bytes
-        const uint64_t ad = pdesc + uint64_t((kk >> 2) * (kTile * 128 >> 4)) + 2 * (kk & 3);
-        const uint64_t bd = vdesc + uint64_t(kk * (2048 >> 4));
-        umma_ss(tmem_base + kOCol, ad, bd, idesc_o, (j | kk) != 0);
+        for (int kk = 0; kk < 8; ++kk) {
+          // A: 16 keys = 32 bytes inside the (kk/4)-th 64-key sub-tile; B: 16 key rows = 2048 bytes
+          const uint64_t ad = pdesc + uint64_t((kk >> 2) * (kTile * 128 >> 4)) + 2 * (kk & 3);
+          const uint64_t bd = vdesc + uint64_t(kk * (2048 >> 4));
+          umma_ss(tm + kOCol, ad, bd, idesc_o, (j | kk) != 0);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(pv_done);
       }
-      umma_commit(&v_empty[s]);
-      umma_commit(pv_done);
+      s = sn;
+      ph = phn;
+      if (++sn == kKvStages) {
+        sn = 0;
+        phn ^= 1u;
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax / correction / epilogue
@@ -284,7 +301,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       l_run += rs;
       fence_proxy_async();  // P stores (generic proxy) -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive_warp(p_full);
     }
     // the last PV must have landed before O is read
     mbar_wait(pv_done, (n_kv - 1) & 1);
@@ -359,12 +376,15 @@ extern "C" int t2v_attn_fwd(const T2VAttnDesc* d, t2v_stream_t stream_) {
     rc = make_tmap_bf16(&tv, d->v, 4, dims, strv, box, "t2v_attn_fwd V");
     if (rc) return rc;
   }
-  // T2V_ATTN_V2=1 selects the two-Q-tile kernel (attn_fwd2.cu: P in TMEM, polynomial exp2).  Measured on B200 (round 2,
-  // profiles/r02_attention.md): (16, 2560, 2560, 5) 219-228 us vs 228 us for this kernel, the small shapes 10-30 % slower
-  // (one CTA per SM) — so the single-tile kernel below stays the default.
-  const char* v2_env = getenv("T2V_ATTN_V2");   // read per call: scripts/attn_ablate.py switches kernels inside one process
-  const int use_v2 = (v2_env != nullptr && v2_env[0] == '1') ? 1 : 0;
-  if (use_v2 && !d->causal && !d->lse2) return launch_attn_fwd2(d, tq, tk, tv, stream);
+  // Kernel choice.  The two-Q-tile kernel (attn_fwd2.cu: P in TMEM, part of the exp2 on the FMA pipe) wins on long sequences —
+  // (16, 2560, 2560, 5): 192 us vs 220 us — and loses 10-30 % on the 640- / 160-token levels and on Lk = 77 (one CTA per SM),
+  // so it serves len_q, len_k >= 1024 and this single-tile kernel the rest (profiles/r02_attention.md).  T2V_ATTN_V2=0 / 1
+  // forces one of them wherever both apply (read per call: scripts/attn_ablate.py switches inside one process).
+  const char* v2_env = getenv("T2V_ATTN_V2");
+  const bool v2_ok = !d->causal && !d->lse2;
+  const bool use_v2 = v2_env != nullptr && (v2_env[0] == '0' || v2_env[0] == '1') ? v2_env[0] == '1'
+                                                                                  : (d->len_q >= 1024 && d->len_k >= 1024);
+  if (use_v2 && v2_ok) return launch_attn_fwd2(d, tq, tk, tv, stream);
   AttnParams p;
   p.heads = d->heads;
   p.len_q = d->len_q;

@@ -40,7 +40,7 @@ constexpr int kA2Tile = 128;
 constexpr int kA2TileBytes = kA2Tile * 64 * 2;  // 16 KB: 128 rows x 64 bf16
 constexpr int kA2Smem = 2 * kA2TileBytes + 2 * kA2Stages * kA2TileBytes + 512 + 2 * 2 * 128 * 4 + 64;
 constexpr int kA2SatDefault = 0;        // 1: the saturating-FMA range reduction (ex2_poly2_sat)
-constexpr int kA2PolyPairsDefault = 7;  // of the 16 column pairs of every 32-column chunk: exp2 on the FMA pipe
+constexpr int kA2PolyPairsDefault = 2;  // of the 16 column pairs of every 32-column chunk: exp2 on the FMA pipe
 
 struct Attn2Params {
   int32_t heads, len_q, len_k, n_q_pairs, n_kv_tiles, kv_batch_div;
@@ -119,9 +119,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* v_full = k_empty + kA2Stages;
   uint64_t* v_empty = v_full + kA2Stages;
   uint64_t* s_full = v_empty + kA2Stages;     // 2 (per Q tile)
-  uint64_t* p_full = s_full + 2;              // 2, 128 arrivals each
+  uint64_t* p_full = s_full + 2;              // 2, 8 arrivals each (one per softmax warp)
   uint64_t* pv_done = p_full + 2;             // 2
-  uint64_t* s_free = pv_done + 2;             // 2, 256 arrivals each: S_t(j) is in registers, its TMEM columns may be overwritten
+  uint64_t* s_free = pv_done + 2;             // 2, 8 arrivals each: S_t(j) is in registers, its TMEM columns may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
   uint32_t* ovf_flag = tmem_slot + 2;                       // [2] per Q tile: some row of the tile overflowed its reference
   float* s_xchg = reinterpret_cast<float*>(bars) + 128;   // [2 tiles][2 halves][128 rows]: row maxima of the halves
@@ -152,8 +152,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 256);
-      mbar_init(&s_free[t], 256);
+      mbar_init(&p_full[t], 8);     // one arrival per softmax warp of the tile
+      mbar_init(&s_free[t], 8);
       mbar_init(&pv_done[t], 1);
     }
     fence_mbar_init();
@@ -185,32 +185,43 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_expect_tx(&v_full[s], kA2TileBytes);
       tma_load_4d(sV + s * kA2TileBytes, &tmV, &v_full[s], 0, h, j * kA2Tile, kvb);
     }
-  } else if (warp == 17 && elect_one()) {
+  } else if (warp == 17) {
     // ------------------------------------------------------------ MMA issuer
+    // The WHOLE warp walks the loop (uniform control flow: descriptor arithmetic and barrier addresses stay on the uniform
+    // datapath); only the tcgen05.mma / commit instructions themselves are predicated on the elected lane.  With the loop
+    // inside a single-thread branch the issuer spent ~12 dependent instructions per MMA (64-bit adds + R2UR moves) and its
+    // own instruction latency — ~2000 cycles per key tile against 1024 cycles of tensor work — was the floor of the kernel
+    // (scripts/attn_ablate.py, variant a3: 126 us with the softmax warps doing nothing).
+    const bool leader = elect_one();
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (TMEM, K-major) x V (MN-major)
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t qdesc0 = umma_desc_sw128(smem_u32(sQ));
-    const uint64_t qdesc1 = umma_desc_sw128(smem_u32(sQ + kA2TileBytes));
+    const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK));
+    const uint64_t vdesc0 = umma_desc_sw128(smem_u32(sV));
+    constexpr uint64_t kTileDesc = kA2TileBytes >> 4;   // one 16 KB tile further, in descriptor (16-byte) units
     mbar_wait(q_full, 0);
-    auto issue_s = [&](int t, int j) {
-      const int s = j % kA2Stages;
+    // S_t(jn) into TMEM columns [128 t, 128 t + 128); stage sn / parity phn of the K ring
+    auto issue_s = [&](int t, int sn, uint32_t phn) {
       if (t == 0) {
-        mbar_wait(&k_full[s], (j / kA2Stages) & 1);
+        mbar_wait(&k_full[sn], phn);
         tc_fence_after();
       }
-      const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + s * kA2TileBytes));
-      const uint64_t qd = t ? qdesc1 : qdesc0;
+      const uint64_t kdesc = kdesc0 + uint64_t(sn) * kTileDesc;
+      const uint64_t qd = qdesc0 + uint64_t(t) * kTileDesc;
+      if (leader) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (kAbl != 5) umma_ss(tmem_base + t * 128, qd + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-      if (t == 1) umma_commit(&k_empty[s]);
-      umma_commit(&s_full[t]);
+        for (int k = 0; k < 4; ++k)
+          if (kAbl != 5) umma_ss(tm + t * 128, qd + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        if (t == 1) umma_commit(&k_empty[sn]);
+        umma_commit(&s_full[t]);
+      }
     };
-    issue_s(0, 0);
-    issue_s(1, 0);
+    issue_s(0, 0, 0);
+    issue_s(1, 0, 0);
+    int s = 0, sn = (kA2Stages > 1) ? 1 : 0;          // ring stage of key tile j / j + 1
+    uint32_t ph = 0, phn = (kA2Stages > 1) ? 0u : 1u;   // and their parities
     for (int j = 0; j < n_kv; ++j) {
-      const int s = j % kA2Stages;
-      const uint32_t ph = (j / kA2Stages) & 1;
       // The softmax threads pull S_t(j) into registers first thing and release its columns (s_free): the next score tile
       // is computed WHILE they exponentiate, so softmax_t(j+1) never waits for the tensor pipe.
       if (j + 1 < n_kv) {
@@ -218,7 +229,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int t = 0; t < 2; ++t) {
           mbar_wait(&s_free[t], j & 1);
           tc_fence_after();
-          issue_s(t, j + 1);
+          issue_s(t, sn, phn);
         }
       }
 #pragma unroll
@@ -229,16 +240,23 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&v_full[s], ph);
           tc_fence_after();
         }
-        const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + s * kA2TileBytes));
+        const uint64_t vdesc = vdesc0 + uint64_t(s) * kTileDesc;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // A: 16 keys = 8 TMEM columns of packed bf16 pairs; B: 16 key rows = 2048 bytes of the MN-major V tile
-          if (kAbl != 4)
-            umma_ts(tmem_base + 384 + t * 64, tmem_base + 256 + t * 64 + kk * 8, vdesc + uint64_t(kk * (2048 >> 4)), idesc_o,
-                    (j | kk) != 0);
+          for (int kk = 0; kk < 8; ++kk) {
+            // A: 16 keys = 8 TMEM columns of packed bf16 pairs; B: 16 key rows = 2048 bytes of the MN-major V tile
+            if (kAbl != 4)
+              umma_ts(tm + 384 + t * 64, tm + 256 + t * 64 + kk * 8, vdesc + uint64_t(kk * (2048 >> 4)), idesc_o, (j | kk) != 0);
+          }
+          if (t == 1) umma_commit(&v_empty[s]);
+          umma_commit(&pv_done[t]);
         }
-        if (t == 1) umma_commit(&v_empty[s]);
-        umma_commit(&pv_done[t]);
+      }
+      s = sn;
+      ph = phn;
+      if (++sn == kA2Stages) {
+        sn = 0;
+        phn ^= 1u;
       }
     }
   } else if (warp < 16) {
@@ -261,10 +279,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       if (kAbl >= 3) {   // ablation: the barrier protocol alone (no TMEM traffic, no arithmetic)
         tc_fence_before();
-        mbar_arrive(&s_free[t]);
+        mbar_arrive_warp(&s_free[t]);
         if (j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);
         tc_fence_before();
-        mbar_arrive(&p_full[t]);
+        mbar_arrive_warp(&p_full[t]);
         continue;
       }
       const int kv_left = p.len_k - j * kA2Tile - hh * 64;  // valid keys of this half (may be <= 0 in the last tile)
@@ -274,7 +292,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld_32x32(s_addr + 32, vb);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&s_free[t]);
+      mbar_arrive_warp(&s_free[t]);
       // exact row maximum over both halves (first tile; slow path): own 64 columns, exchange through shared memory
       auto row_max = [&]() {
         float mx = -INFINITY;
@@ -369,7 +387,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l_run += rs;
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      mbar_arrive_warp(&p_full[t]);
     }
     // total row sum = the two halves' shares
     *my_x = l_run;
@@ -429,7 +447,9 @@ int launch_attn_fwd2(const T2VAttnDesc* d, const CUtensorMap& tq, const CUtensor
       {"", attn_fwd2_kernel<kA2PolyPairsDefault, 0, kA2SatDefault>, false},
       {"p0", attn_fwd2_kernel<0, 0, 0>, false},   {"p4", attn_fwd2_kernel<4, 0, 0>, false},
       {"p2", attn_fwd2_kernel<2, 0, 0>, false},   {"p3", attn_fwd2_kernel<3, 0, 0>, false},
-      {"p5", attn_fwd2_kernel<5, 0, 0>, false},   {"q3", attn_fwd2_kernel<3, 0, 1>, false},
+      {"p5", attn_fwd2_kernel<5, 0, 0>, false},   {"p6", attn_fwd2_kernel<6, 0, 0>, false},
+      {"p8", attn_fwd2_kernel<8, 0, 0>, false},   {"q2", attn_fwd2_kernel<2, 0, 1>, false},
+      {"q6", attn_fwd2_kernel<6, 0, 1>, false},   {"q8", attn_fwd2_kernel<8, 0, 1>, false},   {"q3", attn_fwd2_kernel<3, 0, 1>, false},
       {"q4", attn_fwd2_kernel<4, 0, 1>, false},
       {"p7", attn_fwd2_kernel<7, 0, 0>, false},   {"p16", attn_fwd2_kernel<16, 0, 0>, false},
       {"q5", attn_fwd2_kernel<5, 0, 1>, false},   {"q7", attn_fwd2_kernel<7, 0, 1>, false},

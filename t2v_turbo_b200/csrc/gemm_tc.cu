@@ -314,9 +314,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         ++tap;
       }
     }
-  } else if (warp == 1 && (!PAIR || cta_rank == 0) && elect_one()) {
+  } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
     // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA issues for both)
+    // The whole warp walks the loop — uniform control flow keeps the descriptor arithmetic on the uniform datapath — and only
+    // tcgen05.mma / commit are predicated on the elected lane.  (Inside a single-thread branch every k-block cost a chain of
+    // ~10 dependent R2UR / shift / add instructions before its first MMA, which bounds the narrow tiles: BN = 64 is 128
+    // tensor cycles per k-block.)
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BN, 0, 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem));
+    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem) + kATileBytes);
+    constexpr uint64_t kStageDesc = Cfg::kStageBytes >> 4;   // one ring stage further, in descriptor (16-byte) units
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -328,34 +337,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait_relaxed(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
+      const uint32_t tmem_d = tm + acc * Cfg::kAccStride;
       for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(a_addr + kATileBytes);
+        const uint64_t adesc = adesc0 + uint64_t(stage) * kStageDesc;
+        const uint64_t bdesc = bdesc0 + uint64_t(stage) * kStageDesc;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128B swizzle atom: +2 in addr>>4 units
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128B swizzle atom: +2 in addr>>4 units
+            if (PAIR)
+              umma_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           if (PAIR)
-            umma_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
           else
-            umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
         }
-        if (PAIR)
-          umma_commit_2sm(&empty_bar[stage]);
-        else
-          umma_commit(&empty_bar[stage]);
         if (++stage == p.n_stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      if (PAIR)
-        umma_commit_2sm(&tfull_bar[acc]);
-      else
-        umma_commit(&tfull_bar[acc]);
+      if (leader) {
+        if (PAIR)
+          umma_commit_2sm(&tfull_bar[acc]);
+        else
+          umma_commit(&tfull_bar[acc]);
+      }
     }
   } else if (warp >= 4 && p.epi_mode == 1) {
     // ------------------------------------------------------------ epilogue, smem-staged (8 warps = 2 warpgroups)

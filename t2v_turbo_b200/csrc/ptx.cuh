@@ -52,6 +52,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP: every lane has finished its part (and executed its tcgen05 fence) before the warp barrier, lane 0
+// arrives for all of them.  A per-thread arrive is one shared-memory atomic per lane — 128-256 serialised atomics per
+// hand-off, which measured as the floor of the attention kernels (scripts/attn_ablate.py, variant a3).
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
