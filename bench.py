@@ -28,11 +28,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FRAMES, HEIGHT, WIDTH, STEPS = 16, 320, 512, 4
-# videos per pipeline call per GPU.  Measured on B200 (profiles/r02_batch_sweep.json): 156 / 164 / 180 / 184 frames/s at
-# bs 1 / 2 / 4 / 8 — the UNet's level-2/3 layers and the ~8 us fixed cost of each of its ~1 000 launches amortise over the
-# batch, and under the 1 kW power cap a fuller tensor pipe is the cheaper way to buy frames.  The metric is throughput
-# (frames/s per GPU), so the headline runs at the batch that maximises it; `--batch 1` gives the latency configuration.
-DEFAULT_BATCH = 8
+# videos per pipeline call per GPU.  Measured on B200 (profiles/r02_batch_sweep.json): 156 / 164 / 180 / 189 / 194 / 195
+# frames/s at bs 1 / 2 / 4 / 8 / 12 / 16 — the UNet's level-2/3 layers and the ~8 us fixed cost of each of its ~1 000 launches
+# amortise over the batch, and under the 1 kW power cap a fuller tensor pipe is the cheaper way to buy frames.  The metric is
+# throughput (frames/s per GPU), so the headline runs at the batch where it saturates (activations ~70 GB of the 180 GB);
+# `--batch 1` gives the latency configuration.
+DEFAULT_BATCH = 16
 # BASELINE.md §3 (hooked reference forward): algorithmic FLOPs
 UNET_TFLOP, VAE_TFLOP = 12.581, 25.016
 PIPE_TFLOP = STEPS * UNET_TFLOP + VAE_TFLOP   # 75.34
@@ -471,7 +472,7 @@ def run_lora_step(args, rank, local_rank, world):
 
     def forward_all():
         for k, (i, pk, x, dy) in enumerate(layers):                     # arena order
-            _, saved[k] = lt.lora_forward(pk, x, None, 1.0)
+            _, saved[k], _, _ = lt.lora_forward(pk, x, None, 1.0)
 
     def backward_range(k_hi, k_lo):                                     # layers k_hi-1 .. k_lo, reverse order
         for k in range(k_hi - 1, k_lo - 1, -1):

@@ -19,8 +19,9 @@ arithmetic is a libt2v_b200.so kernel:
 dgrad needs no kernel of its own: dx = dy W is the forward implicit GEMM on transposed (and, for convolutions,
 tap-reversed) weights packed once at load.  Activations are channels-last bf16 like the inference path; the modules
 accept the reference's layouts ([..., K] for Linear, NCHW / NCDHW for the convolutions) and convert at the boundary.
-The dropout keep-mask is drawn with torch (Bernoulli(1 - p) from the caller's RNG: same distribution as nn.Dropout,
-not the same random stream).
+The dropout keep-mask is drawn INSIDE the scale kernel (`t2v_dropout_scale`: Philox4x32-10 keyed by a device-resident seed
+that `ops.dropout_advance` moves between steps — the same distribution as nn.Dropout, not torch's random stream) and kept as
+one byte per element for the adjoint.
 
 The layers between the LoRA layers (GroupNorm, LayerNorm, attention, GEGLU, SiLU, the strided / upsampling convolutions)
 and the whole-UNet traversal live in `train_unet.StudentUNet`; this module is the LoRA layer pair itself, the gradient
@@ -178,14 +179,20 @@ def _base_op(kind, x, w, bias, residual=None, bias_div=None):
     return ops.tconv3(x, w, bias, residual=residual)
 
 
-def lora_forward(pk: _PackedLora, x, mask, mask_scale, bias_rows=None, bias_div=None):
-    """-> (y, t): t = lora_down(x) is kept for the backward.  bias_rows / bias_div: see _base_op (conv2d only)."""
+def lora_forward(pk: _PackedLora, x, mask, mask_scale, bias_rows=None, bias_div=None, drop_p=0.0):
+    """-> (y, t, mask, mask_scale): t = lora_down(x) is kept for the backward.  Either the caller supplies the keep-mask
+    (mask, mask_scale) or — drop_p > 0 — it is drawn inside the scale kernel (`ops.dropout_scale`: no mask kernel, no mask
+    read in the forward) and returned for the backward.  bias_rows / bias_div: see _base_op (conv2d only)."""
     t = _base_op(pk.kind, x, pk.d, None)                                         # [.., r]
     u = ops.linear(t.view(-1, pk.r), pk.u, None)                                 # [M, Cout]
-    branch = ops.scale_mask(u, pk.scale * mask_scale, mask)
+    if drop_p > 0.0 and mask is None:
+        branch, mask = ops.dropout_scale(u, drop_p, pk.scale)
+        mask_scale = 1.0 / (1.0 - drop_p)
+    else:
+        branch = ops.scale_mask(u, pk.scale * mask_scale, mask)
     bias = pk.bias if bias_rows is None else bias_rows
     y = _base_op(pk.kind, x, pk.w, bias, residual=branch.view(*x.shape[:-1], pk.cout), bias_div=bias_div)
-    return y, t
+    return y, t, mask, mask_scale
 
 
 def lora_backward(pk: _PackedLora, x, t, mask, mask_scale, dy, g_up, g_down, need_dx=True):
@@ -213,8 +220,7 @@ class _LoraFn(torch.autograd.Function):
     def forward(ctx, x, layer, up, down):
         pk = layer._packed()
         p = layer.dropout_p if layer.training else 0.0
-        mask, ms = _keep_mask((x.numel() // x.shape[-1], pk.cout), p, x.device)
-        y, t = lora_forward(pk, x, mask, ms)
+        y, t, mask, ms = lora_forward(pk, x, None, 1.0, drop_p=p)
         ctx.layer, ctx.mask, ctx.ms = layer, mask, ms
         ctx.save_for_backward(x, t)
         return y

@@ -924,6 +924,45 @@ def scale_mask(x, scale, mask=None, out=None):
     return out
 
 
+# ---- in-kernel dropout (training): one device-resident 64-bit seed per device, advanced between steps on the device so that
+# captured CUDA graphs draw fresh masks on every replay; every call site takes the next call id (baked into a captured graph).
+_DROPOUT_SEED: dict = {}
+_DROPOUT_CALLS = [0]
+
+
+def dropout_seed(device, seed=None):
+    """The device-resident seed tensor (int64[1]) of `device`; `seed` (re)initialises it (default: torch.initial_seed())."""
+    key = torch.device(device)
+    t = _DROPOUT_SEED.get(key)
+    if t is None or seed is not None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("t2v_turbo_b200: the dropout seed must be created before CUDA-graph capture (run a warm-up call)")
+        val = (torch.initial_seed() if seed is None else int(seed)) & 0x7FFFFFFFFFFFFFFF
+        if t is None:
+            t = torch.empty(1, device=key, dtype=torch.int64)
+            _DROPOUT_SEED[key] = t
+        t.fill_(val)
+    return t
+
+
+def dropout_advance(device):
+    """Advance the device's dropout seed (one tiny kernel; capturable): call once per training step / forward."""
+    dropout_seed(device).add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+
+
+def dropout_scale(x, p, scale=1.0, out=None):
+    """-> (out, keep): out = x * scale / (1 - p) * keep with keep ~ Bernoulli(1 - p) drawn inside the kernel (uint8, kept for
+    the adjoint `scale_mask(dy, scale / (1 - p), keep)`): nn.Dropout(p)(x) * scale in one pass, no separate mask kernel."""
+    assert x.is_cuda and x.dtype == BF16 and x.is_contiguous() and x.numel() % 8 == 0 and 0.0 < p < 1.0
+    if out is None:
+        out = torch.empty_like(x)
+    keep = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    _DROPOUT_CALLS[0] = (_DROPOUT_CALLS[0] + 1) & 0xFFFFFFFF
+    _launch("dropout_scale", 0, lib().t2v_dropout_scale, x.data_ptr(), out.data_ptr(), keep.data_ptr(), x.numel(), float(1.0 - p),
+            float(scale) / (1.0 - p), dropout_seed(x.device).data_ptr(), _DROPOUT_CALLS[0], stream_ptr())
+    return out, keep
+
+
 def adamw_step(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, step, grad_scale=1.0):
     n = param.numel()
     for t in (param, grad, exp_avg, exp_avg_sq):

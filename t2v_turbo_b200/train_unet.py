@@ -32,7 +32,7 @@ import torch.nn as nn
 from . import ops
 from . import unet as U
 from .lora import lora_rank, lora_target_layers
-from .lora_train import LoraArena, _PackedLora, _keep_mask, lora_backward, lora_forward
+from .lora_train import LoraArena, _PackedLora, lora_backward, lora_forward
 
 BF16 = torch.bfloat16
 
@@ -115,8 +115,7 @@ class _Layer:
         if not self.lora:
             return ops.linear(x, self.w, self.bias), (x,)
         pk = self.pk
-        mask, ms = _keep_mask((x.numel() // x.shape[-1], pk.cout), self.p if training else 0.0, x.device)
-        y, t = lora_forward(pk, x, mask, ms, bias_rows=bias_rows, bias_div=bias_div)
+        y, t, mask, ms = lora_forward(pk, x, None, 1.0, bias_rows=bias_rows, bias_div=bias_div, drop_p=self.p if training else 0.0)
         return y, (x, t, mask, ms)
 
     def backward(self, saved, dy, need_dx=True):
@@ -347,9 +346,10 @@ class StudentUNet:
             c["tc"] = []
             for i, (gn, conv) in enumerate(R["tconv"]):
                 yn = ops.groupnorm(y, gn.w, gn.b, rows_per_sample=t * hw, eps=gn.eps, silu=True)
-                mask, ms = _keep_mask(yn.shape, self.tconv_p if (tr and i > 0) else 0.0, yn.device)   # openaimodel3d.py:280-296
-                if mask is not None:
-                    yn = ops.scale_mask(yn, ms, mask)
+                mask, ms = None, 1.0
+                if tr and i > 0 and self.tconv_p > 0.0:                                            # openaimodel3d.py:280-296
+                    yn, mask = ops.dropout_scale(yn, self.tconv_p)
+                    ms = 1.0 / (1.0 - self.tconv_p)
                 y_in = y
                 y, sv = conv.forward(yn.view(b, t, hw, cout), tr)
                 y = y.view(-1, cout)
@@ -527,6 +527,8 @@ class StudentUNet:
             raise RuntimeError("StudentUNet(B200): input must be a CUDA tensor (no CPU fallback)")
         if not self._packed:
             self.pack()
+        if self.training:
+            ops.dropout_advance(x.device)   # fresh in-kernel dropout masks for this forward (capturable: a device-side add)
         u = self.unet
         b, cin, t, hh, ww = x.shape
         self._emb_fwd(timesteps, fps, timestep_cond, b)

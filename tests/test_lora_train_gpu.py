@@ -71,7 +71,7 @@ def test_lora_dropout_mask_is_shared_by_forward_and_backward(cuda_device):
     pk = m._packed()
     mask, ms = lt._keep_mask((256, 192), 0.25, x.device)
     assert 0.70 <= mask.float().mean().item() <= 0.80 and abs(ms - 1 / 0.75) < 1e-6
-    y, t = lt.lora_forward(pk, x.to(BF16), mask, ms)
+    y, t, _, _ = lt.lora_forward(pk, x.to(BF16), mask, ms)
     xb = x.to(BF16).float()
     ref = xb @ m.linear.weight.float().t() + (xb @ m.lora_down.weight.float().t() @ m.lora_up.weight.float().t()) * mask.float() * ms
     assert _rel(y, ref) <= 1e-2
@@ -82,6 +82,67 @@ def test_lora_dropout_mask_is_shared_by_forward_and_backward(cuda_device):
     assert _rel(gu, du.t() @ (xb @ m.lora_down.weight.float().t())) <= 1.5e-2
     assert _rel(gd, (du @ m.lora_up.weight.float()).t() @ xb) <= 1.5e-2
     assert _rel(dx, dy.float() @ m.linear.weight.float() + (du @ m.lora_up.weight.float()) @ m.lora_down.weight.float()) <= 1.5e-2
+
+
+def test_dropout_scale_kernel(cuda_device):
+    """t2v_dropout_scale: out = x * scale / (1 - p) * keep with keep ~ Bernoulli(1 - p) drawn in the kernel (Philox4x32-10) and
+    written for the adjoint.  Checks: out is exactly x * scale' * keep (bf16 rounding of one product), the keep rate and its
+    independence across positions / calls, reproducibility for a fixed (seed, call id), fresh masks after dropout_advance."""
+    from t2v_turbo_b200 import ops
+    p, scale = 0.1, 0.5
+    x = torch.randn(4096, 640, device="cuda").to(BF16)
+    ops.dropout_seed(x.device, seed=1234)
+    y, keep = ops.dropout_scale(x, p, scale)
+    assert keep.dtype == torch.uint8 and keep.shape == x.shape and set(keep.unique().tolist()) <= {0, 1}
+    ref = (x.float() * (scale / (1 - p)) * keep.float()).to(BF16)
+    assert torch.equal(y, ref)
+    n = keep.numel()
+    rate = keep.float().mean().item()
+    sigma = (p * (1 - p) / n) ** 0.5
+    assert abs(rate - (1 - p)) < 5 * sigma, (rate, sigma)                     # keep rate exact to sampling noise
+    k = keep.float() - (1 - p)
+    for shift in (1, 7, 8, 640):                                              # no correlation between neighbouring draws
+        c = (k.flatten()[:-shift] * k.flatten()[shift:]).mean().item() / (p * (1 - p))
+        assert abs(c) < 5 / n ** 0.5, (shift, c)
+    col = keep.float().mean(0)
+    assert (col - (1 - p)).abs().max().item() < 6 * (p * (1 - p) / keep.shape[0]) ** 0.5   # every column sees the same rate
+    # a second call (next call id) draws an independent mask; the same (seed, call id) reproduces the first one
+    y2, keep2 = ops.dropout_scale(x, p, scale)
+    agree = (keep2 == keep).float().mean().item()
+    assert abs(agree - ((1 - p) ** 2 + p ** 2)) < 5e-3, agree
+    ops._DROPOUT_CALLS[0] -= 2
+    y3, keep3 = ops.dropout_scale(x, p, scale)
+    assert torch.equal(keep3, keep) and torch.equal(y3, y)
+    ops._DROPOUT_CALLS[0] -= 1
+    ops.dropout_advance(x.device)                                             # next step: same call id, new seed
+    _, keep4 = ops.dropout_scale(x, p, scale)
+    assert abs((keep4 == keep).float().mean().item() - ((1 - p) ** 2 + p ** 2)) < 5e-3
+    # the adjoint reuses the stored mask
+    dy = torch.randn_like(x)
+    dx = ops.scale_mask(dy, scale / (1 - p), keep)
+    assert torch.equal(dx, (dy.float() * (scale / (1 - p)) * keep.float()).to(BF16))
+
+
+def test_dropout_scale_fresh_masks_under_cuda_graph_replay(cuda_device):
+    """The seed lives on the device and is advanced by a captured add: every replay of a captured step draws a new mask."""
+    from t2v_turbo_b200 import ops
+    x = torch.randn(512, 256, device="cuda").to(BF16)
+    ops.dropout_seed(x.device, seed=7)
+    ops.dropout_scale(x, 0.5)                                                 # warm-up (lazy state) before capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ops.dropout_advance(x.device)
+        _, keep = ops.dropout_scale(x, 0.5)
+    masks = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        masks.append(keep.clone())
+    for a in range(3):
+        assert abs(masks[a].float().mean().item() - 0.5) < 0.01
+        for b in range(a + 1, 3):
+            assert abs((masks[a] == masks[b]).float().mean().item() - 0.5) < 0.01
 
 
 @pytest.mark.parametrize("pts,c,r,taps", [((1000,), 320, 64, None), ((2, 20, 32), 128, 64, "3x3"), ((1, 16, 160), 64, 64, "t3"),
