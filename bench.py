@@ -61,6 +61,15 @@ def ncu_gemm_traffic():
     return sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in rows) / n if n else None
 
 
+def ncu_traffic_batch():
+    """videos per call of the step the ncu capture above was taken on (the per-launch traffic scales with it)"""
+    p = os.path.join(ROOT, "profiles", "r02_launches_step_summary.json")
+    try:
+        return json.load(open(p)).get("_meta", {}).get("batch")
+    except OSError:
+        return None
+
+
 class ClockSampler:
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
@@ -663,7 +672,10 @@ def main():
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     roofline = dict(bound="tensor", kernel="gemm_tc_kernel (all Linear / Conv2d / Conv3d launches of one pipeline call)",
                     achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"], peak_source=pk["src"],
-                    traffic=ncu_gemm_traffic(), traffic_unit="DRAM bytes per launch (ncu, avg over one step)", launches=gemm["calls"], avg_launch_us=gemm["ms"] * 1e3 / max(1, gemm["calls"]),
+                    traffic=ncu_gemm_traffic(), traffic_unit="DRAM bytes per launch (ncu, avg over one step)", traffic_batch=ncu_traffic_batch(),
+                    algorithmic_bytes_per_launch=gemm.get("bytes", 0) / max(1, gemm["calls"]),
+                    algorithmic_bytes_note="per launch: input activation once + weights once + output (+ residual), bf16; conv taps re-read the input through L2",
+                    launches=gemm["calls"], avg_launch_us=gemm["ms"] * 1e3 / max(1, gemm["calls"]),
                     share_of_step=gemm["ms"] / tot_ms,
                     families={k: dict(calls=v["calls"], ms=round(v["ms"], 3), tflops=round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1))
                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})

@@ -27,6 +27,7 @@ LAUNCHES = 0                            # kernels of libt2v_b200.so enqueued so 
 _PROF = None                            # list of (family, flops, ev_start, ev_end) while profiling
 _FLOPS: dict = {}
 _TAG: dict = {}
+_BYTES: dict = {}
 
 
 def start_profile():
@@ -41,11 +42,12 @@ def stop_profile(by_tag=False):
     recs, _PROF = _PROF, None
     torch.cuda.synchronize()
     out = {}
-    for fam, flops, e0, e1, tag in recs:
-        d = out.setdefault((fam + " " + tag) if by_tag else fam, dict(calls=0, ms=0.0, flops=0))
+    for fam, flops, e0, e1, tag, nbytes in recs:
+        d = out.setdefault((fam + " " + tag) if by_tag else fam, dict(calls=0, ms=0.0, flops=0, bytes=0))
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += flops
+        d["bytes"] += nbytes       # algorithmic HBM bytes (each operand / result counted once), where the wrapper states them
     return out
 
 
@@ -59,7 +61,7 @@ def _launch(family, flops, fn, *args):
     e0.record()
     check(fn(*args), "t2v_" + family)
     e1.record()
-    _PROF.append((family, flops, e0, e1, _TAG.pop(family, "")))
+    _PROF.append((family, flops, e0, e1, _TAG.pop(family, ""), _BYTES.pop(family, 0)))
 
 
 # ----------------------------------------------------------------------------- tile planning
@@ -166,6 +168,10 @@ def _gemm_raw(*, a, a_ch, a_ch_total, a_size, a_stride, box, taps, tap_ch_off, w
     d.workspace_bytes = ws.numel() * 4
     _FLOPS["gemm"] = 2 * math.prod(int(v) for v in o_size) * int(n_rows) * len(taps) * (int(a_ch[0]) + int(a_ch[1]))
     if _PROF is not None:
+        m_pts, k_ch = math.prod(int(v) for v in o_size), int(a_ch[0]) + int(a_ch[1])
+        # algorithmic bytes: the input activation once (taps re-read it through L2, not HBM), the weights once, the output,
+        # the residual operand if any (bf16 everywhere)
+        _BYTES["gemm"] = 2 * (m_pts * k_ch + int(n_rows) * len(taps) * k_ch * max(1, int(b_batches)) + m_pts * int(n_out) * (2 if residual is not None else 1))
         _TAG["gemm"] = (f"M={math.prod(int(v) for v in o_size)} N={int(n_rows)} K={len(taps)}x{int(a_ch[0]) + int(a_ch[1])} "
                         f"box={tuple(int(b) for b in box)} bn={block_n} flags={flags} res={int(residual is not None)}")
     _launch("gemm", _FLOPS.pop("gemm", 0), lib().t2v_gemm, C.byref(d), stream_ptr())
