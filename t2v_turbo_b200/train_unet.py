@@ -8,10 +8,11 @@ all LoRA weights, gradients and AdamW moments in ONE flat fp32 arena (`lora_trai
     forward(x, timesteps, context=..., fps=..., timestep_cond=...)  -> eps prediction [B, 4, T, H, W]
     backward(d_eps)                                                  -> LoRA gradients accumulated into arena.grads
 
-The forward is the training-mode arithmetic of the reference modules (LoRA dropout, the TemporalConvBlock dropouts, unfused
+The forward is the training-mode arithmetic of the reference modules (LoRA dropout and the TemporalConvBlock dropouts, their masks
+drawn inside the scale kernel from a device-resident Philox seed; unfused
 LayerNorm / GEGLU so that the backward has the tensors it needs), the backward is written out by hand — no autograd graph:
 
-    GEMM layers     lora_train.lora_forward / lora_backward: 3 + 4 tcgen05 GEMMs and 2 t2v_wgrad launches per layer
+    GEMM layers     lora_train.lora_forward / lora_backward: 3 + 2 tcgen05 GEMMs, t2v_dropout_scale and 2 t2v_wgrad launches per layer
     GroupNorm+SiLU  t2v_groupnorm / t2v_groupnorm_bwd          LayerNorm   t2v_layernorm / t2v_layernorm_bwd
     attention       t2v_attn_fwd (+lse2) / t2v_attn_bwd        temporal    t2v_attn_short_fwd / t2v_attn_short_bwd
     GEGLU           t2v_geglu (forward and adjoint)            emb add     bias rows in the conv epilogue / t2v_colsum_samples
