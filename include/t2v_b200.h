@@ -346,13 +346,15 @@ int t2v_wgrad(const T2VWgradDesc* desc, t2v_stream_t stream);
  * branch in the forward (applied to U(Dx) before the add) and its adjoint on dy in the backward (utils/lora.py:45-50). */
 int t2v_scale_mask(const void* x, const uint8_t* mask, void* out, int64_t n, float scale, t2v_stream_t stream);
 
-/* Training-mode dropout fused with its scale: out[i] = x[i] * scale * keep[i], keep[i] ~ Bernoulli(keep_prob) drawn in the
+/* Training-mode dropout fused with its scale: out[i] = x[i] * scale * keep[i] (+ addend[i]), keep[i] ~ Bernoulli(keep_prob) drawn in the
  * kernel (Philox4x32-10 keyed by *seed, stream (call_id, i / 8)); mask_out[i] = keep[i] (uint8) for the adjoint
  * (t2v_scale_mask on dy).  Replaces nn.Dropout after lora_up (utils/lora.py:37,45-50: `self.dropout(self.lora_up(...)) *
  * self.scale`) and the TemporalConvBlock dropouts (lvdm/modules/networks/openaimodel3d.py:280-296): the same distribution,
- * not torch's random stream.  seed is read on the device, so a captured CUDA graph draws a fresh mask on every replay once
- * the caller advances *seed between steps; n % 8 == 0. */
-int t2v_dropout_scale(const void* x, void* out, uint8_t* mask_out, int64_t n, float keep_prob, float scale,
+ * not torch's random stream.  addend (bf16, may be NULL) folds the residual add that follows the layer
+ * (`x + attn(...)`, `h + out_layers(...)`: attention.py:276-281, openaimodel3d.py:246-250) into the same pass: the layer's base GEMM
+ * takes `out` as its residual operand.  seed is read on the device, so a captured CUDA graph draws a fresh mask on every replay
+ * once the caller advances *seed between steps; n % 8 == 0. */
+int t2v_dropout_scale(const void* x, const void* addend, void* out, uint8_t* mask_out, int64_t n, float keep_prob, float scale,
                       const uint64_t* seed, uint32_t call_id, t2v_stream_t stream);
 
 /* Fused AdamW over the flat fp32 LoRA parameter / gradient arenas (torch.optim.AdamW semantics, one launch for all 575

@@ -193,7 +193,7 @@ SYMBOLS = {
     "t2v_gaussian_sample": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "t2v_wgrad": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "t2v_scale_mask": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
-    "t2v_dropout_scale": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _vp, C.c_uint32, _vp]),
+    "t2v_dropout_scale": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, C.c_uint32, _vp]),
     "t2v_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "t2v_sum_squares": (C.c_int, [_vp, _i64, _vp, _vp]),
     "t2v_mse_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),

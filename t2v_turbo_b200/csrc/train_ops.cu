@@ -31,14 +31,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// out = x * scale * keep, keep ~ Bernoulli(keep_prob) drawn IN the kernel; the keep-mask (1 byte / element) is written for the
+// out = x * scale * keep (+ addend), keep ~ Bernoulli(keep_prob) drawn IN the kernel; the keep-mask (1 byte / element) is written for the
 // backward.  8 bf16 per thread = one Philox call: element j of the group keeps iff its 16 random bits are < thresh
 // (thresh = round(keep_prob * 65536): the keep rate is exact to 2^-17).  Stream = (*seed, call_id, element index / 8):
 // reproducible, independent across calls (call_id) and steps (*seed is advanced on the device between steps, so a captured
 // CUDA graph draws fresh masks on every replay).
-__global__ void __launch_bounds__(256) dropout_scale_kernel(const uint4* __restrict__ x, uint4* __restrict__ out,
-                                                            uint2* __restrict__ mask_out, int64_t n8, uint32_t thresh, float scale,
-                                                            const uint64_t* __restrict__ seed, uint32_t call_id) {
+__global__ void __launch_bounds__(256) dropout_scale_kernel(const uint4* __restrict__ x, const uint4* __restrict__ addend,
+                                                            uint4* __restrict__ out, uint2* __restrict__ mask_out, int64_t n8,
+                                                            uint32_t thresh, float scale, const uint64_t* __restrict__ seed,
+                                                            uint32_t call_id) {
   pdl_launch_dependents();
   pdl_wait();
   const uint64_t sd = *seed;
@@ -46,13 +47,15 @@ __global__ void __launch_bounds__(256) dropout_scale_kernel(const uint4* __restr
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
     const uint4 r = philox4x32_10(make_uint4(uint32_t(i), uint32_t(uint64_t(i) >> 32), call_id, 0x74327662u), key);
     const uint4 v = __ldg(x + i);
+    const uint4 ad = addend != nullptr ? __ldg(addend + i) : make_uint4(0u, 0u, 0u, 0u);   // bf16 zeros
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
     const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t aa[4] = {ad.x, ad.y, ad.z, ad.w};
     uint32_t oo[4], m[2] = {0u, 0u};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool k0 = (rr[j] & 0xffffu) < thresh, k1 = (rr[j] >> 16) < thresh;
-      oo[j] = pack_bf16(k0 ? bf16_lo(vv[j]) * scale : 0.f, k1 ? bf16_hi(vv[j]) * scale : 0.f);
+      oo[j] = pack_bf16((k0 ? bf16_lo(vv[j]) * scale : 0.f) + bf16_lo(aa[j]), (k1 ? bf16_hi(vv[j]) * scale : 0.f) + bf16_hi(aa[j]));
       m[j >> 1] |= (uint32_t(k0) | (uint32_t(k1) << 8)) << (16 * (j & 1));
     }
     out[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
@@ -190,17 +193,18 @@ extern "C" int t2v_scale_mask(const void* x, const uint8_t* mask, void* out, int
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_scale_mask launch");
 }
 
-extern "C" int t2v_dropout_scale(const void* x, void* out, uint8_t* mask_out, int64_t n, float keep_prob, float scale,
-                                 const uint64_t* seed, uint32_t call_id, t2v_stream_t s) {
+extern "C" int t2v_dropout_scale(const void* x, const void* addend, void* out, uint8_t* mask_out, int64_t n, float keep_prob,
+                                 float scale, const uint64_t* seed, uint32_t call_id, t2v_stream_t s) {
   using namespace t2v;
   if (!x || !out || !mask_out || !seed || n < 1 || n % 8) return fail(-1, "t2v_dropout_scale: n must be a positive multiple of 8");
   if (!(keep_prob > 0.f) || keep_prob > 1.f) return fail(-1, "t2v_dropout_scale: keep_prob must be in (0, 1]");
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15 || (reinterpret_cast<uintptr_t>(mask_out) & 7) ||
-      (reinterpret_cast<uintptr_t>(seed) & 7))
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(addend)) & 15 ||
+      (reinterpret_cast<uintptr_t>(mask_out) & 7) || (reinterpret_cast<uintptr_t>(seed) & 7))
     return fail(-2, "t2v_dropout_scale: x / out must be 16-byte, mask_out / seed 8-byte aligned");
   const uint32_t thresh = uint32_t(lrintf(keep_prob * 65536.f));
   launch_kernel(dropout_scale_kernel, dim3(grid_1d(n / 8)), dim3(256), 0, static_cast<cudaStream_t>(s), static_cast<const uint4*>(x),
-                static_cast<uint4*>(out), reinterpret_cast<uint2*>(mask_out), n / 8, thresh, scale, seed, call_id);
+                static_cast<const uint4*>(addend), static_cast<uint4*>(out), reinterpret_cast<uint2*>(mask_out), n / 8, thresh, scale, seed,
+                call_id);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_dropout_scale launch");
 }

@@ -115,8 +115,12 @@ class DistillStep:
         saved = self.student.detach_tapes()
         # teacher CFG estimate and one DDIM step (no grad; the frozen UNet's inference path)
         zt = z.to(torch.bfloat16) if self.teacher.dtype == torch.bfloat16 else z
-        eps_c = self.teacher(zt, S["start_timesteps"], context=prompt_embeds, fps=self.fps).float()
-        eps_u = self.teacher(zt, S["start_timesteps"], context=uncond_prompt_embeds, fps=self.fps).float()
+        # (the reference's two calls — conditional and unconditional, :1118-1144 — as ONE forward over the concatenated batch:
+        # no layer of the UNet mixes samples, and the batched levels run at a better tile fill)
+        nb = zt.shape[0]
+        eps_cu = self.teacher(torch.cat([zt, zt], 0), torch.cat([S["start_timesteps"], S["start_timesteps"]], 0),
+                              context=torch.cat([prompt_embeds, uncond_prompt_embeds], 0), fps=self.fps).float()
+        eps_c, eps_u = eps_cu[:nb].contiguous(), eps_cu[nb:].contiguous()
         eps_cfg = ops.scale_add_rows(eps_c, S["cfg_c"], eps_u, S["cfg_u"])
         x0_cfg = ops.scale_add_rows(z, S["x0_z"], eps_cfg, S["x0_e"])
         x_prev = ops.scale_add_rows(x0_cfg, S["dd_x"], eps_cfg, S["dd_e"])

@@ -179,19 +179,24 @@ def _base_op(kind, x, w, bias, residual=None, bias_div=None):
     return ops.tconv3(x, w, bias, residual=residual)
 
 
-def lora_forward(pk: _PackedLora, x, mask, mask_scale, bias_rows=None, bias_div=None, drop_p=0.0):
+def lora_forward(pk: _PackedLora, x, mask, mask_scale, bias_rows=None, bias_div=None, drop_p=0.0, addend=None):
     """-> (y, t, mask, mask_scale): t = lora_down(x) is kept for the backward.  Either the caller supplies the keep-mask
     (mask, mask_scale) or — drop_p > 0 — it is drawn inside the scale kernel (`ops.dropout_scale`: no mask kernel, no mask
-    read in the forward) and returned for the backward.  bias_rows / bias_div: see _base_op (conv2d only)."""
+    read in the forward) and returned for the backward.  bias_rows / bias_div: see _base_op (conv2d only).  addend ([M, Cout] bf16):
+    the residual the caller would add to y next (`x + attn(...)`, `h + out_layers(...)`); y then already contains it — folded
+    into the dropout pass when there is one, a separate add otherwise."""
     t = _base_op(pk.kind, x, pk.d, None)                                         # [.., r]
     u = ops.linear(t.view(-1, pk.r), pk.u, None)                                 # [M, Cout]
     if drop_p > 0.0 and mask is None:
-        branch, mask = ops.dropout_scale(u, drop_p, pk.scale)
+        branch, mask = ops.dropout_scale(u, drop_p, pk.scale, addend=addend)
         mask_scale = 1.0 / (1.0 - drop_p)
+        addend = None
     else:
         branch = ops.scale_mask(u, pk.scale * mask_scale, mask)
     bias = pk.bias if bias_rows is None else bias_rows
     y = _base_op(pk.kind, x, pk.w, bias, residual=branch.view(*x.shape[:-1], pk.cout), bias_div=bias_div)
+    if addend is not None:
+        y = ops.add(y.view(-1, pk.cout), addend.view(-1, pk.cout)).view(y.shape)
     return y, t, mask, mask_scale
 
 

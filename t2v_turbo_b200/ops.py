@@ -956,15 +956,18 @@ def dropout_advance(device):
     dropout_seed(device).add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
 
 
-def dropout_scale(x, p, scale=1.0, out=None):
-    """-> (out, keep): out = x * scale / (1 - p) * keep with keep ~ Bernoulli(1 - p) drawn inside the kernel (uint8, kept for
-    the adjoint `scale_mask(dy, scale / (1 - p), keep)`): nn.Dropout(p)(x) * scale in one pass, no separate mask kernel."""
+def dropout_scale(x, p, scale=1.0, out=None, addend=None):
+    """-> (out, keep): out = x * scale / (1 - p) * keep (+ addend) with keep ~ Bernoulli(1 - p) drawn inside the kernel (uint8,
+    kept for the adjoint `scale_mask(dy, scale / (1 - p), keep)`): nn.Dropout(p)(x) * scale — and the residual add that follows
+    the layer — in one pass, no separate mask kernel."""
     assert x.is_cuda and x.dtype == BF16 and x.is_contiguous() and x.numel() % 8 == 0 and 0.0 < p < 1.0
+    if addend is not None:
+        assert addend.dtype == BF16 and addend.is_contiguous() and addend.numel() == x.numel()
     if out is None:
         out = torch.empty_like(x)
     keep = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
     _DROPOUT_CALLS[0] = (_DROPOUT_CALLS[0] + 1) & 0xFFFFFFFF
-    _launch("dropout_scale", 0, lib().t2v_dropout_scale, x.data_ptr(), out.data_ptr(), keep.data_ptr(), x.numel(), float(1.0 - p),
+    _launch("dropout_scale", 0, lib().t2v_dropout_scale, x.data_ptr(), ptr(addend), out.data_ptr(), keep.data_ptr(), x.numel(), float(1.0 - p),
             float(scale) / (1.0 - p), dropout_seed(x.device).data_ptr(), _DROPOUT_CALLS[0], stream_ptr())
     return out, keep
 

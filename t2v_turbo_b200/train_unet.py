@@ -112,11 +112,13 @@ class _Layer:
             self._gdown_p.zero_()
 
     # x: channels-last bf16 in the layer's point grid ([M, K] | [n, h, w, C] | [b, t, hw, C])
-    def forward(self, x, training, bias_rows=None, bias_div=None):
+    def forward(self, x, training, bias_rows=None, bias_div=None, addend=None):
+        """addend: the residual added to this layer's output next ([rows, Cout] bf16) — the returned y includes it."""
         if not self.lora:
-            return ops.linear(x, self.w, self.bias), (x,)
+            return ops.linear(x, self.w, self.bias, residual=addend), (x,)
         pk = self.pk
-        y, t, mask, ms = lora_forward(pk, x, None, 1.0, bias_rows=bias_rows, bias_div=bias_div, drop_p=self.p if training else 0.0)
+        y, t, mask, ms = lora_forward(pk, x, None, 1.0, bias_rows=bias_rows, bias_div=bias_div, drop_p=self.p if training else 0.0,
+                                      addend=addend)
         return y, (x, t, mask, ms)
 
     def backward(self, saved, dy, need_dx=True):
@@ -340,8 +342,8 @@ class StudentUNet:
             skip = x2
         else:
             skip, c["skip"] = R["skip"].forward(x2, tr)
-        h2, c["conv2"] = R["conv2"].forward(hn2.view(nf, hh, ww, cout), tr)
-        h2 = ops.add(h2.view(-1, cout), skip)
+        h2, c["conv2"] = R["conv2"].forward(hn2.view(nf, hh, ww, cout), tr, addend=skip)   # h + out_layers(...) (openaimodel3d.py:246-250)
+        h2 = h2.view(-1, cout)
         if R["tconv"] is not None:
             y = h2
             c["tc"] = []
@@ -385,9 +387,9 @@ class StudentUNet:
         return dx.view(nf, hh, ww, cin)
 
     # ------------------------------------------------------------------ transformers
-    def _attn_fwd(self, A, xn, kv_src, geom, temporal, c):
+    def _attn_fwd(self, A, xn, kv_src, geom, temporal, c, skip=None):
         """xn: normalised tokens [rows, C]; kv_src: tokens the keys / values are projected from ([rows, C] or the
-        frame-repeated text context)."""
+        frame-repeated text context); skip: the residual `x + attn(norm(x))` (attention.py:276-281), folded into to_out."""
         b, t, hh, ww = geom
         hw = hh * ww
         tr = self.training
@@ -407,7 +409,7 @@ class StudentUNet:
             o3 = ops.attention(q3, k3, v3, heads=heads, scale=scale, lse2=lse2)
             att = o3.view(-1, inner)
             c["att"] = (q3, k3, v3, o3, lse2)
-        out, c["o"] = A["o"].forward(att, tr)
+        out, c["o"] = A["o"].forward(att, tr, addend=skip)
         return out
 
     def _attn_bwd(self, A, c, d_out, geom, temporal, self_attn):
@@ -444,21 +446,19 @@ class StudentUNet:
         c["x0"] = x0
         n1 = ops.layernorm(x0, ln[0].w, ln[0].b, ln[0].eps)
         c["a1"] = {}
-        x1 = ops.add(self._attn_fwd(T["a1"], n1, n1, geom, temporal, c["a1"]), x0)
+        x1 = self._attn_fwd(T["a1"], n1, n1, geom, temporal, c["a1"], skip=x0)
         c["x1"] = x1
         n2 = ops.layernorm(x1, ln[1].w, ln[1].b, ln[1].eps)
         c["a2"] = {}
         kv_src = n2 if temporal else ctx_rows
-        x2 = ops.add(self._attn_fwd(T["a2"], n2, kv_src, geom, temporal, c["a2"]), x1)
+        x2 = self._attn_fwd(T["a2"], n2, kv_src, geom, temporal, c["a2"], skip=x1)
         c["x2"] = x2
         n3 = ops.layernorm(x2, ln[2].w, ln[2].b, ln[2].eps)
         pre, c["ff1"] = T["ff1"].forward(n3, tr)
         c["pre"] = pre
         g = ops.geglu(pre)
-        f, c["ff2"] = T["ff2"].forward(g, tr)
-        x3 = ops.add(f, x2)
-        o, c["pout"] = T["proj_out"].forward(x3, tr)
-        out = ops.add(o, x_in)
+        x3, c["ff2"] = T["ff2"].forward(g, tr, addend=x2)
+        out, c["pout"] = T["proj_out"].forward(x3, tr, addend=x_in)
         return out.view(*h.shape), c
 
     def _tr_bwd(self, T, c, dout):

@@ -117,6 +117,14 @@ def test_dropout_scale_kernel(cuda_device):
     ops.dropout_advance(x.device)                                             # next step: same call id, new seed
     _, keep4 = ops.dropout_scale(x, p, scale)
     assert abs((keep4 == keep).float().mean().item() - ((1 - p) ** 2 + p ** 2)) < 5e-3
+    # the residual add that follows the layer folded into the same pass (fp32 add before the one bf16 rounding)
+    ops._DROPOUT_CALLS[0] -= 1
+    a = torch.randn_like(x)
+    y5, keep5 = ops.dropout_scale(x, p, scale, addend=a)
+    assert torch.equal(keep5, keep4)
+    ref5 = x.float() * (scale / (1 - p)) * keep5.float() + a.float()
+    assert (y5.float() - ref5).abs().max().item() <= 2.0 ** -8 * ref5.abs().max().item()
+    assert ((y5.float() - ref5).norm() / ref5.norm()).item() < 3e-3
     # the adjoint reuses the stored mask
     dy = torch.randn_like(x)
     dx = ops.scale_mask(dy, scale / (1 - p), keep)
