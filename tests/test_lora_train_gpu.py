@@ -131,6 +131,21 @@ def test_dropout_scale_kernel(cuda_device):
     assert torch.equal(dx, (dy.float() * (scale / (1 - p)) * keep.float()).to(BF16))
 
 
+@pytest.mark.parametrize("shape,p,seed", [((4096, 320), 0.1, 1234), ((24, 64), 0.5, 2 ** 40 + 17), ((1000, 1280), 0.25, 99)])
+def test_dropout_mask_bit_exact_vs_philox_oracle(cuda_device, shape, p, seed):
+    """The keep-mask drawn inside t2v_dropout_scale equals, bit for bit, the mask the numpy Philox4x32-10 oracle draws for the same
+    (seed, call id) — the oracle is pinned on Random123's known-answer vectors in the CPU suite (tests/test_oracle.py)."""
+    import numpy as np
+    from oracle.philox_oracle import keep_mask
+    from t2v_turbo_b200 import ops
+    x = torch.randn(*shape, device="cuda").to(BF16)
+    ops.dropout_seed(x.device, seed=seed)
+    _, keep = ops.dropout_scale(x, p)
+    want = keep_mask(x.numel(), 1.0 - p, seed, ops._DROPOUT_CALLS[0]).reshape(shape)
+    got = keep.cpu().numpy()
+    assert np.array_equal(got, want), f"{int((got != want).sum())} of {got.size} mask bytes differ"
+
+
 def test_dropout_scale_fresh_masks_under_cuda_graph_replay(cuda_device):
     """The seed lives on the device and is advanced by a captured add: every replay of a captured step draws a new mask."""
     from t2v_turbo_b200 import ops
