@@ -105,9 +105,33 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=float(self.rows[0][1]), reasons=reasons, samples=len(sm))
 
 
-def build_pipeline(device, use_graph=True):
+def build_ms_pipeline(device, use_graph=True):
+    """BASELINE configs[4]: ModelScope UNet3DConditionModel + diffusers KL-VAE names over the same kernels, random-init weights."""
+    import torch
+    from t2v_turbo_b200.ms_adapter import DiffusersAutoencoderKL, T2VTurboMSPipeline, UNet3DConditionModel
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    with torch.device(device):
+        unet = UNet3DConditionModel(time_cond_proj_dim=256)
+        vae = DiffusersAutoencoderKL()
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for mod in (unet, vae):
+            for name, p in mod.named_parameters():
+                if p.dim() >= 2:
+                    p.copy_(torch.randn(p.shape, generator=g, device=device) * (0.6 / p[0].numel() ** 0.5))
+                elif name.endswith("weight"):
+                    p.copy_(1.0 + 0.05 * torch.randn(p.shape, generator=g, device=device))
+                else:
+                    p.copy_(0.02 * torch.randn(p.shape, generator=g, device=device))
+    return T2VTurboMSPipeline(unet.eval().half(), vae.eval().half(), scheduler=T2VTurboScheduler(linear_start=0.00085, linear_end=0.012),
+                              use_cuda_graph=use_graph)
+
+
+def build_pipeline(device, use_graph=True, motion=False):
     import torch
     from t2v_turbo_b200.configs import VC2_UNET, VC2_VAE_DDCONFIG
+    if motion:   # BASELINE configs[2]: the v2 checkpoints add the motion-guidance embedding (predict.py:60-77)
+        VC2_UNET = {**VC2_UNET, "motion_cond_proj_dim": 256}
     from t2v_turbo_b200.pipeline import LatentVideoModel, T2VTurboVC2Pipeline
     from t2v_turbo_b200.scheduler import T2VTurboScheduler
     from t2v_turbo_b200.unet import UNetModel
@@ -571,7 +595,9 @@ def main():
     ap.add_argument("--batch", type=int, default=DEFAULT_BATCH, help="videos per pipeline call per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "lora-step", "train-step"],
+    ap.add_argument("--sample-steps", type=int, default=STEPS, help="num_inference_steps of the pipeline workloads (BASELINE configs[2]: 8, 16)")
+    ap.add_argument("--motion-cond", action="store_true", help="VC2 pipeline with the v2 motion conditioning (BASELINE configs[2])")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "ms-pipeline", "lora-step", "train-step"],
                     help="pipeline = the headline metric; lora-step = the data-parallel LoRA training exchange (supplementary)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -593,14 +619,24 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     t2v_dist.init_replicas("nccl", device)
-    pipe = build_pipeline(device, use_graph=not args.no_graph)
+    ms_model = args.workload == "ms-pipeline"
+    n_sample = args.sample_steps
+    H, W = (256, 256) if ms_model else (HEIGHT, WIDTH)
+    headline = not ms_model and n_sample == STEPS and not args.motion_cond      # the BASELINE configs[1] line
+    pipe = build_ms_pipeline(device, use_graph=not args.no_graph) if ms_model else \
+        build_pipeline(device, use_graph=not args.no_graph, motion=args.motion_cond)
     gen = torch.Generator(device=device).manual_seed(1234 + rank)
     bs = args.batch
-    pe_dev = torch.randn(bs, 77, 1024, device=device, dtype=torch.bfloat16, generator=gen)
+    pe_dev = torch.randn(bs, 77, 1024, device=device, dtype=torch.float16 if ms_model else torch.bfloat16, generator=gen)
 
     def call(pe):
-        return pipe(prompt_embeds=pe, height=HEIGHT, width=WIDTH, frames=FRAMES, fps=16, guidance_scale=7.5,
-                    num_inference_steps=STEPS, lcm_origin_steps=50, generator=gen, output_type="pt")
+        if ms_model:
+            return pipe(prompt_embeds=pe, height=H, width=W, frames=FRAMES, guidance_scale=7.5, num_inference_steps=n_sample,
+                        lcm_origin_steps=50, generator=gen, output_type="pt")
+        extra = dict(use_motion_cond=True, motion_gs=0.05, percentage=0.5, lcm_origin_steps=200) if args.motion_cond else \
+            dict(lcm_origin_steps=50)
+        return pipe(prompt_embeds=pe, height=H, width=W, frames=FRAMES, fps=16, guidance_scale=7.5,
+                    num_inference_steps=n_sample, generator=gen, output_type="pt", **extra)
 
     def barrier():
         t2v_dist.barrier(device)
@@ -608,7 +644,7 @@ def main():
     # ---------------- device-resident arm
     for _ in range(args.warmup):
         vid = call(pe_dev)
-    assert tuple(vid.shape) == (bs, 3, FRAMES, HEIGHT, WIDTH)
+    assert tuple(vid.shape) == (bs, 3, FRAMES, H, W)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -624,7 +660,7 @@ def main():
 
     # ---------------- end-to-end arm: host buffers in, host buffers out
     pe_host = pe_dev.cpu().pin_memory()
-    out_host = torch.empty((bs, 3, FRAMES, HEIGHT, WIDTH), dtype=torch.bfloat16).pin_memory()
+    out_host = torch.empty((bs, 3, FRAMES, H, W), dtype=vid.dtype).pin_memory()
     for _ in range(2):
         out_host.copy_(call(pe_host), non_blocking=True)
     barrier()
@@ -654,8 +690,11 @@ def main():
         u1.record()
         torch.cuda.synchronize()
         return u0.elapsed_time(u1) / 10
-    unet_ms_batch = unet_ms(bs)
-    unet_ms_1 = unet_ms(1) if bs > 1 else unet_ms_batch
+    if ms_model or args.motion_cond:      # the UNet-alone latency belongs to the headline configuration only
+        unet_ms_batch = unet_ms_1 = None
+    else:
+        unet_ms_batch = unet_ms(bs)
+        unet_ms_1 = unet_ms(1) if bs > 1 else unet_ms_batch
 
     # ---------------- launches per step + roofline of the dominant kernel family (eager pass, CUDA events per call)
     pipe.use_cuda_graph = False
@@ -683,22 +722,36 @@ def main():
     if rank == 0:
         frames_total = FRAMES * bs * args.steps * world
         value = frames_total / (ms * 1e-3)
-        line = dict(metric="4-step 16x320x512 frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
+        pipe_tflop = None if ms_model else n_sample * UNET_TFLOP + VAE_TFLOP      # 75.34 / 125.67 / 226.32 for 4 / 8 / 16 steps
+        if ms_model:
+            workload = (f"T2VTurboMSPipeline {n_sample}-step, 16x256x256, ModelScope UNet3DConditionModel + diffusers KL-VAE (fp16 at the "
+                        f"boundary, bf16 inside), bs={bs} per GPU")
+        elif headline:
+            workload = WORKLOAD % bs
+        else:
+            workload = (f"T2VTurboVC2Pipeline {n_sample}-step, 16x320x512, VC2 UNet (1.41B"
+                        + (" + motion_cond_proj, use_motion_cond, motion_gs 0.05, percentage 0.5, lcm_origin_steps 200" if args.motion_cond else "")
+                        + f") + KL-VAE decode, bs={bs} per GPU")
+        line = dict(metric=f"{n_sample}-step 16x{H}x{W} frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic",
-                    config=dict(workload=WORKLOAD % bs, videos_per_step=bs,
+                    config=dict(workload=workload, videos_per_step=bs,
                                 parallelism=f"replicas x{world} (no data-path collective)", cuda_graph=not args.no_graph,
-                                l2="working set per step (2.83 GB weights x4 + activations) >> 126 MB L2; no flush needed",
+                                l2="working set per step (2.83 GB weights per UNet forward + activations) >> 126 MB L2; no flush needed",
                                 batch_note="throughput configuration: bs videos per pipeline call (bs=1 latency numbers: unet_fwd_ms, "
                                            "profiles/r02_batch_sweep.json)",
-                                algorithmic_tflop_per_step=PIPE_TFLOP * bs, output_finite=finite),
-                    unet_fwd_ms=unet_ms_1, unet_fwd_ms_per_video_at_batch=unet_ms_batch / bs,
-                    unet_fwd_tflops=UNET_TFLOP * bs / (unet_ms_batch * 1e-3), clocks=clocks,
+                                output_finite=finite),
+                    clocks=clocks,
                     e2e=dict(value=frames_total / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=pe_host.numel() * 2,
                              d2h_bytes_per_step=out_host.numel() * 2),
-                    gpu_launches=launches_per_step * args.steps, roofline=roofline,
-                    tensor_frac_of_step=PIPE_TFLOP * bs / (ms / args.steps * 1e-3) / pk["tflops"])
-        if world == 1 and not args.no_cpu_baseline:
+                    gpu_launches=launches_per_step * args.steps, roofline=roofline)
+        if pipe_tflop is not None:
+            line["config"]["algorithmic_tflop_per_step"] = pipe_tflop * bs
+            line["tensor_frac_of_step"] = pipe_tflop * bs / (ms / args.steps * 1e-3) / pk["tflops"]
+        if unet_ms_1 is not None:
+            line.update(unet_fwd_ms=unet_ms_1, unet_fwd_ms_per_video_at_batch=unet_ms_batch / bs,
+                        unet_fwd_tflops=UNET_TFLOP * bs / (unet_ms_batch * 1e-3))
+        if world == 1 and not args.no_cpu_baseline and headline:
             torch.cuda.synchronize()
             run, kind, threads, cdt, desc = cpu_arm()
             tv, (tu, tf) = run()
