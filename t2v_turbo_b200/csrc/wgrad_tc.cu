@@ -117,27 +117,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         phase ^= 1u;
       }
     }
-  } else if (warp == 1 && elect_one()) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: D[128 ch x 64] += A^T (MN-major) * B (MN-major)
+    // whole-warp loop (uniform-datapath descriptor arithmetic), tcgen05.mma / commit on the elected lane only: an N = 64 MMA is
+    // 32 tensor cycles, less than the ~12 dependent instructions per MMA a single-thread issue loop needs
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int k_steps = p.rows_in_box >> 4;
+    const uint64_t adesc0 = umma_desc_sw128_mn(smem_u32(smem), 128 * 128);
+    const uint64_t bdesc0 = umma_desc_sw128_mn(smem_u32(smem) + kWgABytes, 128 * 128);
+    constexpr uint64_t kStageDesc = kWgStageBytes >> 4;   // one ring stage further, in descriptor (16-byte) units
     int stage = 0;
     uint32_t phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + stage * kWgStageBytes);
-      const uint64_t adesc = umma_desc_sw128_mn(a_addr, 128 * 128);
-      const uint64_t bdesc = umma_desc_sw128_mn(a_addr + kWgABytes, 128 * 128);
-      for (int kk = 0; kk < k_steps; ++kk)   // 16 points = 16 rows of 128 bytes
-        umma_ss(tmem_base, adesc + uint64_t(kk * (2048 >> 4)), bdesc + uint64_t(kk * (2048 >> 4)), idesc, (t > t_begin || kk > 0) ? 1u : 0u);
-      umma_commit(&empty_bar[stage]);
+      const uint64_t adesc = adesc0 + uint64_t(stage) * kStageDesc;
+      const uint64_t bdesc = bdesc0 + uint64_t(stage) * kStageDesc;
+      if (leader) {
+        for (int kk = 0; kk < k_steps; ++kk)   // 16 points = 16 rows of 128 bytes
+          umma_ss(tm, adesc + uint64_t(kk * (2048 >> 4)), bdesc + uint64_t(kk * (2048 >> 4)), idesc, (t > t_begin || kk > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+      }
       if (++stage == kWgStages) {
         stage = 0;
         phase ^= 1u;
       }
     }
-    umma_commit(acc_bar);
+    if (leader) umma_commit(acc_bar);
   } else if (warp >= 2 && t_end > t_begin) {
     // ------------------------------------------------------------ epilogue: thread = channel row, red.add into the arena
     const int lg = warp & 3;               // TMEM lane group of this warp
