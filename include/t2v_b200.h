@@ -462,6 +462,25 @@ int t2v_attn_short_bwd(const T2VShortAttnBwdDesc* desc, t2v_stream_t stream);
 int t2v_huber_loss_grad(const void* a, const void* b, void* grad, float* loss, int64_t n, int32_t dtype, float huber_c,
                         float grad_scale, t2v_stream_t stream);
 
+/* ---- full fine-tune step only (train_latent_t2v_turbo_v2.py:945-1276: every UNet parameter trains) ----
+ * Affine gradients of GroupNorm(+SiLU) (lvdm/basics.py:78-89 GroupNormSpecific; the `normalization(ch)` + SiLU pairs of
+ * openaimodel3d.py:155-159,179-184,275-295):  dgamma[c] += sum dpre * xh,  dbeta[c] += sum dpre,  dpre = dy * act'(xh * gamma + beta),
+ * over all rows of all samples (fp32, accumulated into — the gradient arena).  stats_ws is the workspace t2v_groupnorm_bwd filled
+ * for the same (x, rows_per_sample, groups): fp32 [n_samples][groups][4], slots 0 / 1 = sum x / sum x^2.  channels <= 2560. */
+int t2v_groupnorm_affine_grad(const void* x, int64_t x_row_stride, const void* dy, int64_t dy_row_stride, const float* gamma,
+                              const float* beta, const float* stats_ws, float* dgamma, float* dbeta, int64_t rows,
+                              int64_t rows_per_sample, int32_t channels, int32_t groups, float eps, int32_t silu,
+                              t2v_stream_t stream);
+
+/* Affine gradients of LayerNorm (attention.py:279-281 norm1..3): dgamma[c] += sum_rows dy * xh, dbeta[c] += sum_rows dy
+ * (fp32, accumulated into); channels as t2v_layernorm_bwd. */
+int t2v_layernorm_affine_grad(const void* x, int64_t x_row_stride, const void* dy, int64_t dy_row_stride, float* dgamma,
+                              float* dbeta, int64_t rows, int32_t channels, float eps, t2v_stream_t stream);
+
+/* EMA of the target network's parameters over the flat fp32 arenas (update_ema, utils/common_utils.py:308-319;
+ * train_latent_t2v_turbo_v2.py:1273-1276): target = target * rate + src * (1 - rate). */
+int t2v_ema_update(float* target, const float* src, int64_t n, float rate, t2v_stream_t stream);
+
 /* Weight packing helpers (device-side, run once at load). */
 /* conv weight [Cout][Cin][kh*kw] (torch OIHW / OIDHW flattened taps) -> [Cout][taps][Cin] bf16 */
 int t2v_pack_conv_weight(const void* w, int32_t w_dtype, void* out, int32_t cout, int32_t cin,

@@ -586,9 +586,9 @@ def _rows2d(x, name):
     return x
 
 
-def groupnorm_bwd(x, dy, gamma, beta, *, rows_per_sample, eps, silu, groups=32, dx_add=None, out=None):
+def groupnorm_bwd(x, dy, gamma, beta, *, rows_per_sample, eps, silu, groups=32, dx_add=None, out=None, keep_ws=None):
     """Adjoint of groupnorm (+SiLU) w.r.t. x.  x / dy: bf16 [rows, C] (row strides free); dx_add: optional second gradient
-    path summed into the result."""
+    path summed into the result.  keep_ws: a list that receives the statistics workspace (for groupnorm_affine_grad)."""
     _rows2d(x, "x"); _rows2d(dy, "dy")
     rows, c = x.shape
     if out is None:
@@ -607,6 +607,8 @@ def groupnorm_bwd(x, dy, gamma, beta, *, rows_per_sample, eps, silu, groups=32, 
     d.channels, d.groups, d.eps, d.silu = c, groups, eps, 1 if silu else 0
     d.workspace = ws.data_ptr()
     _launch("groupnorm_bwd", 0, lib().t2v_groupnorm_bwd, C.byref(d), stream_ptr())
+    if keep_ws is not None:
+        keep_ws.append(ws)
     return out
 
 
@@ -917,6 +919,83 @@ def wgrad(a, b, out, *, taps=None, out_strides, alpha=1.0, a_grid=None):
     d.alpha = alpha
     _launch("wgrad", 2 * math.prod(grid) * c * r * len(taps), lib().t2v_wgrad, C.byref(d), stream_ptr())
     return out
+
+
+def wgrad_wide(a, b, out, *, taps=None, out_strides, alpha=1.0):
+    """ops.wgrad for a B operand of ANY width (the base-weight gradients of the full fine-tune step: b = dy with Cout columns):
+    out[j, c, tap] += alpha * sum_points a[point + off(tap), c] * b[point, j], j < b.shape[-1], as ceil(Cout / 64) t2v_wgrad launches
+    over 64-column slices of b read IN PLACE (the B tensor map's row stride is the full width; nothing is copied)."""
+    _check_act(a, "a")
+    _check_act(b, "b")
+    assert out.dtype == torch.float32 and out.is_cuda
+    pts = tuple(a.shape[:-1])
+    assert tuple(b.shape[:-1]) == pts and len(pts) <= 4
+    c, n = a.shape[-1], b.shape[-1]
+    assert n % 8 == 0, n
+    if math.prod(pts) < 16:   # fewer points than one MMA k-step (embedding layers, M = batch): zero rows add nothing
+        assert len(pts) == 1 and taps is None
+        a = torch.cat([a, a.new_zeros(16 - pts[0], c)])
+        b = torch.cat([b, b.new_zeros(16 - pts[0], n)])
+        pts = (16,)
+    grid = tuple(reversed(pts)) + (1,) * (4 - len(pts))       # x1 fastest
+    astr, bstr, acc = [], [], 1
+    for g in grid:
+        astr.append(acc * c)
+        bstr.append(acc * n)
+        acc *= g
+    box = plan_box(grid)
+    if math.prod(box) % 16:
+        box = plan_box(grid, fixed=(16 if grid[0] % 16 == 0 else None, None, None, None))
+    assert math.prod(box) % 16 == 0, f"wgrad: no 16-row tile box for point grid {grid}"
+    taps = taps if taps is not None else [(0, 0, 0, 0)]
+    j_stride, c_stride, tap_stride = (int(v) for v in out_strides)
+    for j0 in range(0, n, 64):
+        cols = min(64, n - j0)
+        d = _lib.WgradDesc()
+        d.a, d.a_ch, d.b, d.b_cols = a.data_ptr(), c, b.data_ptr() + 2 * j0, cols
+        _fill(d.a_size, grid)
+        _fill(d.o_size, grid)
+        _fill(d.a_stride, astr)
+        _fill(d.b_stride, bstr)
+        _fill(d.box, box)
+        d.n_taps = len(taps)
+        for t, off in enumerate(taps):
+            _fill(d.tap_off[t], off)
+        d.out = out.data_ptr() + 4 * j0 * j_stride
+        d.out_j_stride, d.out_c_stride, d.out_tap_stride = j_stride, c_stride, tap_stride
+        d.alpha = alpha
+        _launch("wgrad", 2 * math.prod(grid) * c * cols * len(taps), lib().t2v_wgrad, C.byref(d), stream_ptr())
+    return out
+
+
+def groupnorm_affine_grad(x, dy, gamma, beta, stats_ws, dgamma, dbeta, *, rows_per_sample, eps, silu, groups=32):
+    """dgamma / dbeta (fp32 [C], accumulated into) of groupnorm(+SiLU); stats_ws: the workspace ops.groupnorm_bwd(..., keep_ws=[])
+    filled for the same x (full fine-tune step only)."""
+    _rows2d(x, "x"); _rows2d(dy, "dy")
+    rows, c = x.shape
+    assert dgamma.dtype == torch.float32 and dbeta.dtype == torch.float32 and dgamma.numel() == c and dbeta.numel() == c
+    assert dgamma.is_contiguous() and dbeta.is_contiguous()
+    _launch("groupnorm_affine_grad", 0, lib().t2v_groupnorm_affine_grad, x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0),
+            gamma.data_ptr(), beta.data_ptr(), stats_ws.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, rows_per_sample, c, groups,
+            eps, 1 if silu else 0, stream_ptr())
+
+
+def layernorm_affine_grad(x, dy, dgamma, dbeta, eps=1e-5):
+    """dgamma / dbeta (fp32 [C], accumulated into) of layernorm (full fine-tune step only)."""
+    _rows2d(x, "x"); _rows2d(dy, "dy")
+    rows, c = x.shape
+    assert dgamma.dtype == torch.float32 and dbeta.dtype == torch.float32 and dgamma.numel() == c and dbeta.numel() == c
+    assert dgamma.is_contiguous() and dbeta.is_contiguous()
+    _launch("layernorm_affine_grad", 0, lib().t2v_layernorm_affine_grad, x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0),
+            dgamma.data_ptr(), dbeta.data_ptr(), rows, c, eps, stream_ptr())
+
+
+def ema_update(target, src, rate):
+    """target = target * rate + src * (1 - rate) over flat fp32 arenas (update_ema, utils/common_utils.py:308-319)."""
+    assert target.is_cuda and src.is_cuda and target.dtype == torch.float32 and src.dtype == torch.float32
+    assert target.is_contiguous() and src.is_contiguous() and target.numel() == src.numel()
+    _launch("ema_update", 0, lib().t2v_ema_update, target.data_ptr(), src.data_ptr(), target.numel(), float(rate), stream_ptr())
+    return target
 
 
 def scale_mask(x, scale, mask=None, out=None):

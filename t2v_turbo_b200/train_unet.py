@@ -42,6 +42,12 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
+def _require_cuda(what, device):
+    """The training views run on a CUDA device only: there is no CPU fallback of the product path."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError(f"{what}(B200) runs on a CUDA device only (no CPU fallback)")
+
+
 # =============================================================================== one GEMM layer (LoRA-injected or plain)
 class _Layer:
     """A GEMM layer of the training path.  kind: linear | conv2d | conv3d.  `lora` False = a frozen layer the reference does
@@ -132,6 +138,7 @@ class _Layer:
 
 class _Norm:
     def __init__(self, m):
+        self.module = m
         self.w, self.b, self.eps = _f32(m.weight), _f32(m.bias), m.eps
 
 
@@ -139,8 +146,7 @@ class _Norm:
 class StudentUNet:
     def __init__(self, unet: U.UNetModel, r: int = 64, dropout_p: float = 0.1, scale: float = 1.0, tconv_dropout: float = 0.1):
         dev = unet.time_embed[0].weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("StudentUNet(B200) runs on a CUDA device only (no CPU fallback): call unet.cuda() first")
+        _require_cuda("StudentUNet", dev)      # call unet.cuda() first
         self.unet, self.device, self.r = unet, dev, r
         self.training = True
         self.tconv_p = tconv_dropout
@@ -222,8 +228,19 @@ class StudentUNet:
         self.s_time = (self._L(u.time_embed[0]), self._L(u.time_embed[2]))
         self.s_fps = (self._L(u.fps_embedding[0]), self._L(u.fps_embedding[2])) if u.fps_cond else None
         self.s_cond = self._L(u.time_cond_proj) if u.time_cond_proj is not None else None
+        self.s_motion = self._motion_struct(u)
+
+    def _motion_struct(self, u):
         if u.motion_cond_proj is not None:
-            raise NotImplementedError("StudentUNet: motion_cond_proj (the v2 training path) is not built")
+            raise NotImplementedError("StudentUNet: motion_cond_proj belongs to the v2 full fine-tune step (full_train.FullUNet)")
+        return None
+
+    # norm adjoints: the LoRA step needs dx only; full_train.FullUNet overrides these to add the affine gradients
+    def _gn_bwd(self, norm, x, dy, *, rows_per_sample, silu, dx_add=None):
+        return ops.groupnorm_bwd(x, dy, norm.w, norm.b, rows_per_sample=rows_per_sample, eps=norm.eps, silu=silu, dx_add=dx_add)
+
+    def _ln_bwd(self, norm, x, dy, *, dx_add=None):
+        return ops.layernorm_bwd(x, dy, norm.w, norm.eps, dx_add=dx_add)
 
     def _res_struct(self, rb):
         d = dict(gn1=_Norm(rb.in_layers[0]), conv1=self._L(rb.in_layers[2]), emb=self._L(rb.emb_layers[1]),
@@ -279,7 +296,9 @@ class StudentUNet:
         return self.train(False)
 
     # ------------------------------------------------------------------ embeddings
-    def _emb_fwd(self, timesteps, fps, timestep_cond, bsz):
+    def _emb_fwd(self, timesteps, fps, timestep_cond, bsz, motion_cond=None):
+        if motion_cond is not None:
+            raise NotImplementedError("StudentUNet: motion_cond belongs to the v2 full fine-tune step (full_train.FullUNet)")
         tr, dev = self.training, self.device
         ctx = {}
         t = timesteps.to(device=dev, dtype=torch.float32).reshape(-1)
@@ -373,17 +392,16 @@ class StudentUNet:
                 d_yn = conv.backward(sv, dy.view(b, t, hw, cout)).view(-1, cout)
                 if mask is not None:
                     d_yn = ops.scale_mask(d_yn, ms, mask)
-                dy = ops.groupnorm_bwd(y_in, d_yn, gn.w, gn.b, rows_per_sample=t * hw, eps=gn.eps, silu=True,
-                                       dx_add=d_h2 if i == 0 else None)
+                dy = self._gn_bwd(gn, y_in, d_yn, rows_per_sample=t * hw, silu=True, dx_add=d_h2 if i == 0 else None)
             d_h2 = dy
         d_hn2 = R["conv2"].backward(c["conv2"], d_h2.view(nf, hh, ww, cout)).view(-1, cout)
         d_skip = d_h2 if R["skip"] is None else R["skip"].backward(c["skip"], d_h2)
-        d_h = ops.groupnorm_bwd(c["h"], d_hn2, R["gn2"].w, R["gn2"].b, rows_per_sample=hw, eps=R["gn2"].eps, silu=True)
+        d_h = self._gn_bwd(R["gn2"], c["h"], d_hn2, rows_per_sample=hw, silu=True)
         d_rb = ops.colsum_samples(d_h, t * hw)                                   # fp32 [B, cout]
         self._acc_emb(R["emb"].backward(c["emb"], d_rb.to(BF16)))
         cin = c["x"].shape[-1]
         d_hn = R["conv1"].backward(c["conv1"], d_h.view(nf, hh, ww, cout)).view(-1, cin)
-        dx = ops.groupnorm_bwd(c["x"], d_hn, R["gn1"].w, R["gn1"].b, rows_per_sample=hw, eps=R["gn1"].eps, silu=True, dx_add=d_skip)
+        dx = self._gn_bwd(R["gn1"], c["x"], d_hn, rows_per_sample=hw, silu=True, dx_add=d_skip)
         return dx.view(nf, hh, ww, cin)
 
     # ------------------------------------------------------------------ transformers
@@ -472,14 +490,14 @@ class StudentUNet:
         d_g = T["ff2"].backward(c["ff2"], d_x3)
         d_pre = ops.geglu(c["pre"], d_g)
         d_n3 = T["ff1"].backward(c["ff1"], d_pre)
-        d_x2 = ops.layernorm_bwd(c["x2"], d_n3, ln[2].w, ln[2].eps, dx_add=d_x3)
+        d_x2 = self._ln_bwd(ln[2], c["x2"], d_n3, dx_add=d_x3)
         d_n2 = self._attn_bwd(T["a2"], c["a2"], d_x2, geom, temporal, self_attn=temporal)
-        d_x1 = ops.layernorm_bwd(c["x1"], d_n2, ln[1].w, ln[1].eps, dx_add=d_x2)
+        d_x1 = self._ln_bwd(ln[1], c["x1"], d_n2, dx_add=d_x2)
         d_n1 = self._attn_bwd(T["a1"], c["a1"], d_x1, geom, temporal, self_attn=True)
-        d_x0 = ops.layernorm_bwd(c["x0"], d_n1, ln[0].w, ln[0].eps, dx_add=d_x1)
+        d_x0 = self._ln_bwd(ln[0], c["x0"], d_n1, dx_add=d_x1)
         d_xn = T["proj_in"].backward(c["pin"], d_x0)
         rps = hw * (t if temporal else 1)
-        dx = ops.groupnorm_bwd(c["x_in"], d_xn, T["gn"].w, T["gn"].b, rows_per_sample=rps, eps=T["gn"].eps, silu=False, dx_add=d_out)
+        dx = self._gn_bwd(T["gn"], c["x_in"], d_xn, rows_per_sample=rps, silu=False, dx_add=d_out)
         return dx.view(*dout.shape)
 
     # ------------------------------------------------------------------ sequences
@@ -523,16 +541,15 @@ class StudentUNet:
         return dh
 
     # ------------------------------------------------------------------ forward / backward
-    def forward(self, x, timesteps, context=None, fps=16, timestep_cond=None, **kwargs):
-        if not x.is_cuda:
-            raise RuntimeError("StudentUNet(B200): input must be a CUDA tensor (no CPU fallback)")
+    def forward(self, x, timesteps, context=None, fps=16, timestep_cond=None, motion_cond=None, **kwargs):
+        _require_cuda(type(self).__name__ + " input", x.device)
         if not self._packed:
             self.pack()
         if self.training:
             ops.dropout_advance(x.device)   # fresh in-kernel dropout masks for this forward (capturable: a device-side add)
         u = self.unet
         b, cin, t, hh, ww = x.shape
-        self._emb_fwd(timesteps, fps, timestep_cond, b)
+        self._emb_fwd(timesteps, fps, timestep_cond, b, motion_cond)
         ctx_rows = None
         if context is not None:    # the reference repeats the text context per frame before to_k / to_v (openaimodel3d.py:710)
             ctx_rows = context.to(device=self.device, dtype=BF16).repeat_interleave(t, 0).reshape(-1, context.shape[-1]).contiguous()
@@ -584,7 +601,7 @@ class StudentUNet:
         dy = ops.bcthw_to_frames_pad(d_out, 64)
         c = oc["h"].shape[-1]
         d_hn = conv.backward(oc["conv"], dy).view(-1, c)
-        dh = ops.groupnorm_bwd(oc["h"], d_hn, gn.w, gn.b, rows_per_sample=hh * ww, eps=gn.eps, silu=True)
+        dh = self._gn_bwd(gn, oc["h"], d_hn, rows_per_sample=hh * ww, silu=True)
         d_skips = []
         n_out = len(self._tapes_out)
         for j, (tape, (c_h, c_s)) in enumerate(zip(reversed(self._tapes_out), reversed(self._skip_ch))):
