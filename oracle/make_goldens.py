@@ -345,6 +345,147 @@ def gen_distill_step(name="small"):
                 "timesteps": timesteps, "grad_norms": norms, "grads_full": full}, os.path.join(GOLD, f"distill_step_{name}.pt"))
 
 
+def v2_inputs(spec, bsz=2):
+    """Seeded batch of the v2 latent dataset (preprocess_with_motion_prior.py:392-401 keys) for the v2-step fixture."""
+    g = torch.Generator().manual_seed(6161)
+    shape = (bsz,) + tuple(spec["x_shape"][1:])
+    cd = spec["cfg"]["context_dim"]
+    return dict(index=torch.tensor([171, 63][:bsz]), z_t=torch.randn(shape, generator=g), cond_teacher_out=torch.randn(shape, generator=g),
+                uncond_teacher_out=torch.randn(shape, generator=g), score=torch.randn(shape, generator=g) * 2.0,
+                use_motion_guide=torch.tensor([True, True][:bsz]), prompt_emb=torch.randn(bsz, spec["ctx_len"], cd, generator=g),
+                w=torch.tensor([6.5, 13.0][:bsz]))
+
+
+def gen_v2_step(name="small_motion"):
+    """One full fine-tune step of train_latent_t2v_turbo_v2.py:945-1276 (reward terms off, --use_motion_cond, --use_target_unet)
+    composed from the UNMODIFIED reference pieces — UNetModel with EVERY parameter trainable, the parameter grouping of :799-815
+    executed on the reference's own module tree, guidance_scale_embedding / scalings_for_boundary_conditions /
+    get_predicted_original_sample / get_predicted_noise / extract_into_tensor / huber_loss / update_ema (utils/common_utils.py),
+    DDIMSolver.ddim_step, torch.optim.AdamW over the two groups, clip_grad_norm_ — fp32, eval mode (dropouts off), fixed draws.
+    Sample 0 has index >= (1 - percentage) * N (motion guidance on), sample 1 below it (off)."""
+    import copy
+
+    from lvdm.common import extract_into_tensor
+    from lvdm.modules.attention import TemporalTransformer
+    from ode_solver.ddim_solver import DDIMSolver
+    from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
+    from utils.common_utils import (append_dims, get_predicted_noise, get_predicted_original_sample, guidance_scale_embedding, huber_loss,
+                                    scalings_for_boundary_conditions, update_ema)
+    spec = UNET_CONFIGS[name]
+    unet = ref_unet(spec["cfg"], spec["weight_seed"])
+    unet.requires_grad_(True)
+    target_unet = copy.deepcopy(unet).requires_grad_(False)
+    # the EMA network starts from different values than the student here, so that the target branch and update_ema are exercised
+    with torch.no_grad():
+        gq = torch.Generator().manual_seed(99)
+        for p in target_unet.parameters():
+            p.mul_(1.0 + 0.02 * torch.randn(p.shape, generator=gq))
+    target_sd0 = {k: v.clone() for k, v in target_unet.state_dict().items()}
+    # ---- :799-815, verbatim logic on the reference modules
+    temporal_params, other_params, temporal_names = [], [], []
+    named_modules_dict = dict(unet.named_modules())
+    for n, p in unet.named_parameters():
+        if n.startswith("init_attn.0"):
+            temporal_params.append(p); temporal_names.append(n)
+        elif len(n.split(".")) > 2:
+            module_name = ".".join(n.split(".")[:3])
+            if module_name in named_modules_dict and isinstance(named_modules_dict[module_name], TemporalTransformer):
+                temporal_params.append(p); temporal_names.append(n)
+            else:
+                other_params.append(p)
+        else:
+            other_params.append(p)
+    lr, temporal_lr_scale, wd, ema_decay, max_grad_norm = 1e-5, 3.0, 0.01, 0.95, 1.0
+    optimizer = torch.optim.AdamW([{"params": other_params}, {"params": temporal_params, "lr": lr * temporal_lr_scale}], lr=lr,
+                                  betas=(0.9, 0.999), weight_decay=wd, eps=1e-8)
+    noise_scheduler = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
+    alpha_schedule = torch.sqrt(noise_scheduler.alphas_cumprod)
+    sigma_schedule = torch.sqrt(1 - noise_scheduler.alphas_cumprod)
+    n_ddim, topk, ts_scale, fps, motion_gs_arg, percentage = 200, 5, 10.0, 16, 0.05, 0.5
+    solver = DDIMSolver(noise_scheduler.alphas_cumprod.numpy(), ddim_timesteps=n_ddim, use_scale=False)
+    inp = v2_inputs(spec)
+    index, w = inp["index"], inp["w"]
+    noisy_model_input, cond_teacher_output, uncond_teacher_output = inp["z_t"], inp["cond_teacher_out"], inp["uncond_teacher_out"]
+    score, use_motion_guide = inp["score"], inp["use_motion_guide"]
+    bsz = index.shape[0]
+    index_reshape = index.reshape(bsz, 1, 1, 1, 1)
+    # ---- :985-1039
+    start_timesteps = solver.ddim_timesteps[index]
+    timesteps = start_timesteps - topk
+    timesteps = torch.where(timesteps < 0, torch.zeros_like(timesteps), timesteps)
+    c_skip_start, c_out_start = [append_dims(x, noisy_model_input.ndim) for x in scalings_for_boundary_conditions(start_timesteps, timestep_scaling=ts_scale)]
+    c_skip, c_out = [append_dims(x, noisy_model_input.ndim) for x in scalings_for_boundary_conditions(timesteps, timestep_scaling=ts_scale)]
+    w_embedding = guidance_scale_embedding(w, 256)
+    wv = w.reshape(bsz, 1, 1, 1, 1)
+    motion_gs = motion_gs_arg * torch.ones((bsz,))
+    condition = torch.logical_and(use_motion_guide, index >= (1 - percentage) * n_ddim)
+    motion_gs = torch.where(condition, motion_gs, torch.zeros_like(motion_gs))
+    motion_gs_embedding = guidance_scale_embedding(motion_gs, 256)
+    motion_gs_host = motion_gs.clone()
+    motion_gs = motion_gs.reshape(bsz, 1, 1, 1, 1)
+    context = {"context": inp["prompt_emb"], "fps": fps}
+    # ---- :1043-1060
+    noise_pred = unet(noisy_model_input, start_timesteps, **context, timestep_cond=w_embedding, motion_cond=motion_gs_embedding)
+    pred_x_0 = get_predicted_original_sample(noise_pred, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+    model_pred = c_skip_start * noisy_model_input + c_out_start * pred_x_0
+    # ---- :1168-1256
+    with torch.no_grad():
+        cond_pred_x0 = get_predicted_original_sample(cond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        cond_pred_noise = get_predicted_noise(cond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        uncond_pred_x0 = get_predicted_original_sample(uncond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        uncond_pred_noise = get_predicted_noise(uncond_teacher_output, start_timesteps, noisy_model_input, "epsilon", alpha_schedule, sigma_schedule)
+        pred_x0 = cond_pred_x0 + wv * (cond_pred_x0 - uncond_pred_x0)
+        pred_noise = cond_pred_noise + wv * (cond_pred_noise - uncond_pred_noise)
+        alphas = extract_into_tensor(alpha_schedule, start_timesteps, score.shape)
+        condition5 = torch.logical_and(use_motion_guide.reshape(bsz, 1, 1, 1, 1), index_reshape >= (1 - percentage) * n_ddim)
+        alphas = torch.where(condition5, alphas, torch.ones_like(alphas))
+        pred_noise -= motion_gs * (1 - alphas) ** (0.5) * score
+        x_prev = solver.ddim_step(pred_x0, pred_noise, index)
+        out_t = {}
+        for tag, net in (("ema", target_unet), ("self", unet)):
+            target_noise_pred = net(x_prev.float(), timesteps, **context, timestep_cond=w_embedding, motion_cond=motion_gs_embedding)
+            pred_x_0_t = get_predicted_original_sample(target_noise_pred.to(torch.float32), timesteps, x_prev, "epsilon", alpha_schedule, sigma_schedule)
+            out_t[tag] = c_skip * x_prev + c_out * pred_x_0_t
+    target = out_t["ema"]
+    distill_loss = huber_loss(model_pred, target, 0.001)
+    loss_self = huber_loss(model_pred.detach(), out_t["self"], 0.001)
+    distill_loss.backward()
+    names = [n for n, _ in unet.named_parameters()]
+    grads = {n: p.grad.clone() for n, p in unet.named_parameters()}
+    norms = {n: g.double().norm().item() for n, g in grads.items()}
+    total_norm = float(torch.nn.utils.clip_grad_norm_(unet.parameters(), max_grad_norm))
+    optimizer.step()
+    update_ema(target_unet.parameters(), unet.parameters(), ema_decay)
+    # kept in full (fp16 scaled by the max): a fixed subset of gradients; after the step: the same subset of student / EMA parameters
+    keep = [n for i, n in enumerate(names) if (i % 17 == 0 or n.startswith(("motion_cond_proj", "combine_proj", "time_cond_proj", "out.2", "input_blocks.0.0")))
+            and grads[n].numel() <= 150000]
+    full = {}
+    for n in keep:
+        sc = grads[n].abs().max().item() + 1e-30
+        full[n] = (sc, (grads[n] / sc).half())
+    sd1 = dict(unet.named_parameters())
+    sd_t1 = dict(target_unet.named_parameters())
+    sd0 = seeded_state_dict(unet.state_dict(), spec["weight_seed"])
+    stepped = {}                                                                         # parameter DELTAS of the AdamW step
+    for n in keep:
+        d = sd1[n].detach() - sd0[n]
+        sc = d.abs().max().item() + 1e-30
+        stepped[n] = (sc, (d / sc).half())
+    ema_after = {n: sd_t1[n].detach().clone() for n in [k for k in keep if grads[k].numel() <= 70000][:12]}
+    print(f"  v2 step {name}: loss {distill_loss.item():.6f} (self-target {loss_self.item():.6f}), start t {start_timesteps.tolist()}, "
+          f"t {timesteps.tolist()}, motion_gs {motion_gs_host.tolist()}, grad norm {total_norm:.5f}, {len(temporal_names)} temporal / "
+          f"{len(names) - len(temporal_names)} other parameters, {len(keep)} tensors stored in full")
+    torch.save({"name": name, "inputs": inp, "hyper": dict(lr=lr, temporal_lr_scale=temporal_lr_scale, weight_decay=wd, ema_decay=ema_decay,
+                                                          max_grad_norm=max_grad_norm, n_ddim=n_ddim, topk=topk, motion_gs=motion_gs_arg,
+                                                          percentage=percentage, ts_scale=ts_scale),
+                "target_perturb_seed": 99, "temporal_names": temporal_names, "names": names,
+                "loss": distill_loss.detach().clone(), "loss_self_target": loss_self.detach().clone(),
+                "model_pred": model_pred.detach().clone(), "x_prev": x_prev, "target": target, "target_self": out_t["self"],
+                "start_timesteps": start_timesteps, "timesteps": timesteps, "motion_gs": motion_gs_host,
+                "grad_norms": norms, "total_norm": total_norm, "grads_full": full, "param_delta": stepped, "ema_after": ema_after},
+               os.path.join(GOLD, f"v2_step_{name}.pt"))
+
+
 def gen_distill_tables():
     """Host-side tables / closed forms of the distillation step straight from the reference: DDIMSolver (ode_solver/ddim_solver.py),
     scalings_for_boundary_conditions and guidance_scale_embedding (utils/common_utils.py), and one tensor-level composition of
@@ -512,7 +653,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -527,6 +668,8 @@ if __name__ == "__main__":
             gen_distill_step()
         elif item == "distill_tables":
             gen_distill_tables()
+        elif item == "v2_step":
+            gen_v2_step()
         elif item == "unet_probs":
             gen_unet_probs()
         elif item.startswith("lora_"):

@@ -1,0 +1,212 @@
+"""The hand-written backward passes, checked WITHOUT a GPU: tests/mock_ops.py restates the contract of every kernel wrapper in
+plain torch (fp32), it is patched over `t2v_turbo_b200.ops`, and the training views (StudentUNet: v1 LoRA step; FullUNet / V2Step:
+v2 full fine-tune step) then run their real host composition on CPU.  Compared with
+
+  * the UNMODIFIED reference's gradients (tests/golden/student_grads_small.pt, v2_step_small_motion.pt: oracle/make_goldens.py), and
+  * autograd through the functional oracle (oracle/unet_oracle.py) for EVERY parameter,
+
+at fp32 tolerances (1e-4): a wrong tape, layout, coefficient or a gradient routed to the wrong tensor cannot hide behind bf16
+noise.  What this does not cover — that each CUDA kernel meets the contract restated in mock_ops — is the `-m gpu` suite's job.
+"""
+import os
+
+import pytest
+import torch
+
+import mock_ops
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(got, ref):
+    got, ref = got.double(), ref.double()
+    return ((got - ref).norm() / (ref.norm() + 1e-30)).item()
+
+
+def _unet(name):
+    from oracle.configs import UNET_CONFIGS
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200.unet import UNetModel
+    spec = UNET_CONFIGS[name]
+    m = UNetModel(**spec["cfg"])
+    sd = seeded_state_dict(m.state_dict(), spec["weight_seed"])
+    m.load_state_dict(sd, strict=True)
+    return spec, m.eval(), sd
+
+
+def test_student_unet_composition_vs_reference_lora_gradients(monkeypatch):
+    """v1: StudentUNet forward + backward on CPU through the contract restatements == the reference's own LoRA gradients."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import student_loras, unet_inputs
+    from t2v_turbo_b200.train_unet import StudentUNet
+    g = torch.load(os.path.join(GOLD, "student_grads_small.pt"))
+    spec, m, _ = _unet("small")
+    s = StudentUNet(m, r=64, dropout_p=0.1, scale=1.0).eval()
+    assert [tuple(x) for x in g["shapes"]] == s.arena.shapes
+    s.arena.load_list(student_loras(g["shapes"]))
+    s.pack()
+    inp = unet_inputs(spec, g["timestep"])
+    y = s(inp["x"], inp["timesteps"], context=inp["context"], fps=16, timestep_cond=inp["timestep_cond"])
+    assert _rel(y, g["output"]) < 1e-4
+    s.arena.zero_grad()
+    s.backward(g["d_out"])
+    n = len(s.arena.shapes)
+    ratio = torch.tensor([s.arena.grad(i).double().norm().item() / max(g["grad_norms"][i].item(), 1e-30) for i in range(n)])
+    assert (ratio - 1).abs().max() < 1e-4, (ratio.min(), ratio.max())
+    worst = max(_rel(s.arena.grad(j), sc * t.float()) for j, (sc, t) in g["grads_full"].items())
+    assert worst < 1e-3, worst          # the fixture keeps these tensors as fp16 scaled by their max
+
+
+def test_param_groups_match_the_reference_rule():
+    """full_train.param_groups == train_latent_t2v_turbo_v2.py:799-815 executed on the reference's own module tree (fixture)."""
+    from t2v_turbo_b200.full_train import param_groups
+    g = torch.load(os.path.join(GOLD, "v2_step_small_motion.pt"))
+    _, m, _ = _unet("small_motion")
+    assert [n for n, _ in m.named_parameters()] == g["names"]
+    other, temporal = param_groups(m)
+    assert temporal == g["temporal_names"]
+    assert sorted(other + temporal) == sorted(g["names"]) and not set(other) & set(temporal)
+    # the reference's quirk: the temporal transformer INSIDE middle_block is two components deep and lands in the other group
+    assert any(n.startswith("init_attn.0") for n in temporal) and not any(n.startswith("middle_block") for n in temporal)
+
+
+def test_full_unet_every_parameter_gradient_vs_oracle_autograd(monkeypatch):
+    """v2: FullUNet (all 629 parameter tensors of the small motion-conditioned UNet train) vs autograd through the oracle."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import unet_inputs
+    from oracle.unet_oracle import unet_forward
+    from t2v_turbo_b200.full_train import FullUNet
+    spec, m, sd = _unet("small_motion")
+    s = FullUNet(m).eval()
+    s.pack()
+    inp = unet_inputs(spec, spec["timesteps"][0])
+    kw = dict(fps=16, timestep_cond=inp["timestep_cond"], motion_cond=inp["motion_cond"])
+    y = s(inp["x"], inp["timesteps"], context=inp["context"], **kw)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    yr = unet_forward(sdg, spec["cfg"], inp["x"], inp["timesteps"], inp["context"], **kw)
+    assert _rel(y, yr.detach()) < 1e-4
+    d_out = torch.randn(y.shape, generator=torch.Generator().manual_seed(4243))
+    (yr * d_out).sum().backward()
+    s.arena.zero_grad()
+    s.backward(d_out)
+    assert set(s.arena.names) == {k for k, v in sdg.items() if v.requires_grad}
+    rels = {n: _rel(s.arena.grad(n), sdg[n].grad) for n in s.arena.names}
+    worst = max(rels, key=rels.get)
+    assert rels[worst] < 1e-4, (worst, rels[worst])
+    # the nn.Parameters ARE the arena: state_dict() is the wire format, and a second backward accumulates
+    assert all(p.data_ptr() == s.arena.param(n).data_ptr() for n, p in m.named_parameters())
+    y2 = s(inp["x"], inp["timesteps"], context=inp["context"], **kw)
+    s.backward(d_out)
+    assert _rel(s.arena.grad(worst), 2 * sdg[worst].grad) < 1e-4 and torch.equal(y2, y)
+
+
+class _EvalTarget:
+    """Stand-in for the EMA `UNetModel` (whose fused inference forward needs the GPU): the same weights through an eval-mode FullUNet."""
+    dtype = torch.float32
+
+    def __init__(self, view):
+        self.view = view
+
+    def __call__(self, *a, **k):
+        y = self.view(*a, **k)
+        self.view.detach_tapes()
+        return y
+
+    def invalidate_packed(self):
+        pass
+
+
+def _v2_setup(g, with_ema_target):
+    from t2v_turbo_b200.distill_v2 import V2Step
+    from t2v_turbo_b200.full_train import FullUNet
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.unet import UNetModel
+    spec, m, sd = _unet("small_motion")
+    s = FullUNet(m, with_target=True).eval()
+    s.pack()
+    target = None
+    if with_ema_target:      # the fixture's EMA network: the student's weights times (1 + 0.02 N(0, 1)), drawn in parameter order
+        gq = torch.Generator().manual_seed(g["target_perturb_seed"])
+        m_t = UNetModel(**spec["cfg"])
+        tsd = {}
+        for n, p in m.named_parameters():
+            tsd[n] = sd[n] * (1.0 + 0.02 * torch.randn(p.shape, generator=gq))
+            s.arena.view(s.arena.target, s.arena.index[n]).copy_(tsd[n])
+        m_t.load_state_dict({**sd, **tsd}, strict=True)
+        tv = FullUNet(m_t.eval()).eval()
+        tv.pack()
+        target = _EvalTarget(tv)
+    h = g["hyper"]
+    step = V2Step(s, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012), target_unet=target, num_ddim_timesteps=h["n_ddim"],
+                  topk=h["topk"], motion_gs=h["motion_gs"], percentage=h["percentage"], use_motion_cond=True, loss_type="huber",
+                  huber_c=0.001, timestep_scaling_factor=h["ts_scale"])
+    return s, step, sd
+
+
+def test_v2_step_vs_reference_composition(monkeypatch):
+    """One v2 step (V2Step + train_step_v2: student forward with motion_cond, CFG + motion-prior guidance from the stored teacher
+    outputs, DDIM step, EMA target, pseudo-Huber loss, full backward, clip, two-group AdamW, EMA update) == the same step composed
+    from the UNMODIFIED reference's pieces (gen_v2_step)."""
+    mock_ops.install(monkeypatch)
+    from t2v_turbo_b200.distill_v2 import train_step_v2
+    g = torch.load(os.path.join(GOLD, "v2_step_small_motion.pt"))
+    s, step, sd = _v2_setup(g, with_ema_target=True)
+    inp, h = g["inputs"], g["hyper"]
+    batch = {k: inp[k] for k in ("index", "z_t", "cond_teacher_out", "uncond_teacher_out", "score", "use_motion_guide", "prompt_emb")}
+    out = train_step_v2(step, batch, lr=h["lr"], temporal_lr_scale=h["temporal_lr_scale"], ema_decay=h["ema_decay"],
+                        max_grad_norm=h["max_grad_norm"], weight_decay=h["weight_decay"], fixed=dict(w=inp["w"]))
+    assert out["start_timesteps"].tolist() == g["start_timesteps"].tolist() and out["timesteps"].tolist() == g["timesteps"].tolist()
+    assert torch.allclose(out["motion_gs"].float(), g["motion_gs"]) and g["motion_gs"].tolist()[1] == 0.0 and g["motion_gs"].tolist()[0] > 0
+    for k in ("model_pred", "x_prev", "target"):
+        assert _rel(out[k], g[k]) < 1e-4, (k, _rel(out[k], g[k]))
+    assert abs(float(out["loss"]) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    # gradients: every norm, the stored tensors in full, the clip norm
+    ratio = torch.tensor([s.arena.grad(n).double().norm().item() / max(g["grad_norms"][n], 1e-30) for n in s.arena.names])
+    assert (ratio - 1).abs().max() < 2e-4, (ratio.min(), ratio.max())
+    worst = max(_rel(s.arena.grad(n), sc * t.float()) for n, (sc, t) in g["grads_full"].items())
+    assert worst < 1e-3, worst
+    assert abs(float(s.arena.grad_norm()) - g["total_norm"]) < 1e-4 * g["total_norm"]
+    # the optimizer step: parameter deltas of both lr groups (AdamW's first step moves every weight by ~lr: the temporal group 3x)
+    temporal = set(g["temporal_names"])
+    seen = set()
+    for n, (sc, t) in g["param_delta"].items():
+        d = s.arena.param(n) - sd[n]
+        assert _rel(d, sc * t.float()) < 2e-3, (n, _rel(d, sc * t.float()))
+        seen.add(n in temporal)
+    assert seen == {True, False}, "the fixture must exercise both optimizer groups"
+    # the EMA update of the target parameters
+    for n, t in g["ema_after"].items():
+        assert _rel(s.arena.view(s.arena.target, s.arena.index[n]), t) < 1e-6, n
+
+
+def test_v2_step_self_target(monkeypatch):
+    """--use_target_unet off: the student itself (gradient-free) is the target network (:1240)."""
+    mock_ops.install(monkeypatch)
+    g = torch.load(os.path.join(GOLD, "v2_step_small_motion.pt"))
+    s, step, _ = _v2_setup(g, with_ema_target=False)
+    inp = g["inputs"]
+    batch = {k: inp[k] for k in ("index", "z_t", "cond_teacher_out", "uncond_teacher_out", "score", "prompt_emb")}   # use_motion_guide defaults to True
+    s.arena.zero_grad()
+    out = step(batch, fixed=dict(w=inp["w"]))
+    assert _rel(out["target"], g["target_self"]) < 1e-4
+    assert abs(float(out["loss"]) - float(g["loss_self_target"])) < 1e-5 * float(g["loss_self_target"])
+    assert float(s.arena.grad_norm()) > 0
+
+
+def test_v2_host_draws_motion_condition():
+    """The motion-guidance gate and coefficient on the host (:1019-1031, :1214-1226), incl. the reference's sqrt(1 - sqrt(alpha_bar))."""
+    from t2v_turbo_b200.distill_v2 import V2Step
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    sch = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
+    step = V2Step(None, sch, num_ddim_timesteps=200, topk=5, motion_gs=0.05, percentage=0.5)
+    idx = torch.tensor([199, 100, 99, 150])
+    H = step.host_draws(idx, torch.tensor([True, True, True, False]), fixed=dict(w=torch.tensor([5.0, 6.0, 7.0, 8.0])))
+    assert H["motion_gs"].tolist() == [0.05, 0.05, 0.0, 0.0]                     # index >= 100 and use_motion_guide
+    ac = sch.alphas_cumprod.double()
+    t = H["start_timesteps"]
+    assert t.tolist() == [999, 504, 499, 754] and H["timesteps"].tolist() == [994, 499, 494, 749]
+    exp = -0.05 * (1 - ac[t].sqrt()).sqrt()
+    assert torch.allclose(H["mg"][:2].double(), exp[:2], rtol=1e-6) and H["mg"][2:].abs().max() == 0
+    assert H["mg_emb"].shape == (4, 256) and torch.equal(H["mg_emb"][2], H["mg_emb"][3])
+    step_nc = V2Step(None, sch, use_motion_cond=False)
+    assert "mg_emb" not in step_nc.host_draws(idx, torch.ones(4, dtype=torch.bool))
