@@ -458,6 +458,77 @@ def run_train_step(args, rank, local_rank, world):
                    loss=float(out["loss"]), clocks=clocks))
 
 
+def run_v2_step(args, rank, local_rank, world):
+    """`--workload v2-step` (train_latent_t2v_turbo_v2.py:945-1276 without the reward models): one v2 FULL
+    fine-tune step per rank on one 16x320x512 sample with stored teacher outputs — motion-conditioned student forward (training
+    mode), motion-prior guidance + DDIM step, the EMA network's target forward, pseudo-Huber loss, the hand-written backward with
+    weight / bias / norm-affine gradients for all 1.41 B parameters, the bucketed NCCL all-reduce of the 5.65 GB fp32 gradient
+    arena, global-norm clip, two fused AdamW launches (lr groups), operand refresh and the EMA update.  Eager (no CUDA graphs).
+    NOT part of the default bench and — the round's GPU budget having run out first — never yet executed on a GPU: the line
+    it prints is unmeasured until someone runs it (its host composition is CPU-verified, tests/test_train_composition_cpu.py)."""
+    import torch
+    from t2v_turbo_b200 import dist as t2v_dist, ops
+    from t2v_turbo_b200.configs import VC2_UNET
+    from t2v_turbo_b200.distill_v2 import V2Step, train_step_v2
+    from t2v_turbo_b200.full_train import FullUNet
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.unet import UNetModel
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    t2v_dist.init_replicas("nccl", device)
+    torch.manual_seed(1234)                     # identical initial weights on every rank, like DDP's broadcast
+    cfg = {**VC2_UNET, "time_cond_proj_dim": 256, "motion_cond_proj_dim": 256}
+    with torch.device(device):
+        base, target = UNetModel(**cfg), UNetModel(**cfg)
+    with torch.no_grad():
+        for prm in base.parameters():
+            if prm.dim() > 1 and float(prm.abs().max()) == 0.0:
+                prm.normal_(0, 0.02)
+    student = FullUNet(base.eval(), with_target=True).train()
+    student.pack()
+    student.arena.bind(target, student.arena.target)
+    target = target.eval()
+    target.dtype = torch.bfloat16
+    target.invalidate_packed()
+    red = t2v_dist.ArenaReducer(student.arena.grads, n_buckets=16)
+    step = V2Step(student, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012), target_unet=target)
+    g = torch.Generator(device=device).manual_seed(99 + rank)
+    shape = (1, 4, FRAMES, HEIGHT // 8, WIDTH // 8)
+    batch = dict(index=torch.tensor([150]), use_motion_guide=torch.tensor([True]),
+                 prompt_emb=torch.randn(1, 77, 1024, device=device, generator=g),
+                 **{k: torch.randn(shape, device=device, generator=g) for k in ("z_t", "cond_teacher_out", "uncond_teacher_out", "score")})
+
+    def one():
+        return train_step_v2(step, batch, lr=1e-5, temporal_lr_scale=1.0, ema_decay=0.95, reducer=red, world=world)
+    for _ in range(max(args.warmup, 2)):
+        out = one()
+    torch.cuda.synchronize()
+    n0 = ops.LAUNCHES
+    sampler = ClockSampler(local_rank)
+    t2v_dist.barrier(device)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = one()
+    e1.record()
+    t2v_dist.barrier(device)
+    clocks = sampler.stop()
+    ms = t2v_dist.max_over_ranks([e0.elapsed_time(e1)], device)[0]
+    finite = bool(torch.isfinite(out["loss"]).all()) and bool(torch.isfinite(student.arena.params).all())
+    if rank == 0:
+        _emit(dict(metric="v2 full fine-tune steps/sec (one 16x320x512 sample per rank; student fwd+bwd over all 1.41B parameters, EMA target "
+                          "fwd, all-reduce, AdamW, EMA)", value=world * args.steps / (ms * 1e-3), unit="samples/s", n_gpus=world,
+                   steps=args.steps, warmup=max(args.warmup, 2), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+                   vs_baseline=None, dtype="bf16", data="synthetic",
+                   config=dict(workload="train_latent_t2v_turbo_v2.py:945-1276 without the reward models: VC2 UNet (1.41B, motion-conditioned), "
+                                        "every parameter trains, bs=1 per rank, fp32 gradient arena %d values, 16-bucket NCCL all-reduce after "
+                                        "the backward, two-group fused AdamW, EMA target" % student.arena.padded, parallelism=f"dp{world}",
+                               cuda_graph=False, finite=finite),
+                   gpu_launches=ops.LAUNCHES - n0, loss=float(out["loss"]), clocks=clocks))
+    t2v_dist.shutdown()
+
+
 def run_lora_step(args, rank, local_rank, world):
     """`--workload lora-step` (supplementary; BASELINE config 4's data-parallel exchange): per rank, the 567 LoRA-injected
     layers of the VC2 UNet that are on the tensor-core training path (utils/lora.py:19-230, r = 64) run forward and backward
@@ -597,7 +668,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sample-steps", type=int, default=STEPS, help="num_inference_steps of the pipeline workloads (BASELINE configs[2]: 8, 16)")
     ap.add_argument("--motion-cond", action="store_true", help="VC2 pipeline with the v2 motion conditioning (BASELINE configs[2])")
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "ms-pipeline", "lora-step", "train-step"],
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "ms-pipeline", "lora-step", "train-step", "v2-step"],
                     help="pipeline = the headline metric; lora-step = the data-parallel LoRA training exchange (supplementary)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -608,6 +679,8 @@ def main():
         return
     if args.workload == "train-step":
         return run_train_step(args, rank, local_rank, world)
+    if args.workload == "v2-step":
+        return run_v2_step(args, rank, local_rank, world)
     if args.workload == "lora-step":
         run_lora_step(args, rank, local_rank, world)
         return

@@ -12,10 +12,12 @@ arithmetic, tapes and input-gradient kernels) with a different layer type and th
     GroupNorm       dx: t2v_groupnorm_bwd           dgamma / dbeta: t2v_groupnorm_affine_grad (statistics from dx's workspace)
     LayerNorm       dx: t2v_layernorm_bwd           dgamma / dbeta: t2v_layernorm_affine_grad
 
-All parameters, gradients and AdamW moments live in ONE flat fp32 arena each (`FullArena`), ordered as the two optimizer groups
-of the reference (:799-840): [other | temporal], so that the optimizer is two fused AdamW launches (lr and lr * temporal_lr_scale),
-gradient clipping one reduction, the data-parallel exchange one bucketed all-reduce over 5.65 GB (dist.ArenaReducer), and the EMA
-target (`update_ema`, utils/common_utils.py:308-319) one elementwise launch.  The `UNetModel`'s nn.Parameters are re-pointed at
+All parameters, gradients and AdamW moments live in ONE flat fp32 arena each (`FullArena`), laid out in the order in which the
+backward completes blocks (reversed), so that the data-parallel exchange — a bucketed all-reduce over 5.65 GB, dist.ArenaReducer —
+starts on the output blocks' gradients while the backward is still in the encoder; the two optimizer groups of the reference
+(:799-840, other / temporal: lr and lr * temporal_lr_scale) interleave along that order and are stepped as one fused AdamW launch
+per contiguous run (33 on the VC2 UNet), gradient clipping is one reduction and the EMA target (`update_ema`,
+utils/common_utils.py:308-319) one elementwise launch.  The `UNetModel`'s nn.Parameters are re-pointed at
 the arena (views), so `unet.state_dict()` is the `unet.pt` wire format at any time; the bf16 GEMM operands are re-derived from
 the fp32 arena after every optimizer step (`refresh`).
 
@@ -26,7 +28,6 @@ ended — see DESIGN.md §7.
 """
 from __future__ import annotations
 
-import collections
 import math
 
 import torch
@@ -61,26 +62,45 @@ def param_groups(unet: nn.Module):
     return other, temporal
 
 
+def _depth_key(name: str):
+    """Arena position of a parameter: the order in which the BACKWARD finishes blocks, reversed — embeddings, input blocks,
+    init_attn, middle block, output blocks, out — so that gradients become final from the END of the arena towards its start
+    (what dist.ArenaReducer's bucketed all-reduce overlaps with; the same convention as the LoRA arena of the v1 step)."""
+    parts = name.split(".")
+    top = parts[0]
+    rank = {"input_blocks": 1, "init_attn": 2, "middle_block": 3, "output_blocks": 4, "out": 5}.get(top, 0)
+    idx = int(parts[1]) if top in ("input_blocks", "output_blocks") else 0
+    return (rank, idx)
+
+
 class FullArena:
-    """Flat fp32 storage of every UNet parameter, its gradient and the AdamW moments (+ optionally the EMA target), laid out
-    [other group | temporal group]; every tensor starts on a 16-byte boundary (kernels read gamma / beta / bias rows vectorised)."""
+    """Flat fp32 storage of every UNet parameter, its gradient and the AdamW moments (+ optionally the EMA target).  Tensors are
+    laid out in backward-completion order (`_depth_key`; stable within a block), every tensor starts on a 16-byte boundary
+    (kernels read gamma / beta / bias rows vectorised).  The reference's two optimizer groups (other / temporal, `param_groups`)
+    interleave along the arena: `runs` lists the maximal contiguous ranges of one group, each one fused AdamW launch."""
 
     def __init__(self, unet: nn.Module, device, with_target=False):
         other, temporal = param_groups(unet)
         params = dict(unet.named_parameters())
-        self.names = other + temporal
+        tset = set(temporal)
+        order = {n: i for i, n in enumerate(params)}
+        self.names = sorted(params, key=lambda n: (_depth_key(n), order[n]))
         self.index = {n: i for i, n in enumerate(self.names)}
+        self.is_temporal = [n in tset for n in self.names]
         self.shapes, self.offsets, off = [], [], 0
-        for i, n in enumerate(self.names):
-            if i == len(other):
-                self.split = off
+        for n in self.names:
             self.shapes.append(tuple(params[n].shape))
             self.offsets.append(off)
             off += (params[n].numel() + 3) // 4 * 4
-        if not temporal:
-            self.split = off
         self.numel = sum(math.prod(s) for s in self.shapes)
         self.padded = off
+        self.runs = []                      # [(lo, hi, temporal?)]
+        for i, t in enumerate(self.is_temporal):
+            hi = self.offsets[i + 1] if i + 1 < len(self.names) else off
+            if self.runs and self.runs[-1][2] == t:
+                self.runs[-1] = (self.runs[-1][0], hi, t)
+            else:
+                self.runs.append((self.offsets[i], hi, t))
         self.params = torch.zeros(off, device=device, dtype=torch.float32)
         self.grads = torch.zeros(off, device=device, dtype=torch.float32)
         self.exp_avg = torch.zeros(off, device=device, dtype=torch.float32)
@@ -101,6 +121,13 @@ class FullArena:
     def grad(self, name):
         return self.view(self.grads, self.index[name])
 
+    def first_offset(self, prefix: str) -> int:
+        """Offset of the first tensor whose name starts with `prefix + "."` (a top-level block of the UNet)."""
+        for n, o in zip(self.names, self.offsets):
+            if n.startswith(prefix + "."):
+                return o
+        raise KeyError(prefix)
+
     def bind(self, unet: nn.Module, buf=None):
         """Re-point the module's nn.Parameters at this arena (views of `buf`, default the live parameters): state_dict(),
         load_state_dict() and the inference forward of that module then read / write the arena directly."""
@@ -116,16 +143,16 @@ class FullArena:
         return ops.sum_squares(self.grads).sqrt() * abs(grad_scale)
 
     def adamw_step(self, *, lr, temporal_lr_scale=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0, max_grad_norm=None):
-        """torch.optim.AdamW over the two groups of :829-840 (lr, lr * temporal_lr_scale) as two fused launches; clip_grad_norm_
-        over ALL parameters first (:1267), the clip factor and the data-parallel mean folded into grad_scale."""
+        """torch.optim.AdamW over the two groups of :829-840 (lr, lr * temporal_lr_scale), one fused launch per contiguous run of a
+        group; clip_grad_norm_ over ALL parameters first (:1267), the clip factor and the data-parallel mean folded into grad_scale."""
         if max_grad_norm is not None:
             total = float(self.grad_norm(grad_scale))
             grad_scale = grad_scale * min(1.0, max_grad_norm / (total + 1e-6))
         self.step += 1
-        for lo, hi, group_lr in ((0, self.split, lr), (self.split, self.padded, lr * temporal_lr_scale)):
-            if hi > lo:
-                ops.adamw_step(self.params[lo:hi], self.grads[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], lr=group_lr, betas=betas,
-                               eps=eps, weight_decay=weight_decay, step=self.step, grad_scale=grad_scale)
+        for lo, hi, temporal in self.runs:
+            ops.adamw_step(self.params[lo:hi], self.grads[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                           lr=lr * temporal_lr_scale if temporal else lr, betas=betas, eps=eps, weight_decay=weight_decay, step=self.step,
+                           grad_scale=grad_scale)
 
     def ema_step(self, decay):
         """update_ema(target_unet.parameters(), unet.parameters(), decay) (:1273-1276) over the whole arena in one launch."""
@@ -251,11 +278,12 @@ class FullUNet(StudentUNet):
         self._packed = False
         self._build()
         self._train_norms()
-        # gradient-final offsets for the bucketed exchange: the arena is ordered by optimizer group, not by depth, so the whole
-        # arena is reported final once, after the backward (the 5.65 GB all-reduce then overlaps the optimizer's clip reduction
-        # only; a depth-ordered arena is the obvious refinement and is noted in DESIGN.md)
-        self.on_grads_final = None
-        self._first_offset = collections.defaultdict(lambda: self.arena.padded)     # nothing final until the backward's last hook (offset 0)
+        # first arena offset of every top-level block: once the backward has passed a block, every gradient at or above that
+        # offset is final (the arena is in backward-completion order) -> dist.ArenaReducer.ready overlaps the 5.65 GB exchange
+        self._first_offset = {"middle_block": self.arena.first_offset("middle_block")}
+        for j in range(len(unet.output_blocks)):
+            self._first_offset[f"output_blocks.{j}"] = self.arena.first_offset(f"output_blocks.{j}")
+        self.on_grads_final = None      # callable(offset)
 
     # ------------------------------------------------------------------ structure
     def _L(self, m):

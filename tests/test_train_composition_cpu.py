@@ -100,6 +100,31 @@ def test_full_unet_every_parameter_gradient_vs_oracle_autograd(monkeypatch):
     assert _rel(s.arena.grad(worst), 2 * sdg[worst].grad) < 1e-4 and torch.equal(y2, y)
 
 
+def test_full_unet_gradient_final_hooks_are_truthful(monkeypatch):
+    """The data-parallel exchange trusts `on_grads_final(offset)`: every gradient at or above `offset` must already hold its final
+    value when the hook fires (dist.ArenaReducer all-reduces those buckets while the backward continues), the offsets must fall
+    monotonically to 0, and both optimizer groups must tile the arena as contiguous runs."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import unet_inputs
+    from t2v_turbo_b200.full_train import FullUNet
+    spec, m, _ = _unet("small_motion")
+    s = FullUNet(m).eval()
+    s.pack()
+    a = s.arena
+    assert a.runs[0][0] == 0 and a.runs[-1][1] == a.padded and all(x[1] == y[0] and x[2] != y[2] for x, y in zip(a.runs, a.runs[1:]))
+    assert a.names[-1].startswith("out.") and a.names[0].startswith("time_embed")
+    inp = unet_inputs(spec, spec["timesteps"][0])
+    y = s(inp["x"], inp["timesteps"], context=inp["context"], fps=16, timestep_cond=inp["timestep_cond"], motion_cond=inp["motion_cond"])
+    snaps = []
+    s.on_grads_final = lambda off: snaps.append((off, a.grads[off:].clone()))
+    a.zero_grad()
+    s.backward(torch.randn(y.shape, generator=torch.Generator().manual_seed(1)))
+    offs = [o for o, _ in snaps]
+    assert offs == sorted(offs, reverse=True) and offs[-1] == 0 and len(set(offs)) >= 3 and offs[0] > a.padded // 2, offs
+    for off, snap in snaps:
+        assert torch.equal(a.grads[off:], snap), f"a gradient at or above offset {off} changed after it was reported final"
+
+
 class _EvalTarget:
     """Stand-in for the EMA `UNetModel` (whose fused inference forward needs the GPU): the same weights through an eval-mode FullUNet."""
     dtype = torch.float32
