@@ -1,4 +1,5 @@
-"""ORACLE (test infrastructure), PARITY UNPINNED: the OpenCLIP ViT-H-14 text tower as FrozenOpenCLIPEmbedder drives it
+"""ORACLE (test infrastructure; pinned on transformers.CLIPTextModel, an independent implementation of the same tower, in
+tests/test_text_encoder.py — open_clip itself is absent): the OpenCLIP ViT-H-14 text tower as FrozenOpenCLIPEmbedder drives it
 (lvdm/modules/encoders/condition.py:257-283).  open_clip is not installed here; this restates its published text
 transformer (open_clip/transformer.py: ResidualAttentionBlock = x + attn(ln_1(x)), x + mlp(ln_2(x)); nn.MultiheadAttention
 with an additive -inf upper-triangular mask; mlp = c_fc -> GELU(erf) -> c_proj) under open_clip's key names."""
