@@ -462,6 +462,14 @@ int t2v_attn_short_bwd(const T2VShortAttnBwdDesc* desc, t2v_stream_t stream);
 int t2v_huber_loss_grad(const void* a, const void* b, void* grad, float* loss, int64_t n, int32_t dtype, float huber_c,
                         float grad_scale, t2v_stream_t stream);
 
+/* Workspace sizes for callers that are not the Python host mirror (the caller owns every buffer, see the header comment):
+ * t2v_gemm_workspace_bytes: the fp32 split-K workspace that ALLOWS t2v_gemm to split K for `desc` (o_size and b_rows are read;
+ *   a smaller or NULL workspace is always legal — the GEMM then runs unsplit); zero it once and pass T2V_WS_CLEAN afterwards.
+ * t2v_groupnorm_workspace_bytes: T2VGroupNormDesc.workspace (backward = 0) / T2VGroupNormBwdDesc.workspace (backward = 1).
+ * Both return -1 on a malformed argument; neither touches the device. */
+int64_t t2v_gemm_workspace_bytes(const T2VGemmDesc* desc);
+int64_t t2v_groupnorm_workspace_bytes(int64_t n_samples, int32_t groups, int32_t backward);
+
 /* ---- full fine-tune step only (train_latent_t2v_turbo_v2.py:945-1276: every UNet parameter trains) ----
  * Affine gradients of GroupNorm(+SiLU) (lvdm/basics.py:78-89 GroupNormSpecific; the `normalization(ch)` + SiLU pairs of
  * openaimodel3d.py:155-159,179-184,275-295):  dgamma[c] += sum dpre * xh,  dbeta[c] += sum dpre,  dpre = dy * act'(xh * gamma + beta),

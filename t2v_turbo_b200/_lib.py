@@ -211,6 +211,8 @@ SYMBOLS = {
     "t2v_video_to_uint8": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "t2v_scale_add_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "t2v_lcm_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "t2v_gemm_workspace_bytes": (C.c_int64, [C.POINTER(GemmDesc)]),
+    "t2v_groupnorm_workspace_bytes": (C.c_int64, [_i64, _i32, _i32]),
     "t2v_groupnorm_affine_grad": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _f32, _i32, _vp]),
     "t2v_layernorm_affine_grad": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _f32, _vp]),
     "t2v_ema_update": (C.c_int, [_vp, _vp, _i64, _f32, _vp]),

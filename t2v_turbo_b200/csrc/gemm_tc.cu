@@ -1042,6 +1042,23 @@ static int choose_block_n(int64_t n_rows, int64_t m_tiles, int sms, bool geglu, 
 
 }  // namespace t2v
 
+extern "C" int64_t t2v_gemm_workspace_bytes(const T2VGemmDesc* d) {
+  if (!d) return -1;
+  int64_t n_points = 1;
+  for (int j = 0; j < T2V_MAX_DIMS; ++j) {
+    if (d->o_size[j] < 1) return -1;
+    n_points *= d->o_size[j];
+  }
+  if (d->b_rows < 1) return -1;
+  return ((n_points * d->b_rows * 4 + 15) / 16) * 16;   // fp32 [points][N] partial sums of a split-K launch
+}
+
+extern "C" int64_t t2v_groupnorm_workspace_bytes(int64_t n_samples, int32_t groups, int32_t backward) {
+  if (n_samples < 1 || groups < 1) return -1;
+  // forward: (sum, sum of squares) per (sample, group) + 1 ticket word; backward: (sum x, sum x^2, S1, S2)
+  return backward ? n_samples * groups * 4 * 4 : (n_samples * groups * 2 + 1) * 4;
+}
+
 extern "C" int t2v_gemm(const T2VGemmDesc* d, t2v_stream_t stream_) {
   using namespace t2v;
   if (!d) return fail(-1, "t2v_gemm: null descriptor");

@@ -55,6 +55,20 @@ def test_argument_errors_are_loud(lib):
     assert lib.t2v_lcm_step(None, None, None, None, None, 0, 0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, None) < 0
 
 
+def test_workspace_size_queries(lib):
+    """Host-only entry points: what a non-Python caller must allocate (no device needed)."""
+    from t2v_turbo_b200 import _lib
+    d = _lib.GemmDesc()
+    assert lib.t2v_gemm_workspace_bytes(ctypes.byref(d)) == -1 and lib.t2v_gemm_workspace_bytes(None) == -1      # o_size / b_rows unset
+    for j, v in enumerate((160, 4, 1, 1)):
+        d.o_size[j] = v
+    d.b_rows = 1280
+    assert lib.t2v_gemm_workspace_bytes(ctypes.byref(d)) == 640 * 1280 * 4                 # level-3 Linear: fp32 [points][N]
+    assert lib.t2v_groupnorm_workspace_bytes(16, 32, 0) == (16 * 32 * 2 + 1) * 4
+    assert lib.t2v_groupnorm_workspace_bytes(16, 32, 1) == 16 * 32 * 4 * 4
+    assert lib.t2v_groupnorm_workspace_bytes(0, 32, 0) == -1
+
+
 def test_product_has_no_oracle_or_cpu_fallback():
     """The shipped package must not import the oracle (it is the checker, not the product)."""
     pkg = os.path.join(ROOT, "t2v_turbo_b200")
