@@ -2,12 +2,17 @@
 // LayerNorm, GEGLU, SiLU, the broadcast timestep-embedding add, nearest-2x upsampling / stride-2 subsampling adjoints and
 // gradient accumulation.  All HBM bound: channels-last bf16 activations and gradients, fp32 arithmetic and statistics.
 // Only the LoRA weights train (:862-906), so no kernel here produces gamma / beta / bias gradients.
-#include <cuda_bf16.h>
 #include <math.h>
 
 #include "../../include/t2v_b200.h"
+#ifdef T2V_HOST_EMU   // tests/cuda_emu: the SIMT kernels of this file compiled by g++ and run on CPU threads (test infrastructure only)
+#include "cuda_emu.h"
+#else
+#include <cuda_bf16.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
+#endif
 
 namespace t2v {
 

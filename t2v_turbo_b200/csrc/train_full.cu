@@ -4,12 +4,17 @@
 // gradients the v1 step's kernels (train_bwd.cu) — those are not touched by this file.
 // All HBM bound: one pass over (x, dy) per norm layer, fp32 accumulation, per-CTA shared-memory reduction, one global
 // atomic per channel per CTA into the fp32 gradient arena.
-#include <cuda_bf16.h>
 #include <math.h>
 
 #include "../../include/t2v_b200.h"
+#ifdef T2V_HOST_EMU   // tests/cuda_emu: the SIMT kernels of this file compiled by g++ and run on CPU threads (test infrastructure only)
+#include "cuda_emu.h"
+#else
+#include <cuda_bf16.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
+#endif
 
 namespace t2v {
 
