@@ -154,6 +154,31 @@ class FullArena:
                            lr=lr * temporal_lr_scale if temporal else lr, betas=betas, eps=eps, weight_decay=weight_decay, step=self.step,
                            grad_scale=grad_scale)
 
+    # ---- resume (train_latent_t2v_turbo_v2.py:1283-1313 saves unet.pt / the accelerator state every `checkpointing_steps`)
+    def state_dict(self):
+        """Optimizer-side state for resuming: AdamW moments, step count and the EMA target, keyed by PARAMETER NAME so that it is
+        independent of the arena's internal order (the parameters themselves are `unet.state_dict()`, the `unet.pt` wire format)."""
+        out = {"step": self.step, "exp_avg": {}, "exp_avg_sq": {}}
+        if self.target is not None:
+            out["target"] = {}
+        for i, n in enumerate(self.names):
+            out["exp_avg"][n] = self.view(self.exp_avg, i).detach().cpu().clone()
+            out["exp_avg_sq"][n] = self.view(self.exp_avg_sq, i).detach().cpu().clone()
+            if self.target is not None:
+                out["target"][n] = self.view(self.target, i).detach().cpu().clone()
+        return out
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        if set(sd["exp_avg"]) != set(self.names) or set(sd["exp_avg_sq"]) != set(self.names):
+            raise KeyError("FullArena.load_state_dict: parameter names differ from this model's")
+        self.step = int(sd["step"])
+        for i, n in enumerate(self.names):
+            self.view(self.exp_avg, i).copy_(sd["exp_avg"][n])
+            self.view(self.exp_avg_sq, i).copy_(sd["exp_avg_sq"][n])
+            if self.target is not None and "target" in sd:
+                self.view(self.target, i).copy_(sd["target"][n])
+
     def ema_step(self, decay):
         """update_ema(target_unet.parameters(), unet.parameters(), decay) (:1273-1276) over the whole arena in one launch."""
         if self.target is None:

@@ -218,6 +218,34 @@ def test_v2_step_self_target(monkeypatch):
     assert float(s.arena.grad_norm()) > 0
 
 
+def test_v2_resume_reproduces_the_next_step(monkeypatch):
+    """Save after step 1 (unet.state_dict() = the unet.pt wire format + FullArena.state_dict()), rebuild everything from the files,
+    take step 2 in both: identical parameters, moments and EMA target."""
+    mock_ops.install(monkeypatch)
+    import io
+    from t2v_turbo_b200.distill_v2 import train_step_v2
+    g = torch.load(os.path.join(GOLD, "v2_step_small_motion.pt"))
+    inp = g["inputs"]
+    batch = {k: inp[k] for k in ("index", "z_t", "cond_teacher_out", "uncond_teacher_out", "score", "use_motion_guide", "prompt_emb")}
+    kw = dict(lr=1e-4, temporal_lr_scale=2.0, ema_decay=0.9, fixed=dict(w=inp["w"]))
+    s1, step1, _ = _v2_setup(g, with_ema_target=False)
+    train_step_v2(step1, batch, **kw)
+    buf = io.BytesIO()
+    torch.save({"unet": s1.unet.state_dict(), "opt": s1.arena.state_dict()}, buf)
+    train_step_v2(step1, batch, **kw)
+    buf.seek(0)
+    ck = torch.load(buf)
+    s2, step2, _ = _v2_setup(g, with_ema_target=False)
+    s2.unet.load_state_dict(ck["unet"], strict=True)          # writes straight into the arena (the nn.Parameters are its views)
+    s2.arena.load_state_dict(ck["opt"])
+    s2.refresh()
+    train_step_v2(step2, batch, **kw)
+    assert s2.arena.step == s1.arena.step == 2
+    for a_, b_ in ((s1.arena.params, s2.arena.params), (s1.arena.exp_avg, s2.arena.exp_avg), (s1.arena.exp_avg_sq, s2.arena.exp_avg_sq),
+                   (s1.arena.target, s2.arena.target)):
+        assert torch.equal(a_, b_)
+
+
 def test_v2_host_draws_motion_condition():
     """The motion-guidance gate and coefficient on the host (:1019-1031, :1214-1226), incl. the reference's sqrt(1 - sqrt(alpha_bar))."""
     from t2v_turbo_b200.distill_v2 import V2Step
