@@ -464,8 +464,8 @@ def run_v2_step(args, rank, local_rank, world):
     mode), motion-prior guidance + DDIM step, the EMA network's target forward, pseudo-Huber loss, the hand-written backward with
     weight / bias / norm-affine gradients for all 1.41 B parameters, the bucketed NCCL all-reduce of the 5.65 GB fp32 gradient
     arena, global-norm clip, two fused AdamW launches (lr groups), operand refresh and the EMA update.  Eager (no CUDA graphs).
-    NOT part of the default bench and — the round's GPU budget having run out first — never yet executed on a GPU: the line
-    it prints is unmeasured until someone runs it (its host composition is CPU-verified, tests/test_train_composition_cpu.py)."""
+    NOT part of the default bench and — the round's GPU budget having run out first — this WORKLOAD has never been executed
+    (the step it times has: tests/test_zz_full_train_gpu.py on a small UNet): the line is unmeasured until someone runs it."""
     import torch
     from t2v_turbo_b200 import dist as t2v_dist, ops
     from t2v_turbo_b200.configs import VC2_UNET

@@ -345,6 +345,50 @@ def gen_distill_step(name="small"):
                 "timesteps": timesteps, "grad_norms": norms, "grads_full": full}, os.path.join(GOLD, f"distill_step_{name}.pt"))
 
 
+def gen_full_grads(name="small_motion"):
+    """The v2 student's forward + backward (train_latent_t2v_turbo_v2.py:1043-1050,1264) on the UNMODIFIED reference with EVERY
+    parameter trainable, for a LINEAR loss sum(eps_pred * g) with a seeded g (the distillation loss's sign-like gradient makes any
+    bf16 run noise-dominated, see the step fixtures; this one pins the backward itself), eval mode, fp32 — plus the yardstick for
+    the tolerance: the reference's OWN bf16 forward + backward against these fp32 gradients."""
+    spec = UNET_CONFIGS[name]
+    m = ref_unet(spec["cfg"], spec["weight_seed"])
+    m.requires_grad_(True)
+    inp = unet_inputs(spec, spec["timesteps"][0])
+    kw = dict(context=inp["context"], fps=inp["fps"], timestep_cond=inp["timestep_cond"], motion_cond=inp.get("motion_cond"))
+    y = m(inp["x"], inp["timesteps"], **kw)
+    d_out = torch.randn(y.shape, generator=torch.Generator().manual_seed(4244))
+    (y * d_out).sum().backward()
+    names = [n for n, _ in m.named_parameters()]
+    grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+    norms = {n: g.double().norm().item() for n, g in grads.items()}
+    m16 = m.bfloat16()
+    m16.dtype = torch.bfloat16
+    for p in m16.parameters():
+        p.grad = None
+    kw16 = {k: (v.bfloat16() if torch.is_tensor(v) else v) for k, v in kw.items()}
+    y16 = m16(inp["x"].bfloat16(), inp["timesteps"], **kw16)
+    (y16 * d_out.bfloat16()).sum().backward()
+    g16 = {n: p.grad.float() for n, p in m16.named_parameters()}
+    rel = lambda a, b: ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()      # noqa: E731
+    rel16 = {n: rel(g16[n], grads[n]) for n in names}
+    cat = lambda d: torch.cat([d[n].flatten() for n in names])                                      # noqa: E731
+    ratios = [g16[n].norm().item() / (grads[n].norm().item() + 1e-30) for n in names]
+    ref_bf16 = dict(output_rel=rel(y16.float(), y.detach()), grad_rel_median=sorted(rel16.values())[len(names) // 2],
+                    grad_rel_worst=max(rel16.values()), grad_rel_worst_name=max(rel16, key=rel16.get), grad_rel_concat=rel(cat(g16), cat(grads)),
+                    norm_ratio=(min(ratios), max(ratios)))
+    print("  reference bf16 vs its fp32:", ref_bf16)
+    keep = [n for i, n in enumerate(names) if (i % 13 == 0 or n.startswith(("motion_cond_proj", "combine_proj", "time_cond_proj", "out.", "input_blocks.0.0")))
+            and grads[n].numel() <= 150000]
+    full = {}
+    for n in keep:
+        sc = grads[n].abs().max().item() + 1e-30
+        full[n] = (sc, (grads[n] / sc).half())
+    print(f"  full grads {name}: {len(names)} parameter tensors, out std {y.std():.4f}, grad norm {sum(v * v for v in norms.values()) ** 0.5:.4f}, "
+          f"{len(keep)} tensors stored in full")
+    torch.save({"name": name, "timestep": spec["timesteps"][0], "names": names, "d_out": d_out, "output": y.detach().clone(), "grad_norms": norms,
+                "grads_full": full, "ref_bf16": ref_bf16}, os.path.join(GOLD, f"full_grads_{name}.pt"))
+
+
 def v2_inputs(spec, bsz=2):
     """Seeded batch of the v2 latent dataset (preprocess_with_motion_prior.py:392-401 keys) for the v2-step fixture."""
     g = torch.Generator().manual_seed(6161)
@@ -653,7 +697,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step", "full_grads"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -670,6 +714,8 @@ if __name__ == "__main__":
             gen_distill_tables()
         elif item == "v2_step":
             gen_v2_step()
+        elif item == "full_grads":
+            gen_full_grads()
         elif item == "unet_probs":
             gen_unet_probs()
         elif item.startswith("lora_"):

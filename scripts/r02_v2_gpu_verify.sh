@@ -1,6 +1,7 @@
 #!/bin/bash
-# First GPU run of the v2 full fine-tune step: written when the round's GPU budget was already spent, so this has
-# NOT been executed yet.  One call, ~5 GPU-minutes:   gpurun --timeout 900 -- 'bash scripts/r02_v2_gpu_verify.sh'
+# Full GPU verification + first measurement of the v2 full fine-tune step.  The round's last 1.7 GPU-minutes ran
+# only the two pytest selections of step 1 (profiles/r02_v2_gpu_*_tests.log); THIS SCRIPT as a whole has not been executed.
+# One call, ~5 GPU-minutes:   gpurun --timeout 900 -- 'bash scripts/r02_v2_gpu_verify.sh'
 #   1. the kernel-contract and whole-step tests WITHOUT the xfail mask (--runxfail: a failure is a failure here)
 #   2. compute-sanitizer memcheck over the three new kernels + wgrad_wide
 #   3. the unmeasured bench line (eager, one sample per step) and its launch list

@@ -21,10 +21,10 @@ utils/common_utils.py:308-319) one elementwise launch.  The `UNetModel`'s nn.Par
 the arena (views), so `unet.state_dict()` is the `unet.pt` wire format at any time; the bf16 GEMM operands are re-derived from
 the fp32 arena after every optimizer step (`refresh`).
 
-Status: composed from kernels that are parity-tested on B200 individually, plus three new ones (train_full.cu).  The whole
-composition is checked on CPU against the UNMODIFIED reference's autograd through a restatement of every kernel contract
-(tests/mock_ops.py); its GPU tests exist (tests/test_zz_full_train_gpu.py) but could not be run before the round's GPU budget
-ended — see DESIGN.md §7.
+Status: the whole composition is checked on CPU against the UNMODIFIED reference's autograd through a restatement
+of every kernel contract (tests/mock_ops.py); on B200 the three new kernels (train_full.cu) and `wgrad_wide` pass their contract
+tests and one whole step agrees with the reference composition; the step has not been timed and its backward has not yet been
+pinned under a linear loss on the device (tests/test_zz_full_train_gpu.py).
 """
 from __future__ import annotations
 

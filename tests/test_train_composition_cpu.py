@@ -100,6 +100,28 @@ def test_full_unet_every_parameter_gradient_vs_oracle_autograd(monkeypatch):
     assert _rel(s.arena.grad(worst), 2 * sdg[worst].grad) < 1e-4 and torch.equal(y2, y)
 
 
+def test_full_unet_gradients_vs_the_reference_itself(monkeypatch):
+    """The same, against the UNMODIFIED reference's autograd (tests/golden/full_grads_small_motion.pt: linear loss, all 629 norms and
+    57 tensors in full) — so the oracle used above is itself pinned on the reference for the backward, not only the forward."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import unet_inputs
+    from t2v_turbo_b200.full_train import FullUNet
+    g = torch.load(os.path.join(GOLD, "full_grads_small_motion.pt"))
+    spec, m, _ = _unet("small_motion")
+    assert [n for n, _ in m.named_parameters()] == g["names"]
+    s = FullUNet(m).eval()
+    s.pack()
+    inp = unet_inputs(spec, g["timestep"])
+    y = s(inp["x"], inp["timesteps"], context=inp["context"], fps=16, timestep_cond=inp["timestep_cond"], motion_cond=inp["motion_cond"])
+    assert _rel(y, g["output"]) < 1e-4
+    s.arena.zero_grad()
+    s.backward(g["d_out"])
+    ratio = torch.tensor([s.arena.grad(n).double().norm().item() / max(g["grad_norms"][n], 1e-30) for n in g["names"]])
+    assert (ratio - 1).abs().max() < 1e-4, (ratio.min(), ratio.max())
+    worst = max(_rel(s.arena.grad(n), sc * t.float()) for n, (sc, t) in g["grads_full"].items())
+    assert worst < 1e-3, worst          # fp16-scaled storage
+
+
 def test_full_unet_gradient_final_hooks_are_truthful(monkeypatch):
     """The data-parallel exchange trusts `on_grads_final(offset)`: every gradient at or above `offset` must already hold its final
     value when the hook fires (dist.ArenaReducer all-reduces those buckets while the backward continues), the offsets must fall
