@@ -1,12 +1,16 @@
 // Small / HBM-bound kernels around the tensor-core path: embedding MLP rows (M = batch), sinusoidal
 // embeddings, the 4-channel latent convolution, layout conversion at the UNet boundary, nearest
 // upsampling, channel concat, row softmax, the fused LCM scheduler step and weight packing.
+#include "../../include/t2v_b200.h"
+#ifdef T2V_HOST_EMU   // tests/cuda_emu: the SIMT kernels of this file compiled by g++ and run on CPU threads (test infrastructure only)
+#include "cuda_emu.h"
+#else
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
-#include "../../include/t2v_b200.h"
 #include "host_common.h"
 #include "ptx.cuh"
+#endif
 
 namespace t2v {
 
@@ -114,7 +118,7 @@ conv3x3_small_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* 
                      int wd, int cout) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float s_w[];  // [9*CIN][cout]
+  T2V_DYN_SMEM(float, s_w);  // [9*CIN][cout]
   for (int i = threadIdx.x; i < cout * 9 * CIN; i += blockDim.x) {
     const int oc = i / (9 * CIN), q = i % (9 * CIN);  // global layout [cout][9*CIN]
     s_w[q * cout + oc] = __bfloat162float(w[i]);
@@ -175,7 +179,7 @@ conv3x3_cin4_x4_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16
                        __nv_bfloat16* __restrict__ out, int n, int h, int wd, int cout) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float s_w[];  // [36][cout]
+  T2V_DYN_SMEM(float, s_w);  // [36][cout]
   for (int i = threadIdx.x; i < cout * 36; i += blockDim.x) {
     const int oc = i / 36, q = i % 36;  // global layout [cout][9 taps][4]
     s_w[q * cout + oc] = __bfloat162float(w[i]);

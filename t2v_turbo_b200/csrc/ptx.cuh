@@ -381,6 +381,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 }
 
 // ---------------------------------------------------------------- misc
+// dynamic shared memory of a SIMT kernel (a macro so that tests/cuda_emu can substitute a per-block host buffer)
+#define T2V_DYN_SMEM(type, name) extern __shared__ type name[]
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -1,12 +1,16 @@
 // HBM-bound kernels of the consistency-distillation step (train_t2v_turbo_v1_lora.py:943-1196) around the tensor-core
 // GEMMs: the LoRA branch's dropout * scale (forward and adjoint), the MSE distillation loss with its gradient, the
 // squared gradient norm for clipping and ONE fused AdamW launch over the flat fp32 LoRA arenas (575 layers, 117 M values).
+#include "../../include/t2v_b200.h"
+#ifdef T2V_HOST_EMU   // tests/cuda_emu: the SIMT kernels of this file compiled by g++ and run on CPU threads (test infrastructure only)
+#include "cuda_emu.h"
+#else
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
-#include "../../include/t2v_b200.h"
 #include "host_common.h"
 #include "ptx.cuh"
+#endif
 
 namespace t2v {
 

@@ -29,6 +29,9 @@ struct dim3 {
 struct uint4 { uint32_t x, y, z, w; };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct __nv_bfloat16 { uint16_t bits; };
@@ -50,6 +53,7 @@ struct Ctx {
   dim3 tid, bid, bdim, gdim;
   std::barrier<>* block_bar = nullptr;
   Warp* warp = nullptr;
+  void* dyn_smem = nullptr;          // the block's dynamic shared memory (launch parameter `smem` bytes)
 };
 inline thread_local Ctx ctx;
 }  // namespace emu
@@ -65,6 +69,9 @@ inline thread_local Ctx ctx;
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define T2V_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::ctx.dyn_smem)
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 inline void __syncthreads() { emu::ctx.block_bar->arrive_and_wait(); }
 
@@ -89,8 +96,22 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 inline float __expf(float x) { return expf(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return uint32_t((uint64_t(a) * uint64_t(b)) >> 32); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx.warp->bar.arrive_and_wait(); }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+struct __half { _Float16 v; };
+static_assert(sizeof(__half) == 2, "fp16 storage");
+inline float __half2float(__half h) { return float(h.v); }
+inline __half __float2half_rn(float f) { return __half{_Float16(f)}; }
+inline float __bfloat162float(__nv_bfloat16 b) { return __uint_as_float(uint32_t(b.bits) << 16); }
+inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return __nv_bfloat16{uint16_t((u >> 16) | 0x40u)};
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return __nv_bfloat16{uint16_t(u >> 16)};
+}
 
 namespace t2v {
 
@@ -121,8 +142,9 @@ inline float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 inline float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args... args) {
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args... args) {
   const unsigned nt = block.x * block.y * block.z;
+  std::vector<uint64_t> dyn((smem + 7) / 8 + 1);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -139,6 +161,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
             emu::ctx.gdim = grid;
             emu::ctx.block_bar = &bar;
             emu::ctx.warp = warps[t / 32].get();
+            emu::ctx.dyn_smem = dyn.data();
             kernel(KArgs(args)...);
             emu::ctx.warp->bar.arrive_and_drop();      // an exited thread no longer takes part in barriers
             bar.arrive_and_drop();

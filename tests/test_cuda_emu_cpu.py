@@ -1,4 +1,4 @@
-"""The SIMT kernels of csrc/train_bwd.cu and csrc/train_full.cu EXECUTED on the CPU: the two sources are compiled unchanged by
+"""The SIMT kernels of csrc/train_bwd.cu, train_full.cu, elementwise.cu and train_ops.cu EXECUTED on the CPU: the sources are compiled unchanged by
 g++ against tests/cuda_emu/cuda_emu.h (CUDA threads = OS threads, __syncthreads / warp shuffles = barriers, __shared__ = statics,
 atomicAdd = std::atomic_ref; the host launch code runs too, with a 2-"SM" device so that grids stay small) and called through
 the same C ABI, on CPU tensors.
@@ -20,7 +20,11 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BF16 = torch.bfloat16
 NAMES = ("t2v_groupnorm_bwd", "t2v_layernorm_bwd", "t2v_colsum_samples", "t2v_geglu", "t2v_resample2x", "t2v_ew2d",
-         "t2v_groupnorm_affine_grad", "t2v_layernorm_affine_grad", "t2v_ema_update")
+         "t2v_groupnorm_affine_grad", "t2v_layernorm_affine_grad", "t2v_ema_update",
+         # elementwise.cu / train_ops.cu (all parity-tested on B200; run here as a CPU regression net over the real kernel source)
+         "t2v_lcm_step", "t2v_scale_add_rows", "t2v_dropout_scale", "t2v_scale_mask", "t2v_adamw_step", "t2v_sum_squares",
+         "t2v_mse_loss_grad", "t2v_huber_loss_grad", "t2v_video_to_uint8", "t2v_conv3x3_small_cin", "t2v_pack_conv_weight",
+         "t2v_sinusoidal_embedding", "t2v_bcthw_to_frames_pad", "t2v_frames_to_bcthw", "t2v_concat_channels", "t2v_upsample_nearest2x")
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +35,7 @@ def emu(tmp_path_factory):
     out = tmp_path_factory.mktemp("cuda_emu") / "libt2v_emu.so"
     csrc = os.path.join(ROOT, "t2v_turbo_b200", "csrc")
     cmd = ["g++", "-std=c++20", "-O1", "-x", "c++", "-DT2V_HOST_EMU", "-I", os.path.join(ROOT, "tests", "cuda_emu"), "-shared", "-fPIC",
-           "-pthread", os.path.join(csrc, "train_bwd.cu"), os.path.join(csrc, "train_full.cu"), "-o", str(out)]
+           "-pthread"] + [os.path.join(csrc, f) for f in ("train_bwd.cu", "train_full.cu", "elementwise.cu", "train_ops.cu")] + ["-o", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     lib = C.CDLL(str(out))
@@ -176,3 +180,117 @@ def test_ema_update_kernel_under_emulation(emu, n, offset):
     assert emu.t2v_ema_update(tgt.data_ptr(), src.data_ptr(), n, 0.95, None) == 0
     assert torch.allclose(tgt, ref, rtol=1e-6, atol=1e-7)
     assert emu.t2v_ema_update(tgt.data_ptr(), src.data_ptr(), n, 1.5, None) < 0
+
+
+# ----------------------------------------------------------------------------- (3) elementwise.cu / train_ops.cu: a CPU regression net
+def test_emulated_dropout_mask_bit_exact_vs_philox_oracle(emu):
+    """The in-kernel Philox4x32-10 keep-mask == the numpy oracle (pinned on Random123's known answers), bit for bit — the same
+    assertion the B200 suite makes (tests/test_lora_train_gpu.py), here on the kernel source run under emulation."""
+    import numpy as np
+    from oracle.philox_oracle import keep_mask
+    for (rows, c), p, seed, call in (((40, 64), 0.1, 1234, 1), ((24, 64), 0.5, 2 ** 40 + 17, 77), ((3, 8), 0.25, 99, 2 ** 31 + 5)):
+        x = rnd(rows, c, seed=18).to(BF16)
+        out, keep = torch.empty_like(x), torch.empty(rows, c, dtype=torch.uint8)
+        sd = torch.tensor([seed], dtype=torch.int64)
+        scale = 1.7 / (1.0 - p)
+        assert emu.t2v_dropout_scale(x.data_ptr(), None, out.data_ptr(), keep.data_ptr(), x.numel(), 1.0 - p, scale, sd.data_ptr(), call, None) == 0
+        want = keep_mask(x.numel(), 1.0 - p, seed, call).reshape(rows, c)
+        assert np.array_equal(keep.numpy(), want)
+        assert torch.equal(out, (x.float() * scale * keep.float()).to(BF16))
+        dx = torch.empty_like(x)
+        assert emu.t2v_scale_mask(x.data_ptr(), keep.data_ptr(), dx.data_ptr(), x.numel(), scale, None) == 0
+        assert torch.equal(dx, out)
+
+
+def test_emulated_adamw_matches_torch_optim(emu):
+    n = 4099 - 3                                   # multiple of 4
+    p0, g = rnd(n, seed=19), rnd(n, seed=20) * 0.1
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    prm, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    for step in (1, 2, 3):
+        ref.grad = (g * 0.5).clone()               # grad_scale = 0.5 folds the data-parallel mean
+        opt.step()
+        assert emu.t2v_adamw_step(prm.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 0.5, None) == 0
+    assert torch.allclose(prm, ref.detach(), rtol=1e-5, atol=1e-7)
+    acc = torch.zeros(1)
+    assert emu.t2v_sum_squares(g.data_ptr(), n, acc.data_ptr(), None) == 0
+    assert abs(acc.item() - (g.double() ** 2).sum().item()) < 1e-4 * acc.item()
+
+
+def test_emulated_losses_and_row_affine(emu):
+    a, b = rnd(2, 4, 3, 5, 8, seed=21), rnd(2, 4, 3, 5, 8, seed=22)
+    for name, c in (("mse", None), ("huber", 0.001)):
+        loss, grad = torch.zeros(1), torch.empty_like(a)
+        if c is None:
+            assert emu.t2v_mse_loss_grad(a.data_ptr(), b.data_ptr(), grad.data_ptr(), loss.data_ptr(), a.numel(), 2, 1.0, None) == 0
+            ar = a.clone().requires_grad_(True)
+            ref = F.mse_loss(ar, b)
+        else:
+            assert emu.t2v_huber_loss_grad(a.data_ptr(), b.data_ptr(), grad.data_ptr(), loss.data_ptr(), a.numel(), 2, c, 1.0, None) == 0
+            ar = a.clone().requires_grad_(True)
+            ref = torch.mean(torch.sqrt((ar - b) ** 2 + c ** 2) - c)                        # utils/common_utils.py:302-304
+        ref.backward()
+        assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) and torch.allclose(grad, ar.grad, rtol=1e-4, atol=1e-8), name
+    ka, kb = torch.tensor([0.5, -2.0]), torch.tensor([1.5, 0.25])
+    out = torch.empty_like(a)
+    assert emu.t2v_scale_add_rows(a.data_ptr(), b.data_ptr(), ka.data_ptr(), kb.data_ptr(), out.data_ptr(), 2, a.numel() // 2, 2, None) == 0
+    assert torch.allclose(out, a * ka.view(2, 1, 1, 1, 1) + b * kb.view(2, 1, 1, 1, 1), rtol=1e-6, atol=1e-7)
+
+
+def test_emulated_lcm_step_and_video_post_process(emu):
+    """T2VTurboScheduler.step's arithmetic (scheduler/t2v_turbo_scheduler.py:438-460) and app.py:90-94's uint8 conversion."""
+    x, e, nz = (rnd(1, 4, 4, 6, 8, seed=s_) for s_ in (59, 60, 61))
+    a_t, a_p, c_skip, c_out = torch.tensor(0.0047), torch.tensor(0.35), torch.tensor(2.5e-9), torch.tensor(1.0)
+    sb, sa = (1 - a_t).sqrt(), a_t.sqrt()
+    den = c_out * ((x - sb * e) / sa) + c_skip * x
+    prev = a_p.sqrt() * den + (1 - a_p).sqrt() * nz
+    p2, d2 = torch.empty_like(x), torch.empty_like(x)
+    assert emu.t2v_lcm_step(x.data_ptr(), e.data_ptr(), nz.data_ptr(), p2.data_ptr(), d2.data_ptr(), x.numel(), 2, float(1.0 / sa), float(sb),
+                            float(c_skip), float(c_out), float(a_p.sqrt()), float((1 - a_p).sqrt()), None) == 0
+    assert torch.allclose(d2, den, rtol=1e-5, atol=1e-5) and torch.allclose(p2, prev, rtol=1e-5, atol=1e-5)
+    v = (rnd(2, 3, 4, 16, 24, seed=43) * 0.8).to(BF16)
+    ref = []
+    for vid in v:   # app.py:90-94
+        t = torch.clamp(vid.float(), -1.0, 1.0).permute(1, 0, 2, 3)
+        ref.append((((t + 1.0) / 2.0) * 255).to(torch.uint8).permute(0, 2, 3, 1))
+    out = torch.empty(2, 4, 16, 24, 3, dtype=torch.uint8)
+    assert emu.t2v_video_to_uint8(v.data_ptr(), 0, out.data_ptr(), 2, 4, 16, 24, None) == 0
+    assert torch.equal(out, torch.stack(ref))
+
+
+def test_emulated_small_cin_conv_and_layout_kernels(emu):
+    """The 4-channel latent convolution (dynamic shared memory under emulation), weight packing and the layout conversions."""
+    n, h, w, cin, cout = 2, 6, 8, 4, 16
+    xw = rnd(n, cin, h, w, seed=23).to(BF16)
+    wt = (rnd(cout, cin, 3, 3, seed=24) * 0.2)
+    bias = rnd(cout, seed=25)
+    x_cl = xw.permute(0, 2, 3, 1).contiguous()
+    packed = torch.empty(cout, 9 * cin, dtype=BF16)
+    assert emu.t2v_pack_conv_weight(wt.data_ptr(), 2, packed.data_ptr(), cout, cin, 9, None) == 0
+    assert torch.equal(packed, wt.reshape(cout, cin, 9).permute(0, 2, 1).reshape(cout, -1).to(BF16))
+    out = torch.empty(n, h, w, cout, dtype=BF16)
+    assert emu.t2v_conv3x3_small_cin(x_cl.data_ptr(), packed.data_ptr(), bias.data_ptr(), out.data_ptr(), n, h, w, cin, cout, None) == 0
+    ref = F.conv2d(xw.float(), wt.to(BF16).float(), bias, padding=1).permute(0, 2, 3, 1)
+    close(out, ref, 8e-3, 4e-3, "emulated conv3x3 cin=4")
+    # [B, C, T, H, W] <-> frames, channel padding
+    lat = rnd(2, 4, 3, h, w, seed=26)
+    fr = torch.empty(6, h, w, 64, dtype=BF16)
+    assert emu.t2v_bcthw_to_frames_pad(lat.data_ptr(), 2, fr.data_ptr(), 2, 4, 64, 3, h, w, 1.0, None) == 0
+    assert torch.equal(fr[..., :4], lat.permute(0, 2, 3, 4, 1).reshape(6, h, w, 4).to(BF16)) and (fr[..., 4:] == 0).all()
+    back = torch.empty(2, 4, 3, h, w)
+    assert emu.t2v_frames_to_bcthw(fr.data_ptr(), 64, back.data_ptr(), 2, 2, 4, 3, h, w, None) == 0
+    assert torch.equal(back, lat.to(BF16).float())
+    a_, b_ = rnd(30, 16, seed=27).to(BF16), rnd(30, 8, seed=28).to(BF16)
+    cat = torch.empty(30, 24, dtype=BF16)
+    assert emu.t2v_concat_channels(a_.data_ptr(), 16, b_.data_ptr(), 8, cat.data_ptr(), 30, None) == 0
+    assert torch.equal(cat, torch.cat([a_, b_], 1))
+    up = torch.empty(6, 2 * h, 2 * w, 64, dtype=BF16)
+    assert emu.t2v_upsample_nearest2x(fr.data_ptr(), up.data_ptr(), 6, h, w, 64, None) == 0
+    assert torch.equal(up, fr.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    t = torch.tensor([999.0, 519.0, 0.0])
+    freqs = torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(0, 32, dtype=torch.float32) / 32)
+    emb = torch.empty(3, 64)
+    assert emu.t2v_sinusoidal_embedding(t.data_ptr(), freqs.data_ptr(), emb.data_ptr(), 3, 32, 0, 0, None) == 0
+    arg = t[:, None] * freqs[None]
+    assert torch.allclose(emb, torch.cat([torch.cos(arg), torch.sin(arg)], 1), atol=2e-6)      # lvdm/models/utils_diffusion.py:8-32
