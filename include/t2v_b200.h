@@ -485,6 +485,13 @@ int t2v_groupnorm_affine_grad(const void* x, int64_t x_row_stride, const void* d
 int t2v_layernorm_affine_grad(const void* x, int64_t x_row_stride, const void* dy, int64_t dy_row_stride, float* dgamma,
                               float* dbeta, int64_t rows, int32_t channels, float eps, t2v_stream_t stream);
 
+/* Backward of t2v_softmax_rows (P = softmax(scale * S) per row), in place on dp:
+ *   dS[r, c] = scale * P[r, c] * (dP[r, c] - sum_j dP[r, j] * P[r, j])        bf16 [rows, cols], row strides in elements.
+ * The KL-VAE decoder's AttnBlock (ae_modules.py:48-73) under `vae.decode` WITH grad — the reward terms of the training scripts
+ * (train_t2v_turbo_v1_lora.py:1055-1098, train_latent_t2v_turbo_v2.py:1062-1166). */
+int t2v_softmax_bwd_rows(void* dp, int64_t dp_row_stride, const void* p, int64_t p_row_stride, int64_t rows, int32_t cols,
+                         float scale, t2v_stream_t stream);
+
 /* EMA of the target network's parameters over the flat fp32 arenas (update_ema, utils/common_utils.py:308-319;
  * train_latent_t2v_turbo_v2.py:1273-1276): target = target * rate + src * (1 - rate). */
 int t2v_ema_update(float* target, const float* src, int64_t n, float rate, t2v_stream_t stream);

@@ -198,9 +198,47 @@ __global__ void __launch_bounds__(kThreads) ema_update_kernel(float* __restrict_
     target[i] = fmaf(src[i], alpha, target[i] * rate);
 }
 
+// ------------------------------------------------------------------------------------------------ softmax backward over rows
+// P = softmax(scale * S) row-wise (t2v_softmax_rows).  In place on dP:  dS[r, c] = scale * P[r, c] * (dP[r, c] - sum_j dP[r, j] P[r, j]).
+// The single-head 512-channel attention of the KL-VAE decoder's mid block (ae_modules.py:48-73), whose backward the reward
+// terms of the training scripts need (vae.decode WITH grad, train_t2v_turbo_v1_lora.py:1055-1098).  One CTA per row.
+__global__ void __launch_bounds__(kThreads) softmax_bwd_rows_kernel(__nv_bfloat16* __restrict__ dp, int64_t dp_rs,
+                                                                    const __nv_bfloat16* __restrict__ p, int64_t p_rs, int cols, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[kThreads / 32];
+  const uint16_t* prow = reinterpret_cast<const uint16_t*>(p + int64_t(blockIdx.x) * p_rs);
+  uint16_t* drow = reinterpret_cast<uint16_t*>(dp + int64_t(blockIdx.x) * dp_rs);
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) dot = fmaf(bf16_lo(drow[c]), bf16_lo(prow[c]), dot);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) dot += red[i];
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = scale * bf16_lo(prow[c]) * (bf16_lo(drow[c]) - dot);
+    drow[c] = uint16_t(pack_bf16(v, 0.f) & 0xFFFFu);
+  }
+}
+
 }  // namespace
 
 }  // namespace t2v
+
+extern "C" int t2v_softmax_bwd_rows(void* dp, int64_t dp_row_stride, const void* p, int64_t p_row_stride, int64_t rows, int32_t cols,
+                                    float scale, t2v_stream_t s) {
+  using namespace t2v;
+  if (!dp || !p || rows < 1 || cols < 1) return fail(-1, "t2v_softmax_bwd_rows: bad argument");
+  if (rows > 0x7fffffff) return fail(-2, "t2v_softmax_bwd_rows: too many rows");
+  if (dp_row_stride < cols || p_row_stride < cols) return fail(-3, "t2v_softmax_bwd_rows: row strides must be >= cols");
+  launch_kernel(softmax_bwd_rows_kernel, dim3(unsigned(rows)), dim3(kThreads), 0, static_cast<cudaStream_t>(s),
+                static_cast<__nv_bfloat16*>(dp), dp_row_stride, static_cast<const __nv_bfloat16*>(p), p_row_stride, cols, scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_softmax_bwd_rows launch");
+}
 
 extern "C" int t2v_groupnorm_affine_grad(const void* x, int64_t x_row_stride, const void* dy, int64_t dy_row_stride, const float* gamma,
                                          const float* beta, const float* stats_ws, float* dgamma, float* dbeta, int64_t rows,

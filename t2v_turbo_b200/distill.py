@@ -133,8 +133,13 @@ class DistillStep:
             loss, d_pred = ops.mse_loss_grad(model_pred, target)
         else:
             loss, d_pred = ops.huber_loss_grad(model_pred, target, self.huber_c)
+        out_extra = {}
+        if getattr(self, "reward", None) is not None:     # optional reward branch (:1043-1099): callable(model_pred) -> (loss, d model_pred),
+            r_loss, d_r = self.reward(model_pred)         # e.g. functools.partial(vae_train.reward_gradient, vae, reward_fn=..., frame_idx=...)
+            d_pred = d_pred + d_r.to(d_pred.dtype)
+            out_extra["reward_loss"] = r_loss
         self.student.backward(ops.scale_add_rows(d_pred, S["k_e"]))
-        return dict(loss=loss, model_pred=model_pred, target=target, x_prev=x_prev)
+        return dict(loss=loss, model_pred=model_pred, target=target, x_prev=x_prev, **out_extra)
 
     def __call__(self, latents, prompt_embeds, uncond_prompt_embeds, *, fixed=None, generator=None):
         """latents [B, 4, T, H, W] fp32 (already scaled by the VAE factor); returns dict(loss, model_pred, target, x_prev, ...).
@@ -158,6 +163,8 @@ class GraphedDistillStep:
     segment k+1 runs.  Per step only the host draws (a few hundred bytes) and the batch are copied into static buffers."""
 
     def __init__(self, step: DistillStep, latents, prompt_embeds, uncond_prompt_embeds, reducer=None):
+        if getattr(step, "reward", None) is not None:
+            raise NotImplementedError("GraphedDistillStep: the reward branch runs torch autograd and is not captured; use the eager DistillStep")
         self.step, self.reducer = step, reducer
         dev = latents.device
         self.lat, self.noise = latents.float().clone(), torch.empty_like(latents, dtype=torch.float32)

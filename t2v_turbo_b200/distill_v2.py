@@ -101,8 +101,13 @@ class V2Step:
             loss, d_pred = ops.mse_loss_grad(model_pred, target)
         else:
             loss, d_pred = ops.huber_loss_grad(model_pred, target, self.huber_c)
+        out_extra = {}
+        if getattr(self, "reward", None) is not None:     # optional reward branch (:1043-1099): callable(model_pred) -> (loss, d model_pred),
+            r_loss, d_r = self.reward(model_pred)         # e.g. functools.partial(vae_train.reward_gradient, vae, reward_fn=..., frame_idx=...)
+            d_pred = d_pred + d_r.to(d_pred.dtype)
+            out_extra["reward_loss"] = r_loss
         student.backward(ops.scale_add_rows(d_pred, S["k_e"]))
-        return dict(loss=loss, model_pred=model_pred, target=target, x_prev=x_prev)
+        return dict(loss=loss, model_pred=model_pred, target=target, x_prev=x_prev, **out_extra)
 
     def __call__(self, batch, *, fixed=None, generator=None):
         """batch: the v2 latent-dataset record (formats.V2_LATENT_KEYS): index, z_t, cond_teacher_out, uncond_teacher_out, score,

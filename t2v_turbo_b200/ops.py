@@ -810,6 +810,28 @@ def concat_channels(a, b):
     return out
 
 
+def softmax_bwd_rows_(dp, p, scale=1.0):
+    """In place on dp: dS = scale * P * (dP - rowsum(dP * P)) for P = softmax(scale * S) (adjoint of softmax_rows_); bf16 [.., cols]
+    contiguous."""
+    assert dp.is_cuda and dp.dtype == BF16 and p.dtype == BF16 and dp.is_contiguous() and p.is_contiguous() and dp.shape == p.shape
+    cols = dp.shape[-1]
+    rows = dp.numel() // cols
+    _launch("softmax_bwd_rows", 0, lib().t2v_softmax_bwd_rows, dp.data_ptr(), cols, p.data_ptr(), cols, rows, cols, float(scale), stream_ptr())
+    return dp
+
+
+def bcthw_to_frames_mix(z, scale, mix, bias):
+    """[B, C, T, H, W] (any float dtype) -> bf16 frames [B*T, H, W, C_out] with out[o] = sum_c mix[o, c] * scale * z[c] + bias[o]:
+    `1 / scale_factor * z` + post_quant_conv 1x1 (ddpm3d.py:669, autoencoder.py:111).  mix [C_out, C] / bias [C_out] fp32."""
+    b, c, t, hh, ww = z.shape
+    z = z.contiguous()
+    assert mix.dtype == torch.float32 and bias.dtype == torch.float32 and mix.is_contiguous() and tuple(mix.shape) == (bias.numel(), c)
+    out = torch.empty((b * t, hh, ww, mix.shape[0]), device=z.device, dtype=BF16)
+    _launch("bcthw_to_frames_mix", 0, lib().t2v_bcthw_to_frames_mix, z.data_ptr(), _lib.DTYPE_CODE[z.dtype], out.data_ptr(), b, c, t, hh, ww,
+            float(scale), mix.data_ptr(), bias.data_ptr(), stream_ptr())
+    return out
+
+
 def softmax_rows_(x, scale=1.0):
     cols = x.shape[-1]
     rows = x.numel() // cols

@@ -1,0 +1,273 @@
+"""`vae.decode` WITH grad on B200: the KL-VAE decoder's forward AND its input gradient, for the reward terms of the training scripts
+(train_t2v_turbo_v1_lora.py:1043-1099, train_latent_t2v_turbo_v2.py:1062-1166): a few frames of the student's prediction are decoded,
+a differentiable reward model scores the images, and the reward's gradient flows back through the frozen decoder into the latents
+(SURVEY §8f rank 4).  The reward models themselves (HPSv2 / PickScore / ViCLIP / InternVideo2) are out of scope: any torch module
+can sit on top of the tensor `decode_with_grad` returns.
+
+    img = decode_with_grad(vae, latents)          # [N, zc, h, w] frames (the reference's call form) or [B, zc, T, h, w]
+    reward_fn(img).backward()                     # -> latents.grad, through DecoderGrad.backward
+
+`DecoderGrad` is the training view of `vae.AutoencoderKL`'s decoder (lvdm/modules/networks/ae_modules.py:506-641): the same
+parameters, the UNFUSED forward (each GroupNorm computes its own statistics, q / k / v separate, nearest upsampling as its own
+pass) keeping exactly the tensors the adjoint needs, and a hand-written backward — the VAE's weights are frozen (`vae.requires_grad_
+(False)`, :715-724), so only input gradients are formed:
+
+    3x3 / 1x1 convs      dx = the forward implicit GEMM on the transposed, tap-reversed weight (as in the student backward)
+    GroupNorm (+SiLU)    t2v_groupnorm_bwd
+    ResnetBlock          the two paths above + the shortcut, summed through `dx_add`
+    AttnBlock            single head over 512 channels (ae_modules.py:48-73): P saved; dV = P^T dO, dP = dO V^T, dS = t2v_softmax_bwd_rows,
+                         dQ = dS K, dK = dS^T Q — five batched tcgen05 GEMMs of the forward's two shape classes + three transposes
+    Upsample             conv adjoint + 2x2 pooling (t2v_resample2x mode 2)
+    conv_in / conv_out   the 4- and 3-channel sides run zero-padded to 64 channels in the adjoint GEMMs
+    post_quant_conv      a 4x4 matrix on the latent channels: folded with 1 / scale_factor on the host (plumbing)
+
+Status: host composition verified on CPU against autograd through the VAE oracle (tests/mock_ops.py); the one new
+kernel runs under the host emulation; NOT run on a GPU (written after the round's GPU budget was spent).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .train_unet import _require_cuda
+
+BF16 = torch.bfloat16
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _pad_w(w, cout_p, cin_p):
+    out = torch.zeros((cout_p, cin_p) + tuple(w.shape[2:]), device=w.device, dtype=torch.float32)
+    out[:w.shape[0], :w.shape[1]] = w.detach().float()
+    return out
+
+
+class _Conv:
+    """A frozen 3x3 convolution: forward operand, dgrad operand (transposed, taps reversed), fp32 bias row."""
+
+    def __init__(self, m, pad_in=0, pad_out=0):
+        w = m.weight.detach()
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        self.pc_out, self.pc_in = pad_out or self.cout, pad_in or self.cin
+        wp = _pad_w(w, self.pc_out, self.pc_in) if (pad_in or pad_out) else w.float()
+        self.w = ops.pack_conv_weight(wp)                                                  # [Cout, 9 * Cin]
+        self.w_t = ops.pack_conv_weight(wp.transpose(0, 1).flip((2, 3)).contiguous())     # [Cin, 9 * Cout]
+        b = torch.zeros(self.pc_out, device=w.device, dtype=torch.float32)
+        b[:self.cout] = m.bias.detach().float()
+        self.bias = b.view(1, -1)
+
+    def fwd(self, x, residual=None):
+        return ops.conv3x3(x, self.w, self.bias, bias_div=x.shape[0], residual=residual)
+
+    def bwd(self, dy):
+        return ops.conv3x3(dy, self.w_t, None)
+
+
+class _Lin:
+    """A frozen 1x1 convolution run as a per-pixel Linear."""
+
+    def __init__(self, m):
+        w = m.weight.detach().reshape(m.weight.shape[0], -1)
+        self.w = w.to(BF16).contiguous()
+        self.w_t = w.t().to(BF16).contiguous()
+        self.bias = _f32(m.bias)
+
+    def fwd(self, x, residual=None):
+        return ops.linear(x, self.w, self.bias, residual=residual)
+
+    def bwd(self, dy):
+        return ops.linear(dy, self.w_t, None)
+
+
+class _Gn:
+    def __init__(self, m):
+        self.w, self.b, self.eps = _f32(m.weight), _f32(m.bias), m.eps
+
+
+class DecoderGrad:
+    def __init__(self, vae):
+        d = vae.decoder
+        dev = d.conv_in.weight.device
+        _require_cuda("DecoderGrad", dev)
+        self.vae, self.device = vae, dev
+        self.zc = vae.post_quant_conv.weight.shape[0]
+        self.pq_w = _f32(vae.post_quant_conv.weight).reshape(self.zc, -1)
+        self.pq_b = _f32(vae.post_quant_conv.bias)
+        self.conv_in = _Conv(d.conv_in, pad_in=64)                     # forward: the direct 4-channel kernel; adjoint: padded GEMM
+        self.w_in = ops.pack_conv_weight(d.conv_in.weight.detach())
+        self.b_in = _f32(d.conv_in.bias)
+        self.mid = [self._res(d.mid.block_1), self._attn(d.mid.attn_1), self._res(d.mid.block_2)]
+        self.up = []
+        for i_level in range(d.num_resolutions):
+            up = d.up[i_level]
+            self.up.append(([self._res(b) for b in up.block], _Conv(up.upsample.conv) if i_level != 0 else None))
+        self.norm_out = _Gn(d.norm_out)
+        self.conv_out = _Conv(d.conv_out, pad_out=64)
+        self.out_ch = d.conv_out.weight.shape[0]
+
+    @staticmethod
+    def _res(rb):
+        return ("res", dict(gn1=_Gn(rb.norm1), conv1=_Conv(rb.conv1), gn2=_Gn(rb.norm2), conv2=_Conv(rb.conv2),
+                            nin=_Lin(rb.nin_shortcut) if rb.in_channels != rb.out_channels else None))
+
+    @staticmethod
+    def _attn(a):
+        return ("attn", dict(gn=_Gn(a.norm), q=_Lin(a.q), k=_Lin(a.k), v=_Lin(a.v), o=_Lin(a.proj_out), c=a.in_channels))
+
+    # ------------------------------------------------------------------ blocks
+    @staticmethod
+    def _res_fwd(R, h):
+        n, hh, ww, c = h.shape
+        hw = hh * ww
+        x2 = h.view(-1, c)
+        t = ops.groupnorm(x2, R["gn1"].w, R["gn1"].b, rows_per_sample=hw, eps=R["gn1"].eps, silu=True)
+        t1 = R["conv1"].fwd(t.view(n, hh, ww, c))
+        co = t1.shape[-1]
+        t2 = ops.groupnorm(t1.view(-1, co), R["gn2"].w, R["gn2"].b, rows_per_sample=hw, eps=R["gn2"].eps, silu=True)
+        res = h if R["nin"] is None else R["nin"].fwd(x2).view(n, hh, ww, co)
+        out = R["conv2"].fwd(t2.view(n, hh, ww, co), residual=res)
+        return out, dict(x=x2, t1=t1.view(-1, co), geom=(n, hh, ww))
+
+    @staticmethod
+    def _res_bwd(R, c, dout):
+        n, hh, ww = c["geom"]
+        hw = hh * ww
+        co, ci = c["t1"].shape[-1], c["x"].shape[-1]
+        dout = dout.contiguous()
+        d_t2 = R["conv2"].bwd(dout).view(-1, co)
+        d_t1 = ops.groupnorm_bwd(c["t1"], d_t2, R["gn2"].w, R["gn2"].b, rows_per_sample=hw, eps=R["gn2"].eps, silu=True)
+        d_t = R["conv1"].bwd(d_t1.view(n, hh, ww, co)).view(-1, ci)
+        d_res = dout.view(-1, co) if R["nin"] is None else R["nin"].bwd(dout.view(-1, co))
+        dx = ops.groupnorm_bwd(c["x"], d_t, R["gn1"].w, R["gn1"].b, rows_per_sample=hw, eps=R["gn1"].eps, silu=True, dx_add=d_res)
+        return dx.view(n, hh, ww, ci)
+
+    @staticmethod
+    def _attn_fwd(A, h):
+        n, hh, ww, c = h.shape
+        hw = hh * ww
+        x = h.view(-1, c)
+        xn = ops.groupnorm(x, A["gn"].w, A["gn"].b, rows_per_sample=hw, eps=A["gn"].eps, silu=False)
+        q, k, v = A["q"].fwd(xn).view(n, hw, c), A["k"].fwd(xn).view(n, hw, c), A["v"].fwd(xn).view(n, hw, c)
+        p = ops.bmm_nt(q, k)                                              # [n, hw, hw]
+        ops.softmax_rows_(p, float(c) ** -0.5)
+        o = ops.bmm_nt(p, v.transpose(1, 2).contiguous())                 # P @ V
+        out = A["o"].fwd(o.view(-1, c), residual=x)
+        return out.view(n, hh, ww, c), dict(x=x, q=q, k=k, v=v, p=p, geom=(n, hh, ww))
+
+    @staticmethod
+    def _attn_bwd(A, c, dout):
+        n, hh, ww = c["geom"]
+        hw = hh * ww
+        ch = A["c"]
+        d_out = dout.contiguous().view(-1, ch)
+        d_o = A["o"].bwd(d_out).view(n, hw, ch)
+        q, k, v, p = c["q"], c["k"], c["v"], c["p"]
+        dv = ops.bmm_nt(p.transpose(1, 2).contiguous(), d_o.transpose(1, 2).contiguous())      # P^T dO      [n, hw, c]
+        dp = ops.bmm_nt(d_o, v)                                                                 # dO V^T      [n, hw, hw]
+        ops.softmax_bwd_rows_(dp, p, float(ch) ** -0.5)                                         # -> dS in place
+        dq = ops.bmm_nt(dp, k.transpose(1, 2).contiguous())                                     # dS K        [n, hw, c]
+        dk = ops.bmm_nt(dp.transpose(1, 2).contiguous(), q.transpose(1, 2).contiguous())       # dS^T Q      [n, hw, c]
+        d_xn = ops.add(ops.add(A["q"].bwd(dq.view(-1, ch)), A["k"].bwd(dk.view(-1, ch))), A["v"].bwd(dv.view(-1, ch)))
+        dx = ops.groupnorm_bwd(c["x"], d_xn, A["gn"].w, A["gn"].b, rows_per_sample=hw, eps=A["gn"].eps, silu=False, dx_add=d_out)
+        return dx.view(n, hh, ww, ch)
+
+    # ------------------------------------------------------------------ forward / backward
+    def forward(self, z, scale=1.0):
+        """z: [B, zc, T, h, w] (any float dtype) -> (image [B, 3, T, 8h, 8w] in z.dtype, tape).  `scale` multiplies z first
+        (1 / scale_factor in `decode_first_stage`)."""
+        _require_cuda("DecoderGrad input", z.device)
+        b, zc, t, hh, ww = z.shape
+        fr = ops.bcthw_to_frames_mix(z, scale, self.pq_w, self.pq_b)
+        h = ops.conv3x3_small_cin(fr, self.w_in, self.b_in, self.conv_in.cout)
+        tape = []
+        for kind, S in self.mid:
+            h, c = (self._res_fwd if kind == "res" else self._attn_fwd)(S, h)
+            tape.append((kind, S, c))
+        for i_level in reversed(range(len(self.up))):
+            blocks, ups = self.up[i_level]
+            for kind, S in blocks:
+                h, c = self._res_fwd(S, h)
+                tape.append((kind, S, c))
+            if ups is not None:
+                h = ups.fwd(ops.upsample_nearest2x(h))
+                tape.append(("up", ups, None))
+        n, h2, w2, ch = h.shape
+        hn = ops.groupnorm(h.view(-1, ch), self.norm_out.w, self.norm_out.b, rows_per_sample=h2 * w2, eps=self.norm_out.eps, silu=True)
+        y = self.conv_out.fwd(hn.view(n, h2, w2, ch))                                 # [n, H, W, 64] (3 real channels)
+        img = ops.frames_to_bcthw(y, b, self.out_ch, z.dtype)
+        return img, dict(tape=tape, h_out=h.view(-1, ch), geom=(b, t, hh, ww), scale=scale, z_dtype=z.dtype)
+
+    def backward(self, T, d_img):
+        """d_img: gradient w.r.t. the image [B, 3, T, 8h, 8w] -> gradient w.r.t. z [B, zc, T, h, w] (fp32)."""
+        b, t, hh, ww = T["geom"]
+        dy = ops.bcthw_to_frames_pad(d_img, 64)                                       # [n, H, W, 64], channels >= 3 zero
+        n, h2, w2, _ = dy.shape
+        ch = T["h_out"].shape[-1]
+        d_hn = self.conv_out.bwd(dy).view(-1, ch)
+        dh = ops.groupnorm_bwd(T["h_out"], d_hn, self.norm_out.w, self.norm_out.b, rows_per_sample=h2 * w2, eps=self.norm_out.eps,
+                               silu=True).view(n, h2, w2, ch)
+        for kind, S, c in reversed(T["tape"]):
+            if kind == "res":
+                dh = self._res_bwd(S, c, dh)
+            elif kind == "attn":
+                dh = self._attn_bwd(S, c, dh)
+            else:                                                                     # nearest 2x upsampling + conv
+                dh = ops.resample2x(S.bwd(dh.contiguous()), "pool")
+        d_fr = self.conv_in.bwd(dh.contiguous())[..., :self.zc].float()               # [n, h, w, zc]
+        # post_quant_conv (zc x zc) and the latent scale: fr[o] = sum_c pq_w[o, c] * scale * z[c] + b[o]
+        dz = torch.matmul(d_fr, self.pq_w) * T["scale"]                               # [n, h, w, zc]: plumbing on 4 channels
+        return dz.view(b, t, hh, ww, self.zc).permute(0, 4, 1, 2, 3).contiguous()
+
+
+class _DecodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, view, scale):
+        img, tape = view.forward(z.detach(), scale)
+        ctx.view, ctx.tape, ctx.z_dtype = view, tape, z.dtype
+        return img
+
+    @staticmethod
+    def backward(ctx, d_img):
+        dz = ctx.view.backward(ctx.tape, d_img.contiguous())
+        ctx.tape = None
+        return dz.to(ctx.z_dtype), None, None
+
+
+def decode_with_grad(vae, z, scale=1.0):
+    """`vae.decode(z)` as a differentiable torch op in z (the VAE's weights are frozen).  z: [N, zc, h, w] frames — the call form of
+    the training scripts — or [B, zc, T, h, w]; returns the image in the same arrangement."""
+    view = getattr(vae, "_decoder_grad_view", None)
+    if view is None or view.vae is not vae or getattr(view, "_generation", None) != getattr(vae, "weight_generation", 0):
+        view = DecoderGrad(vae)
+        view._generation = getattr(vae, "weight_generation", 0)
+        vae._decoder_grad_view = view
+    frames = z.dim() == 4
+    z5 = z.unsqueeze(2) if frames else z
+    img = _DecodeFn.apply(z5, view, scale)
+    return img.squeeze(2) if frames else img
+
+
+def reward_gradient(vae, model_pred, reward_fn, *, frame_idx, batch_idx=None, vae_scale_factor=0.18215, reward_scale=1.0, as_video=False):
+    """The reward branch of the training step for a caller-supplied differentiable reward model (train_t2v_turbo_v1_lora.py:1043-1069 image
+    reward, :1070-1099 video reward; train_latent_t2v_turbo_v2.py:1062-1166):
+
+        selected = model_pred[batch_idx][:, :, frame_idx] / vae_scale_factor  -> frames [N, zc, h, w]
+        imgs     = (vae.decode(selected) / 2 + 0.5).clamp(0, 1)                (as_video: reshaped to [B', F, 3, H, W], :1090-1094)
+        loss     = -reward_fn(imgs).mean() * reward_scale
+
+    -> (loss, d loss / d model_pred as fp32 [B, zc, T, h, w], zero outside the selected frames).  The decode and its adjoint are
+    `decode_with_grad` (this module's kernels); the indexing, the clamp and reward_fn run under torch autograd."""
+    mp = model_pred.detach().float().requires_grad_(True)
+    frame_idx = torch.as_tensor(frame_idx, device=mp.device)
+    sel = mp if batch_idx is None else mp[torch.as_tensor(batch_idx, device=mp.device)]
+    sel = sel[:, :, frame_idx] / vae_scale_factor
+    nb, zc, nf = sel.shape[:3]
+    frames = sel.permute(0, 2, 1, 3, 4).reshape(nb * nf, zc, *sel.shape[3:])
+    imgs = (decode_with_grad(vae, frames) / 2 + 0.5).clamp(0, 1)
+    if as_video:
+        imgs = imgs.reshape(nb, nf, *imgs.shape[1:])
+    loss = -reward_fn(imgs).mean() * reward_scale
+    loss.backward()
+    return loss.detach(), mp.grad

@@ -282,6 +282,40 @@ def attention_temporal_bwd(q, k, v, d_o, *, b, t, hw, heads, scale):
     return dq.to(ACT).contiguous(), dk.to(ACT).contiguous(), dv.to(ACT).contiguous()
 
 
+def bmm_nt(a, b, *, out=None, alpha=1.0, block_n=0):
+    assert a.dtype == ACT and b.dtype == ACT and a.stride(2) == 1 and b.stride(2) == 1
+    assert a.shape[0] == b.shape[0] and a.shape[2] == b.shape[2] and a.shape[2] % 64 == 0, (a.shape, b.shape)
+    return (alpha * (a.float() @ b.float().transpose(1, 2))).to(ACT)
+
+
+def softmax_rows_(x, scale=1.0):
+    assert x.dtype == ACT and x.is_contiguous()
+    x.copy_(torch.softmax(x.float() * scale, -1).to(ACT))
+    return x
+
+
+def softmax_bwd_rows_(dp, p, scale=1.0):
+    assert dp.dtype == ACT and p.dtype == ACT and dp.is_contiguous() and p.is_contiguous() and dp.shape == p.shape
+    pf, df = p.float(), dp.float()
+    dp.copy_((scale * pf * (df - (df * pf).sum(-1, keepdim=True))).to(ACT))
+    return dp
+
+
+def conv3x3_small_cin(x, w, bias, cout):
+    _act(x)
+    n, h, wd, cin = x.shape
+    assert w.dtype == ACT and tuple(w.shape) == (cout, 9 * cin) and cin in (4, 8)
+    y = F.conv2d(x.permute(0, 3, 1, 2).float(), _unpack(w, cin, 9).reshape(cout, cin, 3, 3).float(), bias, padding=1)
+    return y.permute(0, 2, 3, 1).to(ACT).contiguous()
+
+
+def bcthw_to_frames_mix(z, scale, mix, bias):
+    b, c, t, hh, ww = z.shape
+    assert mix.dtype == torch.float32 and bias.dtype == torch.float32 and tuple(mix.shape) == (bias.numel(), c)
+    fr = (z.float() * scale).permute(0, 2, 3, 4, 1).reshape(b * t, hh, ww, c)
+    return (fr @ mix.t() + bias).to(ACT).contiguous()
+
+
 # ----------------------------------------------------------------------------- elementwise / layout
 def _geglu_f(pre):
     i = pre.shape[1] // 2
@@ -462,8 +496,9 @@ def install(monkeypatch, act=torch.float32):
         if name in ("install",):
             continue
         monkeypatch.setattr(ops, name, globals()[name], raising=True)
-    for mod in (train_unet, full_train, lora_train):
+    from t2v_turbo_b200 import vae_train
+    for mod in (train_unet, full_train, lora_train, vae_train):
         monkeypatch.setattr(mod, "BF16", act)
-    monkeypatch.setattr(train_unet, "_require_cuda", lambda what, device: None)
-    monkeypatch.setattr(full_train, "_require_cuda", lambda what, device: None)
+    for mod in (train_unet, full_train, vae_train):
+        monkeypatch.setattr(mod, "_require_cuda", lambda what, device: None)
     return ops

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BF16 = torch.bfloat16
 NAMES = ("t2v_groupnorm_bwd", "t2v_layernorm_bwd", "t2v_colsum_samples", "t2v_geglu", "t2v_resample2x", "t2v_ew2d",
-         "t2v_groupnorm_affine_grad", "t2v_layernorm_affine_grad", "t2v_ema_update",
+         "t2v_groupnorm_affine_grad", "t2v_layernorm_affine_grad", "t2v_ema_update", "t2v_softmax_bwd_rows", "t2v_softmax_rows",
          # elementwise.cu / train_ops.cu (all parity-tested on B200; run here as a CPU regression net over the real kernel source)
          "t2v_lcm_step", "t2v_scale_add_rows", "t2v_dropout_scale", "t2v_scale_mask", "t2v_adamw_step", "t2v_sum_squares",
          "t2v_mse_loss_grad", "t2v_huber_loss_grad", "t2v_video_to_uint8", "t2v_conv3x3_small_cin", "t2v_pack_conv_weight",
@@ -171,6 +171,26 @@ def test_layernorm_affine_grad_kernel_under_emulation(emu, rows, c):
     close(dg, 1.0 + (dy.float() * xh).sum(0), 2e-3, 5e-4, f"ln dgamma {rows}x{c}")
     close(db, dy.float().sum(0), 2e-3, 5e-4, f"ln dbeta {rows}x{c}")
     assert emu.t2v_layernorm_affine_grad(x.data_ptr(), c, dy.data_ptr(), c, dg.data_ptr(), db.data_ptr(), rows, 96, 1e-5, None) < 0
+
+
+@pytest.mark.parametrize("rows,cols", [(12, 256), (5, 2560), (3, 100), (1, 7)])
+def test_softmax_bwd_rows_kernel_under_emulation(emu, rows, cols):
+    """The VAE AttnBlock's softmax adjoint (vae.decode WITH grad): forward kernel (B200-verified) and the new backward kernel both run
+    under emulation, the backward against autograd of torch.softmax on the forward kernel's own bf16 probabilities."""
+    s = (rnd(rows, cols, seed=30) * 3.0).to(BF16)
+    scale = 512 ** -0.5
+    p = s.clone()
+    assert emu.t2v_softmax_rows(p.data_ptr(), rows, cols, cols, scale, None) == 0
+    close(p, torch.softmax(s.float() * scale, -1), 8e-3, 4e-3, "emulated softmax_rows")
+    dp = rnd(rows, cols, seed=31).to(BF16)
+    ds = dp.clone()
+    assert emu.t2v_softmax_bwd_rows(ds.data_ptr(), cols, p.data_ptr(), cols, rows, cols, scale, None) == 0
+    pf, df = p.float(), dp.float()
+    close(ds, scale * pf * (df - (df * pf).sum(-1, keepdim=True)), 8e-3, 4e-3, f"softmax_bwd_rows {rows}x{cols}")
+    sr = s.float().requires_grad_(True)                      # and against autograd of the true softmax (bf16 P is the only difference)
+    torch.softmax(sr * scale, -1).backward(df)
+    assert ((ds.float() - sr.grad).norm() / sr.grad.norm()).item() < 2e-2
+    assert emu.t2v_softmax_bwd_rows(ds.data_ptr(), cols - 1, p.data_ptr(), cols, rows, cols, scale, None) < 0
 
 
 @pytest.mark.parametrize("n,offset", [(4096, 0), (100003, 0), (4099, 1), (3, 0), (1, 0)])

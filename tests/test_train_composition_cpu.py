@@ -285,3 +285,97 @@ def test_v2_host_draws_motion_condition():
     assert H["mg_emb"].shape == (4, 256) and torch.equal(H["mg_emb"][2], H["mg_emb"][3])
     step_nc = V2Step(None, sch, use_motion_cond=False)
     assert "mg_emb" not in step_nc.host_draws(idx, torch.ones(4, dtype=torch.bool))
+
+
+# ----------------------------------------------------------------------------- vae.decode WITH grad (the reward terms' path)
+def test_decoder_grad_vs_oracle_autograd(monkeypatch):
+    """vae_train.DecoderGrad: forward == the VAE oracle, the hand-written input gradient == autograd through it (incl. the AttnBlock's
+    softmax adjoint, the upsampling adjoints, the padded 3- / 4-channel ends, post_quant_conv and the latent scale), through the
+    public `decode_with_grad` in both call forms, with a non-linear "reward" on top."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import VAE_CONFIGS
+    from oracle.vae_oracle import decode_first_stage_2dae
+    from oracle.weights import vae_state_dict
+    from t2v_turbo_b200.vae import AutoencoderKL
+    from t2v_turbo_b200.vae_train import decode_with_grad
+    spec = VAE_CONFIGS["small"]
+    v = AutoencoderKL(spec["ddconfig"], spec["embed_dim"])
+    sd = vae_state_dict(v.state_dict(), spec["weight_seed"])
+    v.load_state_dict(sd)
+    v.eval()
+    z = torch.randn(spec["z_shape"], generator=torch.Generator().manual_seed(3))                # [1, 4, 4, 16, 16]
+    side = 16 * 2 ** (len(spec["ddconfig"]["ch_mult"]) - 1)
+    probe = torch.randn(1, 3, 4, side, side, generator=torch.Generator().manual_seed(5))
+
+    def reward(img):            # stands in for a reward model: clamp to [0, 1] like the scripts, then a non-linear score
+        x = (img / 2 + 0.5).clamp(0, 1)
+        return (x * probe).sum() + (x ** 2).mean()
+    z1 = z.clone().requires_grad_(True)
+    img = decode_with_grad(v, z1, scale=1.0 / 0.18215)
+    reward(img).backward()
+    z2 = z.clone().requires_grad_(True)
+    ref = decode_first_stage_2dae(sd, spec["ddconfig"], z2)
+    reward(ref).backward()
+    assert _rel(img.detach(), ref.detach()) < 1e-4, _rel(img.detach(), ref.detach())
+    assert _rel(z1.grad, z2.grad) < 1e-4, _rel(z1.grad, z2.grad)
+    # the training scripts' call form: frames [N, zc, h, w] (selected_latents, train_t2v_turbo_v1_lora.py:1055-1062)
+    zf = z[0].permute(1, 0, 2, 3).contiguous().requires_grad_(True)
+    imgf = decode_with_grad(v, zf, scale=1.0 / 0.18215)
+    assert imgf.shape == (4, 3, side, side) and _rel(imgf.detach(), ref.detach()[0].permute(1, 0, 2, 3)) < 1e-4
+    imgf.square().sum().backward()
+    assert zf.grad.shape == zf.shape and torch.isfinite(zf.grad).all() and zf.grad.abs().max() > 0
+
+
+def test_v2_step_with_reward_branch_vs_oracle_autograd(monkeypatch):
+    """The step with a reward term (train_latent_t2v_turbo_v2.py:1062-1098 shape: frames of model_pred -> vae.decode -> clamp -> reward):
+    `V2Step.reward = partial(vae_train.reward_gradient, vae, reward_fn=...)` adds the reward's gradient — through the hand-written decoder
+    adjoint — to the distillation gradient before the student backward.  Every parameter gradient vs autograd of the SAME total loss
+    composed from the UNet oracle and the VAE oracle."""
+    import functools
+    mock_ops.install(monkeypatch)
+    from oracle.configs import UNET_CONFIGS, VAE_CONFIGS
+    from oracle.unet_oracle import unet_forward
+    from oracle.vae_oracle import decode_first_stage_2dae
+    from oracle.weights import vae_state_dict
+    from t2v_turbo_b200.vae import AutoencoderKL
+    from t2v_turbo_b200.vae_train import reward_gradient
+    g = torch.load(os.path.join(GOLD, "v2_step_small_motion.pt"))
+    s, step, sd = _v2_setup(g, with_ema_target=False)
+    vspec = VAE_CONFIGS["small"]
+    vae = AutoencoderKL(vspec["ddconfig"], vspec["embed_dim"])
+    vsd = vae_state_dict(vae.state_dict(), vspec["weight_seed"])
+    vae.load_state_dict(vsd)
+    vae.eval()
+    frame_idx, scale = [2, 0], 0.37
+
+    def reward_fn(imgs):                      # any differentiable score of images in [0, 1]
+        return -((imgs - 0.3) ** 2).mean((1, 2, 3))
+    step.reward = functools.partial(reward_gradient, vae, reward_fn=reward_fn, frame_idx=frame_idx, reward_scale=scale)
+    inp = g["inputs"]
+    batch = {k: inp[k] for k in ("index", "z_t", "cond_teacher_out", "uncond_teacher_out", "score", "use_motion_guide", "prompt_emb")}
+    s.arena.zero_grad()
+    out = step(batch, fixed=dict(w=inp["w"]))
+    # the same total loss under autograd
+    spec = UNET_CONFIGS["small_motion"]
+    H = step.host_draws(inp["index"], inp["use_motion_guide"], fixed=dict(w=inp["w"]))
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    eps = unet_forward(sdg, spec["cfg"], inp["z_t"], H["start_timesteps"], inp["prompt_emb"], fps=16, timestep_cond=H["w_emb"], motion_cond=H["mg_emb"])
+    v5 = lambda t: t.view(-1, 1, 1, 1, 1)      # noqa: E731
+    model_pred = v5(H["k_z"]) * inp["z_t"] + v5(H["k_e"]) * eps
+    d = model_pred - out["target"]
+    distill = torch.mean(torch.sqrt(d ** 2 + 0.001 ** 2) - 0.001)
+    img = decode_first_stage_2dae(vsd, vspec["ddconfig"], model_pred[:, :, frame_idx])
+    imgs = (img / 2 + 0.5).clamp(0, 1).permute(0, 2, 1, 3, 4).reshape(-1, *img.shape[1:2], *img.shape[3:])
+    r_loss = -reward_fn(imgs).mean() * scale
+    (distill + r_loss).backward()
+    assert _rel(out["model_pred"], model_pred.detach()) < 1e-4
+    r_ref, d_ref = float(r_loss.detach()), float(distill.detach())
+    assert abs(float(out["reward_loss"]) - r_ref) < 1e-5 * abs(r_ref) and abs(float(out["loss"]) - d_ref) < 1e-5 * d_ref
+    rels = {n: _rel(s.arena.grad(n), sdg[n].grad) for n in s.arena.names}
+    worst = max(rels, key=rels.get)
+    assert rels[worst] < 2e-4, (worst, rels[worst])
+    # and the reward really contributes: without it the gradient differs
+    s2, step2, _ = _v2_setup(g, with_ema_target=False)
+    s2.arena.zero_grad()
+    step2(batch, fixed=dict(w=inp["w"]))
+    assert _rel(s2.arena.grads, s.arena.grads) > 1e-3

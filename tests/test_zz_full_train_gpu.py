@@ -246,3 +246,53 @@ def test_v2_step_self_target_and_second_step(cuda_device):
     out2 = step(batch, fixed=dict(w=inp["w"]))
     assert _rel(out2["model_pred"], out["model_pred"]) > 1e-5, "the optimizer step did not change the student's prediction"
     assert torch.isfinite(out1["loss"]).all()
+
+
+# ----------------------------------------------------------------------------- vae.decode WITH grad (never run on a GPU)
+@never_run
+@pytest.mark.parametrize("n,hw,scale", [(2, 256, 128 ** -0.5), (1, 2560, 512 ** -0.5)])
+def test_softmax_bwd_rows(cuda_device, n, hw, scale):
+    ops = _ops()
+    s = (rnd(n, hw, hw, seed=30) * 3.0).to(BF16)
+    p = s.clone()
+    ops.softmax_rows_(p, scale)
+    dp = rnd(n, hw, hw, seed=31).to(BF16)
+    ds = dp.clone()
+    ops.softmax_bwd_rows_(ds, p, scale)
+    ref = p.float().cpu().clone()
+    _mock().softmax_bwd_rows_(dpr := dp.float().cpu().clone(), ref, scale)
+    assert_close(ds.cpu(), dpr, what=f"softmax_bwd_rows {n}x{hw}x{hw}")
+
+
+@never_run
+def test_decoder_grad_vs_oracle_autograd(cuda_device):
+    """vae_train.decode_with_grad on B200 vs autograd through the VAE oracle (fp32, CPU): image and the latent gradient under a
+    clamp + non-linear score, the reference's frame call form.  Bounds: the VAE decode test's (2.0e-2) for the image, 2x that for the
+    gradient through ~30 bf16 layers; never observed."""
+    from oracle.configs import VAE_CONFIGS
+    from oracle.vae_oracle import decode_first_stage_2dae
+    from oracle.weights import vae_state_dict
+    from t2v_turbo_b200.vae import AutoencoderKL
+    from t2v_turbo_b200.vae_train import decode_with_grad
+    spec = VAE_CONFIGS["small"]
+    v = AutoencoderKL(spec["ddconfig"], spec["embed_dim"])
+    sd = vae_state_dict(v.state_dict(), spec["weight_seed"])
+    v.load_state_dict(sd)
+    v = v.cuda().eval()
+    z = torch.randn(spec["z_shape"], generator=torch.Generator().manual_seed(3))
+    side = 16 * 2 ** (len(spec["ddconfig"]["ch_mult"]) - 1)
+    probe = torch.randn(1, 3, 4, side, side, generator=torch.Generator().manual_seed(5))
+
+    def reward(img, pr):
+        x = (img / 2 + 0.5).clamp(0, 1)
+        return (x * pr).sum() + (x ** 2).mean()
+    z1 = z.clone().cuda().requires_grad_(True)
+    img = decode_with_grad(v, z1, scale=1.0 / 0.18215)
+    reward(img, probe.cuda()).backward()
+    torch.cuda.synchronize()
+    z2 = z.clone().requires_grad_(True)
+    ref = decode_first_stage_2dae(sd, spec["ddconfig"], z2)
+    reward(ref, probe).backward()
+    e_img, e_g = _rel(img.detach(), ref.detach()), _rel(z1.grad, z2.grad)
+    print(f"\n[decoder grad small] image rel-L2 {e_img:.3e}, latent-gradient rel-L2 {e_g:.3e}")
+    assert e_img < 2.0e-2 and e_g < 4.0e-2, (e_img, e_g)
