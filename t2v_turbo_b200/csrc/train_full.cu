@@ -1,9 +1,10 @@
-// Kernels that only the FULL fine-tune step needs (train_latent_t2v_turbo_v2.py:945-1276: every UNet parameter trains, an EMA
-// copy is the target network): the affine gradients of GroupNorm(+SiLU) and LayerNorm, and the EMA update of the target
-// parameters (utils/common_utils.py:308-319).  Weight gradients reuse t2v_wgrad, bias gradients t2v_colsum_samples, the input
-// gradients the v1 step's kernels (train_bwd.cu) — those are not touched by this file.
-// All HBM bound: one pass over (x, dy) per norm layer, fp32 accumulation, per-CTA shared-memory reduction, one global
-// atomic per channel per CTA into the fp32 gradient arena.
+// SIMT kernels added for the training paths beyond the v1 LoRA step:
+//  * the FULL fine-tune step (train_latent_t2v_turbo_v2.py:945-1276: every UNet parameter trains, an EMA copy is the target network):
+//    affine gradients of GroupNorm(+SiLU) and LayerNorm, EMA update of the target parameters (utils/common_utils.py:308-319).
+//    Weight gradients reuse t2v_wgrad, bias gradients t2v_colsum_samples, input gradients the v1 step's kernels (train_bwd.cu);
+//  * `vae.decode` WITH grad (the reward terms, train_t2v_turbo_v1_lora.py:1043-1099): the softmax adjoint of the KL-VAE AttnBlock.
+// All HBM bound: one pass over the operands, fp32 accumulation, per-CTA shared-memory reduction, one global atomic per channel per
+// CTA into the fp32 gradient arena.  No TMA / tcgen05 here, so this file also compiles for the host emulation (tests/cuda_emu).
 #include <math.h>
 
 #include "../../include/t2v_b200.h"
