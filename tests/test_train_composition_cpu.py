@@ -379,3 +379,45 @@ def test_v2_step_with_reward_branch_vs_oracle_autograd(monkeypatch):
     s2.arena.zero_grad()
     step2(batch, fixed=dict(w=inp["w"]))
     assert _rel(s2.arena.grads, s.arena.grads) > 1e-3
+
+
+def test_v1_distill_step_vs_reference_composition(monkeypatch):
+    """The v1 step (distill.DistillStep: add_noise, LoRA student, batched teacher CFG + DDIM step, gradient-free target, pseudo-Huber loss,
+    student backward) in fp32 on CPU == the step composed from the UNMODIFIED reference's pieces (tests/golden/distill_step_small.pt).  On
+    the GPU this comparison is noise-dominated (sign-like loss gradient in bf16, tests/test_student_gpu.py); here it is exact to 1e-4."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import UNET_CONFIGS, student_loras
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200.distill import DistillStep
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.train_unet import StudentUNet
+    from t2v_turbo_b200.unet import UNetModel
+    g = torch.load(os.path.join(GOLD, "distill_step_small.pt"))
+    spec = UNET_CONFIGS["small"]
+    base = UNetModel(**spec["cfg"])
+    sd = seeded_state_dict(base.state_dict(), spec["weight_seed"])
+    base.load_state_dict(sd, strict=True)
+    tcfg = dict(spec["cfg"])
+    tcfg["time_cond_proj_dim"] = None
+    teacher_m = UNetModel(**tcfg)
+    teacher_m.load_state_dict({k: v for k, v in sd.items() if not k.startswith("time_cond_proj")}, strict=True)
+    s = StudentUNet(base.eval(), r=64).eval()
+    assert [tuple(x) for x in g["shapes"]] == s.arena.shapes
+    s.arena.load_list(student_loras(g["shapes"]))
+    s.pack()
+    tv = StudentUNet(teacher_m.eval(), r=64).eval()          # lora_up = 0 at initialisation: exactly the frozen teacher's forward
+    tv.pack()
+    step = DistillStep(s, _EvalTarget(tv), T2VTurboScheduler(linear_start=0.00085, linear_end=0.012), num_ddim_timesteps=50, topk=20,
+                       loss_type="huber", huber_c=0.001, timestep_scaling_factor=10.0)
+    inp = g["inputs"]
+    s.arena.zero_grad()
+    out = step(inp["latents"], inp["prompt"], inp["uncond"], fixed=dict(index=inp["index"], noise=inp["noise"], w=inp["w"]))
+    assert out["start_timesteps"].tolist() == g["start_timesteps"].tolist() and out["timesteps"].tolist() == g["timesteps"].tolist()
+    for k in ("model_pred", "x_prev", "target"):
+        assert _rel(out[k], g[k]) < 1e-4, (k, _rel(out[k], g[k]))
+    assert abs(float(out["loss"]) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    n = len(s.arena.shapes)
+    ratio = torch.tensor([s.arena.grad(i).double().norm().item() / max(g["grad_norms"][i].item(), 1e-30) for i in range(n)])
+    assert (ratio - 1).abs().max() < 5e-4, (ratio.min(), ratio.max())
+    worst = max(_rel(s.arena.grad(j), sc * t.float()) for j, (sc, t) in g["grads_full"].items())
+    assert worst < 2e-3, worst
