@@ -565,6 +565,11 @@ def gen_distill_tables():
     target = csn * x_prev + con * get_predicted_original_sample(e_t, tn, x_prev, "epsilon", alpha, sigma)
     out["compose"] = dict(index=index, w=w, lat=lat, noise=noise, e_s=e_s, e_c=e_c, e_u=e_u, e_t=e_t, z=z, model_pred=model_pred, x_prev=x_prev,
                           target=target, start=start, tn=tn)
+    # DDIM inversion step (inverse_ddim.py / motion_prior_sample.py:27-37 -> DDIMSolver.ddim_reverse_step), fp64
+    solver.alpha_cumprods = solver.alpha_cumprods.double() if torch.is_tensor(solver.alpha_cumprods) else torch.from_numpy(solver.alpha_cumprods).double()
+    rts = torch.tensor([999, 499, 19, 4])
+    rx, re = (torch.randn(4, 4, 2, 3, 3, generator=g, dtype=torch.float64) for _ in range(2))
+    out["reverse"] = dict(ts=rts, x_prev=rx, eps=re, x_t=solver.ddim_reverse_step(rx, re, rts), step_ratio=int(solver.step_ratio))
     torch.save(out, os.path.join(GOLD, "distill_tables.pt"))
     print("  distill tables: ddim_timesteps", solver.ddim_timesteps[:4].tolist(), "...", solver.ddim_timesteps[-2:].tolist())
 

@@ -52,11 +52,28 @@ class DDIMSolver:
         self.ddim_timesteps = torch.from_numpy(ts).long()
         self.ddim_alpha_cumprods = torch.from_numpy(alpha_cumprods[ts])
         self.ddim_alpha_cumprods_prev = torch.from_numpy(np.asarray([alpha_cumprods[0]] + alpha_cumprods[ts[:-1]].tolist()))
+        self.alpha_cumprods = torch.from_numpy(alpha_cumprods)
 
     def ddim_step(self, pred_x0, pred_noise, timestep_index):
         a_prev = self.ddim_alpha_cumprods_prev[timestep_index.cpu()].double()
         dev = pred_x0.device
         return ops.scale_add_rows(pred_x0, a_prev.sqrt().float().to(dev), pred_noise, (1.0 - a_prev).sqrt().float().to(dev))
+
+
+    def reverse_coefs(self, ts):
+        """ddim_reverse_step as two per-sample coefficients (fp64 on the host): x_t = ca * x_prev + cb * eps,
+        ca = sqrt(a_next / a), cb = sqrt(1 - a_next) - sqrt(1 - a) * ca with a_next = abar[ts], a = abar[max(ts - step_ratio, 0)]."""
+        ts = ts.cpu().long()
+        prev = (ts - self.step_ratio).clip(min=0)
+        a_next, a = self.alpha_cumprods[ts].double(), self.alpha_cumprods[prev].double()
+        ca = (a_next / a).sqrt()
+        return ca, (1.0 - a_next).sqrt() - (1.0 - a).sqrt() * ca
+
+    def ddim_reverse_step(self, x_prev, pred_noise, ts):
+        """One DDIM INVERSION step (ode_solver/ddim_solver.py:89-97; inverse_ddim.py:46-60, motion_prior_sample.py:27-37)."""
+        ca, cb = self.reverse_coefs(ts)
+        dev = x_prev.device
+        return ops.scale_add_rows(x_prev, ca.float().to(dev), pred_noise, cb.float().to(dev))
 
 
 class DistillStep:

@@ -65,3 +65,16 @@ def test_host_draws_ranges():
     assert (H["timesteps"] == torch.clamp(H["start_timesteps"] - 20, min=0)).all()
     assert all(H[k].dtype == torch.float32 and H[k].shape == (64,) for k in st.COEFS)
     assert H["w_emb"].shape == (64, 256)
+
+
+def test_ddim_reverse_step_coefficients(tables):
+    """DDIM inversion (ode_solver/ddim_solver.py:89-97) as two per-sample coefficients == the reference's fp64 arithmetic, incl. the clip
+    of the previous timestep at 0."""
+    from t2v_turbo_b200.distill import DDIMSolver
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    r = tables["reverse"]
+    s = DDIMSolver(T2VTurboScheduler(linear_start=0.00085, linear_end=0.012).alphas_cumprod.numpy(), ddim_timesteps=50)
+    assert s.step_ratio == r["step_ratio"]
+    ca, cb = s.reverse_coefs(r["ts"])
+    x_t = ca.view(-1, 1, 1, 1, 1) * r["x_prev"] + cb.view(-1, 1, 1, 1, 1) * r["eps"]
+    assert ((x_t - r["x_t"]).abs().max() / r["x_t"].abs().max()).item() < 1e-6       # the scheduler's abar table is fp32
