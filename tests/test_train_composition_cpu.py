@@ -100,6 +100,39 @@ def test_full_unet_every_parameter_gradient_vs_oracle_autograd(monkeypatch):
     assert _rel(s.arena.grad(worst), 2 * sdg[worst].grad) < 1e-4 and torch.equal(y2, y)
 
 
+def test_full_unet_vc2_topology_every_gradient_vs_oracle_autograd(monkeypatch):
+    """The same on the FULL VC2 topology (all four levels, 12 input / 12 output blocks, head counts 2/4/8/8, stride-2 and upsampling
+    convs at every level) at 128 base channels: all 1487 parameter tensors — the same tensor list and the same 33 optimizer-group runs
+    as the 1.41 B model — against autograd through the oracle, batch 2 with per-sample timesteps and motion scales."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import UNET_CONFIGS, unet_inputs
+    from oracle.unet_oracle import unet_forward
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200.full_train import FullUNet
+    from t2v_turbo_b200.unet import UNetModel
+    spec = dict(UNET_CONFIGS["mid"])
+    spec.update(cfg={**spec["cfg"], "motion_cond_proj_dim": 256}, motion_gs=(0.05, 0.0), x_shape=(2, 4, 8, 16, 16))
+    m = UNetModel(**spec["cfg"])
+    sd = seeded_state_dict(m.state_dict(), 8)
+    m.load_state_dict(sd, strict=True)
+    s = FullUNet(m.eval()).eval()
+    s.pack()
+    assert len(s.arena.names) == 1487 and len(s.arena.runs) == 33
+    inp = unet_inputs(spec, (759, 279))
+    kw = dict(fps=16, timestep_cond=inp["timestep_cond"], motion_cond=inp["motion_cond"])
+    y = s(inp["x"], inp["timesteps"], context=inp["context"], **kw)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    yr = unet_forward(sdg, spec["cfg"], inp["x"], inp["timesteps"], inp["context"], **kw)
+    assert _rel(y, yr.detach()) < 1e-4
+    d_out = torch.randn(y.shape, generator=torch.Generator().manual_seed(4243))
+    (yr * d_out).sum().backward()
+    s.arena.zero_grad()
+    s.backward(d_out)
+    rels = {n: _rel(s.arena.grad(n), sdg[n].grad) for n in s.arena.names}
+    worst = max(rels, key=rels.get)
+    assert rels[worst] < 1e-4, (worst, rels[worst])
+
+
 def test_full_unet_gradients_vs_the_reference_itself(monkeypatch):
     """The same, against the UNMODIFIED reference's autograd (tests/golden/full_grads_small_motion.pt: linear loss, all 629 norms and
     57 tensors in full) — so the oracle used above is itself pinned on the reference for the backward, not only the forward."""
