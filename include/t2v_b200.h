@@ -492,6 +492,16 @@ int t2v_layernorm_affine_grad(const void* x, int64_t x_row_stride, const void* d
 int t2v_softmax_bwd_rows(void* dp, int64_t dp_row_stride, const void* p, int64_t p_row_stride, int64_t rows, int32_t cols,
                          float scale, t2v_stream_t stream);
 
+/* Adjoint of the PROBABILITIES export of t2v_attn_short_fwd w.r.t. q and k (temporal self-attention, head dim 64, len <= 16):
+ *   P = softmax(scale q k^T),  dS = P * (dP - rowsum(dP * P)),  dq = scale dS k,  dk = scale dS^T q.
+ * q / k: bf16 token matrices [(outer, len, inner), heads * 64] with row strides in elements (views of a fused projection are fine);
+ * d_probs: fp32 [(seq * heads + head)][query][key], seq = outer * n_inner + inner (the export's layout); dq / dk: bf16, contiguous
+ * [rows, heads * 64].  The motion-prior score of the v2 preprocessing (motion_prior_sample.py:59-84: the gradient w.r.t. the latents
+ * of a loss on the temporal attention probabilities of output_blocks.3-11). */
+int t2v_attn_short_probs_bwd(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride, const float* d_probs,
+                             void* dq, void* dk, int32_t n_outer, int32_t n_inner, int32_t heads, int32_t len, float scale,
+                             t2v_stream_t stream);
+
 /* EMA of the target network's parameters over the flat fp32 arenas (update_ema, utils/common_utils.py:308-319;
  * train_latent_t2v_turbo_v2.py:1273-1276): target = target * rate + src * (1 - rate). */
 int t2v_ema_update(float* target, const float* src, int64_t n, float rate, t2v_stream_t stream);

@@ -389,6 +389,47 @@ def gen_full_grads(name="small_motion"):
                 "grads_full": full, "ref_bf16": ref_bf16}, os.path.join(GOLD, f"full_grads_{name}.pt"))
 
 
+def gen_motion_score(name="small"):
+    """The motion-prior score of the v2 preprocessing (motion_prior_sample.py:40-84) on the UNMODIFIED reference: the teacher UNet built
+    with record_attn_probs=True (no time_cond_proj), `get_temp_attn_prob` restated over EVERY recording module (the reference hard-codes
+    output_blocks.3-11, which are exactly the recording ones of the VC2 UNet; the small config has fewer output blocks),
+    utils.common_utils.compute_temp_loss, torch.autograd.grad w.r.t. the latents — fp32."""
+    from utils.common_utils import compute_temp_loss
+    spec = UNET_CONFIGS[name]
+    cfg = {**spec["cfg"], "time_cond_proj_dim": None, "record_attn_probs": True}
+    from lvdm.modules.networks.openaimodel3d import UNetModel
+    m = UNetModel(**cfg).eval()
+    sd = seeded_state_dict(m.state_dict(), spec["weight_seed"])
+    m.load_state_dict(sd, strict=True)
+    m.requires_grad_(False)
+    g = torch.Generator().manual_seed(7171)
+    shape = spec["x_shape"]
+    cd = spec["cfg"]["context_dim"]
+    latents, example = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    ctx_inf, ctx_orig = torch.randn(shape[0], spec["ctx_len"], cd, generator=g), torch.randn(shape[0], spec["ctx_len"], cd, generator=g)
+    ts = torch.tensor([699])
+    temp_loss_scale = 20.0
+
+    def get_temp_attn_prob(unet, latent, ts, context):          # motion_prior_sample.py:40-56
+        out = unet(latent, ts, **context)
+        probs = {n: mod.attention_probs for n, mod in unet.named_modules()
+                 if n.endswith("blocks.0.attn1") and getattr(mod, "record_attn_probs", False)}
+        return out, probs
+    with torch.no_grad():
+        _, probs_example = get_temp_attn_prob(m, example, ts, {"context": ctx_orig, "fps": 16})
+        probs_example = {k: v.clone() for k, v in probs_example.items()}
+    with torch.set_grad_enabled(True):                           # :73-83
+        latents.requires_grad_(True)
+        cond_teacher_output, probs = get_temp_attn_prob(m, latents, ts, {"context": ctx_inf, "fps": 16})
+        loss = temp_loss_scale * compute_temp_loss(probs, probs_example)
+        score = torch.autograd.grad(loss, latents)[0].detach()
+    print(f"  motion score {name}: {len(probs)} recording layers {list(probs)}, loss {loss.item():.6f}, score std {score.std():.4e}")
+    torch.save({"name": name, "cfg": cfg, "latents": latents.detach(), "example": example, "ctx_inf": ctx_inf, "ctx_orig": ctx_orig, "ts": ts,
+                "temp_loss_scale": temp_loss_scale, "layers": list(probs), "loss": loss.detach(), "score": score,
+                "cond_teacher_output": cond_teacher_output.detach(), "probs": {k: v.detach().half() for k, v in probs.items()}},
+               os.path.join(GOLD, f"motion_score_{name}.pt"))
+
+
 def v2_inputs(spec, bsz=2):
     """Seeded batch of the v2 latent dataset (preprocess_with_motion_prior.py:392-401 keys) for the v2-step fixture."""
     g = torch.Generator().manual_seed(6161)
@@ -702,7 +743,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step", "full_grads"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step", "full_grads", "motion_score"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -721,6 +762,8 @@ if __name__ == "__main__":
             gen_v2_step()
         elif item == "full_grads":
             gen_full_grads()
+        elif item == "motion_score":
+            gen_motion_score()
         elif item == "unet_probs":
             gen_unet_probs()
         elif item.startswith("lora_"):

@@ -216,6 +216,7 @@ SYMBOLS = {
     "t2v_groupnorm_affine_grad": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _f32, _i32, _vp]),
     "t2v_layernorm_affine_grad": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _f32, _vp]),
     "t2v_ema_update": (C.c_int, [_vp, _vp, _i64, _f32, _vp]),
+    "t2v_attn_short_probs_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "t2v_softmax_bwd_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _vp]),
     "t2v_pack_conv_weight": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp]),
     "t2v_pack_geglu_rows": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),

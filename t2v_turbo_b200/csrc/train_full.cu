@@ -225,9 +225,132 @@ __global__ void __launch_bounds__(kThreads) softmax_bwd_rows_kernel(__nv_bfloat1
   }
 }
 
+// ------------------------------------------------------------------------------------------------ temporal attention: d(probs) -> dq, dk
+// The motion-prior score of the v2 preprocessing (motion_prior_sample.py:59-84) differentiates a loss on the temporal attention
+// PROBABILITIES P = softmax(scale q k^T) (exported by t2v_attn_short_fwd) w.r.t. the latents: this is the adjoint of that export,
+//   dS = P * (dP - rowsum(dP * P)),   dq = scale * dS k,   dk = scale * dS^T q          per (sequence, head), len <= 16, head dim 64.
+// One warp per (sequence, head): q, k staged in shared memory as fp32, lane i owns query row i (softmax row in registers), then
+// row i of dq and row i of dk.  Tokens are laid out [(outer, t, inner), heads * 64] like t2v_attn_short_fwd's operands.
+constexpr int kPbWarps = 4;
+constexpr int kPbMaxLen = 16;
+
+struct ProbsBwdParams {
+  const __nv_bfloat16* q; const __nv_bfloat16* k;
+  const float* dp;
+  __nv_bfloat16* dq; __nv_bfloat16* dk;
+  int64_t q_rs, k_rs;                 // row strides (elements) of q / k; dq / dk are contiguous [rows, heads * 64]
+  int32_t n_outer, n_inner, heads, len;
+  float scale;
+};
+
+__global__ void __launch_bounds__(kPbWarps * 32) attn_short_probs_bwd_kernel(const ProbsBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_q[kPbWarps][kPbMaxLen][64];
+  __shared__ float s_k[kPbWarps][kPbMaxLen][64];
+  __shared__ float s_ds[kPbWarps][kPbMaxLen][kPbMaxLen + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_items = int64_t(p.n_outer) * p.n_inner * p.heads;
+  const int t = p.len;
+  const int64_t o_rs = int64_t(p.heads) * 64;
+  for (int64_t item = int64_t(blockIdx.x) * kPbWarps + warp; item < n_items; item += int64_t(gridDim.x) * kPbWarps) {
+    const int head = int(item % p.heads);
+    const int64_t seq = item / p.heads;
+    const int64_t outer = seq / p.n_inner, inner = seq % p.n_inner;
+    // token row of frame r: (outer * len + r) * n_inner + inner
+    for (int r = 0; r < t; ++r) {
+      const int64_t row = (outer * t + r) * p.n_inner + inner;
+      const uint32_t uq = __ldg(reinterpret_cast<const uint32_t*>(p.q + row * p.q_rs + head * 64) + lane);
+      const uint32_t uk = __ldg(reinterpret_cast<const uint32_t*>(p.k + row * p.k_rs + head * 64) + lane);
+      s_q[warp][r][2 * lane] = bf16_lo(uq);
+      s_q[warp][r][2 * lane + 1] = bf16_hi(uq);
+      s_k[warp][r][2 * lane] = bf16_lo(uk);
+      s_k[warp][r][2 * lane + 1] = bf16_hi(uk);
+    }
+    __syncwarp();
+    if (lane < t) {
+      float sc[kPbMaxLen];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kPbMaxLen; ++j) {
+        float a = 0.f;
+        if (j < t) {
+          for (int d = 0; d < 64; ++d) a = fmaf(s_q[warp][lane][d], s_k[warp][j][d], a);
+          a *= p.scale;
+          mx = fmaxf(mx, a);
+        }
+        sc[j] = a;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < kPbMaxLen; ++j) {
+        sc[j] = j < t ? __expf(sc[j] - mx) : 0.f;
+        sum += sc[j];
+      }
+      const float inv = 1.0f / sum;
+      const float* dprow = p.dp + (item * t + lane) * t;
+      float dpv[kPbMaxLen];
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < kPbMaxLen; ++j) {
+        sc[j] *= inv;
+        dpv[j] = j < t ? __ldg(dprow + j) : 0.f;
+        dot = fmaf(dpv[j], sc[j], dot);
+      }
+#pragma unroll
+      for (int j = 0; j < kPbMaxLen; ++j)
+        if (j < t) s_ds[warp][lane][j] = sc[j] * (dpv[j] - dot);
+    }
+    __syncwarp();
+    if (lane < t) {
+      const int64_t row = (outer * t + lane) * p.n_inner + inner;
+      uint32_t* oq = reinterpret_cast<uint32_t*>(p.dq + row * o_rs + head * 64);
+      uint32_t* ok = reinterpret_cast<uint32_t*>(p.dk + row * o_rs + head * 64);
+      for (int d = 0; d < 64; d += 2) {
+        float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f;
+        for (int j = 0; j < t; ++j) {
+          const float a = s_ds[warp][lane][j], b = s_ds[warp][j][lane];
+          q0 = fmaf(a, s_k[warp][j][d], q0);
+          q1 = fmaf(a, s_k[warp][j][d + 1], q1);
+          k0 = fmaf(b, s_q[warp][j][d], k0);
+          k1 = fmaf(b, s_q[warp][j][d + 1], k1);
+        }
+        oq[d >> 1] = pack_bf16(q0 * p.scale, q1 * p.scale);
+        ok[d >> 1] = pack_bf16(k0 * p.scale, k1 * p.scale);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 }  // namespace t2v
+
+extern "C" int t2v_attn_short_probs_bwd(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride, const float* d_probs,
+                                        void* dq, void* dk, int32_t n_outer, int32_t n_inner, int32_t heads, int32_t len, float scale,
+                                        t2v_stream_t s) {
+  using namespace t2v;
+  if (!q || !k || !d_probs || !dq || !dk) return fail(-1, "t2v_attn_short_probs_bwd: null pointer");
+  if (n_outer < 1 || n_inner < 1 || heads < 1 || len < 1 || len > kPbMaxLen)
+    return fail(-2, "t2v_attn_short_probs_bwd: need n_outer, n_inner, heads >= 1 and 1 <= len <= %d (got len %d)", kPbMaxLen, len);
+  if (q_row_stride % 2 || k_row_stride % 2 || q_row_stride < int64_t(heads) * 64 || k_row_stride < int64_t(heads) * 64 ||
+      ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk)) & 3))
+    return fail(-3, "t2v_attn_short_probs_bwd: rows must be 4-byte aligned with strides >= heads * 64");
+  ProbsBwdParams p;
+  p.q = static_cast<const __nv_bfloat16*>(q); p.k = static_cast<const __nv_bfloat16*>(k);
+  p.dp = d_probs;
+  p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk);
+  p.q_rs = q_row_stride; p.k_rs = k_row_stride;
+  p.n_outer = n_outer; p.n_inner = n_inner; p.heads = heads; p.len = len; p.scale = scale;
+  const int64_t n_items = int64_t(n_outer) * n_inner * heads;
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  int64_t g = (n_items + kPbWarps - 1) / kPbWarps;
+  if (g > int64_t(sms) * 8) g = int64_t(sms) * 8;
+  launch_kernel(attn_short_probs_bwd_kernel, dim3(unsigned(g)), dim3(kPbWarps * 32), 0, static_cast<cudaStream_t>(s), p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "t2v_attn_short_probs_bwd launch");
+}
 
 extern "C" int t2v_softmax_bwd_rows(void* dp, int64_t dp_row_stride, const void* p, int64_t p_row_stride, int64_t rows, int32_t cols,
                                     float scale, t2v_stream_t s) {

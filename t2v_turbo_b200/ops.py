@@ -810,6 +810,20 @@ def concat_channels(a, b):
     return out
 
 
+def attention_temporal_probs_bwd(q, k, d_probs, *, b, t, hw, heads, scale):
+    """Adjoint of attention_temporal's `probs` export w.r.t. q / k: q, k [(b t hw), H*64] views (row strides free), d_probs fp32
+    [(b*hw*heads), t, t] -> contiguous (dq, dk).  t <= 16."""
+    rows, inner = q.shape
+    assert rows == b * t * hw and inner == heads * 64 and k.shape == q.shape
+    assert q.is_cuda and q.dtype == BF16 and k.dtype == BF16 and q.stride(1) == 1 and k.stride(1) == 1
+    assert d_probs.dtype == torch.float32 and d_probs.is_contiguous() and tuple(d_probs.shape) == (b * hw * heads, t, t)
+    dq = torch.empty((rows, inner), device=q.device, dtype=BF16)
+    dk = torch.empty((rows, inner), device=q.device, dtype=BF16)
+    _launch("attn_short_probs_bwd", 0, lib().t2v_attn_short_probs_bwd, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), d_probs.data_ptr(),
+            dq.data_ptr(), dk.data_ptr(), b, hw, heads, t, float(scale), stream_ptr())
+    return dq, dk
+
+
 def softmax_bwd_rows_(dp, p, scale=1.0):
     """In place on dp: dS = scale * P * (dP - rowsum(dP * P)) for P = softmax(scale * S) (adjoint of softmax_rows_); bf16 [.., cols]
     contiguous."""

@@ -242,6 +242,15 @@ class StudentUNet:
     def _ln_bwd(self, norm, x, dy, *, dx_add=None):
         return ops.layernorm_bwd(x, dy, norm.w, norm.eps, dx_add=dx_add)
 
+    # temporal attention-probability export and its adjoint (motion_prior.ScoreUNet overrides these; no-ops for the training steps)
+    def _probs_out(self, A, geom):
+        return None
+
+    def _probs_grad(self, A, q, k, dq, dk, geom):
+        return dq, dk
+
+    _want_input_grad = False      # True: backward() also returns d loss / d x (ScoreUNet); the training steps never need it
+
     def _res_struct(self, rb):
         d = dict(gn1=_Norm(rb.in_layers[0]), conv1=self._L(rb.in_layers[2]), emb=self._L(rb.emb_layers[1]),
                  gn2=_Norm(rb.out_layers[0]), conv2=self._L(rb.out_layers[3]), cout=rb.out_channels,
@@ -417,7 +426,7 @@ class StudentUNet:
         v, c["v"] = A["v"].forward(kv_src, tr)
         inner = q.shape[-1]
         if temporal:
-            att = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=heads, scale=scale)
+            att = ops.attention_temporal(q, k, v, b=b, t=t, hw=hw, heads=heads, scale=scale, probs=self._probs_out(A, geom))
             c["att"] = (q, k, v)
         else:
             bt = b * t
@@ -438,6 +447,7 @@ class StudentUNet:
         if temporal:
             q, k, v = c["att"]
             dq, dk, dv = ops.attention_temporal_bwd(q, k, v, d_att, b=b, t=t, hw=hw, heads=A["heads"], scale=A["scale"])
+            dq, dk = self._probs_grad(A, q, k, dq, dk, geom)
         else:
             q3, k3, v3, o3, lse2 = c["att"]
             dq, dk, dv = ops.attention_bwd(q3, k3, v3, o3, d_att.view(*o3.shape), lse2, heads=A["heads"], scale=A["scale"])
@@ -536,8 +546,7 @@ class StudentUNet:
             elif kind == "up":
                 dh = ops.resample2x(S.backward(c, dh), "pool")
             elif kind == "conv_in":
-                S.backward(c, dh, need_dx=False)
-                dh = None
+                dh = S.backward(c, dh, need_dx=self._want_input_grad)
         return dh
 
     # ------------------------------------------------------------------ forward / backward
@@ -623,3 +632,4 @@ class StudentUNet:
             self.on_grads_final(0)
         # release the saved activations
         self._tapes_in = self._tape_mid = self._tapes_out = self._out_ctx = self._emb_ctx = None
+        return dh          # None unless _want_input_grad: then d loss / d x as frames [B*T, H, W, 64] (the first in_channels are real)

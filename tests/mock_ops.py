@@ -267,11 +267,29 @@ def _tattn_f(q, k, v, b, t, hw, heads, scale):
     return o.view(b, hw, t, -1).permute(0, 2, 1, 3).reshape(b * t * hw, -1)
 
 
+def _tprobs_f(q, k, b, t, hw, heads, scale):
+    """softmax(scale q k^T) in the export's layout [(b hw heads), t, t] (the reference's "(b h) i j" with b = pixels)."""
+    def seq(x):
+        return x.float().view(b, t, hw, heads, 64).permute(0, 2, 3, 1, 4).reshape(b * hw * heads, t, 64)
+    return torch.softmax(seq(q) @ seq(k).transpose(1, 2) * scale, -1)
+
+
 def attention_temporal(q, k, v, *, b, t, hw, heads, scale, out=None, probs=None):
-    assert probs is None
     for x in (q, k, v):
         assert x.dtype == ACT and x.dim() == 2 and x.stride(1) == 1 and x.shape == (b * t * hw, heads * 64)
+    if probs is not None:
+        assert probs.is_contiguous() and tuple(probs.shape) == (b * hw * heads, t, t)
+        probs.copy_(_tprobs_f(q, k, b, t, hw, heads, scale).to(probs.dtype))
     return _tattn_f(q, k, v, b, t, hw, heads, scale).to(ACT)
+
+
+def attention_temporal_probs_bwd(q, k, d_probs, *, b, t, hw, heads, scale):
+    assert q.dtype == ACT and k.dtype == ACT and q.stride(1) == 1 and k.stride(1) == 1 and t <= 16
+    assert d_probs.dtype == torch.float32 and d_probs.is_contiguous() and tuple(d_probs.shape) == (b * hw * heads, t, t)
+    qr, kr = q.detach().float().requires_grad_(True), k.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        dq, dk = torch.autograd.grad(_tprobs_f(qr, kr, b, t, hw, heads, scale), (qr, kr), d_probs)
+    return dq.to(ACT).contiguous(), dk.to(ACT).contiguous()
 
 
 def attention_temporal_bwd(q, k, v, d_o, *, b, t, hw, heads, scale):
@@ -496,9 +514,9 @@ def install(monkeypatch, act=torch.float32):
         if name in ("install",):
             continue
         monkeypatch.setattr(ops, name, globals()[name], raising=True)
-    from t2v_turbo_b200 import vae_train
-    for mod in (train_unet, full_train, lora_train, vae_train):
+    from t2v_turbo_b200 import motion_prior, vae_train
+    for mod in (train_unet, full_train, lora_train, vae_train, motion_prior):
         monkeypatch.setattr(mod, "BF16", act)
-    for mod in (train_unet, full_train, vae_train):
+    for mod in (train_unet, full_train, vae_train, motion_prior):
         monkeypatch.setattr(mod, "_require_cuda", lambda what, device: None)
     return ops

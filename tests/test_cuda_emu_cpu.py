@@ -20,7 +20,7 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BF16 = torch.bfloat16
 NAMES = ("t2v_groupnorm_bwd", "t2v_layernorm_bwd", "t2v_colsum_samples", "t2v_geglu", "t2v_resample2x", "t2v_ew2d",
-         "t2v_groupnorm_affine_grad", "t2v_layernorm_affine_grad", "t2v_ema_update", "t2v_softmax_bwd_rows", "t2v_softmax_rows",
+         "t2v_groupnorm_affine_grad", "t2v_layernorm_affine_grad", "t2v_ema_update", "t2v_softmax_bwd_rows", "t2v_softmax_rows", "t2v_attn_short_probs_bwd",
          # elementwise.cu / train_ops.cu (all parity-tested on B200; run here as a CPU regression net over the real kernel source)
          "t2v_lcm_step", "t2v_scale_add_rows", "t2v_dropout_scale", "t2v_scale_mask", "t2v_adamw_step", "t2v_sum_squares",
          "t2v_mse_loss_grad", "t2v_huber_loss_grad", "t2v_video_to_uint8", "t2v_conv3x3_small_cin", "t2v_pack_conv_weight",
@@ -191,6 +191,34 @@ def test_softmax_bwd_rows_kernel_under_emulation(emu, rows, cols):
     torch.softmax(sr * scale, -1).backward(df)
     assert ((ds.float() - sr.grad).norm() / sr.grad.norm()).item() < 2e-2
     assert emu.t2v_softmax_bwd_rows(ds.data_ptr(), cols - 1, p.data_ptr(), cols, rows, cols, scale, None) < 0
+
+
+@pytest.mark.parametrize("b,t,hw,heads,strided", [(2, 4, 6, 2, False), (1, 16, 5, 5, True), (1, 3, 9, 1, False)])
+def test_attn_short_probs_bwd_kernel_under_emulation(emu, b, t, hw, heads, strided):
+    """Adjoint of the temporal attention-probability export w.r.t. q / k (the motion-prior score's path) against autograd of
+    softmax(scale q k^T) in the export's "(b hw heads) i j" layout; q / k also as column slices of a fused projection."""
+    inner = heads * 64
+    rows = b * t * hw
+    if strided:
+        big = rnd(rows, 3 * inner, seed=32).to(BF16)
+        q, k = big[:, :inner], big[:, inner:2 * inner]
+    else:
+        q, k = rnd(rows, inner, seed=33).to(BF16), rnd(rows, inner, seed=34).to(BF16)
+    dp = rnd(b * hw * heads, t, t, seed=35)
+    dq, dk = torch.empty(rows, inner, dtype=BF16), torch.empty(rows, inner, dtype=BF16)
+    scale = 0.125
+    assert emu.t2v_attn_short_probs_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), dp.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                        b, hw, heads, t, scale, None) == 0
+    qr, kr = q.float().clone().requires_grad_(True), k.float().clone().requires_grad_(True)
+
+    def seqs(x):      # [(b t hw), H*64] -> [(b hw H), t, 64]
+        return x.view(b, t, hw, heads, 64).permute(0, 2, 3, 1, 4).reshape(b * hw * heads, t, 64)
+    probs = torch.softmax(seqs(qr) @ seqs(kr).transpose(1, 2) * scale, -1)
+    (probs * dp).sum().backward()
+    close(dq, qr.grad, 8e-3, 4e-3, f"probs_bwd dq b={b} t={t} hw={hw} H={heads}")
+    close(dk, kr.grad, 8e-3, 4e-3, f"probs_bwd dk b={b} t={t} hw={hw} H={heads}")
+    assert emu.t2v_attn_short_probs_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), dp.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                        b, hw, heads, 17, scale, None) < 0
 
 
 @pytest.mark.parametrize("n,offset", [(4096, 0), (100003, 0), (4099, 1), (3, 0), (1, 0)])

@@ -454,3 +454,34 @@ def test_v1_distill_step_vs_reference_composition(monkeypatch):
     assert (ratio - 1).abs().max() < 5e-4, (ratio.min(), ratio.max())
     worst = max(_rel(s.arena.grad(j), sc * t.float()) for j, (sc, t) in g["grads_full"].items())
     assert worst < 2e-3, worst
+
+
+# ----------------------------------------------------------------------------- the motion-prior score (v2 preprocessing)
+def test_motion_prior_score_vs_reference_autograd(monkeypatch):
+    """motion_prior.get_motion_prior_score (ScoreUNet: probabilities exported in the forward, their gradient injected into the temporal
+    attention adjoints, input gradient through conv_in) == the UNMODIFIED reference's `torch.autograd.grad(loss, latents)` with its own
+    compute_temp_loss (tests/golden/motion_score_small.pt)."""
+    mock_ops.install(monkeypatch)
+    from oracle.weights import seeded_state_dict
+    from oracle.configs import UNET_CONFIGS
+    from t2v_turbo_b200.motion_prior import ScoreUNet, get_motion_prior_score, temp_loss_and_grad
+    from t2v_turbo_b200.unet import UNetModel
+    g = torch.load(os.path.join(GOLD, "motion_score_small.pt"))
+    m = UNetModel(**g["cfg"])
+    m.load_state_dict(seeded_state_dict(m.state_dict(), UNET_CONFIGS["small"]["weight_seed"]), strict=True)
+    view = ScoreUNet(m.eval())
+    assert view.probe_names == g["layers"]
+    view.pack()
+    score, eps = get_motion_prior_score(view, g["latents"], g["ts"], g["example"], {"context": g["ctx_orig"], "fps": 16},
+                                        {"context": g["ctx_inf"], "fps": 16}, g["temp_loss_scale"])
+    assert _rel(eps, g["cond_teacher_output"]) < 1e-4
+    assert score.shape == g["score"].shape and _rel(score, g["score"]) < 2e-4, _rel(score, g["score"])
+    # the exported probabilities and the loss value
+    _, probs = view(g["latents"], g["ts"], context=g["ctx_inf"], fps=16)
+    view.detach_tapes()
+    for n in g["layers"]:
+        assert (probs[n] - g["probs"][n].float()).abs().max() < 1e-3           # fixture keeps them in fp16
+    _, pe = view(g["example"], g["ts"], context=g["ctx_orig"], fps=16)
+    view.detach_tapes()
+    loss, _ = temp_loss_and_grad(probs, pe, g["temp_loss_scale"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])

@@ -296,3 +296,40 @@ def test_decoder_grad_vs_oracle_autograd(cuda_device):
     e_img, e_g = _rel(img.detach(), ref.detach()), _rel(z1.grad, z2.grad)
     print(f"\n[decoder grad small] image rel-L2 {e_img:.3e}, latent-gradient rel-L2 {e_g:.3e}")
     assert e_img < 2.0e-2 and e_g < 4.0e-2, (e_img, e_g)
+
+
+# ----------------------------------------------------------------------------- the motion-prior score (never run on a GPU)
+@never_run
+@pytest.mark.parametrize("b,t,hw,heads", [(2, 4, 64, 2), (1, 16, 160, 5)])
+def test_attention_temporal_probs_bwd(cuda_device, b, t, hw, heads):
+    ops = _ops()
+    inner = heads * 64
+    qkv = rnd(b * t * hw, 3 * inner, seed=32).to(BF16)
+    q, k = qkv[:, :inner], qkv[:, inner:2 * inner]                      # views of a fused projection
+    dp = rnd(b * hw * heads, t, t, seed=35)
+    dq, dk = ops.attention_temporal_probs_bwd(q, k, dp, b=b, t=t, hw=hw, heads=heads, scale=0.125)
+    rq, rk = _mock().attention_temporal_probs_bwd(q.float().cpu().contiguous(), k.float().cpu().contiguous(), dp.cpu(), b=b, t=t, hw=hw,
+                                                   heads=heads, scale=0.125)
+    assert_close(dq.cpu(), rq, what=f"probs_bwd dq b={b} t={t} hw={hw} H={heads}")
+    assert_close(dk.cpu(), rk, what=f"probs_bwd dk b={b} t={t} hw={hw} H={heads}")
+
+
+@never_run
+def test_motion_prior_score_vs_reference(cuda_device):
+    """get_motion_prior_score on B200 vs the unmodified reference's autograd (fp32 fixture).  The score is a gradient through ~40 bf16
+    layers of a loss on softmax outputs; bound: 2x the student-gradient yardstick (worst 6e-2), never observed."""
+    from oracle.configs import UNET_CONFIGS
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200.motion_prior import ScoreUNet, get_motion_prior_score
+    from t2v_turbo_b200.unet import UNetModel
+    g = torch.load(os.path.join(GOLD, "motion_score_small.pt"))
+    m = UNetModel(**g["cfg"])
+    m.load_state_dict(seeded_state_dict(m.state_dict(), UNET_CONFIGS["small"]["weight_seed"]), strict=True)
+    view = ScoreUNet(m.cuda().eval())
+    view.pack()
+    score, eps = get_motion_prior_score(view, g["latents"].cuda(), g["ts"].cuda(), g["example"].cuda(), {"context": g["ctx_orig"].cuda(), "fps": 16},
+                                        {"context": g["ctx_inf"].cuda(), "fps": 16}, g["temp_loss_scale"])
+    torch.cuda.synchronize()
+    e_eps, e_s = _rel(eps, g["cond_teacher_output"]), _rel(score, g["score"])
+    print(f"\n[motion score small] eps rel-L2 {e_eps:.3e}, score rel-L2 {e_s:.3e}")
+    assert e_eps < 3e-2 and e_s < 1.2e-1, (e_eps, e_s)
