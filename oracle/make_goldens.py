@@ -430,6 +430,57 @@ def gen_motion_score(name="small"):
                os.path.join(GOLD, f"motion_score_{name}.pt"))
 
 
+def gen_preprocess_sample(name="small"):
+    """preprocess_scripts/preprocess_with_motion_prior.py:326-401 for one video, composed from the UNMODIFIED reference pieces: the teacher
+    UNet (record_attn_probs=True), T2VTurboScheduler.add_noise, DDIMSolver.ddim_reverse_step in the script's reverse_ddim_loop, the
+    unconditional forward, get_motion_prior_score restated as in gen_motion_score — fp32; the record as the script pickles it (before
+    the fp16 cast)."""
+    from lvdm.modules.networks.openaimodel3d import UNetModel
+    from ode_solver.ddim_solver import DDIMSolver
+    from scheduler.t2v_turbo_scheduler import T2VTurboScheduler
+    from utils.common_utils import compute_temp_loss
+    spec = UNET_CONFIGS[name]
+    cfg = {**spec["cfg"], "time_cond_proj_dim": None, "record_attn_probs": True}
+    m = UNetModel(**cfg).eval()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), spec["weight_seed"]), strict=True)
+    m.requires_grad_(False)
+    ns = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
+    solver = DDIMSolver(ns.alphas_cumprod.numpy(), ddim_timesteps=50, use_scale=False)
+    g = torch.Generator().manual_seed(8181)
+    shape = spec["x_shape"]
+    cd = spec["cfg"]["context_dim"]
+    latents, noise = torch.randn(shape, generator=g) * 0.8, torch.randn(shape, generator=g)
+    prompt, uncond = torch.randn(1, spec["ctx_len"], cd, generator=g), torch.randn(1, spec["ctx_len"], cd, generator=g) * 0.5
+    index = torch.tensor([2])
+    temp_loss_scale, fps = 20.0, 16
+    context, uncond_context = {"context": prompt, "fps": fps}, {"context": uncond, "fps": fps}
+
+    def probs_of(unet):
+        return {n: mod.attention_probs for n, mod in unet.named_modules() if n.endswith("blocks.0.attn1") and getattr(mod, "record_attn_probs", False)}
+    with torch.no_grad():
+        start_timesteps = solver.ddim_timesteps[index]
+        z_ts = ns.add_noise(latents, noise, start_timesteps)
+        inter, cur = [], latents
+        for i in range(index.item() + 1):                       # reverse_ddim_loop, motion_prior_sample.py:27-37
+            ts = solver.ddim_timesteps[torch.full((1,), i, dtype=torch.long)].long()
+            cur = solver.ddim_reverse_step(cur, m(cur, ts, **context), ts)
+            inter.append(cur)
+        z_examples, z_examples_prev = inter[-1], (inter[-2] if index.item() > 0 else latents)
+        uncond_teacher_output = m(z_ts, start_timesteps, **uncond_context)
+        m(z_examples, start_timesteps, **context)
+        probs_example = {k: v.clone() for k, v in probs_of(m).items()}
+    with torch.set_grad_enabled(True):
+        z = z_ts.clone().requires_grad_(True)
+        cond_teacher_output = m(z, start_timesteps, **context)
+        loss = temp_loss_scale * compute_temp_loss(probs_of(m), probs_example)
+        scores = torch.autograd.grad(loss, z)[0].detach()
+    print(f"  preprocess sample {name}: index {index.item()}, t {start_timesteps.tolist()}, loss {loss.item():.5f}, score std {scores.std():.4e}")
+    rec = dict(index=index[0], z_t=z_ts[0], cond_teacher_out=cond_teacher_output.detach()[0], uncond_teacher_out=uncond_teacher_output[0],
+               score=scores[0], z_example=z_examples[0], z_example_prev=z_examples_prev[0], prompt_emb=prompt[0])
+    torch.save({"name": name, "cfg": cfg, "latents": latents, "noise": noise, "prompt": prompt, "uncond": uncond, "temp_loss_scale": temp_loss_scale,
+                "record": rec}, os.path.join(GOLD, f"preprocess_sample_{name}.pt"))
+
+
 def v2_inputs(spec, bsz=2):
     """Seeded batch of the v2 latent dataset (preprocess_with_motion_prior.py:392-401 keys) for the v2-step fixture."""
     g = torch.Generator().manual_seed(6161)
@@ -743,7 +794,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step", "full_grads", "motion_score"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step", "full_grads", "motion_score", "preprocess_sample"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -764,6 +815,8 @@ if __name__ == "__main__":
             gen_full_grads()
         elif item == "motion_score":
             gen_motion_score()
+        elif item == "preprocess_sample":
+            gen_preprocess_sample()
         elif item == "unet_probs":
             gen_unet_probs()
         elif item.startswith("lora_"):

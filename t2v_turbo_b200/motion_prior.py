@@ -214,3 +214,40 @@ def get_motion_prior_score(view: ScoreUNet, latents, ts, example_latent, origina
     _, d_probs = temp_loss_and_grad(probs, probs_example, temp_loss_scale)
     score = view.backward(d_probs)
     return score.to(latents.dtype), cond_teacher_output
+
+
+def reverse_ddim_loop(unet_fn, latents, context, solver, num_inference_steps):
+    """motion_prior_sample.py:27-37: DDIM inversion of a clean latent, one step per solver timestep; returns every intermediate latent.
+    unet_fn(latents, ts, **context) -> eps (no grad: the fused inference `UNetModel`, or a ScoreUNet's forward)."""
+    out = []
+    for i in range(num_inference_steps):
+        ts = solver.ddim_timesteps[torch.tensor([i])].long()
+        eps = unet_fn(latents, ts.to(latents.device), **context)
+        latents = solver.ddim_reverse_step(latents, eps.to(latents.dtype), ts)
+        out.append(latents)
+    return out
+
+
+def preprocess_sample(view: ScoreUNet, scheduler, solver, latents, prompt_emb, uncond_emb, *, index, noise, temp_loss_scale, fps=16,
+                      unet_fn=None):
+    """The device work of preprocess_scripts/preprocess_with_motion_prior.py:326-401 for ONE video (the script's batch size): from the
+    scaled VAE latent [1, C, T, h, w] and the text embeddings to the record of the v2 latent dataset — z_t = add_noise(latents, noise,
+    t), the DDIM-inverted example latents (index + 1 teacher forwards), the unconditional teacher output, and the motion-prior score with
+    the conditional teacher output — ready for `formats.dumps_v2_sample(**record)`.  unet_fn: optional faster no-grad forward (the fused
+    inference UNetModel of the same weights); default: the ScoreUNet's own forward."""
+    if unet_fn is None:
+        def unet_fn(x, ts, **ctx):
+            y, _ = view(x, ts, **ctx)
+            view.detach_tapes()
+            return y
+    index = torch.as_tensor(index).reshape(1).long()
+    start_t = solver.ddim_timesteps[index.cpu()]
+    ctx = {"context": prompt_emb, "fps": fps}
+    z_t = scheduler.add_noise(latents, noise, start_t.to(latents.device))                          # :341-343
+    inter = reverse_ddim_loop(unet_fn, latents, ctx, solver, int(index.item()) + 1)                # :346-353
+    z_example = inter[-1]
+    z_example_prev = inter[-2] if int(index.item()) > 0 else latents
+    uncond_out = unet_fn(z_t, start_t.to(latents.device), context=uncond_emb, fps=fps)             # :355
+    score, cond_out = get_motion_prior_score(view, z_t, start_t.to(latents.device), z_example, ctx, ctx, temp_loss_scale)   # :358-368
+    return dict(index=index[0], z_t=z_t[0], cond_teacher_out=cond_out[0], uncond_teacher_out=uncond_out[0], score=score[0],
+                z_example=z_example[0], z_example_prev=z_example_prev[0], prompt_emb=prompt_emb[0])

@@ -485,3 +485,39 @@ def test_motion_prior_score_vs_reference_autograd(monkeypatch):
     view.detach_tapes()
     loss, _ = temp_loss_and_grad(probs, pe, g["temp_loss_scale"])
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])
+
+
+def test_preprocess_sample_vs_reference_composition(monkeypatch):
+    """motion_prior.preprocess_sample — add_noise, the DDIM inversion loop (index + 1 teacher forwards), the unconditional teacher output,
+    the motion-prior score — == preprocess_with_motion_prior.py:326-401 composed from the UNMODIFIED reference's pieces, and the record
+    survives the latent dataset's wire format (formats.dumps_v2_sample / loads_v2_sample, fp16)."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import UNET_CONFIGS
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200 import formats
+    from t2v_turbo_b200.distill import DDIMSolver
+    from t2v_turbo_b200.motion_prior import ScoreUNet, preprocess_sample
+    from t2v_turbo_b200.scheduler import T2VTurboScheduler
+    from t2v_turbo_b200.unet import UNetModel
+    g = torch.load(os.path.join(GOLD, "preprocess_sample_small.pt"))
+    m = UNetModel(**g["cfg"])
+    m.load_state_dict(seeded_state_dict(m.state_dict(), UNET_CONFIGS["small"]["weight_seed"]), strict=True)
+    view = ScoreUNet(m.eval())
+    view.pack()
+    sch = T2VTurboScheduler(linear_start=0.00085, linear_end=0.012)
+    solver = DDIMSolver(sch.alphas_cumprod.numpy(), ddim_timesteps=50)
+    ref = g["record"]
+
+    class _AddNoise:          # T2VTurboScheduler.add_noise refuses CPU tensors (its kernel is GPU-only and GPU-tested): closed form here
+        @staticmethod
+        def add_noise(x, n, t):
+            a = sch.alphas_cumprod[t.cpu()].view(-1, 1, 1, 1, 1)
+            return a.sqrt() * x + (1 - a).sqrt() * n
+    rec = preprocess_sample(view, _AddNoise, solver, g["latents"], g["prompt"], g["uncond"], index=ref["index"], noise=g["noise"],
+                            temp_loss_scale=g["temp_loss_scale"])
+    assert set(rec) == set(formats.V2_SAMPLE_KEYS) and int(rec["index"]) == int(ref["index"])
+    for k in formats.V2_SAMPLE_KEYS:
+        if k != "index":
+            assert _rel(rec[k], ref[k]) < 3e-4, (k, _rel(rec[k], ref[k]))
+    back = formats.loads_v2_sample(formats.dumps_v2_sample(**rec), frames=g["latents"].shape[2])
+    assert _rel(back["score"].float(), ref["score"]) < 2e-3 and back["z_t"].dtype == torch.float16
