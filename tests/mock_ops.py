@@ -509,7 +509,7 @@ def install(monkeypatch, act=torch.float32):
     """Patch the restatements over t2v_turbo_b200.ops and the activation dtype over the training modules."""
     global ACT
     ACT = act
-    from t2v_turbo_b200 import distill, full_train, lora_train, ops, train_unet
+    from t2v_turbo_b200 import full_train, lora_train, ops, train_unet
     for name in ALL:
         if name in ("install",):
             continue

@@ -10,7 +10,6 @@ noise.  What this does not cover — that each CUDA kernel meets the contract re
 """
 import os
 
-import pytest
 import torch
 
 import mock_ops
