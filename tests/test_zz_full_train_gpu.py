@@ -173,6 +173,25 @@ def test_v2_step_vs_reference_composition(cuda_device):
     assert (ratio - 1).abs().max() < 0.25 and rels[wn] < 0.45, (ratio.min(), ratio.max(), wn, rels[wn])
 
 
+def test_v2_step_self_target_and_second_step(cuda_device):
+    from t2v_turbo_b200.distill_v2 import train_step_v2
+    g, s, step, _ = _setup(with_ema=False)
+    inp = g["inputs"]
+    batch = {k: inp[k].cuda() for k in ("index", "z_t", "cond_teacher_out", "uncond_teacher_out", "score", "prompt_emb")}
+    s.arena.zero_grad()
+    out = step(batch, fixed=dict(w=inp["w"]))
+    assert _rel(out["target"], g["target_self"]) < 3e-2
+    assert abs(float(out["loss"]) - float(g["loss_self_target"])) < 3e-2 * float(g["loss_self_target"])
+    s.train()                                        # dropouts on: finite gradients, and a step changes the prediction
+    out1 = train_step_v2(step, batch, lr=1e-4, fixed=dict(w=inp["w"]))
+    assert torch.isfinite(s.arena.grads).all() and float(s.arena.grad_norm()) > 0
+    s.eval()
+    s.arena.zero_grad()
+    out2 = step(batch, fixed=dict(w=inp["w"]))
+    assert _rel(out2["model_pred"], out["model_pred"]) > 1e-5, "the optimizer step did not change the student's prediction"
+    assert torch.isfinite(out1["loss"]).all()
+
+
 @never_run
 def test_v2_step_clip_optimizer_and_ema(cuda_device):
     g, s, out, p0 = _run_reference_step()
@@ -227,25 +246,6 @@ def test_full_unet_backward_vs_reference_autograd_linear_loss(cuda_device):
     assert e_y <= 1.15 * rb["output_rel"], (e_y, rb["output_rel"])
     assert (ratio - 1).abs().max() < 3e-2, (ratio.min(), ratio.max())
     assert rels[wn] <= 1.3 * rb["grad_rel_worst"] and total <= 1.15 * rb["grad_rel_concat"], (wn, rels[wn], total)
-
-
-def test_v2_step_self_target_and_second_step(cuda_device):
-    from t2v_turbo_b200.distill_v2 import train_step_v2
-    g, s, step, _ = _setup(with_ema=False)
-    inp = g["inputs"]
-    batch = {k: inp[k].cuda() for k in ("index", "z_t", "cond_teacher_out", "uncond_teacher_out", "score", "prompt_emb")}
-    s.arena.zero_grad()
-    out = step(batch, fixed=dict(w=inp["w"]))
-    assert _rel(out["target"], g["target_self"]) < 3e-2
-    assert abs(float(out["loss"]) - float(g["loss_self_target"])) < 3e-2 * float(g["loss_self_target"])
-    s.train()                                        # dropouts on: finite gradients, and a step changes the prediction
-    out1 = train_step_v2(step, batch, lr=1e-4, fixed=dict(w=inp["w"]))
-    assert torch.isfinite(s.arena.grads).all() and float(s.arena.grad_norm()) > 0
-    s.eval()
-    s.arena.zero_grad()
-    out2 = step(batch, fixed=dict(w=inp["w"]))
-    assert _rel(out2["model_pred"], out["model_pred"]) > 1e-5, "the optimizer step did not change the student's prediction"
-    assert torch.isfinite(out1["loss"]).all()
 
 
 # ----------------------------------------------------------------------------- vae.decode WITH grad (never run on a GPU)
