@@ -144,7 +144,11 @@ class FullArena:
 
     def adamw_step(self, *, lr, temporal_lr_scale=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0, max_grad_norm=None):
         """torch.optim.AdamW over the two groups of :829-840 (lr, lr * temporal_lr_scale), one fused launch per contiguous run of a
-        group; clip_grad_norm_ over ALL parameters first (:1267), the clip factor and the data-parallel mean folded into grad_scale."""
+        group; clip_grad_norm_ over ALL parameters first (:1267), the clip factor and the data-parallel mean folded into grad_scale.
+        One deliberate difference from torch: a parameter that received NO gradient in a step (torch: `.grad is None`, skipped) is
+        stepped here with a zero gradient — its moments decay and, if weight_decay > 0, it is decayed.  That only concerns
+        motion_cond_proj / combine_proj when a motion-conditioned model is trained with use_motion_cond off; the v2 script's default
+        weight decay is 0."""
         if max_grad_norm is not None:
             total = float(self.grad_norm(grad_scale))
             grad_scale = grad_scale * min(1.0, max_grad_norm / (total + 1e-6))

@@ -270,4 +270,6 @@ def reward_gradient(vae, model_pred, reward_fn, *, frame_idx, batch_idx=None, va
         imgs = imgs.reshape(nb, nf, *imgs.shape[1:])
     loss = -reward_fn(imgs).mean() * reward_scale
     loss.backward()
+    if mp.grad is None:
+        raise RuntimeError("reward_gradient: reward_fn's result does not depend on the decoded images")
     return loss.detach(), mp.grad
