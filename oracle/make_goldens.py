@@ -181,13 +181,15 @@ def gen_lora_layers():
     torch.save(out, os.path.join(GOLD, "lora_layers.pt"))
 
 
-def gen_student_grads(name="small"):
+def gen_student_grads(name="small", every=5, x_shape=None, with_bf16=True):
     """The student forward + backward of train_t2v_turbo_v1_lora.py:640-656,1040-1048,1190 on the UNMODIFIED reference: the UNet
     with LoRA injected by the reference's own `inject_trainable_lora_extended` (r = 64, target {"UNetModel"}), seeded LoRA
     weights (both up and down non-zero so every gradient is exercised), eval mode (all dropouts off: deterministic), fp32.
     loss = sum(eps_pred * g) for a seeded g.  Stores the LoRA list (wire order), g, the output and every LoRA gradient."""
     from utils.lora import extract_lora_ups_down, inject_trainable_lora_extended
-    spec = UNET_CONFIGS[name]
+    spec = dict(UNET_CONFIGS[name])
+    if x_shape is not None:
+        spec["x_shape"] = x_shape
     m = ref_unet(spec["cfg"], spec["weight_seed"])
     m.requires_grad_(False)
     params, _ = inject_trainable_lora_extended(m, target_replace_module={"UNetModel"}, r=64)
@@ -234,7 +236,7 @@ def gen_student_grads(name="small"):
     # the fixture keeps every norm and, to stay small, the full tensors of a fixed subset of layers (first / last three and
     # every fifth), each as fp16 scaled by its max (5e-4 of the tensor's scale: far below the parity tolerance)
     n_layers = len(grads) // 2
-    keep = sorted(set(range(3)) | set(range(n_layers - 3, n_layers)) | set(range(0, n_layers, 5)))
+    keep = sorted(set(range(3)) | set(range(n_layers - 3, n_layers)) | set(range(0, n_layers, every)))
     full = {}
     for li in keep:
         for j in (2 * li, 2 * li + 1):
@@ -242,8 +244,9 @@ def gen_student_grads(name="small"):
             full[j] = (sc, (grads[j] / sc).half())
     print(f"  student grads {name}: {n_layers} LoRA layers, out std {y.std():.4f}, grad norm {norms.pow(2).sum().sqrt():.4f}, "
           f"{len(keep)} layers stored in full")
-    torch.save({"name": name, "timestep": spec["timesteps"][0], "shapes": shapes, "d_out": d_out, "output": y.detach().clone(),
-                "grad_norms": norms, "grads_full": full, "ref_bf16": ref_bf16}, os.path.join(GOLD, f"student_grads_{name}.pt"))
+    torch.save({"name": name, "timestep": spec["timesteps"][0], "x_shape": tuple(spec["x_shape"]), "shapes": shapes, "d_out": d_out,
+                "output": y.detach().clone(), "grad_norms": norms, "grads_full": full, "ref_bf16": ref_bf16},
+               os.path.join(GOLD, f"student_grads_{name}.pt"))
 
 
 def distill_inputs(spec, bsz=2):
@@ -794,7 +797,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step", "full_grads", "motion_score", "preprocess_sample"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
+    todo = a.only.split(",") if a.only else ["scheduler", "unet_small", "unet_mid", "vae_small", "vae_enc_small", "lora_small", "pipeline", "unet_small_motion", "pipeline_v2", "lora_layers", "unet_probs", "student_grads", "distill_step", "distill_tables", "v2_step", "full_grads", "motion_score", "preprocess_sample", "student_grads_mid"] + (["unet_full", "vae_full", "vae_enc_full", "unet_full_t", "unet_full_b2"] if a.full else [])
     for item in todo:
         print("generating", item)
         if item == "scheduler":
@@ -805,6 +808,8 @@ if __name__ == "__main__":
             gen_lora_layers()
         elif item == "student_grads":
             gen_student_grads()
+        elif item == "student_grads_mid":      # the full VC2 topology (575 LoRA layers) at 128 base channels, a small latent
+            gen_student_grads("mid", every=40, x_shape=(1, 4, 8, 16, 16))
         elif item == "distill_step":
             gen_distill_step()
         elif item == "distill_tables":

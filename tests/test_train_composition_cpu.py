@@ -56,6 +56,32 @@ def test_student_unet_composition_vs_reference_lora_gradients(monkeypatch):
     assert worst < 1e-3, worst          # the fixture keeps these tensors as fp16 scaled by their max
 
 
+def test_student_unet_vc2_topology_vs_reference_lora_gradients(monkeypatch):
+    """The same on the FULL VC2 topology (all 575 LoRA layers incl. the rank-4 conv_in / out, every level's stride-2 and upsampling
+    convs, head counts 2/4/8/8) at 128 base channels: all 1150 LoRA gradient norms and 20 layers in full against the unmodified
+    reference's autograd (tests/golden/student_grads_mid.pt)."""
+    mock_ops.install(monkeypatch)
+    from oracle.configs import student_loras, unet_inputs
+    from t2v_turbo_b200.train_unet import StudentUNet
+    g = torch.load(os.path.join(GOLD, "student_grads_mid.pt"))
+    spec, m, _ = _unet("mid")
+    spec = {**spec, "x_shape": tuple(g["x_shape"])}
+    s = StudentUNet(m, r=64, dropout_p=0.1, scale=1.0).eval()
+    assert [tuple(x) for x in g["shapes"]] == s.arena.shapes and len(s.arena.shapes) == 2 * 575
+    s.arena.load_list(student_loras(g["shapes"]))
+    s.pack()
+    inp = unet_inputs(spec, g["timestep"])
+    y = s(inp["x"], inp["timesteps"], context=inp["context"], fps=16, timestep_cond=inp["timestep_cond"])
+    assert _rel(y, g["output"]) < 1e-4
+    s.arena.zero_grad()
+    s.backward(g["d_out"])
+    n = len(s.arena.shapes)
+    ratio = torch.tensor([s.arena.grad(i).double().norm().item() / max(g["grad_norms"][i].item(), 1e-30) for i in range(n)])
+    assert (ratio - 1).abs().max() < 2e-4, (ratio.min(), ratio.max())
+    worst = max(_rel(s.arena.grad(j), sc * t.float()) for j, (sc, t) in g["grads_full"].items())
+    assert worst < 1e-3, worst
+
+
 def test_param_groups_match_the_reference_rule():
     """full_train.param_groups == train_latent_t2v_turbo_v2.py:799-815 executed on the reference's own module tree (fixture)."""
     from t2v_turbo_b200.full_train import param_groups

@@ -333,3 +333,37 @@ def test_motion_prior_score_vs_reference(cuda_device):
     e_eps, e_s = _rel(eps, g["cond_teacher_output"]), _rel(score, g["score"])
     print(f"\n[motion score small] eps rel-L2 {e_eps:.3e}, score rel-L2 {e_s:.3e}")
     assert e_eps < 3e-2 and e_s < 1.2e-1, (e_eps, e_s)
+
+
+@never_run
+def test_student_unet_vc2_topology_vs_reference_lora_gradients(cuda_device):
+    """The v1 student on the FULL VC2 topology at 128 base channels (575 LoRA layers; 2x2-pixel frames at the deepest level — GEMM
+    geometries no other GPU test reaches) against the unmodified reference's autograd, yardstick = the reference's own bf16 backward
+    (stored in the fixture: median 4.8e-2 / worst 7.6e-2 / concatenated 4.2e-2).  The same comparison passes on CPU at 2e-4
+    (tests/test_train_composition_cpu.py); never run on a GPU."""
+    from oracle.configs import UNET_CONFIGS, student_loras, unet_inputs
+    from oracle.weights import seeded_state_dict
+    from t2v_turbo_b200.train_unet import StudentUNet
+    from t2v_turbo_b200.unet import UNetModel
+    g = torch.load(os.path.join(GOLD, "student_grads_mid.pt"))
+    spec = {**UNET_CONFIGS["mid"], "x_shape": tuple(g["x_shape"])}
+    m = UNetModel(**spec["cfg"])
+    m.load_state_dict(seeded_state_dict(m.state_dict(), spec["weight_seed"]), strict=True)
+    s = StudentUNet(m.cuda().eval(), r=64).eval()
+    s.arena.load_list(student_loras(g["shapes"]))
+    s.pack()
+    inp = unet_inputs(spec, g["timestep"])
+    y = s(inp["x"].cuda(), inp["timesteps"].cuda(), context=inp["context"].cuda(), fps=16, timestep_cond=inp["timestep_cond"].cuda())
+    e_y = _rel(y, g["output"])
+    s.arena.zero_grad()
+    s.backward(g["d_out"].cuda())
+    torch.cuda.synchronize()
+    n = len(s.arena.shapes)
+    ratio = torch.tensor([s.arena.grad(i).double().norm().item() / max(g["grad_norms"][i].item(), 1e-30) for i in range(n)])
+    rels = {j: _rel(s.arena.grad(j), sc * t.float()) for j, (sc, t) in g["grads_full"].items()}
+    total = _rel(torch.cat([s.arena.grad(j).flatten() for j in rels]), torch.cat([(sc * t.float()).flatten() for sc, t in g["grads_full"].values()]))
+    rb = g["ref_bf16"]
+    print(f"\n[student mid] forward {e_y:.3e}; grad-norm ratio {ratio.min():.4f} .. {ratio.max():.4f}; stored tensors worst {max(rels.values()):.3e} "
+          f"concatenated {total:.3e}; reference bf16: {rb}")
+    assert e_y <= 1.15 * rb["output_rel"] and (ratio - 1).abs().max() < 3e-2
+    assert max(rels.values()) <= 1.3 * rb["grad_rel_worst"] and total <= 1.15 * rb["grad_rel_concat"]
