@@ -470,7 +470,7 @@ def run_v2_step(args, rank, local_rank, world):
     import torch
     from t2v_turbo_b200 import dist as t2v_dist, ops
     from t2v_turbo_b200.configs import VC2_UNET
-    from t2v_turbo_b200.distill_v2 import V2Step, train_step_v2
+    from t2v_turbo_b200.distill_v2 import V2Step, attach_ema_target, train_step_v2
     from t2v_turbo_b200.full_train import FullUNet
     from t2v_turbo_b200.scheduler import T2VTurboScheduler
     from t2v_turbo_b200.unet import UNetModel
@@ -487,10 +487,7 @@ def run_v2_step(args, rank, local_rank, world):
                 prm.normal_(0, 0.02)
     student = FullUNet(base.eval(), with_target=True).train()
     student.pack()
-    student.arena.bind(target, student.arena.target)
-    target = target.eval()
-    target.dtype = torch.bfloat16
-    target.invalidate_packed()
+    target = attach_ema_target(student, target)
     red = t2v_dist.ArenaReducer(student.arena.grads, n_buckets=16)
     step = V2Step(student, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012), target_unet=target)
     g = torch.Generator(device=device).manual_seed(99 + rank)

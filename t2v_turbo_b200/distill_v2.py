@@ -125,6 +125,20 @@ class V2Step:
         return out
 
 
+def attach_ema_target(student, target_unet, dtype=torch.bfloat16):
+    """Make `target_unet` (a fresh `UNetModel` of the student's configuration, on the student's device) the EMA network of a
+    `FullUNet(..., with_target=True)` (train_latent_t2v_turbo_v2.py:733-746): its parameters become views of the student's target arena —
+    which starts as a copy of the student's weights and is advanced by `arena.ema_step` —, it runs the fused inference forward in
+    `dtype`, and its packed weights are dropped so that the next forward re-packs from the arena."""
+    if student.arena.target is None:
+        raise RuntimeError("attach_ema_target: build the student with FullUNet(unet, with_target=True)")
+    student.arena.bind(target_unet, student.arena.target)
+    target_unet.eval()
+    target_unet.dtype = dtype
+    target_unet.invalidate_packed()
+    return target_unet
+
+
 def train_step_v2(step: V2Step, batch, *, lr, temporal_lr_scale=1.0, ema_decay=0.95, reducer=None, world=1, max_grad_norm=1.0,
                   weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, **kw):
     """zero_grad -> V2Step -> (bucketed NCCL all-reduce of the 5.65 GB gradient arena) -> clip_grad_norm_ + AdamW over the two

@@ -10,6 +10,7 @@ noise.  What this does not cover — that each CUDA kernel meets the contract re
 """
 import os
 
+import pytest
 import torch
 
 import mock_ops
@@ -324,6 +325,28 @@ def test_v2_resume_reproduces_the_next_step(monkeypatch):
     for a_, b_ in ((s1.arena.params, s2.arena.params), (s1.arena.exp_avg, s2.arena.exp_avg), (s1.arena.exp_avg_sq, s2.arena.exp_avg_sq),
                    (s1.arena.target, s2.arena.target)):
         assert torch.equal(a_, b_)
+
+
+def test_attach_ema_target_aliases_the_target_arena(monkeypatch):
+    """The EMA network's nn.Parameters are views of arena.target: an `ema_step` changes what its next forward packs, its state_dict()
+    is the EMA checkpoint, and nothing aliases the student's live parameters."""
+    mock_ops.install(monkeypatch)
+    from t2v_turbo_b200.distill_v2 import attach_ema_target
+    from t2v_turbo_b200.full_train import FullUNet
+    from t2v_turbo_b200.unet import UNetModel
+    spec, m, sd = _unet("small_motion")
+    s = FullUNet(m, with_target=True)
+    t = attach_ema_target(s, UNetModel(**spec["cfg"]))
+    assert t.dtype == torch.bfloat16 and not t.training
+    a = s.arena
+    for n, p in t.named_parameters():
+        assert p.data_ptr() == a.view(a.target, a.index[n]).data_ptr() and torch.equal(p, sd[n])
+    a.params.add_(1.0)
+    a.ema_step(0.75)
+    n0 = a.names[5]
+    assert torch.allclose(dict(t.named_parameters())[n0], sd[n0] + 0.25) and torch.allclose(t.state_dict()[n0], sd[n0] + 0.25)
+    with pytest.raises(RuntimeError):
+        attach_ema_target(FullUNet(_unet("small_motion")[1]), UNetModel(**spec["cfg"]))
 
 
 def test_v2_host_draws_motion_condition():

@@ -142,9 +142,8 @@ def _setup(with_ema=True):
             s.arena.view(s.arena.target, s.arena.index[n]).copy_(sd[n] * (1.0 + 0.02 * torch.randn(p.shape, generator=gq)))
         target = UNetModel(**spec["cfg"])
         target.load_state_dict(sd, strict=True)
-        target = target.cuda().eval()
-        s.arena.bind(target, s.arena.target)           # the EMA network's parameters ARE the target arena
-        target.invalidate_packed()
+        from t2v_turbo_b200.distill_v2 import attach_ema_target
+        target = attach_ema_target(s, target.cuda(), dtype=torch.float32)     # the EMA network's parameters ARE the target arena
     h = g["hyper"]
     step = V2Step(s, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012), target_unet=target, num_ddim_timesteps=h["n_ddim"],
                   topk=h["topk"], motion_gs=h["motion_gs"], percentage=h["percentage"], use_motion_cond=True,
