@@ -140,18 +140,25 @@ def attach_ema_target(student, target_unet, dtype=torch.bfloat16):
 
 
 def train_step_v2(step: V2Step, batch, *, lr, temporal_lr_scale=1.0, ema_decay=0.95, reducer=None, world=1, max_grad_norm=1.0,
-                  weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, **kw):
+                  weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, accumulate=False, grad_scale=1.0, **kw):
     """zero_grad -> V2Step -> (bucketed NCCL all-reduce of the 5.65 GB gradient arena) -> clip_grad_norm_ + AdamW over the two
-    lr groups -> refresh the bf16 operands -> EMA of the target parameters (:1264-1276)."""
+    lr groups -> refresh the bf16 operands -> EMA of the target parameters (:1264-1276).
+    Gradient accumulation (`accelerator.accumulate(unet)`, :945; --gradient_accumulation_steps): call with accumulate=True for the
+    first N - 1 micro-batches — the backward adds into the arena, no exchange, no optimizer step — and normally for the last one with
+    grad_scale = 1 / N (accelerate averages the micro-batch losses); the arena is zeroed only at the start of a new accumulation."""
     student = step.student
     arena = student.arena
-    arena.zero_grad()
+    if not getattr(arena, "_accumulating", False):
+        arena.zero_grad()
+    arena._accumulating = bool(accumulate)
     if reducer is not None:
-        student.on_grads_final = reducer.ready
+        student.on_grads_final = None if accumulate else reducer.ready      # exchange only once, on the last micro-batch
     out = step(batch, **kw)
+    if accumulate:
+        return out
     if reducer is not None:
         reducer.finish()
-    arena.adamw_step(lr=lr, temporal_lr_scale=temporal_lr_scale, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=1.0 / world,
+    arena.adamw_step(lr=lr, temporal_lr_scale=temporal_lr_scale, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale / world,
                      max_grad_norm=max_grad_norm)
     student.refresh()
     if step.target_unet is not None:

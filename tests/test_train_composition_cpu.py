@@ -327,6 +327,55 @@ def test_v2_resume_reproduces_the_next_step(monkeypatch):
         assert torch.equal(a_, b_)
 
 
+def test_v2_gradient_accumulation_and_video_reward_form(monkeypatch):
+    """accumulate=True micro-batches add into the arena without stepping; the last call steps once with grad_scale = 1 / N: identical to
+    one step on the mean gradient.  And the video-reward call form of reward_gradient (as_video: [B, F, 3, H, W], :1090-1094)."""
+    mock_ops.install(monkeypatch)
+    from t2v_turbo_b200.distill_v2 import train_step_v2
+    g = torch.load(os.path.join(GOLD, "v2_step_small_motion.pt"))
+    inp = g["inputs"]
+    keys = ("index", "z_t", "cond_teacher_out", "uncond_teacher_out", "score", "use_motion_guide", "prompt_emb")
+    halves = [{k: inp[k][i:i + 1] for k in keys} for i in (0, 1)]
+    ws = [inp["w"][i:i + 1] for i in (0, 1)]
+    s1, step1, _ = _v2_setup(g, with_ema_target=False)
+    p0 = s1.arena.params.clone()
+    train_step_v2(step1, halves[0], lr=1e-4, accumulate=True, max_grad_norm=None, fixed=dict(w=ws[0]))
+    assert torch.equal(s1.arena.params, p0) and s1.arena.step == 0 and float(s1.arena.grad_norm()) > 0
+    g_first = s1.arena.grads.clone()
+    train_step_v2(step1, halves[1], lr=1e-4, grad_scale=0.5, max_grad_norm=None, fixed=dict(w=ws[1]))
+    assert s1.arena.step == 1 and not torch.equal(s1.arena.grads, g_first)
+    # reference: the two micro-batch gradients summed by hand, one AdamW step on their mean
+    s2, step2, _ = _v2_setup(g, with_ema_target=False)
+    s2.arena.zero_grad()
+    step2(halves[0], fixed=dict(w=ws[0]))
+    step2(halves[1], fixed=dict(w=ws[1]))
+    assert _rel(s1.arena.grads, s2.arena.grads) < 1e-6
+    s2.arena.adamw_step(lr=1e-4, weight_decay=0.0, grad_scale=0.5)
+    assert torch.allclose(s1.arena.params, s2.arena.params, rtol=0, atol=1e-9)
+    train_step_v2(step1, halves[0], lr=1e-4, accumulate=True, max_grad_norm=None, fixed=dict(w=ws[0]))   # a new accumulation starts from zero
+    g_new = s1.arena.grads.clone()
+    s1.arena.zero_grad()
+    step1(halves[0], fixed=dict(w=ws[0]))
+    assert torch.equal(g_new, s1.arena.grads)
+    # video-reward form
+    from oracle.configs import VAE_CONFIGS
+    from oracle.weights import vae_state_dict
+    from t2v_turbo_b200.vae import AutoencoderKL
+    from t2v_turbo_b200.vae_train import reward_gradient
+    vspec = VAE_CONFIGS["small"]
+    vae = AutoencoderKL(vspec["ddconfig"], vspec["embed_dim"])
+    vae.load_state_dict(vae_state_dict(vae.state_dict(), vspec["weight_seed"]))
+    seen = {}
+
+    def video_rm(imgs):
+        seen["shape"] = tuple(imgs.shape)
+        return imgs.mean((1, 2, 3, 4))
+    mp_ = torch.randn(2, 4, 4, 8, 8, generator=torch.Generator().manual_seed(9))
+    loss, d = reward_gradient(vae.eval(), mp_, video_rm, frame_idx=[0, 2, 3], batch_idx=[1], reward_scale=2.0, as_video=True)
+    assert seen["shape"] == (1, 3, 3, 32, 32) and d.shape == mp_.shape
+    assert d[0].abs().max() == 0 and d[1][:, 1].abs().max() == 0 and d[1][:, 0].abs().max() > 0 and torch.isfinite(loss)
+
+
 def test_attach_ema_target_aliases_the_target_arena(monkeypatch):
     """The EMA network's nn.Parameters are views of arena.target: an `ema_step` changes what its next forward packs, its state_dict()
     is the EMA checkpoint, and nothing aliases the student's live parameters."""
