@@ -12,7 +12,10 @@ STATUS.  Written after the round's GPU budget was all but spent; the last 1.7 GP
     wrong, not the step; the assertions that run reached are ordinary now with the v1 test's sanity bounds, the ones it did NOT
     reach (clip norm, AdamW deltas, EMA) and the new LINEAR-loss test that pins the backward itself against the reference's
     autograd (the v1 suite's approach) have never executed and stay NON-STRICT xfail: they run, XPASS is evidence, a failure
-    does not redden the suite.  The file sorts last so that nothing runs after it in the same process.
+    does not redden the suite.  Each of them (and the ones added later for the decoder gradient, the motion-prior score and the
+    mid-size student) runs in ITS OWN PROCESS with a timeout (`test_never_run_in_its_own_process`), so a hang or a sticky CUDA error
+    in never-executed device code cannot stall or poison anything else; what they measure is appended to
+    gpurun_out/r02_never_run_observed.jsonl and their logs to gpurun_out/r02_never_run_child_logs.txt.  The file sorts last.
 
 Kernel contracts are checked against tests/mock_ops.py evaluated on the CPU in fp32 on the same bf16-rounded inputs.
 """
@@ -25,8 +28,16 @@ import mock_ops
 from test_kernels_gpu import BF16, _ops, assert_close, rnd
 
 pytestmark = pytest.mark.gpu
-never_run = pytest.mark.xfail(strict=False, reason="v2 full fine-tune step: this part never ran on a GPU (round-2 budget exhausted); "
-                                                   "composition CPU-verified, kernels GPU-verified")
+_CHILD = bool(os.environ.get("T2V_ZZ_CHILD"))
+NEVER_RUN = []
+
+
+def never_run(fn):
+    """A test whose device code has never executed.  It runs in ITS OWN PROCESS (test_never_run_in_its_own_process below spawns
+    `pytest this_file::name --runxfail` with a timeout), so a hang, an illegal address or a sticky CUDA error in one of them can neither
+    stall the suite nor poison the tests that run after it; in the parent process the body is skipped."""
+    NEVER_RUN.append(fn.__name__)
+    return pytest.mark.skipif(not _CHILD, reason="never-run device code: executed in a child process by test_never_run_in_its_own_process")(fn)
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -384,3 +395,29 @@ def test_student_unet_vc2_topology_vs_reference_lora_gradients(cuda_device):
     _observe("student_unet_vc2_topology", forward_rel=e_y, ratio_min=ratio.min(), ratio_max=ratio.max(), worst_rel=max(rels.values()), concat_rel=total)
     assert e_y <= 1.15 * rb["output_rel"] and (ratio - 1).abs().max() < 4e-2
     assert max(rels.values()) <= 1.5 * rb["grad_rel_worst"] and total <= 1.3 * rb["grad_rel_concat"]
+
+
+# ----------------------------------------------------------------------------- the isolation harness for everything marked @never_run
+@pytest.mark.xfail(strict=False, reason="device code that never ran on a GPU (round-2 budget exhausted): an XPASS here is the first evidence, "
+                                        "a failure is recorded but does not redden the suite; host composition CPU-verified")
+@pytest.mark.parametrize("name", NEVER_RUN)
+def test_never_run_in_its_own_process(cuda_device, name):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", f"{os.path.abspath(__file__)}::{name}", "-m", "gpu", "--runxfail", "-q", "-s", "-p", "no:cacheprovider"]
+    try:
+        r = subprocess.run(cmd, cwd=root, env={**os.environ, "T2V_ZZ_CHILD": "1"}, capture_output=True, text=True, timeout=900)
+        rc, out = r.returncode, r.stdout[-6000:] + r.stderr[-2000:]
+    except subprocess.TimeoutExpired as e:
+        rc, out = -9, f"TIMEOUT after 900 s\n{(e.stdout or b'')[-3000:]!r}"
+    try:
+        d = os.path.join(os.environ.get("GRAFT_REPO_ROOT", root), "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "r02_never_run_child_logs.txt"), "a") as f:
+            f.write(f"===== {name}: rc={rc}\n{out}\n")
+    except OSError:
+        pass
+    import re
+    assert rc == 0, f"{name} failed in its child process (rc={rc}):\n{out[-1500:]}"
+    assert re.search(r"\b\d+ passed", out) and not re.search(r"\b\d+ skipped", out), f"{name}: the child did not actually run it:\n{out[-600:]}"
