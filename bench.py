@@ -463,8 +463,8 @@ def run_v2_step(args, rank, local_rank, world):
     fine-tune step per rank on one 16x320x512 sample with stored teacher outputs — motion-conditioned student forward (training
     mode), motion-prior guidance + DDIM step, the EMA network's target forward, pseudo-Huber loss, the hand-written backward with
     weight / bias / norm-affine gradients for all 1.41 B parameters, the bucketed NCCL all-reduce of the 5.65 GB fp32 gradient
-    arena overlapped with that backward, global-norm clip, fused AdamW over the two lr groups (33 launches), operand refresh and the
-    EMA update.  Eager (no CUDA graphs).
+    arena overlapped with that backward, global-norm clip, fused AdamW over the two lr groups (33 launches), operand refresh (and, with
+    --no-graph, the EMA target + its update).  Default: the self-target step as a chain of CUDA graphs; --no-graph: eager + EMA target.
     NOT part of the default bench and — the round's GPU budget having run out first — this WORKLOAD has never been executed
     (the step it times has: tests/test_zz_full_train_gpu.py on a small UNet): the line is unmeasured until someone runs it."""
     import torch
@@ -485,9 +485,10 @@ def run_v2_step(args, rank, local_rank, world):
         for prm in base.parameters():
             if prm.dim() > 1 and float(prm.abs().max()) == 0.0:
                 prm.normal_(0, 0.02)
-    student = FullUNet(base.eval(), with_target=True).train()
+    use_graph = not args.no_graph            # graphs: the self-target step (the script's default, --use_target_unet off); --no-graph: eager + EMA target
+    student = FullUNet(base.eval(), with_target=not use_graph).train()
     student.pack()
-    target = attach_ema_target(student, target)
+    target = None if use_graph else attach_ema_target(student, target)
     red = t2v_dist.ArenaReducer(student.arena.grads, n_buckets=16)
     step = V2Step(student, T2VTurboScheduler(linear_start=0.00085, linear_end=0.012), target_unet=target)
     g = torch.Generator(device=device).manual_seed(99 + rank)
@@ -495,6 +496,13 @@ def run_v2_step(args, rank, local_rank, world):
     batch = dict(index=torch.tensor([150]), use_motion_guide=torch.tensor([True]),
                  prompt_emb=torch.randn(1, 77, 1024, device=device, generator=g),
                  **{k: torch.randn(shape, device=device, generator=g) for k in ("z_t", "cond_teacher_out", "uncond_teacher_out", "score")})
+
+    launches_per_step = None
+    if use_graph:
+        from t2v_turbo_b200.distill_v2 import GraphedV2Step
+        n_a = ops.LAUNCHES
+        step = GraphedV2Step(step, batch, reducer=red)       # runs the device step twice: warm-up + capture
+        launches_per_step = (ops.LAUNCHES - n_a) // 2
 
     def one():
         return train_step_v2(step, batch, lr=1e-5, temporal_lr_scale=1.0, ema_decay=0.95, reducer=red, world=world)
@@ -514,6 +522,7 @@ def run_v2_step(args, rank, local_rank, world):
     clocks = sampler.stop()
     ms = t2v_dist.max_over_ranks([e0.elapsed_time(e1)], device)[0]
     finite = bool(torch.isfinite(out["loss"]).all()) and bool(torch.isfinite(student.arena.params).all())
+    launches = (ops.LAUNCHES - n0) + (launches_per_step * args.steps if use_graph else 0)
     if rank == 0:
         _emit(dict(metric="v2 full fine-tune steps/sec (one 16x320x512 sample per rank; student fwd+bwd over all 1.41B parameters, EMA target "
                           "fwd, all-reduce, AdamW, EMA)", value=world * args.steps / (ms * 1e-3), unit="samples/s", n_gpus=world,
@@ -521,9 +530,9 @@ def run_v2_step(args, rank, local_rank, world):
                    vs_baseline=None, dtype="bf16", data="synthetic",
                    config=dict(workload="train_latent_t2v_turbo_v2.py:945-1276 without the reward models: VC2 UNet (1.41B, motion-conditioned), "
                                         "every parameter trains, bs=1 per rank, fp32 gradient arena %d values, 16-bucket NCCL all-reduce overlapped "
-                                        "with the backward, two-group fused AdamW, EMA target" % student.arena.padded, parallelism=f"dp{world}",
-                               cuda_graph=False, finite=finite),
-                   gpu_launches=ops.LAUNCHES - n0, loss=float(out["loss"]), clocks=clocks))
+                                        "with the backward, two-group fused AdamW" % student.arena.padded, parallelism=f"dp{world}",
+                               cuda_graph=use_graph, target="self" if use_graph else "ema", finite=finite),
+                   gpu_launches=launches, loss=float(out["loss"]), clocks=clocks))
     t2v_dist.shutdown()
 
 

@@ -125,6 +125,78 @@ class V2Step:
         return out
 
 
+class GraphedV2Step:
+    """V2Step.device_step captured ONCE as a chain of CUDA graphs and replayed per step — the design of distill.GraphedDistillStep
+    (verified on B200 for the v1 step): the eager v2 step is tens of thousands of small launches through ctypes, i.e. host bound; the
+    capture is cut wherever the backward reports a block of the gradient arena final (`FullUNet.on_grads_final`), so the bucketed
+    all-reduce of the 5.65 GB arena keeps its overlap; per step only the host draws and the batch are copied into static buffers.
+    Self-target mode only (`--use_target_unet` off, the script's default): the student's bf16 operands are refreshed IN PLACE, so the
+    captured kernels keep reading valid buffers, whereas the EMA network's inference weights are re-packed into new buffers after
+    every update.  The reward hook (torch autograd) is not capturable either.  Never run on a GPU."""
+
+    BATCH_KEYS = ("z_t", "cond_teacher_out", "uncond_teacher_out", "score")
+
+    def __init__(self, step: V2Step, batch, reducer=None):
+        if step.target_unet is not None:
+            raise NotImplementedError("GraphedV2Step: the EMA target re-packs its weights out of place; capture the self-target step "
+                                      "(target_unet=None) or run the eager V2Step")
+        if getattr(step, "reward", None) is not None:
+            raise NotImplementedError("GraphedV2Step: the reward branch runs torch autograd and is not captured; use the eager V2Step")
+        self.step, self.reducer = step, reducer
+        dev = batch["z_t"].device
+        self.bufs = {k: batch[k].to(dev).float().contiguous().clone() for k in self.BATCH_KEYS}
+        self.prompt = batch["prompt_emb"].to(dev).clone()
+        bsz = batch["index"].numel()
+        H = step.host_draws(batch["index"], torch.ones(bsz, dtype=torch.bool))
+        self.S = {k: v.to(dev) for k, v in H.items() if torch.is_tensor(v) and k not in ("index", "w", "motion_gs")}
+        student = step.student
+        student.on_grads_final = None
+        student.arena.zero_grad()
+        self._run()                                   # warm-up: lazy allocations, kernel attributes, the dropout seed
+        torch.cuda.synchronize()
+        self.segments = []                            # [(graph, arena offset that is final after it)]
+        pool = torch.cuda.graph_pool_handle()
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            cur = [torch.cuda.CUDAGraph()]
+            cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
+
+            def cut(offset):
+                cur[0].capture_end()
+                self.segments.append((cur[0], offset))
+                cur[0] = torch.cuda.CUDAGraph()
+                cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
+            student.on_grads_final = cut
+            self.out = self._run()
+            cur[0].capture_end()
+            self.segments.append((cur[0], 0))
+        torch.cuda.current_stream().wait_stream(stream)
+        student.on_grads_final = None
+
+    def _run(self):
+        b = self.bufs
+        return self.step.device_step(self.S, b["z_t"], b["cond_teacher_out"], b["uncond_teacher_out"], b["score"], self.prompt)
+
+    def __call__(self, batch, *, fixed=None, generator=None):
+        umg = batch.get("use_motion_guide")
+        if umg is None:
+            umg = torch.ones(batch["index"].numel(), dtype=torch.bool)
+        H = self.step.host_draws(batch["index"], umg, fixed, generator)
+        for k, buf in self.S.items():
+            buf.copy_(H[k], non_blocking=True)
+        for k in self.BATCH_KEYS:
+            self.bufs[k].copy_(batch[k])
+        self.prompt.copy_(batch["prompt_emb"])
+        for g, offset in self.segments:
+            g.replay()
+            if self.reducer is not None:
+                self.reducer.ready(offset)
+        out = dict(self.out)
+        out.update(start_timesteps=H["start_timesteps"], timesteps=H["timesteps"], w=H["w"], motion_gs=H["motion_gs"])
+        return out
+
+
 def attach_ema_target(student, target_unet, dtype=torch.bfloat16):
     """Make `target_unet` (a fresh `UNetModel` of the student's configuration, on the student's device) the EMA network of a
     `FullUNet(..., with_target=True)` (train_latent_t2v_turbo_v2.py:733-746): its parameters become views of the student's target arena —
@@ -146,12 +218,16 @@ def train_step_v2(step: V2Step, batch, *, lr, temporal_lr_scale=1.0, ema_decay=0
     Gradient accumulation (`accelerator.accumulate(unet)`, :945; --gradient_accumulation_steps): call with accumulate=True for the
     first N - 1 micro-batches — the backward adds into the arena, no exchange, no optimizer step — and normally for the last one with
     grad_scale = 1 / N (accelerate averages the micro-batch losses); the arena is zeroed only at the start of a new accumulation."""
-    student = step.student
+    graphed = isinstance(step, GraphedV2Step)
+    student = step.step.student if graphed else step.student
     arena = student.arena
     if not getattr(arena, "_accumulating", False):
         arena.zero_grad()
     arena._accumulating = bool(accumulate)
-    if reducer is not None:
+    if graphed:
+        if accumulate:
+            raise NotImplementedError("train_step_v2: gradient accumulation with a GraphedV2Step (its replay drives the reducer)")
+    elif reducer is not None:
         student.on_grads_final = None if accumulate else reducer.ready      # exchange only once, on the last micro-batch
     out = step(batch, **kw)
     if accumulate:
@@ -161,7 +237,8 @@ def train_step_v2(step: V2Step, batch, *, lr, temporal_lr_scale=1.0, ema_decay=0
     arena.adamw_step(lr=lr, temporal_lr_scale=temporal_lr_scale, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale / world,
                      max_grad_norm=max_grad_norm)
     student.refresh()
-    if step.target_unet is not None:
+    target_unet = None if graphed else step.target_unet
+    if target_unet is not None:
         arena.ema_step(ema_decay)
-        step.target_unet.invalidate_packed()
+        target_unet.invalidate_packed()
     return out
