@@ -503,6 +503,7 @@ def run_v2_step(args, rank, local_rank, world):
         n_a = ops.LAUNCHES
         step = GraphedV2Step(step, batch, reducer=red)       # runs the device step twice: warm-up + capture
         launches_per_step = (ops.LAUNCHES - n_a) // 2
+        student.graph_refresh()                              # the per-step operand refresh (~600 layers) as one graph replay
 
     def one():
         return train_step_v2(step, batch, lr=1e-5, temporal_lr_scale=1.0, ema_decay=0.95, reducer=red, world=world)
